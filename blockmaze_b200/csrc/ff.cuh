@@ -1,0 +1,341 @@
+// BN254 (alt_bn128) prime-field arithmetic for sm_100a: 8 x 32-bit limbs, Montgomery form with R = 2^256.
+//
+// Replaces the reference's 4 x 64-bit Fp_model (libff/algebra/fields/fp.tcc:23-190 mul_reduce, :407-507 add/sub,
+// fp_aux.tcc x86-64 asm) with carry-chained 32-bit IMAD sequences (mad.lo.cc / madc.hi.cc).  The Montgomery
+// representative x*2^256 mod p is bit-identical to libff's mont_repr, so proving-key bytes are used as stored.
+//
+// The multiplication is an interleaved (CIOS) product-scanning scheme that keeps the running sum split into an
+// "even" and an "odd" column accumulator so that every row of partial products is one uninterrupted carry chain
+// of mad.lo.cc/madc.hi.cc pairs (ptxas fuses each pair into one IMAD.WIDE.U32.X): 2*8*8 wide multiply-adds per
+// modmul plus 8 single multiplies for the Montgomery quotients.
+//
+// The same source compiles for the host (carry flag emulated in C) so the algorithm is unit-tested on CPU and the
+// host-side glue (proof assembly, pairing) shares one implementation.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ZK_HD __host__ __device__ __forceinline__
+#define ZK_D __device__ __forceinline__
+#else
+#define ZK_HD inline
+#define ZK_D inline
+#endif
+
+namespace zk {
+
+// ---------------------------------------------------------------------------------------------------------------
+// carry-flag primitives: PTX on device, C emulation on host
+struct Carry {
+#if !defined(__CUDA_ARCH__)
+    uint32_t cf = 0;
+#endif
+    // d = a + b, set carry
+    ZK_HD void add_cc(uint32_t &d, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+#else
+        uint64_t s = (uint64_t)a + b; d = (uint32_t)s; cf = (uint32_t)(s >> 32);
+#endif
+    }
+    ZK_HD void addc_cc(uint32_t &d, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+#else
+        uint64_t s = (uint64_t)a + b + cf; d = (uint32_t)s; cf = (uint32_t)(s >> 32);
+#endif
+    }
+    ZK_HD void addc(uint32_t &d, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("addc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+#else
+        d = a + b + cf;
+#endif
+    }
+    ZK_HD void sub_cc(uint32_t &d, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+#else
+        uint64_t s = (uint64_t)a - b; d = (uint32_t)s; cf = (uint32_t)((s >> 32) & 1);   // cf = borrow
+#endif
+    }
+    ZK_HD void subc_cc(uint32_t &d, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+#else
+        uint64_t s = (uint64_t)a - b - cf; d = (uint32_t)s; cf = (uint32_t)((s >> 32) & 1);
+#endif
+    }
+    // d = 0 - 0 - borrow  -> 0 or 0xffffffff
+    ZK_HD void subc(uint32_t &d, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("subc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+#else
+        d = a - b - cf;
+#endif
+    }
+    // lo/hi(a*b) + c with carry handling
+    ZK_HD void mad_lo_cc(uint32_t &d, uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+#else
+        uint64_t s = (uint64_t)(uint32_t)((uint64_t)a * b) + c; d = (uint32_t)s; cf = (uint32_t)(s >> 32);
+#endif
+    }
+    ZK_HD void madc_lo_cc(uint32_t &d, uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+#else
+        uint64_t s = (uint64_t)(uint32_t)((uint64_t)a * b) + c + cf; d = (uint32_t)s; cf = (uint32_t)(s >> 32);
+#endif
+    }
+    ZK_HD void madc_hi_cc(uint32_t &d, uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+#else
+        uint64_t s = (((uint64_t)a * b) >> 32) + c + cf; d = (uint32_t)s; cf = (uint32_t)(s >> 32);
+#endif
+    }
+    ZK_HD void madc_hi(uint32_t &d, uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+#else
+        d = (uint32_t)(((uint64_t)a * b) >> 32) + c + cf;
+#endif
+    }
+};
+
+ZK_HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+ZK_HD uint32_t mul_hi(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// field parameter packs (alt_bn128_init.cpp:96-144).  Limbs little-endian.
+struct FrParams {   // scalar field r
+    static constexpr uint32_t INV = 0xefffffffu;   // -r^-1 mod 2^32
+    ZK_HD static constexpr uint32_t mod(int i) {
+        return i == 0 ? 0xf0000001u : i == 1 ? 0x43e1f593u : i == 2 ? 0x79b97091u : i == 3 ? 0x2833e848u :
+               i == 4 ? 0x8181585du : i == 5 ? 0xb85045b6u : i == 6 ? 0xe131a029u : 0x30644e72u;
+    }
+    ZK_HD static constexpr uint32_t one(int i) {     // R mod r
+        return i == 0 ? 0x4ffffffbu : i == 1 ? 0xac96341cu : i == 2 ? 0x9f60cd29u : i == 3 ? 0x36fc7695u :
+               i == 4 ? 0x7879462eu : i == 5 ? 0x666ea36fu : i == 6 ? 0x9a07df2fu : 0x0e0a77c1u;
+    }
+    ZK_HD static constexpr uint32_t r2(int i) {      // R^2 mod r
+        return i == 0 ? 0xae216da7u : i == 1 ? 0x1bb8e645u : i == 2 ? 0xe35c59e3u : i == 3 ? 0x53fe3ab1u :
+               i == 4 ? 0x53bb8085u : i == 5 ? 0x8c49833du : i == 6 ? 0x7f4e44a5u : 0x0216d0b1u;
+    }
+};
+struct FqParams {   // base field q
+    static constexpr uint32_t INV = 0xe4866389u;   // -q^-1 mod 2^32
+    ZK_HD static constexpr uint32_t mod(int i) {
+        return i == 0 ? 0xd87cfd47u : i == 1 ? 0x3c208c16u : i == 2 ? 0x6871ca8du : i == 3 ? 0x97816a91u :
+               i == 4 ? 0x8181585du : i == 5 ? 0xb85045b6u : i == 6 ? 0xe131a029u : 0x30644e72u;
+    }
+    ZK_HD static constexpr uint32_t one(int i) {     // R mod q
+        return i == 0 ? 0xc58f0d9du : i == 1 ? 0xd35d438du : i == 2 ? 0xf5c70b3du : i == 3 ? 0x0a78eb28u :
+               i == 4 ? 0x7879462cu : i == 5 ? 0x666ea36fu : i == 6 ? 0x9a07df2fu : 0x0e0a77c1u;
+    }
+    ZK_HD static constexpr uint32_t r2(int i) {      // R^2 mod q
+        return i == 0 ? 0x538afa89u : i == 1 ? 0xf32cfc5bu : i == 2 ? 0xd44501fbu : i == 3 ? 0xb5e71911u :
+               i == 4 ? 0x0a417ff6u : i == 5 ? 0x47ab1effu : i == 6 ? 0xcab8351fu : 0x06d89f71u;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+template <class P> struct Fp {
+    uint32_t v[8];
+
+    ZK_HD static Fp zero() { Fp r; for (int i = 0; i < 8; i++) r.v[i] = 0; return r; }
+    ZK_HD static Fp one() { Fp r; for (int i = 0; i < 8; i++) r.v[i] = P::one(i); return r; }
+    ZK_HD static Fp r2() { Fp r; for (int i = 0; i < 8; i++) r.v[i] = P::r2(i); return r; }
+    ZK_HD static Fp modulus() { Fp r; for (int i = 0; i < 8; i++) r.v[i] = P::mod(i); return r; }
+
+    ZK_HD bool is_zero() const { uint32_t o = 0; for (int i = 0; i < 8; i++) o |= v[i]; return o == 0; }
+    ZK_HD bool operator==(const Fp &b) const { uint32_t o = 0; for (int i = 0; i < 8; i++) o |= v[i] ^ b.v[i]; return o == 0; }
+    ZK_HD bool operator!=(const Fp &b) const { return !(*this == b); }
+
+    // r = a - p if a >= p (input < 2p)
+    ZK_HD void reduce_once() {
+        Carry c; uint32_t t[8], brw;
+        c.sub_cc(t[0], v[0], P::mod(0));
+#pragma unroll
+        for (int i = 1; i < 8; i++) c.subc_cc(t[i], v[i], P::mod(i));
+        c.subc(brw, 0, 0);
+        if (brw == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = t[i];
+        }
+    }
+
+    ZK_HD friend Fp operator+(const Fp &a, const Fp &b) {
+        Fp r; Carry c;
+        c.add_cc(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) c.addc_cc(r.v[i], a.v[i], b.v[i]);   // no overflow: a,b < p < 2^254
+        r.reduce_once();
+        return r;
+    }
+    ZK_HD friend Fp operator-(const Fp &a, const Fp &b) {
+        Fp r; Carry c; uint32_t brw;
+        c.sub_cc(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) c.subc_cc(r.v[i], a.v[i], b.v[i]);
+        c.subc(brw, 0, 0);            // 0xffffffff if a < b
+        Carry d;
+        d.add_cc(r.v[0], r.v[0], P::mod(0) & brw);
+#pragma unroll
+        for (int i = 1; i < 8; i++) d.addc_cc(r.v[i], r.v[i], P::mod(i) & brw);
+        return r;
+    }
+    ZK_HD Fp neg() const { return is_zero() ? *this : modulus_minus(*this); }
+    ZK_HD static Fp modulus_minus(const Fp &a) {
+        Fp r; Carry c;
+        c.sub_cc(r.v[0], P::mod(0), a.v[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) c.subc_cc(r.v[i], P::mod(i), a.v[i]);
+        return r;
+    }
+    ZK_HD Fp dbl() const { return *this + *this; }
+
+    // Montgomery product a*b*R^-1 mod p, inputs and output fully reduced (< p).
+    //
+    // acc[0] ("E") holds 64-bit partial products whose low limb sits at an EVEN absolute column, acc[1] ("O") those at an
+    // ODD column; the running sum is E + O.  Row i adds a*b_i and m_i*p at columns i..i+8, so nothing is ever shifted:
+    // every multiply-add has destination == addend and ptxas fuses each mad.lo.cc/madc.hi.cc pair into one
+    // IMAD.WIDE.U32.X.  H = acc[i&1] owns column i ("hot"), C = the other one has a dangling high limb there, which is
+    // merged first (add.cc) so that the quotient digit m_i sees the whole column; its carry rides into C's chain.
+    ZK_HD friend Fp operator*(const Fp &a, const Fp &b) {
+        uint32_t acc[2][18];
+#pragma unroll
+        for (int k = 0; k < 18; k++) { acc[0][k] = 0; acc[1][k] = 0; }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t *H = acc[i & 1], *Cc = acc[(i & 1) ^ 1];
+            const uint32_t bi = b.v[i];
+            Carry c;
+            if (i == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    H[j] = mul_lo(a.v[j], bi);      H[j + 1] = mul_hi(a.v[j], bi);
+                    Cc[j + 1] = mul_lo(a.v[j + 1], bi); Cc[j + 2] = mul_hi(a.v[j + 1], bi);
+                }
+            } else {
+                c.add_cc(H[i], H[i], Cc[i]);
+#pragma unroll
+                for (int j = 1; j < 8; j += 2) {
+                    c.madc_lo_cc(Cc[i + j], a.v[j], bi, Cc[i + j]);
+                    if (j < 7) c.madc_hi_cc(Cc[i + j + 1], a.v[j], bi, Cc[i + j + 1]);
+                    else c.madc_hi(Cc[i + j + 1], a.v[j], bi, Cc[i + j + 1]);
+                }
+                Carry d;
+                d.mad_lo_cc(H[i], a.v[0], bi, H[i]);
+                d.madc_hi_cc(H[i + 1], a.v[0], bi, H[i + 1]);
+#pragma unroll
+                for (int j = 2; j < 8; j += 2) {
+                    d.madc_lo_cc(H[i + j], a.v[j], bi, H[i + j]);
+                    d.madc_hi_cc(H[i + j + 1], a.v[j], bi, H[i + j + 1]);
+                }
+                d.addc(Cc[i + 8], Cc[i + 8], 0);
+            }
+            const uint32_t m = mul_lo(H[i], P::INV);
+            Carry e;
+            e.mad_lo_cc(Cc[i + 1], P::mod(1), m, Cc[i + 1]);
+            e.madc_hi_cc(Cc[i + 2], P::mod(1), m, Cc[i + 2]);
+#pragma unroll
+            for (int j = 3; j < 8; j += 2) {
+                e.madc_lo_cc(Cc[i + j], P::mod(j), m, Cc[i + j]);
+                if (j < 7) e.madc_hi_cc(Cc[i + j + 1], P::mod(j), m, Cc[i + j + 1]);
+                else e.madc_hi(Cc[i + j + 1], P::mod(j), m, Cc[i + j + 1]);
+            }
+            Carry f;
+            f.mad_lo_cc(H[i], P::mod(0), m, H[i]);
+            f.madc_hi_cc(H[i + 1], P::mod(0), m, H[i + 1]);
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) {
+                f.madc_lo_cc(H[i + j], P::mod(j), m, H[i + j]);
+                f.madc_hi_cc(H[i + j + 1], P::mod(j), m, H[i + j + 1]);
+            }
+            f.addc(Cc[i + 8], Cc[i + 8], 0);
+        }
+        // after row 7 (H = O, C = E): result = columns 8..15 of E + O
+        Fp r; Carry c;
+        c.add_cc(r.v[0], acc[0][8], acc[1][8]);
+#pragma unroll
+        for (int k = 1; k < 7; k++) c.addc_cc(r.v[k], acc[0][8 + k], acc[1][8 + k]);
+        c.addc(r.v[7], acc[0][15], 0);
+        r.reduce_once();
+        return r;
+    }
+    ZK_HD Fp sqr() const { return *this * *this; }
+
+    // canonical <-> Montgomery
+    ZK_HD Fp to_mont() const { return *this * r2(); }
+    ZK_HD Fp from_mont() const { Fp o = zero(); o.v[0] = 1; return *this * o; }
+
+    // a^e for a little-endian 8-limb exponent (plain integer), square-and-multiply MSB first
+    ZK_HD Fp pow(const uint32_t e[8]) const {
+        Fp r = one(); bool started = false;
+        for (int i = 255; i >= 0; i--) {
+            if (started) r = r.sqr();
+            if ((e[i >> 5] >> (i & 31)) & 1) { r = started ? r * *this : *this; started = true; }
+        }
+        return r;
+    }
+    ZK_HD Fp pow_u64(uint64_t e) const {
+        uint32_t ee[8] = {(uint32_t)e, (uint32_t)(e >> 32), 0, 0, 0, 0, 0, 0};
+        return pow(ee);
+    }
+    // Fermat inverse a^(p-2); returns 0 for 0
+    ZK_HD Fp inverse() const {
+        uint32_t e[8]; Carry c;
+        c.sub_cc(e[0], P::mod(0), 2);
+        for (int i = 1; i < 8; i++) c.subc_cc(e[i], P::mod(i), 0);
+        return pow(e);
+    }
+};
+
+typedef Fp<FrParams> Fr;
+typedef Fp<FqParams> Fq;
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fq2 = Fq[u]/(u^2 + 1)   (libff/algebra/fields/fp2.tcc; non_residue = -1, alt_bn128_init.cpp:151)
+struct Fq2 {
+    Fq c0, c1;
+    ZK_HD static Fq2 zero() { Fq2 r; r.c0 = Fq::zero(); r.c1 = Fq::zero(); return r; }
+    ZK_HD static Fq2 one() { Fq2 r; r.c0 = Fq::one(); r.c1 = Fq::zero(); return r; }
+    ZK_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    ZK_HD bool operator==(const Fq2 &b) const { return c0 == b.c0 && c1 == b.c1; }
+    ZK_HD bool operator!=(const Fq2 &b) const { return !(*this == b); }
+    ZK_HD friend Fq2 operator+(const Fq2 &a, const Fq2 &b) { Fq2 r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; return r; }
+    ZK_HD friend Fq2 operator-(const Fq2 &a, const Fq2 &b) { Fq2 r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; return r; }
+    ZK_HD Fq2 neg() const { Fq2 r; r.c0 = c0.neg(); r.c1 = c1.neg(); return r; }
+    ZK_HD Fq2 dbl() const { Fq2 r; r.c0 = c0.dbl(); r.c1 = c1.dbl(); return r; }
+    ZK_HD friend Fq2 operator*(const Fq2 &a, const Fq2 &b) {      // Karatsuba, 3 base multiplications
+        Fq aa = a.c0 * b.c0, bb = a.c1 * b.c1;
+        Fq2 r;
+        r.c1 = (a.c0 + a.c1) * (b.c0 + b.c1) - aa - bb;
+        r.c0 = aa - bb;
+        return r;
+    }
+    ZK_HD Fq2 sqr() const {                                         // complex squaring, 2 base multiplications
+        Fq ab = c0 * c1;
+        Fq2 r;
+        r.c0 = (c0 + c1) * (c0 - c1);
+        r.c1 = ab.dbl();
+        return r;
+    }
+    ZK_HD Fq2 mul_fq(const Fq &s) const { Fq2 r; r.c0 = c0 * s; r.c1 = c1 * s; return r; }
+    ZK_HD Fq2 inverse() const {
+        Fq t = (c0.sqr() + c1.sqr()).inverse();
+        Fq2 r; r.c0 = c0 * t; r.c1 = (c1 * t).neg();
+        return r;
+    }
+};
+
+} // namespace zk

@@ -1,0 +1,161 @@
+"""ctypes bindings of include/zkb200.h (layer 2) and of the BlockMaze cgo surface (layer 1).
+
+Wire formats: field elements 32-byte little-endian canonical; G1 affine 64 B (x y); G2 affine 128 B (x.c0 x.c1 y.c0 y.c1).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzkb200.so")
+CIRCUITS = ("mint", "send", "deposit", "redeem")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError("blockmaze_b200: %s is missing -- run `python __graft_entry__.py` (nvcc, sm_100a). "
+                      "There is no CPU fallback." % LIB_PATH)
+lib = C.CDLL(LIB_PATH)
+
+lib.zkb200_init.argtypes = [C.c_int]
+lib.zkb200_last_error.restype = C.c_char_p
+lib.zkb200_pk_load.restype = C.c_void_p
+lib.zkb200_pk_load.argtypes = [C.c_char_p]
+lib.zkb200_pk_free.argtypes = [C.c_void_p]
+lib.zkb200_pk_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+lib.zkb200_prove.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_float)]
+lib.zkb200_qap_witness_map.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
+lib.zkb200_domain_op.restype = C.c_long
+lib.zkb200_domain_op.argtypes = [C.c_size_t, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
+lib.zkb200_msm_g1.argtypes = [C.c_size_t, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p]
+lib.zkb200_msm_g2.argtypes = [C.c_size_t, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p]
+lib.zkb200_field_op.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p]
+lib.zkb200_bench_ntt.restype = C.c_float
+lib.zkb200_bench_ntt.argtypes = [C.c_int, C.c_int, C.c_int]
+lib.zkb200_bench_msm.restype = C.c_float
+lib.zkb200_bench_msm.argtypes = [C.c_int, C.c_size_t, C.c_int, C.c_int]
+lib.zkb200_bench_imad_peak.restype = C.c_float
+lib.zkb200_bench_imad_peak.argtypes = [C.c_int]
+
+DOMAIN_OPS = {"FFT": 0, "iFFT": 1, "cosetFFT": 2, "icosetFFT": 3, "divide_by_Z_on_coset": 4}
+FIELD_OPS = {"mul": 0, "add": 1, "sub": 2, "sqr": 3, "to_mont": 4, "from_mont": 5, "inverse": 6}
+
+
+class ZkError(RuntimeError):
+    pass
+
+
+def last_error():
+    return (lib.zkb200_last_error() or b"").decode()
+
+
+def init(device=0):
+    if lib.zkb200_init(device) != 0:
+        raise ZkError(last_error())
+
+
+def domain_size(min_size):
+    kind = C.c_int(0)
+    m = lib.zkb200_domain_op(min_size, 0, None, 0, C.byref(kind))
+    if m < 0:
+        raise ZkError(last_error())
+    return m, ("step_radix2" if kind.value else "basic_radix2")
+
+
+def domain_op(min_size, op, data):
+    """data: bytes of m canonical 32-byte elements; returns the transformed bytes."""
+    buf = C.create_string_buffer(bytes(data), len(data))
+    m = lib.zkb200_domain_op(min_size, DOMAIN_OPS[op], buf, len(data) // 32, None)
+    if m < 0:
+        raise ZkError(last_error())
+    return buf.raw
+
+
+def msm_g1(bases, scalars, window_bits=0):
+    out = C.create_string_buffer(64)
+    if lib.zkb200_msm_g1(len(scalars) // 32, bytes(bases), bytes(scalars), window_bits, out) != 0:
+        raise ZkError(last_error())
+    return out.raw
+
+
+def msm_g2(bases, scalars, window_bits=0):
+    out = C.create_string_buffer(128)
+    if lib.zkb200_msm_g2(len(scalars) // 32, bytes(bases), bytes(scalars), window_bits, out) != 0:
+        raise ZkError(last_error())
+    return out.raw
+
+
+def field_op(field, op, a, b=None):
+    """Raw Montgomery-representation field op on the GPU.  field: 'fr'|'fq'."""
+    n = len(a) // 32
+    out = C.create_string_buffer(32 * n)
+    if lib.zkb200_field_op(0 if field == "fr" else 1, FIELD_OPS[op], n, bytes(a), bytes(b) if b is not None else None, out) != 0:
+        raise ZkError(last_error())
+    return out.raw
+
+
+class ProvingKey:
+    """A proving key resident on the GPU (zkb200_pk_load)."""
+
+    def __init__(self, path):
+        self.handle = lib.zkb200_pk_load(os.fsencode(path))
+        if not self.handle:
+            raise ZkError(last_error())
+        info = (C.c_uint64 * 8)()
+        secs = (C.c_double * 3)()
+        lib.zkb200_pk_info(self.handle, info, secs)
+        (self.num_variables, self.num_inputs, self.num_constraints, self.domain_size, kind, self.nnz, self.num_coefficients,
+         self.b_entries) = [int(x) for x in info]
+        self.domain_kind = "step_radix2" if kind else "basic_radix2"
+        self.load_seconds, self.parse_seconds, self.decompress_seconds = [float(x) for x in secs]
+
+    def prove(self, assignment, r, s):
+        """assignment: bytes (num_variables*32) or None to reuse the resident one; r, s: ints.
+        Returns dict(rc, proof_hex, parts(384 B), timings_ms[gpu, qap, msm_h, host])."""
+        hexbuf = C.create_string_buffer(513)
+        parts = C.create_string_buffer(384)
+        tim = (C.c_float * 4)()
+        if assignment is not None and len(assignment) != self.num_variables * 32:
+            raise ValueError("assignment must be num_variables*32 bytes")
+        rc = lib.zkb200_prove(self.handle, assignment, int(r).to_bytes(32, "little"), int(s).to_bytes(32, "little"), hexbuf, parts, tim)
+        if rc < 0:
+            raise ZkError(last_error())
+        return dict(rc=rc, proof_hex=hexbuf.value.decode(), parts=parts.raw, timings_ms=list(tim), launches=lib.zkb200_last_launches())
+
+    def qap_witness_map(self, assignment):
+        out = C.create_string_buffer((self.domain_size + 1) * 32)
+        sat = C.c_int(0)
+        if lib.zkb200_qap_witness_map(self.handle, assignment, out, C.byref(sat)) != 0:
+            raise ZkError(last_error())
+        return out.raw, bool(sat.value)
+
+    def close(self):
+        if self.handle:
+            lib.zkb200_pk_free(self.handle)
+            self.handle = None
+
+
+def smoke():
+    """One small invocation of the hot path on cuda:0, checked against the oracle (test infrastructure)."""
+    import random
+    import sys
+    sys.path.insert(0, os.path.dirname(_HERE))
+    from oracle import bn254_oracle as O
+    init(0)
+    rng = random.Random(1)
+    for ms in (1 << 10, 768):
+        dom = O.get_evaluation_domain(ms)
+        v = [rng.randrange(O.R_MOD) for _ in range(dom.m)]
+        raw = b"".join(x.to_bytes(32, "little") for x in v)
+        got = domain_op(ms, "cosetFFT", raw)
+        exp = b"".join(x.to_bytes(32, "little") for x in dom.cosetFFT(v, O.FR_GENERATOR))
+        assert got == exp, "NTT mismatch against the oracle"
+    n = 64
+    pts, P = [], O.G1_ONE
+    for _ in range(n):
+        P = O.G1.add(P, O.G1.dbl(P))
+        pts.append(O.G1.to_affine(P))
+    sc = [rng.randrange(O.R_MOD) for _ in range(n)]
+    sc[3], sc[5] = 0, 1
+    bases = b"".join(x.to_bytes(32, "little") + y.to_bytes(32, "little") for x, y in pts)
+    got = msm_g1(bases, b"".join(x.to_bytes(32, "little") for x in sc))
+    exp = O.G1.to_affine(O.G1.multi_exp_with_mixed_addition([O.G1.from_affine(p) for p in pts], sc))
+    assert got == exp[0].to_bytes(32, "little") + exp[1].to_bytes(32, "little"), "MSM mismatch against the oracle"
+    print("blockmaze_b200 smoke ok")

@@ -1,0 +1,333 @@
+// C-ABI layer (2) of include/zkb200.h: resident proving keys, prover, kernel-level entry points and device benchmarks.
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/zkb200.h"
+#include "prover.cuh"
+#include "ntt.cuh"
+#include "msm.cuh"
+
+using namespace zk;
+using namespace zkp;
+
+static std::string g_err;
+static int g_device = -1;
+static std::mutex g_mu;
+
+static int ensure_device() {
+    if (g_device >= 0) { cudaSetDevice(g_device); return 0; }
+    const char *e = getenv("ZKB200_DEVICE");
+    return zkb200_init(e ? atoi(e) : 0);
+}
+
+template <class F> __global__ void to_mont_generic_kernel(F *a, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = a[i].to_mont();
+}
+template <class F> __global__ void field_op_kernel(const F *a, const F *b, F *out, size_t n, int op) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = a[i], y = b ? b[i] : F::zero(), z;
+    switch (op) {
+    case 0: z = x * y; break;
+    case 1: z = x + y; break;
+    case 2: z = x - y; break;
+    case 3: z = x.sqr(); break;
+    case 4: z = x.to_mont(); break;
+    case 5: z = x.from_mont(); break;
+    default: z = x.inverse(); break;
+    }
+    out[i] = z;
+}
+
+__global__ void fill_scalars_kernel(uint32_t *out, size_t n, uint64_t seed) {      // splitmix64 stream, reduced below 2^253
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int w = 0; w < 4; w++) {
+        uint64_t z = seed + (i * 4 + w + 1) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+        out[i * 8 + 2 * w] = (uint32_t)z; out[i * 8 + 2 * w + 1] = (uint32_t)(z >> 32);
+    }
+    out[i * 8 + 7] &= 0x1fffffffu;
+}
+template <class F> __global__ void gen_bases_kernel(Affine<F> gen, Affine<F> *out, size_t n) {   // P_i = (i+1) * 0x9E3779B97F4A7C15 * G (mod 2^64 scalar)
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = (i + 1) * 0x9E3779B97F4A7C15ull | 1ull;
+    uint32_t kk[8] = {(uint32_t)k, (uint32_t)(k >> 32), 0, 0, 0, 0, 0, 0};
+    XYZZ<F> g = XYZZ<F>::from_affine(gen), r = XYZZ<F>::inf();
+    for (int b = 63; b >= 0; b--) { r = r.dbl(); if ((kk[b >> 5] >> (b & 31)) & 1) r.add(g); }
+    out[i] = r.to_affine();
+}
+
+__global__ void imad_peak_kernel(uint32_t *out, int iters, int wide) {
+    uint32_t a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 3;
+    uint64_t w0 = a, w1 = b, w2 = a ^ b, w3 = a + b, w4 = 5, w5 = 7, w6 = 11, w7 = 13;
+    uint32_t x0 = a, x1 = b, x2 = a ^ b, x3 = a + b, x4 = 5, x5 = 7, x6 = 11, x7 = 13;
+    if (wide) {
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w0) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w1) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w2) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w3) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w4) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w5) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w6) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w7) : "r"(a), "r"(b));
+            }
+        }
+        out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)(w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7);
+    } else {
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x0) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x1) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x2) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x3) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x4) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x5) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x6) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x7) : "r"(a), "r"(b));
+            }
+        }
+        out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+    }
+}
+// every exported function below is declared extern "C" in include/zkb200.h, which fixes its linkage
+
+int zkb200_init(int device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { g_err = "no CUDA device: the B200 prover has no CPU fallback"; return -1; }
+    if (device < 0 || device >= count) { g_err = "bad device index"; return -1; }
+    g_device = device;
+    device_init(device);
+    ntt_init_attrs();            // this translation unit's own instances of the NTT kernels
+    return 0;
+}
+const char *zkb200_last_error(void) { return g_err.c_str(); }
+
+void *zkb200_pk_load(const char *path) {
+    if (ensure_device()) return nullptr;
+    std::string err;
+    DevicePk *pk = pk_load(path, g_device, err);
+    if (!pk) g_err = err;
+    return pk;
+}
+void zkb200_pk_free(void *pk) { pk_free((DevicePk *)pk); }
+int zkb200_pk_info(void *h, uint64_t info[8], double seconds[3]) {
+    DevicePk *pk = (DevicePk *)h;
+    if (!pk) return -1;
+    info[0] = pk->num_vars; info[1] = pk->num_inputs; info[2] = pk->num_constraints; info[3] = pk->dom->m; info[4] = pk->dom->step ? 1 : 0;
+    info[5] = (uint64_t)pk->a.nnz + pk->b.nnz + pk->c.nnz; info[6] = pk->ncoef; info[7] = pk->nB;
+    if (seconds) { seconds[0] = pk->load_seconds; seconds[1] = pk->parse_seconds; seconds[2] = pk->decompress_seconds; }
+    return 0;
+}
+
+static void put_fq(uint8_t *o, const zkh::HFq &x) { uint64_t c[4]; x.to_canonical(c); memcpy(o, c, 32); }
+static void put_g1(uint8_t *o, const zkh::HG1Affine &a) { if (a.is_inf()) { memset(o, 0, 64); return; } put_fq(o, a.x); put_fq(o + 32, a.y); }
+static void put_g2(uint8_t *o, const zkh::HG2Affine &a) {
+    if (a.is_inf()) { memset(o, 0, 128); return; }
+    put_fq(o, a.x.c0); put_fq(o + 32, a.x.c1); put_fq(o + 64, a.y.c0); put_fq(o + 96, a.y.c1);
+}
+
+static const char *DEFAULT_PROOF =   // (G1::one, G2::one, G1::one): r1cs_gg_ppzksnark_proof default ctor (r1cs_gg_ppzksnark.hpp:309-315)
+    "0000000000000000000000000000000000000000000000000000000000000001"
+    "0000000000000000000000000000000000000000000000000000000000000002"
+    "198e9393920d483a7260bfb731fb5d25f1aa493335a9e71297e485b7aef312c2"
+    "1800deef121f1e76426a00665e5c4479674322d4f75edadd46debd5cd992f6ed"
+    "090689d0585ff075ec9e99ad690c3395bc4b313370b38ef355acdadcd122975b"
+    "12c85ea5db8c6deb4aab71808dcb408fe3d1e7690c43d37b4ce6cc0166fa7daa"
+    "0000000000000000000000000000000000000000000000000000000000000001"
+    "0000000000000000000000000000000000000000000000000000000000000002";
+
+int zkb200_prove(void *h, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32], char *proof_hex_out, uint8_t *parts, float *timings_ms) {
+    DevicePk *pk = (DevicePk *)h;
+    if (!pk) return -1;
+    std::lock_guard<std::mutex> lk(g_mu);
+    uint64_t rr[4], ss[4]; memcpy(rr, r, 32); memcpy(ss, s, 32);
+    ProofPoints pp;
+    const auto t0 = std::chrono::steady_clock::now();
+    prove(pk, assignment, rr, ss, pp);
+    const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (parts) { put_g1(parts, pp.At); put_g2(parts + 64, pp.Bt_g); put_g1(parts + 192, pp.Bt_h); put_g1(parts + 256, pp.Ht); put_g1(parts + 320, pp.Lt); }
+    if (timings_ms) { timings_ms[0] = pp.gpu_ms; timings_ms[1] = pp.qap_ms; timings_ms[2] = pp.msm_h_ms; timings_ms[3] = (float)(total_ms - pp.gpu_ms); }
+    const std::string hex = pp.satisfied ? proof_hex(pp) : std::string(DEFAULT_PROOF);
+    memcpy(proof_hex_out, hex.data(), 512); proof_hex_out[512] = 0;
+    return pp.satisfied ? 0 : 1;
+}
+int zkb200_qap_witness_map(void *h, const uint8_t *assignment, uint8_t *out_H, int *satisfied) {
+    DevicePk *pk = (DevicePk *)h;
+    if (!pk) return -1;
+    std::lock_guard<std::mutex> lk(g_mu);
+    return qap_witness_map(pk, assignment, out_H, satisfied);
+}
+int zkb200_last_launches(void) { return launches_last_prove(); }
+
+// ---- evaluation domains ---------------------------------------------------------------------------------------------------
+static std::map<std::pair<int, uint64_t>, Domain *> g_domains;
+static Domain *get_domain(uint64_t min_size) {
+    auto key = std::make_pair(g_device, min_size);
+    auto it = g_domains.find(key);
+    if (it != g_domains.end()) return it->second;
+    Domain *d = Domain::build(min_size);
+    g_domains[key] = d;
+    return d;
+}
+long zkb200_domain_op(size_t min_size, int op, uint8_t *data, size_t n, int *kind) {
+    if (ensure_device()) return -1;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Domain *d = get_domain(min_size);
+    if (!d) { g_err = "no evaluation domain for that size"; return -1; }
+    if (kind) *kind = d->step ? 1 : 0;
+    if (!data) return d->m;
+    if (n != d->m || op < 0 || op > 4) { g_err = "domain_op: wrong vector length or op"; return -1; }
+    Fr *buf, *tmp;
+    ZK_CUDA(cudaMalloc(&buf, n * 32)); ZK_CUDA(cudaMalloc(&tmp, n * 32));
+    ZK_CUDA(cudaMemcpy(buf, data, n * 32, cudaMemcpyHostToDevice));
+    to_mont_kernel<<<(unsigned)((n + 255) / 256), 256>>>(buf, (uint32_t)n);
+    domain_op(0, *d, op, buf, tmp);
+    from_mont_kernel<<<(unsigned)((n + 255) / 256), 256>>>(buf, tmp, (uint32_t)n);
+    ZK_CUDA(cudaMemcpy(data, tmp, n * 32, cudaMemcpyDeviceToHost));
+    ZK_CUDA(cudaFree(buf)); ZK_CUDA(cudaFree(tmp));
+    return d->m;
+}
+
+// ---- MSM -------------------------------------------------------------------------------------------------------------------
+static int default_window(size_t n) {
+    int c = 0; while ((1ull << c) < n) c++;
+    c -= 4; if (c < 4) c = 4; if (c > 16) c = 16;
+    return c;
+}
+template <class AffT, class HP>
+static int msm_host_entry(size_t n, const uint8_t *bases, const uint8_t *scalars, int window_bits, bool g2, HP &result) {
+    if (ensure_device()) return -1;
+    std::lock_guard<std::mutex> lk(g_mu);
+    const int c = window_bits > 0 ? window_bits : default_window(n);
+    AffT *d_bases; uint32_t *d_scalars;
+    ZK_CUDA(cudaMalloc(&d_bases, (n + 1) * sizeof(AffT))); ZK_CUDA(cudaMalloc(&d_scalars, (n + 1) * 32));
+    ZK_CUDA(cudaMemcpy(d_bases, bases, n * sizeof(AffT), cudaMemcpyHostToDevice));
+    ZK_CUDA(cudaMemcpy(d_scalars, scalars, n * 32, cudaMemcpyHostToDevice));
+    const size_t nf = n * sizeof(AffT) / 32;
+    if (nf) to_mont_generic_kernel<Fq><<<(unsigned)((nf + 255) / 256), 256>>>((Fq *)d_bases, nf);
+    MsmPlan plan; plan.init((uint32_t)n, c, 1024, !g2, g2);
+    msm_run(0, plan, ScalarRef{d_scalars, nullptr, 0, 0}, nullptr, g2 ? nullptr : d_bases, g2 ? d_bases : nullptr);
+    ZK_CUDA(cudaStreamSynchronize(0));
+    if constexpr (sizeof(AffT) == 64) result = msm_finish_g1(plan); else result = msm_finish_g2(plan);
+    plan.release();
+    ZK_CUDA(cudaFree(d_bases)); ZK_CUDA(cudaFree(d_scalars));
+    return 0;
+}
+int zkb200_msm_g1(size_t n, const uint8_t *bases, const uint8_t *scalars, int window_bits, uint8_t out[64]) {
+    zkh::HG1 r;
+    if (msm_host_entry<G1Affine>(n, bases, scalars, window_bits, false, r)) return -1;
+    put_g1(out, r.to_affine());
+    return 0;
+}
+int zkb200_msm_g2(size_t n, const uint8_t *bases, const uint8_t *scalars, int window_bits, uint8_t out[128]) {
+    zkh::HG2 r;
+    if (msm_host_entry<G2Affine>(n, bases, scalars, window_bits, true, r)) return -1;
+    put_g2(out, r.to_affine());
+    return 0;
+}
+
+int zkb200_field_op(int field, int op, size_t n, const uint8_t *a, const uint8_t *b, uint8_t *out) {
+    if (ensure_device()) return -1;
+    std::lock_guard<std::mutex> lk(g_mu);
+    void *da, *db = nullptr, *dout;
+    ZK_CUDA(cudaMalloc(&da, n * 32)); ZK_CUDA(cudaMalloc(&dout, n * 32));
+    ZK_CUDA(cudaMemcpy(da, a, n * 32, cudaMemcpyHostToDevice));
+    if (b) { ZK_CUDA(cudaMalloc(&db, n * 32)); ZK_CUDA(cudaMemcpy(db, b, n * 32, cudaMemcpyHostToDevice)); }
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (field == 0) field_op_kernel<Fr><<<grid, 128>>>((const Fr *)da, (const Fr *)db, (Fr *)dout, n, op);
+    else field_op_kernel<Fq><<<grid, 128>>>((const Fq *)da, (const Fq *)db, (Fq *)dout, n, op);
+    ZK_CUDA(cudaGetLastError());
+    ZK_CUDA(cudaMemcpy(out, dout, n * 32, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(dout); if (db) cudaFree(db);
+    return 0;
+}
+
+// ---- device-resident benchmarks ------------------------------------------------------------------------------------------
+float zkb200_bench_ntt(int logn, int batch, int iters) {
+    if (ensure_device()) return -1;
+    if (logn < 1 || logn > 28 || batch < 1) return -1;
+    Domain *d = get_domain(1ull << logn);
+    const size_t n = 1ull << logn;
+    Fr *src, *dst;
+    ZK_CUDA(cudaMalloc(&src, n * 32 * batch)); ZK_CUDA(cudaMalloc(&dst, n * 32 * batch));
+    fill_scalars_kernel<<<(unsigned)((n * batch + 255) / 256), 256>>>((uint32_t *)src, n * batch, 7);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const PowMul none{nullptr, nullptr, 0};
+    for (int b = 0; b < batch; b++) ntt_launch(0, src + b * n, dst + b * n, (const Fr *)d->tw_big_f, logn, none, none);   // warm-up
+    ZK_CUDA(cudaDeviceSynchronize());
+    cudaEventRecord(e0, 0);
+    for (int it = 0; it < iters; it++)
+        for (int b = 0; b < batch; b++) ntt_launch(0, src + b * n, dst + b * n, (const Fr *)d->tw_big_f, logn, none, none);
+    cudaEventRecord(e1, 0);
+    ZK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(src); cudaFree(dst);
+    return ms / (float)(iters * batch);
+}
+
+float zkb200_bench_msm(int group, size_t n, int window_bits, int iters) {
+    if (ensure_device()) return -1;
+    const int c = window_bits > 0 ? window_bits : default_window(n);
+    uint32_t *sc; ZK_CUDA(cudaMalloc(&sc, n * 32));
+    fill_scalars_kernel<<<(unsigned)((n + 255) / 256), 256>>>(sc, n, 11);
+    void *bases;
+    if (group == 1) {
+        ZK_CUDA(cudaMalloc(&bases, n * sizeof(G1Affine)));
+        G1Affine g; g.x = Fq::one(); g.y = Fq::one() + Fq::one();
+        gen_bases_kernel<Fq><<<(unsigned)((n + 127) / 128), 128>>>(g, (G1Affine *)bases, n);
+    } else {
+        ZK_CUDA(cudaMalloc(&bases, n * sizeof(G2Affine)));
+        // G2 generator (alt_bn128_init.cpp:265-269), Montgomery form computed on the host
+        const char *gs[4] = {"10857046999023057135944570762232829481370756359578518086990519993285655852781",
+                             "11559732032986387107991004021392285783925812861821192530917403151452391805634",
+                             "8495653923123431417604973247489272438418190587263600148770280649306958101930",
+                             "4082367875863433681332203403145435568316851327593401208105741076214120093531"};
+        zkh::HFq v[4]; for (int i = 0; i < 4; i++) zkh::HFq::from_dec(gs[i], strlen(gs[i]), v[i]);
+        G2Affine g; memcpy(&g, v, 128);
+        gen_bases_kernel<Fq2><<<(unsigned)((n + 127) / 128), 128>>>(g, (G2Affine *)bases, n);
+    }
+    ZK_CUDA(cudaDeviceSynchronize());
+    MsmPlan plan; plan.init((uint32_t)n, c, 0, group == 1, group == 2);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    msm_run(0, plan, ScalarRef{sc, nullptr, 0, 0}, nullptr, group == 1 ? bases : nullptr, group == 2 ? bases : nullptr);
+    ZK_CUDA(cudaDeviceSynchronize());
+    cudaEventRecord(e0, 0);
+    for (int it = 0; it < iters; it++)
+        msm_run(0, plan, ScalarRef{sc, nullptr, 0, 0}, nullptr, group == 1 ? bases : nullptr, group == 2 ? bases : nullptr);
+    cudaEventRecord(e1, 0);
+    ZK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    plan.release(); cudaFree(sc); cudaFree(bases);
+    return ms / (float)iters;
+}
+
+float zkb200_bench_imad_peak(int wide) {
+    if (ensure_device()) return -1;
+    cudaDeviceProp prop; cudaGetDeviceProperties(&prop, g_device);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    uint32_t *out; ZK_CUDA(cudaMalloc(&out, (size_t)blocks * threads * 4));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    imad_peak_kernel<<<blocks, threads>>>(out, 64, wide);
+    ZK_CUDA(cudaDeviceSynchronize());
+    cudaEventRecord(e0, 0);
+    imad_peak_kernel<<<blocks, threads>>>(out, iters, wide);
+    cudaEventRecord(e1, 0);
+    ZK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    const double ops = (double)blocks * threads * iters * 64.0;
+    return (float)(ops / (ms * 1e-3) / 1e12);
+}
+
+

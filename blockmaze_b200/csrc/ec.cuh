@@ -9,6 +9,14 @@
 #pragma once
 #include "ff.cuh"
 
+// Group operations are deliberately NOT inlined on the device: one G2 addition is ~45 base-field multiplications
+// (~15k SASS instructions); a call costs nothing next to that and keeps kernels small enough for the instruction cache.
+#if defined(__CUDACC__)
+#define ZK_EC __host__ __device__ __noinline__
+#else
+#define ZK_EC inline
+#endif
+
 namespace zk {
 
 template <class F> struct Affine {
@@ -29,7 +37,7 @@ template <class F> struct XYZZ {
     ZK_HD XYZZ neg() const { XYZZ p = *this; p.Y = Y.neg(); return p; }
 
     // dbl-2008-s-1
-    ZK_HD XYZZ dbl() const {
+    ZK_EC XYZZ dbl() const {
         if (is_inf()) return *this;
         F U = Y.dbl(), V = U.sqr(), W = U * V, S = X * V;
         F XX = X.sqr(), M = XX.dbl() + XX;
@@ -41,7 +49,7 @@ template <class F> struct XYZZ {
         return r;
     }
     // mdbl-2008-s-1: 2 * affine
-    ZK_HD static XYZZ dbl_affine(const Affine<F> &a) {
+    ZK_EC static XYZZ dbl_affine(const Affine<F> &a) {
         if (a.is_inf()) return inf();
         F U = a.y.dbl(), V = U.sqr(), W = U * V, S = a.x * V;
         F XX = a.x.sqr(), M = XX.dbl() + XX;
@@ -53,7 +61,7 @@ template <class F> struct XYZZ {
         return r;
     }
     // madd-2008-s: this += affine
-    ZK_HD void add_affine(const Affine<F> &a) {
+    ZK_EC void add_affine(const Affine<F> &a) {
         if (a.is_inf()) return;
         if (is_inf()) { X = a.x; Y = a.y; ZZ = F::one(); ZZZ = F::one(); return; }
         F U2 = a.x * ZZ, S2 = a.y * ZZZ;
@@ -70,7 +78,7 @@ template <class F> struct XYZZ {
         ZZZ = ZZZ * PPP;
     }
     // add-2008-s: this += other
-    ZK_HD void add(const XYZZ &o) {
+    ZK_EC void add(const XYZZ &o) {
         if (o.is_inf()) return;
         if (is_inf()) { *this = o; return; }
         F U1 = X * o.ZZ, U2 = o.X * ZZ, S1 = Y * o.ZZZ, S2 = o.Y * ZZZ;
@@ -87,16 +95,18 @@ template <class F> struct XYZZ {
         ZZZ = ZZZ * o.ZZZ * PPP;
     }
     // k * this for a small non-negative integer k (double-and-add, MSB first)
-    ZK_HD XYZZ mul_small(uint32_t k) const {
+    ZK_EC XYZZ mul_small(uint32_t k) const {
         XYZZ r = inf();
-        for (int b = 31; b >= 0; b--) {
+        int top = 31;
+        while (top > 0 && !((k >> top) & 1)) top--;
+        for (int b = top; b >= 0; b--) {
             r = r.dbl();
             if ((k >> b) & 1) r.add(*this);
         }
         return r;
     }
     // scalar as 8 little-endian limbs (plain integer)
-    ZK_HD XYZZ mul(const uint32_t k[8]) const {
+    ZK_EC XYZZ mul(const uint32_t k[8]) const {
         XYZZ r = inf();
         for (int b = 255; b >= 0; b--) {
             r = r.dbl();
@@ -105,7 +115,7 @@ template <class F> struct XYZZ {
         return r;
     }
     // host-side normalisation (one field inversion)
-    ZK_HD Affine<F> to_affine() const {
+    ZK_EC Affine<F> to_affine() const {
         if (is_inf()) return Affine<F>::inf();
         // x = X/ZZ, y = Y/ZZZ ; 1/ZZ = ZZ^2 ... use 1/ZZZ and ZZ: 1/ZZ = ZZZ^2 / ZZ^4 is no cheaper; invert both via one inversion
         F zz_zzz = ZZ * ZZZ;

@@ -1,0 +1,595 @@
+// GPU pipeline of the Groth16 prover for BlockMaze's circuits (replaces r1cs_gg_ppzksnark_prover,
+// libsnark/zk_proof_systems/ppzksnark/r1cs_gg_ppzksnark/r1cs_gg_ppzksnark.tcc:390-506, and everything below it:
+// r1cs_to_qap_witness_map r1cs_to_qap.tcc:205-334, libfqfft domains, libff multi_exp).  One DevicePk per (circuit, GPU):
+// bases, constraint matrices, twiddles and all work buffers stay resident in HBM; a proof is one H2D copy of the
+// assignment, ~45 kernel launches on four streams, and a D2H copy of a few hundred partial sums.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include "prover.cuh"
+#include "pk_format.hpp"
+#include "ntt.cuh"
+#include "msm.cuh"
+
+namespace zkp {
+using namespace zk;
+using zkh::HFr; using zkh::HFq; using zkh::HFq2; using zkh::HG1; using zkh::HG2; using zkh::HG1Affine; using zkh::HG2Affine;
+
+static int g_launches = 0;
+#define ZK_LAUNCH(kernel, grid, block, smem, stream, ...) do { kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); g_launches++; } while (0)
+
+void cuda_check(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) {
+        fprintf(stderr, "zkb200: CUDA failure %s: %s -- the B200 prover has no CPU fallback, aborting\n", what, cudaGetErrorString(e));
+        abort();
+    }
+}
+int launches_last_prove() { return g_launches; }
+
+static inline Fr to_dev(const HFr &x) { Fr r; memcpy(r.v, x.v, 32); return r; }
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+static bool g_attrs_done[64];
+void device_init(int device) {
+    ZK_CUDA(cudaSetDevice(device));
+    if (device < 64 && !g_attrs_done[device]) { ntt_init_attrs(); g_attrs_done[device] = true; }
+}
+
+// =====================================================================================================================
+// evaluation domains
+static HFr root_of_unity(int logn) {     // libff get_root_of_unity (field_utils.tcc:36-51): square the 2^28-th root down
+    HFr w; const char *s = "19103219067921713944291392827692070036145651957329286315305642004821462161904";
+    HFr::from_dec(s, strlen(s), w);
+    for (int i = 28; i > logn; i--) w = w.sqr();
+    return w;
+}
+static int ilog2_ceil(uint64_t n) { int r = (n & (n - 1)) == 0 ? 0 : 1; while (n > 1) { n >>= 1; r++; } return r; }
+
+static void *dev_pow_table(HFr base, HFr scale, uint32_t count, uint64_t stride) {
+    Fr *out; ZK_CUDA(cudaMalloc(&out, (size_t)(count ? count : 1) * 32));
+    if (count) { pow_table_kernel<<<cdiv(cdiv(count, 64), 128), 128>>>(out, to_dev(base), to_dev(scale), count, stride); ZK_CUDA(cudaGetLastError()); }
+    return out;
+}
+static void *dev_const(const HFr *v, size_t n) {
+    void *p; ZK_CUDA(cudaMalloc(&p, n * 32)); ZK_CUDA(cudaMemcpy(p, v, n * 32, cudaMemcpyHostToDevice)); return p;
+}
+
+Domain *Domain::build(uint64_t min_size) {
+    if (min_size <= 1) return nullptr;
+    // get_evaluation_domain.tcc:33-52: basic(min) | step(min) | basic(big+rounded_small) | step(big+rounded_small)
+    const int L = ilog2_ceil(min_size);
+    uint64_t m = 0; bool step = false;
+    if (min_size == (1ull << L)) { m = min_size; }
+    else {
+        const uint64_t big = 1ull << (L - 1), small = min_size - big, rs = 1ull << ilog2_ceil(small);
+        if (small == rs) { m = min_size; step = true; }
+        else if (rs == big) { m = 2 * big; }
+        else { m = big + rs; step = true; }
+    }
+    if (ilog2_ceil(m) > 28) return nullptr;
+    Domain *d = new Domain();
+    d->m = (uint32_t)m; d->step = step;
+    const HFr g = HFr::from_u64(5), ginv = g.inverse(), one = HFr::one();
+    if (!step) {
+        d->big = d->m; d->small = 0; d->log_big = ilog2_ceil(m); d->compr = 1;
+    } else {
+        d->big = 1u << (ilog2_ceil(m) - 1); d->small = d->m - d->big;
+        d->log_big = ilog2_ceil(d->big); d->log_small = ilog2_ceil(d->small); d->compr = d->big / d->small;
+    }
+    const HFr wb = root_of_unity(d->log_big);
+    d->tw_big_f = dev_pow_table(wb, one, d->big / 2, 1);
+    d->tw_big_i = dev_pow_table(wb.inverse(), one, d->big / 2, 1);
+    const HFr big_inv = HFr::from_u64(d->big).inverse(), m_inv = HFr::from_u64(d->m).inverse();
+    d->c_big_inv = dev_const(&big_inv, 1);
+    d->c_m_inv = dev_const(&m_inv, 1);
+    d->over_two = HFr::from_u64(2).inverse();
+    const uint32_t nhi = (d->m >> 10) + 1;
+    d->g_lo = dev_pow_table(g, one, 1024, 1);
+    d->g_hi = dev_pow_table(g, one, nhi, 1024);
+    d->g_hi_ninv = dev_pow_table(g, m_inv, nhi, 1024);
+    d->gi_lo = dev_pow_table(ginv, one, 1024, 1);
+    d->gi_hi = dev_pow_table(ginv, one, nhi, 1024);
+    d->gi_hi_ninv = dev_pow_table(ginv, m_inv, nhi, 1024);
+    if (!step) {
+        // basic_radix2_domain::divide_by_Z_on_coset (basic_radix2_domain.tcc:102-110): Z(g) = g^m - 1
+        HFr z = (g.pow64(d->m) - one).inverse();
+        d->zt = dev_const(&z, 1); d->z1 = z;
+    } else {
+        const HFr ws = root_of_unity(d->log_small), om = root_of_unity(d->log_big + 1);
+        d->tw_small_f = dev_pow_table(ws, one, d->small / 2, 1);
+        d->tw_small_i = dev_pow_table(ws.inverse(), one, d->small / 2, 1);
+        d->tw_step_f = dev_pow_table(om, one, d->big, 1);
+        d->tw_step_i = dev_pow_table(om.inverse(), one, d->big, 1);
+        const HFr small_inv = HFr::from_u64(d->small).inverse();
+        d->c_small_inv = dev_const(&small_inv, 1);
+        // step_radix2_domain::divide_by_Z_on_coset (step_radix2_domain.tcc:221-248)
+        const HFr Z0 = g.pow64(d->big) - one;
+        const HFr c_sm_Z0 = g.pow64(d->small) * Z0, o_sm_Z0 = om.pow64(d->small) * Z0, o_2sm = om.pow64(2ull * d->small);
+        std::vector<HFr> zt(d->compr);
+        HFr elt = one;
+        for (uint32_t e = 0; e < d->compr; e++) { zt[e] = (c_sm_Z0 * elt - o_sm_Z0).inverse(); elt = elt * o_2sm; }
+        d->zt = dev_const(zt.data(), zt.size());
+        const HFr go = g * om;
+        d->z1 = ((go.pow64(d->big) - one) * (go.pow64(d->small) - om.pow64(d->small))).inverse();
+    }
+    ZK_CUDA(cudaDeviceSynchronize());
+    return d;
+}
+void Domain::release() {
+    void *ps[] = {tw_big_f, tw_big_i, tw_small_f, tw_small_i, tw_step_f, tw_step_i, g_lo, g_hi, g_hi_ninv, gi_lo, gi_hi, gi_hi_ninv,
+                  c_big_inv, c_small_inv, c_m_inv, zt};
+    for (void *p : ps) if (p) cudaFree(p);
+}
+
+static PowMul pm_none() { return PowMul{nullptr, nullptr, 0}; }
+static PowMul pm_const(const void *c) { return PowMul{(const Fr *)c, nullptr, 0}; }
+static PowMul pm_two(const void *lo, const void *hi) { return PowMul{(const Fr *)lo, (const Fr *)hi, 10}; }
+
+static void ntt(cudaStream_t st, const void *src, void *dst, const void *tw, int logn, PowMul pre, PowMul post) {
+    if (logn == 0) { ZK_CUDA(cudaMemcpyAsync(dst, src, 32, cudaMemcpyDeviceToDevice, st)); return; }
+    NttPass ps[4]; g_launches += ntt_plan_passes(logn, ps);
+    ntt_launch(st, (const Fr *)src, (Fr *)dst, (const Fr *)tw, logn, pre, post);
+}
+
+// inverse transform src -> dst (dst != src), coefficient i additionally multiplied by `post` (e.g. g^i for the coset shift
+// that follows, or g^-i for icosetFFT).  For the basic domain the 1/m factor must be folded into `post` by the caller.
+static void domain_ifft(cudaStream_t st, const Domain &d, void *src, void *dst, PowMul post_basic, PowMul post_step) {
+    Fr *s = (Fr *)src, *t = (Fr *)dst;
+    if (!d.step) { ntt(st, s, t, d.tw_big_i, d.log_big, pm_none(), post_basic); return; }
+    ntt(st, s, t, d.tw_big_i, d.log_big, pm_none(), pm_const(d.c_big_inv));
+    ntt(st, s + d.big, t + d.big, d.tw_small_i, d.log_small, pm_none(), pm_const(d.c_small_inv));
+    ZK_LAUNCH(step_ifft_post_kernel, cdiv(d.small, 128), 128, 0, st, t, (const Fr *)d.tw_step_f, (const Fr *)d.tw_step_i, d.big, d.small,
+              to_dev(d.over_two), post_step);
+}
+// forward transform src -> dst (dst != src; src is clobbered for the step domain), input coefficient i first multiplied by `pre`
+static void domain_fft(cudaStream_t st, const Domain &d, void *src, void *dst, PowMul pre) {
+    Fr *s = (Fr *)src, *t = (Fr *)dst;
+    if (!d.step) { ntt(st, s, t, d.tw_big_f, d.log_big, pre, pm_none()); return; }
+    ZK_LAUNCH(step_fft_pre_kernel, cdiv(d.small, 128), 128, 0, st, s, (const Fr *)d.tw_step_f, d.big, d.small, pre);
+    ntt(st, s, t, d.tw_big_f, d.log_big, pm_none(), pm_none());
+    ntt(st, s + d.big, t + d.big, d.tw_small_f, d.log_small, pm_none(), pm_none());
+}
+
+void domain_op(cudaStream_t st, const Domain &d, int op, void *data, void *tmp) {
+    const size_t bytes = (size_t)d.m * 32;
+    switch (op) {
+    case OP_FFT:
+    case OP_COSET_FFT:
+        ZK_CUDA(cudaMemcpyAsync(tmp, data, bytes, cudaMemcpyDeviceToDevice, st));
+        domain_fft(st, d, tmp, data, op == OP_COSET_FFT ? pm_two(d.g_lo, d.g_hi) : pm_none());
+        break;
+    case OP_IFFT:
+        ZK_CUDA(cudaMemcpyAsync(tmp, data, bytes, cudaMemcpyDeviceToDevice, st));
+        domain_ifft(st, d, tmp, data, pm_const(d.c_m_inv), pm_none());
+        break;
+    case OP_ICOSET_FFT:
+        ZK_CUDA(cudaMemcpyAsync(tmp, data, bytes, cudaMemcpyDeviceToDevice, st));
+        domain_ifft(st, d, tmp, data, pm_two(d.gi_lo, d.gi_hi_ninv), pm_two(d.gi_lo, d.gi_hi));
+        break;
+    case OP_DIVIDE_BY_Z:
+        ZK_LAUNCH(divide_by_z_kernel, cdiv(d.m, 256), 256, 0, st, (Fr *)data, d.m, d.big, d.compr, (const Fr *)d.zt, to_dev(d.z1));
+        break;
+    }
+}
+
+// =====================================================================================================================
+// sparse A.w / B.w / C.w  (linear_combination::evaluate, libsnark/relations/variable.tcc:262; r1cs_to_qap.tcc:227-236,281-285)
+// one thread per constraint row; coefficient dictionary index 0 = +1, 1 = -1 (no multiplication)
+__global__ void spmv_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const uint32_t *__restrict__ coef,
+                            const Fr *__restrict__ dict, const Fr *__restrict__ w, Fr *__restrict__ out, uint32_t rows) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    Fr acc = Fr::zero();
+    for (uint32_t k = rowptr[i], e = rowptr[i + 1]; k < e; k++) {
+        const uint32_t ci = __ldg(coef + k);
+        Fr x = ldg_fr(w + __ldg(col + k));
+        if (ci == 0) acc = acc + x;
+        else if (ci == 1) acc = acc - x;
+        else acc = acc + x * ldg_fr(dict + ci);
+    }
+    st_fr(out + i, acc);
+}
+// the extra rows  aA[num_constraints + i] = (1, w_1 .. w_inputs)[i]  (r1cs_to_qap.tcc:227-230)
+__global__ void input_rows_kernel(const Fr *w, Fr *outA, uint32_t nc, uint32_t count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) st_fr(outA + nc + i, ld_fr(w + i));
+}
+// r1cs_constraint_system::is_satisfied (r1cs.tcc:133-164) on the evaluation vectors: flag |= (A_i * B_i != C_i)
+__global__ void sat_check_kernel(const Fr *A, const Fr *B, const Fr *C, uint32_t nc, uint32_t *flag) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    if (ld_fr(A + i) * ld_fr(B + i) != ld_fr(C + i)) atomicOr(flag, 1u);
+}
+
+// =====================================================================================================================
+// proving-key point decompression (alt_bn128_g1.cpp:420-465, alt_bn128_g2.cpp:433-478) -- one thread per point
+struct SqrtConsts { uint32_t e_sqrt[8]; Fq half; Fq2 twist_b; Fq b; };   // (q+1)/4, 1/2, b' = 3/(9+u), b = 3
+__device__ __forceinline__ Fq fq_sqrt(const Fq &a, const uint32_t e[8], bool &ok) { Fq r = a.pow(e); ok = (r.sqr() == a); return r; }
+
+__global__ void decompress_g1_kernel(const zkpk::CompressedG1 *in, uint32_t n, SqrtConsts k, Affine<Fq> *out, uint8_t *skip, uint32_t *bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const zkpk::CompressedG1 c = in[i];
+    Affine<Fq> p = Affine<Fq>::inf();
+    const bool inf = (c.flags >> 1) & 1;
+    if (!inf) {
+        Fq x; memcpy(x.v, c.x, 32);
+        bool ok; Fq y = fq_sqrt(x.sqr() * x + k.b, k.e_sqrt, ok);
+        if (!ok) atomicAdd(bad, 1u);
+        if ((y.from_mont().v[0] & 1) != (uint32_t)(c.flags & 1)) y = y.neg();
+        p.x = x; p.y = y;
+    }
+    out[i] = p;
+    if (skip) skip[i] = inf ? 1 : 0;
+}
+__global__ void decompress_g2_kernel(const zkpk::CompressedG2 *in, uint32_t n, SqrtConsts k, Affine<Fq2> *out, uint32_t *bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const zkpk::CompressedG2 c = in[i];
+    Affine<Fq2> p = Affine<Fq2>::inf();
+    if (!((c.flags >> 1) & 1)) {
+        Fq2 x; memcpy(x.c0.v, c.x, 32); memcpy(x.c1.v, c.x + 32, 32);
+        const Fq2 a = x.sqr() * x + k.twist_b;
+        Fq2 y; bool ok;
+        if (a.c1.is_zero()) {
+            Fq r0 = fq_sqrt(a.c0, k.e_sqrt, ok);
+            if (ok) { y.c0 = r0; y.c1 = Fq::zero(); }
+            else { y.c0 = Fq::zero(); y.c1 = fq_sqrt(a.c0.neg(), k.e_sqrt, ok); }
+        } else {
+            const Fq nrm = fq_sqrt(a.c0.sqr() + a.c1.sqr(), k.e_sqrt, ok);
+            Fq x0 = Fq::zero();
+            if (ok) {
+                x0 = fq_sqrt((a.c0 + nrm) * k.half, k.e_sqrt, ok);
+                if (!ok) x0 = fq_sqrt((a.c0 - nrm) * k.half, k.e_sqrt, ok);
+            }
+            y.c0 = x0; y.c1 = a.c1 * x0.dbl().inverse();
+            if (ok) ok = (y.sqr() == a);
+        }
+        if (!ok) atomicAdd(bad, 1u);
+        if ((y.c0.from_mont().v[0] & 1) != (uint32_t)(c.flags & 1)) y = y.neg();
+        p.x = x; p.y = y;
+    }
+    out[i] = p;
+}
+
+static SqrtConsts sqrt_consts() {
+    SqrtConsts k;
+    uint64_t e[4]; memcpy(e, zkh::FqTag::MOD, 32);
+    e[0] += 1;                                   // q + 1 (no carry: low limb of q is not all ones)
+    for (int i = 0; i < 4; i++) e[i] = (e[i] >> 2) | (i < 3 ? e[i + 1] << 62 : 0);
+    memcpy(k.e_sqrt, e, 32);
+    HFq half = HFq::from_u64(2).inverse(); memcpy(k.half.v, half.v, 32);
+    HFq2 nine_u{HFq::from_u64(9), HFq::one()};
+    HFq2 tb = HFq2{HFq::from_u64(3), HFq::zero()} * nine_u.inverse();
+    memcpy(k.twist_b.c0.v, tb.c0.v, 32); memcpy(k.twist_b.c1.v, tb.c1.v, 32);
+    HFq b = HFq::from_u64(3); memcpy(k.b.v, b.v, 32);
+    return k;
+}
+
+template <class C, class A>
+static void decompress_vec(const std::vector<C> &v, A **out, uint8_t **skip, bool g2, uint32_t *d_bad, const SqrtConsts &k) {
+    const uint32_t n = (uint32_t)v.size();
+    C *d_in; ZK_CUDA(cudaMalloc(&d_in, sizeof(C) * (size_t)(n ? n : 1)));
+    ZK_CUDA(cudaMemcpy(d_in, v.data(), sizeof(C) * (size_t)n, cudaMemcpyHostToDevice));
+    ZK_CUDA(cudaMalloc(out, sizeof(A) * (size_t)(n + 8)));
+    if (skip) ZK_CUDA(cudaMalloc(skip, n + 8));
+    if (n) {
+        if constexpr (sizeof(A) == 64) decompress_g1_kernel<<<cdiv(n, 128), 128>>>((const zkpk::CompressedG1 *)d_in, n, k, (Affine<Fq> *)*out, skip ? *skip : nullptr, d_bad);
+        else decompress_g2_kernel<<<cdiv(n, 128), 128>>>((const zkpk::CompressedG2 *)d_in, n, k, (Affine<Fq2> *)*out, d_bad);
+        ZK_CUDA(cudaGetLastError());
+    }
+    ZK_CUDA(cudaDeviceSynchronize());
+    ZK_CUDA(cudaFree(d_in));
+    (void)g2;
+}
+
+// =====================================================================================================================
+// MSM
+void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2) {
+    n = n_; c = c_; windows = (255 + c - 1) / c; nb = 1u << (c - 1); ones = ones_; total = windows * nb + ones;
+    seg = 16; if (seg > nb) seg = nb;
+    const uint32_t widest = nb > ones ? nb : ones;
+    bpw = cdiv(cdiv(widest, seg), MSM_RED_THREADS);
+    ZK_CUDA(cudaMalloc(&counts, (size_t)(total + 1) * 4));
+    ZK_CUDA(cudaMalloc(&offsets, (size_t)(total + 1) * 4));
+    ZK_CUDA(cudaMalloc(&cursors, (size_t)(total + 1) * 4));
+    entries_cap = (size_t)n * windows + 16;
+    ZK_CUDA(cudaMalloc(&entries, entries_cap * 4));
+    const size_t nout = (size_t)(windows + 1) * bpw;
+    if (g1) {
+        ZK_CUDA(cudaMalloc(&buckets_g1, (size_t)total * sizeof(G1XYZZ)));
+        ZK_CUDA(cudaMalloc(&out_g1, nout * sizeof(G1XYZZ)));
+        ZK_CUDA(cudaMallocHost(&h_out_g1, nout * sizeof(G1XYZZ)));
+    }
+    if (g2) {
+        ZK_CUDA(cudaMalloc(&buckets_g2, (size_t)total * sizeof(G2XYZZ)));
+        ZK_CUDA(cudaMalloc(&out_g2, nout * sizeof(G2XYZZ)));
+        ZK_CUDA(cudaMallocHost(&h_out_g2, nout * sizeof(G2XYZZ)));
+    }
+}
+void MsmPlan::release() {
+    void *ps[] = {counts, offsets, cursors, entries, buckets_g1, buckets_g2, out_g1, out_g2};
+    for (void *p : ps) if (p) cudaFree(p);
+    if (h_out_g1) cudaFreeHost(h_out_g1);
+    if (h_out_g2) cudaFreeHost(h_out_g2);
+    *this = MsmPlan();
+}
+
+void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, const void *bases_g1, const void *bases_g2) {
+    const MsmShape sh = msm_shape(p.c, p.ones);
+    ScalarSrc src{(const uint32_t *)sc.scalars, sc.map, sc.offset, sc.montgomery};
+    ZK_CUDA(cudaMemsetAsync(p.counts, 0, (size_t)(p.total + 1) * 4, st));
+    ZK_CUDA(cudaMemsetAsync(p.cursors, 0, (size_t)(p.total + 1) * 4, st));
+    if (p.n) ZK_LAUNCH(msm_count_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, p.n, sh, (uint32_t *)p.counts);
+    ZK_LAUNCH(msm_scan_kernel, 1, 1024, 0, st, (const uint32_t *)p.counts, (uint32_t *)p.offsets, p.total);
+    if (p.n) ZK_LAUNCH(msm_scatter_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, p.n, sh, (const uint32_t *)p.offsets, (uint32_t *)p.cursors,
+                       (uint32_t *)p.entries);
+    const dim3 rgrid(p.bpw, sh.windows + 1);
+    const size_t nout = (size_t)(sh.windows + 1) * p.bpw;
+    if (bases_g1) {
+        ZK_LAUNCH(msm_accumulate_kernel<Fq>, cdiv(p.total, 128), 128, 0, st, (const G1Affine *)bases_g1, (const uint32_t *)p.offsets,
+                  (const uint32_t *)p.entries, p.total, (G1XYZZ *)p.buckets_g1);
+        ZK_LAUNCH(msm_reduce_kernel<Fq>, rgrid, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(G1XYZZ), st, (const G1XYZZ *)p.buckets_g1, sh, p.seg,
+                  p.bpw, (G1XYZZ *)p.out_g1);
+        ZK_CUDA(cudaMemcpyAsync(p.h_out_g1, p.out_g1, nout * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, st));
+    }
+    if (bases_g2) {
+        ZK_LAUNCH(msm_accumulate_kernel<Fq2>, cdiv(p.total, 128), 128, 0, st, (const G2Affine *)bases_g2, (const uint32_t *)p.offsets,
+                  (const uint32_t *)p.entries, p.total, (G2XYZZ *)p.buckets_g2);
+        ZK_LAUNCH(msm_reduce_kernel<Fq2>, rgrid, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(G2XYZZ), st, (const G2XYZZ *)p.buckets_g2, sh, p.seg,
+                  p.bpw, (G2XYZZ *)p.out_g2);
+        ZK_CUDA(cudaMemcpyAsync(p.h_out_g2, p.out_g2, nout * sizeof(G2XYZZ), cudaMemcpyDeviceToHost, st));
+    }
+}
+
+template <class P> static P msm_finish(const MsmPlan &p, const void *h_out) {
+    const P *part = (const P *)h_out;
+    P acc = P::inf();
+    for (int w = p.windows - 1; w >= 0; w--) {
+        for (int i = 0; i < p.c; i++) acc = acc.dbl();
+        for (uint32_t b = 0; b < p.bpw; b++) acc = acc.add(part[(size_t)w * p.bpw + b]);
+    }
+    for (uint32_t b = 0; b < p.bpw; b++) acc = acc.add(part[(size_t)p.windows * p.bpw + b]);
+    return acc;
+}
+HG1 msm_finish_g1(const MsmPlan &p) { return msm_finish<HG1>(p, p.h_out_g1); }
+HG2 msm_finish_g2(const MsmPlan &p) { return msm_finish<HG2>(p, p.h_out_g2); }
+
+// =====================================================================================================================
+// proving key
+static void upload_csr(const zkpk::Csr &h, DeviceCsr &d) {
+    d.nnz = (uint32_t)h.col.size();
+    ZK_CUDA(cudaMalloc(&d.rowptr, h.rowptr.size() * 4));
+    ZK_CUDA(cudaMalloc(&d.col, (size_t)(d.nnz + 1) * 4));
+    ZK_CUDA(cudaMalloc(&d.coef, (size_t)(d.nnz + 1) * 4));
+    ZK_CUDA(cudaMemcpy(d.rowptr, h.rowptr.data(), h.rowptr.size() * 4, cudaMemcpyHostToDevice));
+    ZK_CUDA(cudaMemcpy(d.col, h.col.data(), (size_t)d.nnz * 4, cudaMemcpyHostToDevice));
+    ZK_CUDA(cudaMemcpy(d.coef, h.coef.data(), (size_t)d.nnz * 4, cudaMemcpyHostToDevice));
+}
+static int pick_window(uint32_t n) {       // dense 254-bit scalars: about log2(n) - 4, clamped
+    int c = ilog2_ceil(n ? n : 1) - 4;
+    if (c < 6) c = 6;
+    if (c > 16) c = 16;
+    return c;
+}
+
+template <class A> static A fetch_point(const void *dev, size_t idx) {
+    A a; ZK_CUDA(cudaMemcpy(&a, (const char *)dev + idx * sizeof(A), sizeof(A), cudaMemcpyDeviceToHost)); return a;
+}
+
+DevicePk *pk_load(const char *path, int device, std::string &err) {
+    const double t0 = now_s();
+    std::ifstream fh(path, std::ios::binary | std::ios::ate);
+    if (!fh.is_open()) { err = std::string("cannot open proving key ") + path; return nullptr; }
+    const size_t len = (size_t)fh.tellg();
+    std::vector<uint8_t> data(len);
+    fh.seekg(0); fh.read((char *)data.data(), (std::streamsize)len);
+    zkpk::ParsedPk P;
+    if (!zkpk::parse_pk(data.data(), len, P)) { err = P.error; return nullptr; }
+    data.clear(); data.shrink_to_fit();
+    const double t1 = now_s();
+
+    device_init(device);
+    DevicePk *pk = new DevicePk();
+    pk->device = device; pk->parse_seconds = t1 - t0;
+    pk->num_inputs = P.num_inputs; pk->num_vars = P.num_inputs + P.num_aux; pk->num_constraints = P.num_constraints;
+    if (P.A.size() != pk->num_vars + 1 || P.L.size() != pk->num_vars - pk->num_inputs || P.B_domain != pk->num_vars + 1) {
+        err = "proving key query sizes do not match its constraint system"; delete pk; return nullptr;
+    }
+    pk->dom = Domain::build(pk->num_constraints + pk->num_inputs + 1);
+    if (!pk->dom || P.H.size() != pk->dom->m - 1) { err = "proving key H_query does not match the evaluation domain"; delete pk; return nullptr; }
+
+    // points: decompress on the GPU
+    const SqrtConsts k = sqrt_consts();
+    uint32_t *d_bad; ZK_CUDA(cudaMalloc(&d_bad, 4)); ZK_CUDA(cudaMemset(d_bad, 0, 4));
+    const double t2 = now_s();
+    decompress_vec<zkpk::CompressedG1, G1Affine>(P.A, (G1Affine **)&pk->A, &pk->A_skip, false, d_bad, k);
+    decompress_vec<zkpk::CompressedG1, G1Affine>(P.B_g1, (G1Affine **)&pk->B1, &pk->B_skip, false, d_bad, k);
+    decompress_vec<zkpk::CompressedG2, G2Affine>(P.B_g2, (G2Affine **)&pk->B2, nullptr, true, d_bad, k);
+    decompress_vec<zkpk::CompressedG1, G1Affine>(P.H, (G1Affine **)&pk->H, &pk->H_skip, false, d_bad, k);
+    decompress_vec<zkpk::CompressedG1, G1Affine>(P.L, (G1Affine **)&pk->L, &pk->L_skip, false, d_bad, k);
+    std::vector<zkpk::CompressedG1> fixed1 = {P.alpha_g1, P.beta_g1, P.delta_g1};
+    std::vector<zkpk::CompressedG2> fixed2 = {P.beta_g2, P.delta_g2};
+    G1Affine *f1; G2Affine *f2;
+    decompress_vec<zkpk::CompressedG1, G1Affine>(fixed1, &f1, nullptr, false, d_bad, k);
+    decompress_vec<zkpk::CompressedG2, G2Affine>(fixed2, &f2, nullptr, true, d_bad, k);
+    pk->alpha_g1 = fetch_point<HG1Affine>(f1, 0); pk->beta_g1 = fetch_point<HG1Affine>(f1, 1); pk->delta_g1 = fetch_point<HG1Affine>(f1, 2);
+    pk->beta_g2 = fetch_point<HG2Affine>(f2, 0); pk->delta_g2 = fetch_point<HG2Affine>(f2, 1);
+    cudaFree(f1); cudaFree(f2);
+    uint32_t bad = 0; ZK_CUDA(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost)); cudaFree(d_bad);
+    pk->decompress_seconds = now_s() - t2;
+    if (bad) { err = "proving key holds " + std::to_string(bad) + " x-coordinates that are not on the curve"; pk_free(pk); return nullptr; }
+    pk->nA = (uint32_t)P.A.size(); pk->nB = (uint32_t)P.B_g1.size(); pk->nH = (uint32_t)P.H.size(); pk->nL = (uint32_t)P.L.size();
+    // a B entry whose G1 half is infinity but G2 half is not cannot be expressed with one skip flag; libsnark never emits one
+    ZK_CUDA(cudaMalloc(&pk->B_idx, (size_t)(pk->nB + 1) * 4));
+    ZK_CUDA(cudaMemcpy(pk->B_idx, P.B_idx.data(), (size_t)pk->nB * 4, cudaMemcpyHostToDevice));
+
+    upload_csr(P.a, pk->a); upload_csr(P.b, pk->b); upload_csr(P.c, pk->c);
+    pk->ncoef = (uint32_t)P.coef_dict.size();
+    pk->coef_dict = dev_const(P.coef_dict.data(), P.coef_dict.size());
+
+    const size_t nw = pk->num_vars + 1, m = pk->dom->m;
+    ZK_CUDA(cudaMalloc(&pk->w_can, nw * 32)); ZK_CUDA(cudaMalloc(&pk->w_mont, nw * 32));
+    ZK_CUDA(cudaMemset(pk->w_can, 0, nw * 32));
+    const uint64_t one_can[4] = {1, 0, 0, 0};
+    ZK_CUDA(cudaMemcpy(pk->w_can, one_can, 32, cudaMemcpyHostToDevice));
+    ZK_CUDA(cudaMallocHost(&pk->h_w_pinned, nw * 32));
+    ZK_CUDA(cudaMalloc(&pk->bufA, m * 32)); ZK_CUDA(cudaMalloc(&pk->bufB, m * 32)); ZK_CUDA(cudaMalloc(&pk->bufC, m * 32));
+    ZK_CUDA(cudaMalloc(&pk->tmp, m * 32));
+    ZK_CUDA(cudaMalloc(&pk->sat_flag, 4)); ZK_CUDA(cudaMallocHost(&pk->h_sat_flag, 4));
+
+    // witness MSMs: ~97 % of the scalars are 0/1 and nearly all others are <= 64 bits, so small windows; H is dense
+    pk->mA.init(pk->nA, 11, 4096, true, false);
+    pk->mB.init(pk->nB, 11, 4096, true, true);
+    pk->mL.init(pk->nL, 11, 4096, true, false);
+    pk->mH.init(pk->nH, pick_window(pk->nH), 0, true, false);
+
+    ZK_CUDA(cudaStreamCreateWithFlags(&pk->s_main, cudaStreamNonBlocking)); ZK_CUDA(cudaStreamCreateWithFlags(&pk->s_a, cudaStreamNonBlocking));
+    ZK_CUDA(cudaStreamCreateWithFlags(&pk->s_b, cudaStreamNonBlocking)); ZK_CUDA(cudaStreamCreateWithFlags(&pk->s_l, cudaStreamNonBlocking));
+    cudaEvent_t *evs[] = {&pk->ev_w, &pk->ev_a, &pk->ev_b, &pk->ev_l};
+    for (auto *e : evs) ZK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    cudaEvent_t *tev[] = {&pk->ev_t0, &pk->ev_t1, &pk->ev_q0, &pk->ev_q1, &pk->ev_h0, &pk->ev_h1};
+    for (auto *e : tev) ZK_CUDA(cudaEventCreate(e));
+    ZK_CUDA(cudaDeviceSynchronize());
+    pk->load_seconds = now_s() - t0;
+    return pk;
+}
+
+void pk_free(DevicePk *pk) {
+    if (!pk) return;
+    cudaSetDevice(pk->device);
+    cudaDeviceSynchronize();
+    void *ps[] = {pk->A, pk->B1, pk->B2, pk->H, pk->L, pk->A_skip, pk->B_skip, pk->H_skip, pk->L_skip, pk->B_idx, pk->a.rowptr, pk->a.col, pk->a.coef,
+                  pk->b.rowptr, pk->b.col, pk->b.coef, pk->c.rowptr, pk->c.col, pk->c.coef, pk->coef_dict, pk->w_can, pk->w_mont, pk->bufA, pk->bufB,
+                  pk->bufC, pk->tmp, pk->sat_flag};
+    for (void *p : ps) if (p) cudaFree(p);
+    if (pk->h_w_pinned) cudaFreeHost(pk->h_w_pinned);
+    if (pk->h_sat_flag) cudaFreeHost(pk->h_sat_flag);
+    pk->mA.release(); pk->mB.release(); pk->mH.release(); pk->mL.release();
+    if (pk->dom) { pk->dom->release(); delete pk->dom; }
+    cudaStream_t ss[] = {pk->s_main, pk->s_a, pk->s_b, pk->s_l};
+    for (auto s : ss) if (s) cudaStreamDestroy(s);
+    cudaEvent_t es[] = {pk->ev_w, pk->ev_a, pk->ev_b, pk->ev_l, pk->ev_t0, pk->ev_t1, pk->ev_q0, pk->ev_q1, pk->ev_h0, pk->ev_h1};
+    for (auto e : es) if (e) cudaEventDestroy(e);
+    delete pk;
+}
+
+// =====================================================================================================================
+// the per-proof pipeline
+static void upload_assignment(DevicePk *pk, const uint8_t *assignment, cudaStream_t st) {
+    const size_t n = pk->num_vars;
+    if (assignment) {
+        memcpy(pk->h_w_pinned, assignment, n * 32);
+        ZK_CUDA(cudaMemcpyAsync((char *)pk->w_can + 32, pk->h_w_pinned, n * 32, cudaMemcpyHostToDevice, st));
+    }
+    ZK_CUDA(cudaMemcpyAsync(pk->w_mont, pk->w_can, (n + 1) * 32, cudaMemcpyDeviceToDevice, st));
+    ZK_LAUNCH(to_mont_kernel, cdiv(n + 1, 256), 256, 0, st, (Fr *)pk->w_mont, (uint32_t)(n + 1));
+}
+
+// r1cs_to_qap_witness_map (r1cs_to_qap.tcc:205-334) on stream st.  Result: coefficients_for_H[0..m) in pk->tmp (Montgomery form).
+static void qap_pipeline(DevicePk *pk, cudaStream_t st) {
+    const Domain &d = *pk->dom;
+    const uint32_t nc = (uint32_t)pk->num_constraints, m = d.m;
+    const Fr *w = (const Fr *)pk->w_mont, *dict = (const Fr *)pk->coef_dict;
+    Fr *A = (Fr *)pk->bufA, *B = (Fr *)pk->bufB, *C = (Fr *)pk->bufC, *T = (Fr *)pk->tmp;
+    ZK_CUDA(cudaMemsetAsync(A + nc, 0, (size_t)(m - nc) * 32, st));
+    ZK_CUDA(cudaMemsetAsync(B + nc, 0, (size_t)(m - nc) * 32, st));
+    ZK_CUDA(cudaMemsetAsync(C + nc, 0, (size_t)(m - nc) * 32, st));
+    ZK_LAUNCH(spmv_kernel, cdiv(nc, 128), 128, 0, st, pk->a.rowptr, pk->a.col, pk->a.coef, dict, w, A, nc);
+    ZK_LAUNCH(spmv_kernel, cdiv(nc, 128), 128, 0, st, pk->b.rowptr, pk->b.col, pk->b.coef, dict, w, B, nc);
+    ZK_LAUNCH(spmv_kernel, cdiv(nc, 128), 128, 0, st, pk->c.rowptr, pk->c.col, pk->c.coef, dict, w, C, nc);
+    ZK_CUDA(cudaMemsetAsync(pk->sat_flag, 0, 4, st));
+    ZK_LAUNCH(sat_check_kernel, cdiv(nc, 256), 256, 0, st, A, B, C, nc, pk->sat_flag);
+    ZK_CUDA(cudaMemcpyAsync(pk->h_sat_flag, pk->sat_flag, 4, cudaMemcpyDeviceToHost, st));
+    ZK_LAUNCH(input_rows_kernel, 1, 64, 0, st, w, A, nc, (uint32_t)pk->num_inputs + 1);
+    // iFFT then cosetFFT of each of A, B, C: coefficient i is multiplied by g^i (and 1/m for the basic domain) on the way
+    Fr *bufs[3] = {A, B, C};
+    for (Fr *X : bufs) {
+        domain_ifft(st, d, X, T, pm_none(), pm_two(d.g_lo, d.g_hi));
+        if (!d.step) domain_fft(st, d, T, X, pm_two(d.g_lo, d.g_hi_ninv));
+        else domain_fft(st, d, T, X, pm_none());
+    }
+    ZK_LAUNCH(qap_pointwise_kernel, cdiv(m, 256), 256, 0, st, A, B, C, m, d.big, d.compr, (const Fr *)d.zt, to_dev(d.z1));
+    domain_ifft(st, d, A, T, pm_two(d.gi_lo, d.gi_hi_ninv), pm_two(d.gi_lo, d.gi_hi));
+}
+
+int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied) {
+    device_init(pk->device);
+    cudaStream_t st = pk->s_main;
+    upload_assignment(pk, assignment, st);
+    qap_pipeline(pk, st);
+    const uint32_t m = pk->dom->m;
+    ZK_LAUNCH(from_mont_kernel, cdiv(m, 256), 256, 0, st, (const Fr *)pk->tmp, (Fr *)pk->bufB, m);
+    ZK_CUDA(cudaMemcpyAsync(out_H, pk->bufB, (size_t)m * 32, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(cudaStreamSynchronize(st));
+    memset(out_H + (size_t)m * 32, 0, 32);          // coefficients_for_H[m] = 0 (no ZK patch: d1 = d2 = d3 = 0)
+    if (satisfied) *satisfied = (*pk->h_sat_flag == 0);
+    return 0;
+}
+
+static HG1 g1_mul(const HG1Affine &p, const uint64_t k[4]) { return HG1::from_affine(p).mul(k); }
+
+int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const uint64_t s[4], ProofPoints &out) {
+    device_init(pk->device);
+    g_launches = 0;
+    cudaStream_t st = pk->s_main;
+    ZK_CUDA(cudaEventRecord(pk->ev_t0, st));
+    upload_assignment(pk, assignment, st);
+    ZK_CUDA(cudaEventRecord(pk->ev_w, st));
+    ZK_CUDA(cudaStreamWaitEvent(pk->s_a, pk->ev_w, 0));
+    ZK_CUDA(cudaStreamWaitEvent(pk->s_b, pk->ev_w, 0));
+    ZK_CUDA(cudaStreamWaitEvent(pk->s_l, pk->ev_w, 0));
+    // A, B, L queries: scalars are the canonical padded assignment [1 | w]  (r1cs_gg_ppzksnark.tcc:437-484)
+    msm_run(pk->s_a, pk->mA, ScalarRef{pk->w_can, nullptr, 0, 0}, pk->A_skip, pk->A, nullptr);
+    msm_run(pk->s_b, pk->mB, ScalarRef{pk->w_can, pk->B_idx, 0, 0}, pk->B_skip, pk->B1, pk->B2);
+    msm_run(pk->s_l, pk->mL, ScalarRef{pk->w_can, nullptr, (uint32_t)pk->num_inputs + 1, 0}, pk->L_skip, pk->L, nullptr);
+    ZK_CUDA(cudaEventRecord(pk->ev_a, pk->s_a)); ZK_CUDA(cudaEventRecord(pk->ev_b, pk->s_b)); ZK_CUDA(cudaEventRecord(pk->ev_l, pk->s_l));
+    // H: QAP witness map, then the dense MSM over coefficients_for_H[0 .. m-1)
+    ZK_CUDA(cudaEventRecord(pk->ev_q0, st));
+    qap_pipeline(pk, st);
+    ZK_CUDA(cudaEventRecord(pk->ev_q1, st));
+    ZK_CUDA(cudaEventRecord(pk->ev_h0, st));
+    msm_run(st, pk->mH, ScalarRef{pk->tmp, nullptr, 0, 1}, pk->H_skip, pk->H, nullptr);
+    ZK_CUDA(cudaEventRecord(pk->ev_h1, st));
+    ZK_CUDA(cudaStreamWaitEvent(st, pk->ev_a, 0)); ZK_CUDA(cudaStreamWaitEvent(st, pk->ev_b, 0)); ZK_CUDA(cudaStreamWaitEvent(st, pk->ev_l, 0));
+    ZK_CUDA(cudaEventRecord(pk->ev_t1, st));
+    ZK_CUDA(cudaStreamSynchronize(st));
+    ZK_CUDA(cudaEventElapsedTime(&out.gpu_ms, pk->ev_t0, pk->ev_t1));
+    ZK_CUDA(cudaEventElapsedTime(&out.qap_ms, pk->ev_q0, pk->ev_q1));
+    ZK_CUDA(cudaEventElapsedTime(&out.msm_h_ms, pk->ev_h0, pk->ev_h1));
+    out.satisfied = (*pk->h_sat_flag == 0);
+
+    // host: Horner over the per-window sums, then the proof combination (r1cs_gg_ppzksnark.tcc:487-495)
+    const HG1 eA = msm_finish_g1(pk->mA), eB1 = msm_finish_g1(pk->mB), eH = msm_finish_g1(pk->mH), eL = msm_finish_g1(pk->mL);
+    const HG2 eB2 = msm_finish_g2(pk->mB);
+    out.At = eA.to_affine(); out.Bt_h = eB1.to_affine(); out.Ht = eH.to_affine(); out.Lt = eL.to_affine(); out.Bt_g = eB2.to_affine();
+    uint64_t rs[4]; (HFr::from_canonical(r) * HFr::from_canonical(s)).to_canonical(rs);
+    const HG1 gA = HG1::from_affine(pk->alpha_g1).add(eA).add(g1_mul(pk->delta_g1, r));
+    const HG1 g1B = HG1::from_affine(pk->beta_g1).add(eB1).add(g1_mul(pk->delta_g1, s));
+    const HG2 g2B = HG2::from_affine(pk->beta_g2).add(eB2).add(HG2::from_affine(pk->delta_g2).mul(s));
+    const HG1 gC = eH.add(eL).add(gA.mul(s)).add(g1B.mul(r)).add(g1_mul(pk->delta_g1, rs).neg());
+    out.A = gA.to_affine(); out.B = g2B.to_affine(); out.C = gC.to_affine();
+    return 0;
+}
+
+static void hex_fq(const HFq &x, std::string &o) {
+    uint64_t c[4]; x.to_canonical(c);
+    char buf[65];
+    snprintf(buf, sizeof buf, "%016llx%016llx%016llx%016llx", (unsigned long long)c[3], (unsigned long long)c[2], (unsigned long long)c[1],
+             (unsigned long long)c[0]);
+    o += buf;
+}
+std::string proof_hex(const ProofPoints &p) {
+    // A.x A.y B.x.c1 B.x.c0 B.y.c1 B.y.c0 C.x C.y (mintcgo.cpp:130-187); infinity prints as the affine form of (0,1,0)
+    std::string o; o.reserve(512);
+    auto g1 = [&](const HG1Affine &a) { if (a.is_inf()) { hex_fq(HFq::zero(), o); hex_fq(HFq::one(), o); } else { hex_fq(a.x, o); hex_fq(a.y, o); } };
+    g1(p.A);
+    if (p.B.is_inf()) { hex_fq(HFq::zero(), o); hex_fq(HFq::zero(), o); hex_fq(HFq::zero(), o); hex_fq(HFq::one(), o); }
+    else { hex_fq(p.B.x.c1, o); hex_fq(p.B.x.c0, o); hex_fq(p.B.y.c1, o); hex_fq(p.B.y.c0, o); }
+    g1(p.C);
+    return o;
+}
+
+} // namespace zkp

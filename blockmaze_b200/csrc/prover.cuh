@@ -1,0 +1,109 @@
+// Device-side state of the B200 Groth16 prover: evaluation domains, resident proving keys, MSM work areas.
+// Declarations shared by prover.cu (GPU pipeline) and cabi.cpp (C-ABI).  See DESIGN.md for the data layout in HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "host_field.hpp"
+
+namespace zkp {
+
+void cuda_check(cudaError_t e, const char *what);     // aborts loudly: there is no CPU fallback
+#define ZK_CUDA(x) ::zkp::cuda_check((x), #x)
+
+// ---- evaluation domain (libfqfft get_evaluation_domain: basic_radix2 or step_radix2) ------------------------------
+struct Domain {
+    uint32_t m = 0, big = 0, small = 0;      // basic: big = m, small = 0
+    int log_big = 0, log_small = 0;
+    bool step = false;
+    uint32_t compr = 1;
+    // twiddles (device, Montgomery): w_n^j j < n/2 for the two power-of-two sub-transforms, forward and inverse
+    void *tw_big_f = nullptr, *tw_big_i = nullptr, *tw_small_f = nullptr, *tw_small_i = nullptr;
+    // step only: omega^j / omega^-j, j < big, omega = primitive (2*big)-th root
+    void *tw_step_f = nullptr, *tw_step_i = nullptr;
+    // two-level power tables of the coset generator g = 5: lo[i & 1023], hi[i >> 10]
+    void *g_lo = nullptr, *g_hi = nullptr;              // g^i
+    void *g_hi_ninv = nullptr;                          // g^i / m        (basic: iFFT scale folded into the coset shift)
+    void *gi_lo = nullptr, *gi_hi = nullptr;            // g^-i
+    void *gi_hi_ninv = nullptr;                         // g^-i / m
+    void *c_big_inv = nullptr, *c_small_inv = nullptr, *c_m_inv = nullptr;   // single constants 1/big, 1/small, 1/m
+    void *zt = nullptr;                                 // 1/Z on the coset, `compr` distinct values for i < big
+    zkh::HFr z1, over_two;                              // 1/Z for i >= big (step); 1/2
+    static Domain *build(uint64_t min_size);            // selection rule of get_evaluation_domain.tcc:33-52
+    void release();
+};
+
+enum DomainOp { OP_FFT = 0, OP_IFFT = 1, OP_COSET_FFT = 2, OP_ICOSET_FFT = 3, OP_DIVIDE_BY_Z = 4 };
+// in place on device buffer `data` (m Montgomery elements); `tmp` is scratch of the same size
+void domain_op(cudaStream_t st, const Domain &d, int op, void *data, void *tmp);
+
+// ---- MSM work area ---------------------------------------------------------------------------------------------------
+struct MsmPlan {
+    uint32_t n = 0;             // number of bases
+    int c = 0, windows = 0;
+    uint32_t nb = 0, ones = 0, total = 0;
+    uint32_t seg = 0, bpw = 0;  // reduce: buckets per thread, CTAs per window
+    uint32_t ones_bpw = 0;
+    void *counts = nullptr, *offsets = nullptr, *cursors = nullptr, *entries = nullptr;
+    size_t entries_cap = 0;
+    void *buckets_g1 = nullptr, *buckets_g2 = nullptr;
+    void *out_g1 = nullptr, *out_g2 = nullptr;           // device partial sums  [(windows+1) * bpw]
+    void *h_out_g1 = nullptr, *h_out_g2 = nullptr;       // pinned host copies
+    void init(uint32_t n, int c, uint32_t ones, bool g1, bool g2);
+    void release();
+};
+struct ScalarRef { const void *scalars; const uint32_t *map; uint32_t offset; int montgomery; };
+// sort digits (count / scan / scatter) then accumulate+reduce for G1 and/or G2 bases; results land in plan.h_out_* after
+// the stream is synchronised.
+void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, const void *bases_g1, const void *bases_g2);
+zkh::HG1 msm_finish_g1(const MsmPlan &p);      // host: per-window sums -> Horner
+zkh::HG2 msm_finish_g2(const MsmPlan &p);
+
+// ---- proving key resident on one GPU -------------------------------------------------------------------------------------
+struct DeviceCsr { uint32_t *rowptr = nullptr, *col = nullptr, *coef = nullptr; uint32_t nnz = 0; };
+struct DevicePk {
+    int device = 0;
+    uint64_t num_inputs = 0, num_vars = 0, num_constraints = 0;
+    Domain *dom = nullptr;
+    // bases (affine, Montgomery, AoS) and infinity flags
+    void *A = nullptr, *B1 = nullptr, *B2 = nullptr, *H = nullptr, *L = nullptr;
+    uint8_t *A_skip = nullptr, *B_skip = nullptr, *H_skip = nullptr, *L_skip = nullptr;
+    uint32_t nA = 0, nB = 0, nH = 0, nL = 0;
+    uint32_t *B_idx = nullptr;
+    zkh::HG1Affine alpha_g1, beta_g1, delta_g1;
+    zkh::HG2Affine beta_g2, delta_g2;
+    DeviceCsr a, b, c;
+    void *coef_dict = nullptr; uint32_t ncoef = 0;
+    // per-proof work buffers
+    void *w_can = nullptr, *w_mont = nullptr;            // (num_vars + 1) scalars: [1 | assignment]
+    void *h_w_pinned = nullptr;
+    void *bufA = nullptr, *bufB = nullptr, *bufC = nullptr, *tmp = nullptr;   // m Fr each
+    uint32_t *sat_flag = nullptr; uint32_t *h_sat_flag = nullptr;
+    MsmPlan mA, mB, mH, mL;
+    cudaStream_t s_main = nullptr, s_a = nullptr, s_b = nullptr, s_l = nullptr;
+    cudaEvent_t ev_w = nullptr, ev_a = nullptr, ev_b = nullptr, ev_l = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_q0 = nullptr, ev_q1 = nullptr,
+                ev_h0 = nullptr, ev_h1 = nullptr;
+    double load_seconds = 0, parse_seconds = 0, decompress_seconds = 0;
+};
+
+DevicePk *pk_load(const char *path, int device, std::string &err);
+void pk_free(DevicePk *pk);
+
+struct ProofPoints {
+    zkh::HG1Affine A, C; zkh::HG2Affine B;
+    zkh::HG1Affine At, Bt_h, Ht, Lt; zkh::HG2Affine Bt_g;   // the five MSM results (parity hooks)
+    bool satisfied = true;
+    float gpu_ms = 0, qap_ms = 0, msm_h_ms = 0;          // CUDA-event timings of the last run
+};
+// assignment: num_vars canonical 32-byte LE scalars in HOST memory (copied H2D inside), or nullptr to reuse the
+// assignment already resident on the device (bench "value" leg).
+int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const uint64_t s[4], ProofPoints &out);
+// QAP witness map only; writes (m+1)*32 bytes canonical to host `out_H`
+int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied);
+
+void device_init(int device);
+std::string proof_hex(const ProofPoints &p);           // mintcgo.cpp:112-187 layout
+int launches_last_prove();                             // number of kernels launched by the last prove() call
+
+} // namespace zkp

@@ -1,0 +1,122 @@
+/* zkb200.h -- C-ABI of the B200-native Groth16 prover for BlockMaze (libzkb200.so).
+ *
+ * Two layers, both plain C (pointers, sizes, integers -- no C++/CUDA/torch types):
+ *
+ *  (1) the reference's own cgo surface, re-exported verbatim so that go-ethereum/zktx/zktx.go links against this
+ *      library in place of libzk_mint.so / libzk_send.so / libzk_deposit.so / libzk_redeem.so
+ *      (reference headers: libsnark-vnt/src/mint/mintcgo.hpp:9-24, send/sendcgo.hpp:9-30, deposit/depositcgo.hpp:9-33,
+ *      redeem/redeemcgo.hpp:9-24; Go call sites go-ethereum/zktx/zktx.go:122-550);
+ *  (2) the zkb200_* entry points underneath: resident proving keys, the prover on a caller-supplied assignment,
+ *      and the two hot kernels (evaluation-domain transforms, multi-scalar multiplication) for parity tests and the sweep.
+ *
+ * Wire formats of layer (2), all little-endian: field element = 32 bytes canonical (non-Montgomery); G1 affine = x y (64 B);
+ * G2 affine = x.c0 x.c1 y.c0 y.c1 (128 B); all-zero bytes = point at infinity.
+ * There is no CPU fallback: every compute entry point runs on the GPU selected with zkb200_init and aborts loudly on a
+ * CUDA failure.
+ */
+#ifndef ZKB200_H
+#define ZKB200_H
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * (1) BlockMaze cgo surface.  256-bit arguments are "0x" + 64 hex chars, 160-bit ones "0x" + 40 (zktx.go:384-397);
+ * returned strings are heap buffers owned by the caller exactly as in the reference (which never frees them).
+ * Proof strings hold 512 lowercase hex chars + NUL: A.x A.y B.x.c1 B.x.c0 B.y.c1 B.y.c0 C.x C.y (mintcgo.cpp:176-187).
+ * An unsatisfiable witness yields the "default proof" of the three group generators (mintcgo.cpp:207-211), which
+ * starts with 63 '0' characters -- the condition go-ethereum tests (internal/ethapi/api.go:1486). */
+
+/* libsnark-vnt/src/mint/mintcgo.hpp:9-24 (mintcgo.cpp:239-266, 268-321, 323-418) */
+char *genCMT(uint64_t value, char *sn_string, char *r_string);
+char *computePRF(char *sk_string, char *r_string);
+char *genMintproof(uint64_t value, uint64_t value_old, char *sn_old_string, char *r_old_string, char *sn_string, char *r_string,
+                   char *cmtA_old_string, char *cmtA_string, uint64_t value_s, char *sk_string);
+bool verifyMintproof(char *data, char *cmtA_old_string, char *sn_old_string, char *cmtA_string, uint64_t value_s);
+
+/* libsnark-vnt/src/send/sendcgo.hpp:9-30 (sendcgo.cpp:239-300, 302-368, 370-470) */
+char *genCMTS(uint64_t value_s, char *pk_string, char *r_s_string, char *sn_old_string);
+char *computeCRH(char *pk_string, char *r_string);
+char *genSendproof(uint64_t value_A, char *r_s_string, char *sn_string, char *r_string, char *cmt_s_string, char *cmtA_string,
+                   uint64_t value_s, char *pk_recv_string, uint64_t value_A_new, char *sn_A_new, char *r_A_new, char *cmt_A_new,
+                   char *sk_string, char *pk_sender_string);
+bool verifySendproof(char *data, char *cmtA_old_string, char *sn_old_string, char *cmtS_string, char *cmtA_new_string);
+
+/* libsnark-vnt/src/deposit/depositcgo.hpp:9-33 (depositcgo.cpp:304-327, 329-448, 450-560) */
+char *genRoot(char *cmtarray, int n);
+char *genDepositproof(uint64_t value, uint64_t value_old, char *sn_old_string, char *r_old_string, char *sn_string, char *r_string,
+                      char *sns_string, char *rs_string, char *cmtB_old_string, char *cmtB_string, uint64_t value_s, char *pk_string,
+                      char *sn_A_oldstring, char *cmtS_string, char *cmtarray, int n, char *RT, char *sk_string);
+bool verifyDepositproof(char *data, char *RT, char *pk, char *cmtb_old, char *snold, char *cmtb, char *sns);
+
+/* libsnark-vnt/src/redeem/redeemcgo.hpp:9-24 (redeemcgo.cpp:269-322, 324-420) */
+char *genRedeemproof(uint64_t value, uint64_t value_old, char *sn_old_string, char *r_old_string, char *sn_string, char *r_string,
+                     char *cmtA_old_string, char *cmtA_string, uint64_t value_s, char *sk_string);
+bool verifyRedeemproof(char *data, char *cmtA_old_string, char *sn_old_string, char *cmtA_string, uint64_t value_s);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * (2) zkb200 layer */
+
+/* circuits, in the order used by every *_circuit argument */
+enum { ZKB200_MINT = 0, ZKB200_SEND = 1, ZKB200_DEPOSIT = 2, ZKB200_REDEEM = 3 };
+
+/* Select the CUDA device this process proves on (default 0, or env ZKB200_DEVICE).  Returns 0, or -1 if no GPU. */
+int zkb200_init(int device);
+/* Directory holding <circuit>pk.txt / <circuit>vk.txt.  Default: env ZKB200_KEY_DIR, else /usr/local/prfKey
+ * (hard-coded in the reference: mintcgo.cpp:302,336). */
+void zkb200_set_key_dir(const char *dir);
+/* Pin the prover randomness: the next proofs draw (r, s) from this std::random_device-style 32-bit word stream exactly as
+ * libff's Fr::random_element does (fp.tcc:695-721, bigint.tcc:167-179).  n_words = 0 returns to /dev/urandom. */
+void zkb200_set_random_words(const uint32_t *words, size_t n_words);
+
+/* Replaces r1cs_gg_ppzksnark_proving_key operator>> (r1cs_gg_ppzksnark.tcc:68-88): parse the file, decompress the points
+ * on the GPU, keep everything resident.  Returns a handle or NULL (zkb200_last_error() says why). */
+void *zkb200_pk_load(const char *path);
+void zkb200_pk_free(void *pk);
+/* info[0..7] = num_variables, num_inputs, num_constraints, domain m, domain kind (0 basic_radix2, 1 step_radix2),
+ * nnz(A)+nnz(B)+nnz(C), distinct coefficients, B_query entries.  seconds[0..2] = total load, parse, GPU decompression. */
+int zkb200_pk_info(void *pk, uint64_t info[8], double seconds[3]);
+const char *zkb200_last_error(void);
+
+/* Replaces r1cs_gg_ppzksnark_prover (r1cs_gg_ppzksnark.tcc:390-506) for a caller-supplied full assignment
+ * (primary || auxiliary, num_variables x 32 B) and explicit r, s.  assignment == NULL re-proves the assignment already
+ * resident on the GPU.  proof_hex: 513 bytes.  parts (optional, 384 B): the five MSM results At | Bt.g | Bt.h | Ht | Lt.
+ * timings_ms (optional, 4 floats): GPU total, QAP witness map, H MSM (CUDA events), host finish.
+ * Returns 0 = proof, 1 = constraint system not satisfied (proof_hex = default proof), <0 = error. */
+int zkb200_prove(void *pk, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32], char *proof_hex, uint8_t *parts,
+                 float *timings_ms);
+/* Replaces r1cs_to_qap_witness_map (r1cs_to_qap.tcc:205-334): out_H receives (m+1) x 32 B coefficients_for_H. */
+int zkb200_qap_witness_map(void *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied);
+/* kernels launched by the last zkb200_prove call */
+int zkb200_last_launches(void);
+
+/* Replaces libfqfft::get_evaluation_domain(min_size) + domain->{FFT,iFFT,cosetFFT,icosetFFT,divide_by_Z_on_coset}
+ * (get_evaluation_domain.tcc:33-52, basic_radix2_domain.tcc:26-112, step_radix2_domain.tcc:21-248).
+ * op: 0 FFT, 1 iFFT, 2 cosetFFT (g = 5), 3 icosetFFT, 4 divide_by_Z_on_coset.  data: n = domain size elements, in place.
+ * Returns the domain size m (call with data == NULL to query it; *kind = 0 basic, 1 step), or -1. */
+long zkb200_domain_op(size_t min_size, int op, uint8_t *data, size_t n, int *kind);
+
+/* Replaces libff::multi_exp<G, Fr, multi_exp_method_BDLO12> and multi_exp_with_mixed_addition (multiexp.tcc:402-496).
+ * window_bits = 0 picks a default. */
+int zkb200_msm_g1(size_t n, const uint8_t *bases, const uint8_t *scalars, int window_bits, uint8_t out[64]);
+int zkb200_msm_g2(size_t n, const uint8_t *bases, const uint8_t *scalars, int window_bits, uint8_t out[128]);
+
+/* Device field layer check: out = a (op) b on raw MONTGOMERY representatives, computed by a CUDA kernel.
+ * field: 0 Fr, 1 Fq.  op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 to_mont(a), 5 from_mont(a), 6 inverse(a). */
+int zkb200_field_op(int field, int op, size_t n, const uint8_t *a, const uint8_t *b, uint8_t *out);
+
+/* Device-resident benchmarks (inputs generated / kept in HBM, timed with CUDA events on the launching stream).
+ * zkb200_bench_ntt: `iters` forward size-2^logn transforms over a buffer of `batch` independent vectors; returns ms per transform.
+ * zkb200_bench_msm: dense 254-bit MSM over n synthetic bases (group: 1 = G1, 2 = G2); returns ms per MSM. */
+float zkb200_bench_ntt(int logn, int batch, int iters);
+float zkb200_bench_msm(int group, size_t n, int window_bits, int iters);
+/* dependent-free 32-bit multiply-add throughput of the GPU in 1e12 IMAD/s (the MSM roofline denominator) */
+float zkb200_bench_imad_peak(int wide);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

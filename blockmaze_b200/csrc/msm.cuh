@@ -7,7 +7,8 @@
 //                 k*2^(c-1) + |d| - 1.  Scalars equal to 0 are dropped; scalars equal to 1 (45 % of a BlockMaze witness) are
 //                 spread round-robin over a separate range of "ones" buckets instead of all landing in bucket (0,1).
 //   2. count / scan / scatter : a counting sort of (bucket -> point index | sign) built from global atomics.
-//   3. accumulate : one thread per bucket walks its list with XYZZ += affine mixed additions (8M+2S).
+//   3. accumulate : buckets are cut into tasks of <= 48 entries; one thread per task does XYZZ += affine mixed additions
+//                   (8M+2S) and a few segmented pairwise passes fold the tasks of oversized buckets.
 //   4. reduce  : per window, sum_j (j+1)*B_j by segmented running sums + a shared-memory tree; ones buckets are summed.
 //   5. the per-window partial sums (a few dozen points) go back to the host, which does the final Horner combination.
 #pragma once
@@ -144,22 +145,65 @@ template <class F> __device__ __forceinline__ XYZZ<F> ld_xyzz(const XYZZ<F> *p) 
     return v;
 }
 
-// one thread per bucket
-template <class F>
-static __global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ offsets,
-                                                             const uint32_t *__restrict__ entries, uint32_t total_buckets,
-                                                             XYZZ<F> *__restrict__ buckets) {
+// ---- bucket accumulation, load-balanced ------------------------------------------------------------------------------
+// Bucket sizes are wildly uneven in practice (the top window of a 254-bit scalar has only 2-3 live bits, so a handful of
+// buckets hold n/4 points each; witness scalars repeat), so buckets are cut into TASKS of at most MSM_TASK entries:
+//   task_count : tasks_b = ceil(count_b / MSM_TASK), scanned into task_off[]
+//   accumulate : one thread per task sums its <= MSM_TASK points (XYZZ += affine) into partial[task]
+//   combine    : log2(max tasks per bucket) segmented pairwise passes fold partial[] so that partial[task_off[b]] = bucket b
+constexpr uint32_t MSM_TASK = 48;
+
+static __global__ void msm_task_count_kernel(const uint32_t *__restrict__ offsets, uint32_t total_buckets, uint32_t *__restrict__ task_counts,
+                                             uint32_t *__restrict__ max_tasks) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= total_buckets) return;
-    const uint32_t lo = offsets[b], hi = offsets[b + 1];
+    const uint32_t cnt = offsets[b + 1] - offsets[b];
+    const uint32_t t = (cnt + MSM_TASK - 1) / MSM_TASK;
+    task_counts[b] = t;
+    if (t > 1) atomicMax(max_tasks, t);
+}
+
+template <class F>
+static __global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ offsets,
+                                                             const uint32_t *__restrict__ entries, const uint32_t *__restrict__ task_off,
+                                                             uint32_t total_buckets, XYZZ<F> *__restrict__ partial,
+                                                             uint32_t *__restrict__ task_rank, uint32_t *__restrict__ task_span) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= task_off[total_buckets]) return;
+    // bucket of task t: last b with task_off[b] <= t
+    uint32_t lo = 0, hi = total_buckets;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(task_off + mid) <= t) lo = mid; else hi = mid; }
+    const uint32_t b = lo, rank = t - __ldg(task_off + b);
+    const uint32_t e0 = offsets[b] + rank * MSM_TASK, e1 = min(e0 + MSM_TASK, offsets[b + 1]);
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t e = lo; e < hi; e++) {
+    for (uint32_t e = e0; e < e1; e++) {
         const uint32_t ent = __ldg(entries + e);
         Affine<F> p = ld_affine(bases + (ent & 0x7fffffffu));
         if (ent & 0x80000000u) p.y = p.y.neg();
         acc.add_affine(p);
     }
-    st_xyzz(buckets + b, acc);
+    st_xyzz(partial + t, acc);
+    task_rank[t] = rank;
+    task_span[t] = __ldg(task_off + b + 1) - __ldg(task_off + b);
+}
+// pass with stride s: partial[t] += partial[t + s] when rank % 2s == 0 and rank + s < span
+template <class F>
+static __global__ void __launch_bounds__(128) msm_combine_kernel(XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ task_rank,
+                                                          const uint32_t *__restrict__ task_span, const uint32_t *__restrict__ task_off,
+                                                          uint32_t total_buckets, const uint32_t *__restrict__ max_tasks, uint32_t s) {
+    if (s >= *max_tasks) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= task_off[total_buckets]) return;
+    const uint32_t rank = task_rank[t];
+    if ((rank & (2 * s - 1)) != 0 || rank + s >= task_span[t]) return;
+    XYZZ<F> a = ld_xyzz(partial + t);
+    a.add(ld_xyzz(partial + t + s));
+    st_xyzz(partial + t, a);
+}
+template <class F> __device__ __forceinline__ XYZZ<F> msm_bucket(const XYZZ<F> *partial, const uint32_t *task_off, uint32_t b) {
+    const uint32_t t0 = __ldg(task_off + b);
+    if (__ldg(task_off + b + 1) == t0) return XYZZ<F>::inf();
+    return ld_xyzz(partial + t0);
 }
 
 // Per window w (blockIdx.y) and segment block (blockIdx.x): every thread owns `seg` consecutive buckets [lo, lo+seg) and computes
@@ -168,20 +212,20 @@ static __global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine
 // For blockIdx.y == windows the "ones" buckets are summed with weight 1.
 constexpr int MSM_RED_THREADS = 64;
 template <class F>
-static __global__ void __launch_bounds__(MSM_RED_THREADS) msm_reduce_kernel(const XYZZ<F> *__restrict__ buckets, MsmShape sh, uint32_t seg,
-                                                                     uint32_t blocks_per_window, XYZZ<F> *__restrict__ out) {
+static __global__ void __launch_bounds__(MSM_RED_THREADS) msm_reduce_kernel(const XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ task_off, MsmShape sh,
+                                                                     uint32_t seg, uint32_t blocks_per_window, XYZZ<F> *__restrict__ out) {
     extern __shared__ uint32_t red_sm[];
     XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(red_sm);
     const uint32_t w = blockIdx.y;
     const bool ones = (w == (uint32_t)sh.windows);
     const uint32_t count = ones ? sh.ones : sh.nb;
-    const XYZZ<F> *base = buckets + (size_t)w * sh.nb;           // ones region starts at windows*nb as well
+    const uint32_t base = w * sh.nb;                              // ones region starts at windows*nb as well
     const uint32_t lo = (blockIdx.x * MSM_RED_THREADS + threadIdx.x) * seg;
     XYZZ<F> S = XYZZ<F>::inf(), T = XYZZ<F>::inf();
     if (lo < count) {
         const uint32_t hi = min(lo + seg, count);
         for (uint32_t j = hi; j-- > lo;) {
-            S.add(ld_xyzz(base + j));
+            S.add(msm_bucket(partial, task_off, base + j));
             if (!ones) T.add(S);
         }
         if (ones) T = S;

@@ -297,20 +297,28 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2) {
     ZK_CUDA(cudaMalloc(&cursors, (size_t)(total + 1) * 4));
     entries_cap = (size_t)n * windows + 16;
     ZK_CUDA(cudaMalloc(&entries, entries_cap * 4));
+    task_cap = total + (uint32_t)(((size_t)n * windows) / MSM_TASK) + 1;
+    combine_passes = 0;
+    for (uint32_t p = cdiv(n ? n : 1, MSM_TASK); p > 1; p = (p + 1) / 2) combine_passes++;
+    ZK_CUDA(cudaMalloc(&task_counts, (size_t)(total + 1) * 4));
+    ZK_CUDA(cudaMalloc(&task_off, (size_t)(total + 1) * 4));
+    ZK_CUDA(cudaMalloc(&task_rank, (size_t)task_cap * 4));
+    ZK_CUDA(cudaMalloc(&task_span, (size_t)task_cap * 4));
+    ZK_CUDA(cudaMalloc(&max_tasks, 4));
     const size_t nout = (size_t)(windows + 1) * bpw;
     if (g1) {
-        ZK_CUDA(cudaMalloc(&buckets_g1, (size_t)total * sizeof(G1XYZZ)));
+        ZK_CUDA(cudaMalloc(&buckets_g1, (size_t)task_cap * sizeof(G1XYZZ)));
         ZK_CUDA(cudaMalloc(&out_g1, nout * sizeof(G1XYZZ)));
         ZK_CUDA(cudaMallocHost(&h_out_g1, nout * sizeof(G1XYZZ)));
     }
     if (g2) {
-        ZK_CUDA(cudaMalloc(&buckets_g2, (size_t)total * sizeof(G2XYZZ)));
+        ZK_CUDA(cudaMalloc(&buckets_g2, (size_t)task_cap * sizeof(G2XYZZ)));
         ZK_CUDA(cudaMalloc(&out_g2, nout * sizeof(G2XYZZ)));
         ZK_CUDA(cudaMallocHost(&h_out_g2, nout * sizeof(G2XYZZ)));
     }
 }
 void MsmPlan::release() {
-    void *ps[] = {counts, offsets, cursors, entries, buckets_g1, buckets_g2, out_g1, out_g2};
+    void *ps[] = {counts, offsets, cursors, entries, buckets_g1, buckets_g2, out_g1, out_g2, task_counts, task_off, task_rank, task_span, max_tasks};
     for (void *p : ps) if (p) cudaFree(p);
     if (h_out_g1) cudaFreeHost(h_out_g1);
     if (h_out_g2) cudaFreeHost(h_out_g2);
@@ -326,19 +334,30 @@ void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, con
     ZK_LAUNCH(msm_scan_kernel, 1, 1024, 0, st, (const uint32_t *)p.counts, (uint32_t *)p.offsets, p.total);
     if (p.n) ZK_LAUNCH(msm_scatter_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, p.n, sh, (const uint32_t *)p.offsets, (uint32_t *)p.cursors,
                        (uint32_t *)p.entries);
+    ZK_CUDA(cudaMemsetAsync(p.max_tasks, 0, 4, st));
+    ZK_LAUNCH(msm_task_count_kernel, cdiv(p.total, 256), 256, 0, st, (const uint32_t *)p.offsets, p.total, (uint32_t *)p.task_counts,
+              (uint32_t *)p.max_tasks);
+    ZK_LAUNCH(msm_scan_kernel, 1, 1024, 0, st, (const uint32_t *)p.task_counts, (uint32_t *)p.task_off, p.total);
     const dim3 rgrid(p.bpw, sh.windows + 1);
     const size_t nout = (size_t)(sh.windows + 1) * p.bpw;
+    const uint32_t *toff = (const uint32_t *)p.task_off, *trank = (const uint32_t *)p.task_rank, *tspan = (const uint32_t *)p.task_span;
     if (bases_g1) {
-        ZK_LAUNCH(msm_accumulate_kernel<Fq>, cdiv(p.total, 128), 128, 0, st, (const G1Affine *)bases_g1, (const uint32_t *)p.offsets,
-                  (const uint32_t *)p.entries, p.total, (G1XYZZ *)p.buckets_g1);
-        ZK_LAUNCH(msm_reduce_kernel<Fq>, rgrid, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(G1XYZZ), st, (const G1XYZZ *)p.buckets_g1, sh, p.seg,
+        ZK_LAUNCH(msm_accumulate_kernel<Fq>, cdiv(p.task_cap, 128), 128, 0, st, (const G1Affine *)bases_g1, (const uint32_t *)p.offsets,
+                  (const uint32_t *)p.entries, toff, p.total, (G1XYZZ *)p.buckets_g1, (uint32_t *)p.task_rank, (uint32_t *)p.task_span);
+        for (uint32_t k = 0; k < p.combine_passes; k++)
+            ZK_LAUNCH(msm_combine_kernel<Fq>, cdiv(p.task_cap, 128), 128, 0, st, (G1XYZZ *)p.buckets_g1, trank, tspan, toff, p.total,
+                      (const uint32_t *)p.max_tasks, 1u << k);
+        ZK_LAUNCH(msm_reduce_kernel<Fq>, rgrid, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(G1XYZZ), st, (const G1XYZZ *)p.buckets_g1, toff, sh, p.seg,
                   p.bpw, (G1XYZZ *)p.out_g1);
         ZK_CUDA(cudaMemcpyAsync(p.h_out_g1, p.out_g1, nout * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, st));
     }
     if (bases_g2) {
-        ZK_LAUNCH(msm_accumulate_kernel<Fq2>, cdiv(p.total, 128), 128, 0, st, (const G2Affine *)bases_g2, (const uint32_t *)p.offsets,
-                  (const uint32_t *)p.entries, p.total, (G2XYZZ *)p.buckets_g2);
-        ZK_LAUNCH(msm_reduce_kernel<Fq2>, rgrid, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(G2XYZZ), st, (const G2XYZZ *)p.buckets_g2, sh, p.seg,
+        ZK_LAUNCH(msm_accumulate_kernel<Fq2>, cdiv(p.task_cap, 128), 128, 0, st, (const G2Affine *)bases_g2, (const uint32_t *)p.offsets,
+                  (const uint32_t *)p.entries, toff, p.total, (G2XYZZ *)p.buckets_g2, (uint32_t *)p.task_rank, (uint32_t *)p.task_span);
+        for (uint32_t k = 0; k < p.combine_passes; k++)
+            ZK_LAUNCH(msm_combine_kernel<Fq2>, cdiv(p.task_cap, 128), 128, 0, st, (G2XYZZ *)p.buckets_g2, trank, tspan, toff, p.total,
+                      (const uint32_t *)p.max_tasks, 1u << k);
+        ZK_LAUNCH(msm_reduce_kernel<Fq2>, rgrid, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(G2XYZZ), st, (const G2XYZZ *)p.buckets_g2, toff, sh, p.seg,
                   p.bpw, (G2XYZZ *)p.out_g2);
         ZK_CUDA(cudaMemcpyAsync(p.h_out_g2, p.out_g2, nout * sizeof(G2XYZZ), cudaMemcpyDeviceToHost, st));
     }

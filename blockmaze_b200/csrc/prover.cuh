@@ -47,7 +47,9 @@ struct MsmPlan {
     uint32_t ones_bpw = 0;
     void *counts = nullptr, *offsets = nullptr, *cursors = nullptr, *entries = nullptr;
     size_t entries_cap = 0;
-    void *buckets_g1 = nullptr, *buckets_g2 = nullptr;
+    void *task_counts = nullptr, *task_off = nullptr, *task_rank = nullptr, *task_span = nullptr, *max_tasks = nullptr;
+    uint32_t task_cap = 0, combine_passes = 0;
+    void *buckets_g1 = nullptr, *buckets_g2 = nullptr;   // per-task partial sums
     void *out_g1 = nullptr, *out_g2 = nullptr;           // device partial sums  [(windows+1) * bpw]
     void *h_out_g1 = nullptr, *h_out_g2 = nullptr;       // pinned host copies
     void init(uint32_t n, int c, uint32_t ones, bool g1, bool g2);

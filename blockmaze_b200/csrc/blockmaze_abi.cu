@@ -1,0 +1,250 @@
+// C-ABI layer (1) of include/zkb200.h: BlockMaze's cgo surface (libzk_mint / libzk_send / libzk_deposit / libzk_redeem),
+// re-exported from one library.  Argument parsing, returned-buffer semantics and the failure encoding follow
+// SRC/{mint,send,deposit,redeem}/*cgo.cpp; the proving itself runs on the GPU against proving keys that are parsed once per
+// process and stay resident (the reference re-reads and re-parses the key file inside every gen*proof call,
+// mintcgo.cpp:299-302).
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <random>
+#include <string>
+#include <vector>
+#include "../../include/zkb200.h"
+#include "prover.cuh"
+#include "witness.hpp"
+
+using namespace zkw;
+
+static std::mutex g_abi_mu;
+static std::string g_key_dir;
+static std::vector<uint32_t> g_words;
+static size_t g_word_pos = 0;
+static void *g_pk[4] = {nullptr, nullptr, nullptr, nullptr};
+static const char *CIRCUIT_NAMES[4] = {"mint", "send", "deposit", "redeem"};
+
+static std::string key_dir() {
+    if (!g_key_dir.empty()) return g_key_dir;
+    const char *e = getenv("ZKB200_KEY_DIR");
+    return e ? std::string(e) : std::string("/usr/local/prfKey");        // hard-coded in the reference (mintcgo.cpp:302)
+}
+
+void zkb200_set_key_dir(const char *dir) {
+    std::lock_guard<std::mutex> lk(g_abi_mu);
+    g_key_dir = dir ? dir : "";
+    for (int c = 0; c < 4; c++) if (g_pk[c]) { zkb200_pk_free(g_pk[c]); g_pk[c] = nullptr; }
+}
+void zkb200_set_random_words(const uint32_t *words, size_t n_words) {
+    std::lock_guard<std::mutex> lk(g_abi_mu);
+    g_words.assign(words, words + n_words);
+    g_word_pos = 0;
+}
+
+// Fr::random_element (fp.tcc:695-721, bigint.tcc:167-179): 8 x 32-bit words -> mont_repr, clear bits >= 254, retry while >= r.
+// The field element is the one whose MONTGOMERY representative is that integer; returns its canonical value.
+static void next_random_fr(uint64_t out[4]) {
+    static std::random_device rd;
+    for (;;) {
+        uint32_t w[8];
+        for (int i = 0; i < 8; i++) {
+            if (!g_words.empty()) { w[i] = g_words[g_word_pos % g_words.size()]; g_word_pos++; }
+            else w[i] = rd();
+        }
+        uint64_t m[4];
+        for (int i = 0; i < 4; i++) m[i] = (uint64_t)w[2 * i] | ((uint64_t)w[2 * i + 1] << 32);
+        m[3] &= 0x3fffffffffffffffull;
+        if (!zkh::HFr::geq_mod(m)) { zkh::HFr::raw(m).to_canonical(out); return; }
+    }
+}
+
+static void *circuit_pk(int circuit) {
+    if (!g_pk[circuit]) {
+        const std::string path = key_dir() + "/" + CIRCUIT_NAMES[circuit] + "pk.txt";
+        g_pk[circuit] = zkb200_pk_load(path.c_str());
+        if (!g_pk[circuit]) {
+            // the reference's behaviour on a missing key file is undefined (assert compiled out, mintcgo.cpp:69); fail loudly instead
+            fprintf(stderr, "zkb200: cannot load %s: %s\n", path.c_str(), zkb200_last_error());
+            abort();
+        }
+    }
+    return g_pk[circuit];
+}
+
+static char *dup_hex(const std::string &s, size_t cap) {       // `new char[cap]`, NUL-terminated, like the reference helpers
+    char *p = new char[cap];
+    memset(p, 0, cap);
+    memcpy(p, s.data(), s.size() < cap - 1 ? s.size() : cap - 1);
+    return p;
+}
+static char *prove_with(int circuit, const Assignment &a) {
+    std::lock_guard<std::mutex> lk(g_abi_mu);
+    void *pk = circuit_pk(circuit);
+    uint64_t r[4], s[4];
+    next_random_fr(r); next_random_fr(s);                      // r first, then s (r1cs_gg_ppzksnark.tcc:418-419)
+    char *p = new char[1153];                                  // the reference returns new char[1153] with 512 hex chars (mintcgo.cpp:316-320)
+    memset(p, 0, 1153);
+    const int rc = zkb200_prove(pk, a.data(), (const uint8_t *)r, (const uint8_t *)s, p, nullptr, nullptr);
+    if (rc == 1) printf("can not generate %s proof\n", CIRCUIT_NAMES[circuit]);      // mintcgo.cpp:209
+    return p;
+}
+
+// ---- helpers ---------------------------------------------------------------------------------------------------------------
+char *genCMT(uint64_t value, char *sn_string, char *r_string) {
+    uint8_t sn[32], r[32], cm[32];
+    parse_hex_blob(sn_string, sn, 32); parse_hex_blob(r_string, r, 32);
+    note_cm(value, sn, r, cm);
+    return dup_hex(blob_to_hex(cm, 32), 68);
+}
+char *computePRF(char *sk_string, char *r_string) {
+    uint8_t sk[32], r[32], o[32];
+    parse_hex_blob(sk_string, sk, 32); parse_hex_blob(r_string, r, 32);
+    compute_prf(sk, r, o);
+    return dup_hex(blob_to_hex(o, 32), 68);
+}
+char *genCMTS(uint64_t value_s, char *pk_string, char *r_s_string, char *sn_old_string) {
+    uint8_t pk[20], r[32], sn[32], cm[32];
+    parse_hex_blob(pk_string, pk, 20); parse_hex_blob(r_s_string, r, 32); parse_hex_blob(sn_old_string, sn, 32);
+    notes_cm(value_s, pk, r, sn, cm);
+    return dup_hex(blob_to_hex(cm, 32), 68);
+}
+char *computeCRH(char *pk_string, char *r_string) {
+    uint8_t pk[20], r[32], o[32];
+    parse_hex_blob(pk_string, pk, 20); parse_hex_blob(r_string, r, 32);
+    compute_crh(pk, r, o);
+    return dup_hex(blob_to_hex(o, 32), 68);
+}
+static size_t parse_cmtarray(const char *cmtarray, int n, std::vector<uint8_t> &leaves) {
+    // n concatenated 66-character strings "0x" + 64 hex (depositcgo.cpp:304-315); the reference holds at most 256 of them
+    const size_t cnt = n < 0 ? 0 : (n > 256 ? 256 : (size_t)n);
+    leaves.assign(cnt * 32, 0);
+    const size_t len = cmtarray ? strlen(cmtarray) : 0;
+    for (size_t i = 0; i < cnt; i++) {
+        if (i * 66 >= len) break;
+        std::string piece(cmtarray + i * 66, std::min<size_t>(66, len - i * 66));
+        parse_hex_blob(piece.c_str(), &leaves[i * 32], 32);
+    }
+    return cnt;
+}
+char *genRoot(char *cmtarray, int n) {
+    std::vector<uint8_t> leaves;
+    const size_t cnt = parse_cmtarray(cmtarray, n, leaves);
+    uint8_t rt[32];
+    merkle_root((const uint8_t(*)[32])leaves.data(), cnt, rt);
+    return dup_hex(blob_to_hex(rt, 32), 68);
+}
+
+// ---- proofs ------------------------------------------------------------------------------------------------------------------
+static void parse_note(Note &n, uint64_t value, const char *sn, const char *r) { n.value = value; parse_hex_blob(sn, n.sn, 32); parse_hex_blob(r, n.r, 32); }
+
+char *genMintproof(uint64_t value, uint64_t value_old, char *sn_old_string, char *r_old_string, char *sn_string, char *r_string,
+                   char *cmtA_old_string, char *cmtA_string, uint64_t value_s, char *sk_string) {
+    Note note_old, note; uint8_t cmtA_old[32], cmtA[32], sk[32];
+    parse_note(note_old, value_old, sn_old_string, r_old_string); parse_note(note, value, sn_string, r_string);
+    parse_hex_blob(cmtA_old_string, cmtA_old, 32); parse_hex_blob(cmtA_string, cmtA, 32); parse_hex_blob(sk_string, sk, 32);
+    return prove_with(ZKB200_MINT, mint_witness(note_old, note, cmtA_old, cmtA, value_s, sk));
+}
+char *genRedeemproof(uint64_t value, uint64_t value_old, char *sn_old_string, char *r_old_string, char *sn_string, char *r_string,
+                     char *cmtA_old_string, char *cmtA_string, uint64_t value_s, char *sk_string) {
+    Note note_old, note; uint8_t cmtA_old[32], cmtA[32], sk[32];
+    parse_note(note_old, value_old, sn_old_string, r_old_string); parse_note(note, value, sn_string, r_string);
+    parse_hex_blob(cmtA_old_string, cmtA_old, 32); parse_hex_blob(cmtA_string, cmtA, 32); parse_hex_blob(sk_string, sk, 32);
+    printf("Trying to generate redeem proof...\n");            // redeemcgo.cpp:310
+    return prove_with(ZKB200_REDEEM, redeem_witness(note_old, note, cmtA_old, cmtA, value_s, sk));
+}
+char *genSendproof(uint64_t value_A, char *r_s_string, char *sn_string, char *r_string, char *cmt_s_string, char *cmtA_string, uint64_t value_s,
+                   char *pk_recv_string, uint64_t value_A_new, char *sn_A_new, char *r_A_new, char *cmt_A_new, char *sk_string,
+                   char *pk_sender_string) {
+    // sendcgo.cpp:318-334: the "A" note is the old one; NoteS(value_s, pk_recv, r_s, sn)
+    Note note_old, note_new; NoteS notes; uint8_t cmtS[32], cmtA[32], cmtAnew[32], sk[32], pk_sender[20];
+    parse_note(note_old, value_A, sn_string, r_string); parse_note(note_new, value_A_new, sn_A_new, r_A_new);
+    notes.value = value_s; parse_hex_blob(pk_recv_string, notes.pk, 20); parse_hex_blob(r_s_string, notes.r, 32); memcpy(notes.sn_old, note_old.sn, 32);
+    parse_hex_blob(cmt_s_string, cmtS, 32); parse_hex_blob(cmtA_string, cmtA, 32); parse_hex_blob(cmt_A_new, cmtAnew, 32);
+    parse_hex_blob(sk_string, sk, 32); parse_hex_blob(pk_sender_string, pk_sender, 20);
+    printf("Trying to generate send proof...\n");              // sendcgo.cpp:352
+    return prove_with(ZKB200_SEND, send_witness(note_old, notes, note_new, cmtA, cmtS, cmtAnew, sk, pk_sender));
+}
+char *genDepositproof(uint64_t value, uint64_t value_old, char *sn_old_string, char *r_old_string, char *sn_string, char *r_string,
+                      char *sns_string, char *rs_string, char *cmtB_old_string, char *cmtB_string, uint64_t value_s, char *pk_string,
+                      char *sn_A_oldstring, char *cmtS_string, char *cmtarray, int n, char *RT, char *sk_string) {
+    (void)RT;                                                  // accepted but ignored by the reference too (depositcgo.cpp:402-403)
+    Note note_old, note; NoteS note_s; uint8_t sn_s[32], cmtB_old[32], cmtB[32], cmtS[32], sk[32];
+    parse_note(note_old, value_old, sn_old_string, r_old_string); parse_note(note, value, sn_string, r_string);
+    note_s.value = value_s; parse_hex_blob(pk_string, note_s.pk, 20); parse_hex_blob(rs_string, note_s.r, 32);
+    parse_hex_blob(sn_A_oldstring, note_s.sn_old, 32);
+    parse_hex_blob(sns_string, sn_s, 32); parse_hex_blob(cmtB_old_string, cmtB_old, 32); parse_hex_blob(cmtB_string, cmtB, 32);
+    parse_hex_blob(cmtS_string, cmtS, 32); parse_hex_blob(sk_string, sk, 32);
+    std::vector<uint8_t> leaves;
+    const size_t cnt = parse_cmtarray(cmtarray, n, leaves);
+    // depositcgo.cpp:373-400: leaves up to the FIRST occurrence of cmtS go to the tree; the witness is re-created at every later
+    // occurrence (dropping what it had collected since), so the effective leaf list is  leaves[0..first] ++ leaves[last+1..]
+    long first = -1, last = -1;
+    for (size_t i = 0; i < cnt; i++) if (memcmp(&leaves[i * 32], cmtS, 32) == 0) { if (first < 0) first = (long)i; last = (long)i; }
+    printf("Trying to generate deposit proof...\n");           // depositcgo.cpp:421
+    if (first < 0) {
+        // the reference throws from IncrementalMerkleTree::path() here (uncaught C++ exception under cgo); report failure instead
+        printf("can not generate deposit proof\n");
+        char *p = new char[1153]; memset(p, 0, 1153);
+        uint64_t zero[4] = {0, 0, 0, 0};
+        std::lock_guard<std::mutex> lk(g_abi_mu);
+        Assignment bad; bad.num_vars = DEPOSIT_VARS; bad.tape.assign(((size_t)DEPOSIT_VARS + 1) * 4, 0);
+        zkb200_prove(circuit_pk(ZKB200_DEPOSIT), bad.data(), (const uint8_t *)zero, (const uint8_t *)zero, p, nullptr, nullptr);
+        return p;
+    }
+    std::vector<uint8_t> eff(leaves.begin(), leaves.begin() + (first + 1) * 32);
+    eff.insert(eff.end(), leaves.begin() + (last + 1) * 32, leaves.end());
+    uint8_t siblings[MERKLE_DEPTH][32], rt[32];
+    merkle_path((const uint8_t(*)[32])eff.data(), eff.size() / 32, (size_t)first, siblings, rt);
+    return prove_with(ZKB200_DEPOSIT, deposit_witness(note_s, note_old, note, cmtS, cmtB_old, cmtB, rt, (size_t)first, siblings, sn_s, sk));
+}
+
+// ---- witness-only entry points (parity hooks for the assignment layout) -----------------------------------------------------
+extern "C" {
+long zkb200_witness_mint(uint64_t value, uint64_t value_old, const char *sn_old, const char *r_old, const char *sn, const char *r,
+                         const char *cmtA_old_s, const char *cmtA_s, uint64_t value_s, const char *sk_s, int redeem, uint8_t *out, size_t cap) {
+    Note note_old, note; uint8_t cmtA_old[32], cmtA[32], sk[32];
+    parse_note(note_old, value_old, sn_old, r_old); parse_note(note, value, sn, r);
+    parse_hex_blob(cmtA_old_s, cmtA_old, 32); parse_hex_blob(cmtA_s, cmtA, 32); parse_hex_blob(sk_s, sk, 32);
+    Assignment a = redeem ? redeem_witness(note_old, note, cmtA_old, cmtA, value_s, sk) : mint_witness(note_old, note, cmtA_old, cmtA, value_s, sk);
+    if (cap < a.num_vars) return -1;
+    memcpy(out, a.data(), (size_t)a.num_vars * 32);
+    return a.num_vars;
+}
+long zkb200_witness_send(uint64_t value_A, const char *r_s, const char *sn, const char *r, const char *cmt_s, const char *cmtA_s, uint64_t value_s,
+                         const char *pk_recv, uint64_t value_A_new, const char *sn_A_new, const char *r_A_new, const char *cmt_A_new, const char *sk_s,
+                         const char *pk_sender_s, uint8_t *out, size_t cap) {
+    Note note_old, note_new; NoteS notes; uint8_t cmtS[32], cmtA[32], cmtAnew[32], sk[32], pk_sender[20];
+    parse_note(note_old, value_A, sn, r); parse_note(note_new, value_A_new, sn_A_new, r_A_new);
+    notes.value = value_s; parse_hex_blob(pk_recv, notes.pk, 20); parse_hex_blob(r_s, notes.r, 32); memcpy(notes.sn_old, note_old.sn, 32);
+    parse_hex_blob(cmt_s, cmtS, 32); parse_hex_blob(cmtA_s, cmtA, 32); parse_hex_blob(cmt_A_new, cmtAnew, 32);
+    parse_hex_blob(sk_s, sk, 32); parse_hex_blob(pk_sender_s, pk_sender, 20);
+    Assignment a = send_witness(note_old, notes, note_new, cmtA, cmtS, cmtAnew, sk, pk_sender);
+    if (cap < a.num_vars) return -1;
+    memcpy(out, a.data(), (size_t)a.num_vars * 32);
+    return a.num_vars;
+}
+long zkb200_witness_deposit(uint64_t value, uint64_t value_old, const char *sn_old, const char *r_old, const char *sn, const char *r, const char *sns,
+                            const char *rs, const char *cmtB_old_s, const char *cmtB_s, uint64_t value_s, const char *pk, const char *sn_A_old,
+                            const char *cmtS_s, const char *cmtarray, int n, const char *RT, const char *sk_s, uint8_t *out, size_t cap) {
+    (void)RT;
+    Note note_old, note; NoteS note_s; uint8_t sn_s[32], cmtB_old[32], cmtB[32], cmtS[32], sk[32];
+    parse_note(note_old, value_old, sn_old, r_old); parse_note(note, value, sn, r);
+    note_s.value = value_s; parse_hex_blob(pk, note_s.pk, 20); parse_hex_blob(rs, note_s.r, 32); parse_hex_blob(sn_A_old, note_s.sn_old, 32);
+    parse_hex_blob(sns, sn_s, 32); parse_hex_blob(cmtB_old_s, cmtB_old, 32); parse_hex_blob(cmtB_s, cmtB, 32);
+    parse_hex_blob(cmtS_s, cmtS, 32); parse_hex_blob(sk_s, sk, 32);
+    std::vector<uint8_t> leaves;
+    const size_t cnt = parse_cmtarray(cmtarray, n, leaves);
+    long first = -1, last = -1;
+    for (size_t i = 0; i < cnt; i++) if (memcmp(&leaves[i * 32], cmtS, 32) == 0) { if (first < 0) first = (long)i; last = (long)i; }
+    if (first < 0) return -2;
+    std::vector<uint8_t> eff(leaves.begin(), leaves.begin() + (first + 1) * 32);
+    eff.insert(eff.end(), leaves.begin() + (last + 1) * 32, leaves.end());
+    uint8_t siblings[MERKLE_DEPTH][32], rt[32];
+    merkle_path((const uint8_t(*)[32])eff.data(), eff.size() / 32, (size_t)first, siblings, rt);
+    Assignment a = deposit_witness(note_s, note_old, note, cmtS, cmtB_old, cmtB, rt, (size_t)first, siblings, sn_s, sk);
+    if (cap < a.num_vars) return -1;
+    memcpy(out, a.data(), (size_t)a.num_vars * 32);
+    return a.num_vars;
+}
+}
+
+// ---- verification: see verifier.cu -------------------------------------------------------------------------------------------

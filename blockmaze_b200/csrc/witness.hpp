@@ -1,0 +1,59 @@
+// Host-side "witness handling" for BlockMaze's four circuits: byte-level helpers of the cgo layer (hex blobs, SHA-256
+// commitments, the depth-8 incremental Merkle tree) and native generators of the FULL variable assignment that the
+// reference obtains by running its gadgetlib1 circuits (protoboard::full_variable_assignment).
+//
+// The assignment layout is an artefact of gadget construction order in the reference (protoboard::allocate_var_index,
+// libsnark/gadgetlib1/protoboard.tcc:37-49); each generator below documents the order it reproduces.  Parity is checked
+// element-for-element against the reference gadgets (tests/test_witness.py via oracle/_ref).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace zkw {
+
+// ---- byte helpers (uint256.h base_blob::SetHex/GetHex, util.h, Note.h) -------------------------------------------------
+// SetHex: skips leading whitespace and "0x", reads hex digits from the END of the string into data[0..]  (uint256.h:200-226)
+void parse_hex_blob(const char *s, uint8_t *out, size_t nbytes);
+std::string blob_to_hex(const uint8_t *data, size_t nbytes);          // GetHex: reversed bytes as lowercase hex
+void sha256(const uint8_t *data, size_t len, uint8_t out[32]);        // CSHA256 Write+Finalize (standard padding)
+void sha256_compress(const uint8_t left[32], const uint8_t right[32], uint8_t out[32]);   // FinalizeNoPadding: one block from the IV
+void note_cm(uint64_t value, const uint8_t sn[32], const uint8_t r[32], uint8_t out[32]);                          // Note::cm
+void notes_cm(uint64_t value, const uint8_t pk[20], const uint8_t r[32], const uint8_t sn_old[32], uint8_t out[32]); // NoteS::cm
+void compute_prf(const uint8_t sk[32], const uint8_t r[32], uint8_t out[32]);                                      // Compute_PRF
+void compute_crh(const uint8_t pk[20], const uint8_t r[32], uint8_t out[32]);                                      // Compute_CRH
+
+// Depth-8 tree over `n` leaves padded with zero leaves (ZCIncrementalMerkleTree::root()).
+constexpr int MERKLE_DEPTH = 8;      // INCREMENTAL_MERKLE_TREE_DEPTH (deposit/VNT.h:6)
+void merkle_root(const uint8_t (*leaves)[32], size_t n, uint8_t out[32]);
+// Authentication path of leaf `index`: siblings[d] for level d counted from the LEAF (d = 0) up; returns the root.
+void merkle_path(const uint8_t (*leaves)[32], size_t n, size_t index, uint8_t siblings[MERKLE_DEPTH][32], uint8_t root[32]);
+
+// ---- full assignments -----------------------------------------------------------------------------------------------------
+struct Assignment {
+    std::vector<uint64_t> tape;       // (num_vars + 1) x 4 limbs, variable i at tape[4*i..], variable 0 = constant ONE
+    uint32_t num_vars = 0;
+    const uint8_t *data() const { return reinterpret_cast<const uint8_t *>(tape.data() + 4); }   // num_vars x 32 B canonical LE
+};
+
+struct Note { uint64_t value; uint8_t sn[32]; uint8_t r[32]; };
+struct NoteS { uint64_t value; uint8_t pk[20]; uint8_t r[32]; uint8_t sn_old[32]; };
+
+// mint_gadget::generate_r1cs_witness (SRC/mint/circuit/gadget.tcc:194-246)
+Assignment mint_witness(const Note &note_old, const Note &note, const uint8_t cmtA_old[32], const uint8_t cmtA[32], uint64_t value_s,
+                        const uint8_t sk[32]);
+// redeem_gadget::generate_r1cs_witness (SRC/redeem/circuit/gadget.tcc)
+Assignment redeem_witness(const Note &note_old, const Note &note, const uint8_t cmtA_old[32], const uint8_t cmtA[32], uint64_t value_s,
+                          const uint8_t sk[32]);
+// send_gadget::generate_r1cs_witness (SRC/send/circuit/gadget.tcc)
+Assignment send_witness(const Note &note_old, const NoteS &note_s, const Note &note, const uint8_t cmtA_old[32], const uint8_t cmtS[32],
+                        const uint8_t cmtA[32], const uint8_t sk[32], const uint8_t pk_sender[20]);
+// deposit_gadget::generate_r1cs_witness (SRC/deposit/circuit/gadget.tcc); path as produced by merkle_path()
+Assignment deposit_witness(const NoteS &note_s, const Note &note_old, const Note &note, const uint8_t cmtS[32], const uint8_t cmtB_old[32],
+                           const uint8_t cmtB[32], const uint8_t rt[32], size_t leaf_index, const uint8_t siblings[MERKLE_DEPTH][32],
+                           const uint8_t sn_s[32], const uint8_t sk[32]);
+
+constexpr uint32_t MINT_VARS = 151512, SEND_VARS = 227046, DEPOSIT_VARS = 457127, REDEEM_VARS = 151579;
+
+} // namespace zkw

@@ -23,7 +23,7 @@ static size_t g_word_pos = 0;
 static void *g_pk[4] = {nullptr, nullptr, nullptr, nullptr};
 static const char *CIRCUIT_NAMES[4] = {"mint", "send", "deposit", "redeem"};
 
-static std::string key_dir() {
+std::string zkw::key_dir() {
     if (!g_key_dir.empty()) return g_key_dir;
     const char *e = getenv("ZKB200_KEY_DIR");
     return e ? std::string(e) : std::string("/usr/local/prfKey");        // hard-coded in the reference (mintcgo.cpp:302)

@@ -1,0 +1,352 @@
+// verify{Mint,Send,Deposit,Redeem}proof of BlockMaze's cgo surface (SRC/*/*cgo.cpp verify*proof), i.e.
+// r1cs_gg_ppzksnark_verifier_strong_IC (r1cs_gg_ppzksnark.tcc:524-623) over alt_bn128: public-input packing, a 4-6 term
+// accumulation, three Miller loops and one final exponentiation.  ~10 ms in the reference and not on the prover's hot
+// path, so it stays on the host; it must reproduce libff's reduced pairing EXACTLY because the verification key stores
+// alpha_g1_beta_g2 as a GT element computed by libff:
+//   Miller loop      alt_bn128_pairing.cpp:252-420   (flipped ate loop, loop count 6z+2, two Frobenius correction steps)
+//   final exponent   alt_bn128_pairing.cpp:105-228   (easy part (q^6-1)(q^2+1); hard part a fixed multiple
+//                                                      2z(6z^2+3z+1) of (q^4-q^2+1)/r, Fuentes-Castaneda et al.)
+// Tower: Fq2 = Fq[u]/(u^2+1), Fq6 = Fq2[v]/(v^3 - xi), Fq12 = Fq6[w]/(w^2 - v), xi = 9 + u (alt_bn128_init.cpp:151-189).
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/zkb200.h"
+#include "host_field.hpp"
+#include "witness.hpp"
+
+using namespace zkh;
+
+namespace {
+
+struct Fq6 {
+    HFq2 c0, c1, c2;
+    static Fq6 zero() { return Fq6{HFq2::zero(), HFq2::zero(), HFq2::zero()}; }
+    static Fq6 one() { return Fq6{HFq2::one(), HFq2::zero(), HFq2::zero()}; }
+    Fq6 operator+(const Fq6 &o) const { return Fq6{c0 + o.c0, c1 + o.c1, c2 + o.c2}; }
+    Fq6 operator-(const Fq6 &o) const { return Fq6{c0 - o.c0, c1 - o.c1, c2 - o.c2}; }
+    Fq6 neg() const { return Fq6{c0.neg(), c1.neg(), c2.neg()}; }
+    bool operator==(const Fq6 &o) const { return c0 == o.c0 && c1 == o.c1 && c2 == o.c2; }
+};
+static HFq2 mul_xi(const HFq2 &a) {          // (a0 + a1 u)(9 + u) = (9 a0 - a1) + (9 a1 + a0) u
+    HFq a0_8 = a.c0.dbl().dbl().dbl(), a1_8 = a.c1.dbl().dbl().dbl();
+    return HFq2{a0_8 + a.c0 - a.c1, a1_8 + a.c1 + a.c0};
+}
+static Fq6 mul(const Fq6 &a, const Fq6 &b) {
+    const HFq2 v0 = a.c0 * b.c0, v1 = a.c1 * b.c1, v2 = a.c2 * b.c2;
+    Fq6 r;
+    r.c0 = v0 + mul_xi((a.c1 + a.c2) * (b.c1 + b.c2) - v1 - v2);
+    r.c1 = (a.c0 + a.c1) * (b.c0 + b.c1) - v0 - v1 + mul_xi(v2);
+    r.c2 = (a.c0 + a.c2) * (b.c0 + b.c2) - v0 - v2 + v1;
+    return r;
+}
+static Fq6 mul_by_v(const Fq6 &a) { return Fq6{mul_xi(a.c2), a.c0, a.c1}; }     // multiply by v: Fq12's non-residue
+static Fq6 inverse(const Fq6 &a) {
+    const HFq2 t0 = a.c0.sqr() - mul_xi(a.c1 * a.c2), t1 = mul_xi(a.c2.sqr()) - a.c0 * a.c1, t2 = a.c1.sqr() - a.c0 * a.c2;
+    const HFq2 d = (a.c0 * t0 + mul_xi(a.c2 * t1 + a.c1 * t2)).inverse();
+    return Fq6{t0 * d, t1 * d, t2 * d};
+}
+struct Fq12 {
+    Fq6 c0, c1;
+    static Fq12 one() { return Fq12{Fq6::one(), Fq6::zero()}; }
+    bool operator==(const Fq12 &o) const { return c0 == o.c0 && c1 == o.c1; }
+    Fq12 conj() const { return Fq12{c0, c1.neg()}; }       // unitary_inverse
+};
+static Fq12 mul(const Fq12 &a, const Fq12 &b) {
+    const Fq6 v0 = mul(a.c0, b.c0), v1 = mul(a.c1, b.c1);
+    return Fq12{v0 + mul_by_v(v1), mul(a.c0 + a.c1, b.c0 + b.c1) - v0 - v1};
+}
+static Fq12 sqr(const Fq12 &a) { return mul(a, a); }
+static Fq12 inverse(const Fq12 &a) {
+    const Fq6 d = inverse(mul(a.c0, a.c0) - mul_by_v(mul(a.c1, a.c1)));
+    return Fq12{mul(a.c0, d), mul(a.c1, d).neg()};
+}
+
+// Frobenius constants, derived at start-up from gamma = xi^((q-1)/6) instead of being tabulated (alt_bn128_init.cpp:156-189)
+struct Frob {
+    HFq2 g1, g2, g3, g4, g5;      // gamma^k
+    Frob() {
+        uint64_t e[4]; memcpy(e, FqTag::MOD, 32); e[0] -= 1;          // q - 1
+        unsigned __int128 rem = 0;                                      // divide by 6
+        for (int i = 3; i >= 0; i--) { unsigned __int128 cur = (rem << 64) | e[i]; e[i] = (uint64_t)(cur / 6); rem = cur % 6; }
+        const HFq2 xi{HFq::from_u64(9), HFq::one()};
+        HFq2 r = HFq2::one();
+        for (int i = 255; i >= 0; i--) { r = r.sqr(); if ((e[i >> 6] >> (i & 63)) & 1) r = r * xi; }
+        g1 = r; g2 = g1 * g1; g3 = g2 * g1; g4 = g2 * g2; g5 = g4 * g1;
+    }
+};
+static const Frob &frob() { static Frob f; return f; }
+static HFq2 conj2(const HFq2 &a) { return HFq2{a.c0, a.c1.neg()}; }
+// x -> x^q on Fq12 (Fp12_2over3over2_model::Frobenius_map(1), fp12_2over3over2.tcc:159-163)
+static Fq12 frobenius(const Fq12 &a) {
+    const Frob &F = frob();
+    Fq12 r;
+    r.c0 = Fq6{conj2(a.c0.c0), conj2(a.c0.c1) * F.g2, conj2(a.c0.c2) * F.g4};
+    r.c1 = Fq6{conj2(a.c1.c0) * F.g1, conj2(a.c1.c1) * F.g3, conj2(a.c1.c2) * F.g5};
+    return r;
+}
+static Fq12 pow_z(const Fq12 &a) {           // a^z, z = 4965661367192848881 (alt_bn128_init.cpp:327)
+    const uint64_t z = 4965661367192848881ull;
+    Fq12 r = Fq12::one();
+    for (int i = 63; i >= 0; i--) { r = sqr(r); if ((z >> i) & 1) r = mul(r, a); }
+    return r;
+}
+static Fq12 final_exponentiation(const Fq12 &elt) {
+    // first chunk: elt^((q^6-1)(q^2+1))
+    const Fq12 C = mul(elt.conj(), inverse(elt));
+    const Fq12 f = mul(frobenius(frobenius(C)), C);
+    // last chunk (alt_bn128_pairing.cpp:137-228); exp_by_neg_z = conj(pow_z) on the cyclotomic subgroup
+    const Fq12 A = pow_z(f).conj(), B = sqr(A), Cc = sqr(B), D = mul(Cc, B), E = pow_z(D).conj(), Fv = sqr(E), G = pow_z(Fv).conj();
+    const Fq12 H = D.conj(), I = G.conj(), J = mul(I, E), K = mul(J, H), L = mul(K, B), M = mul(K, E), N = mul(M, f);
+    const Fq12 O = frobenius(L), P = mul(O, N), Q = frobenius(frobenius(K)), R = mul(Q, P), S = f.conj(), T = mul(S, L);
+    const Fq12 U = frobenius(frobenius(frobenius(T)));
+    return mul(U, R);
+}
+
+struct EllCoeffs { HFq2 ell_0, ell_VW, ell_VV; };
+struct G2Proj { HFq2 X, Y, Z; };
+static HFq2 twist_b() { static HFq2 b = HFq2{HFq::from_u64(3), HFq::zero()} * HFq2{HFq::from_u64(9), HFq::one()}.inverse(); return b; }
+static HFq2 scale(const HFq2 &a, const HFq &s) { return HFq2{a.c0 * s, a.c1 * s}; }
+static void doubling_step(G2Proj &cur, EllCoeffs &c) {           // alt_bn128_pairing.cpp:252-278
+    static const HFq two_inv = HFq::from_u64(2).inverse();
+    static const HFq2 xi{HFq::from_u64(9), HFq::one()};
+    const HFq2 X = cur.X, Y = cur.Y, Z = cur.Z;
+    const HFq2 A = scale(X * Y, two_inv), B = Y.sqr(), C = Z.sqr(), D = C + C + C, E = twist_b() * D, F = E + E + E;
+    const HFq2 G = scale(B + F, two_inv), H = (Y + Z).sqr() - (B + C), I = E - B, J = X.sqr(), E2 = E.sqr();
+    cur.X = A * (B - F); cur.Y = G.sqr() - (E2 + E2 + E2); cur.Z = B * H;
+    c.ell_0 = xi * I; c.ell_VW = H.neg(); c.ell_VV = J + J + J;
+}
+static void addition_step(const HFq2 &x2, const HFq2 &y2, G2Proj &cur, EllCoeffs &c) {      // alt_bn128_pairing.cpp:280-302
+    static const HFq2 xi{HFq::from_u64(9), HFq::one()};
+    const HFq2 X1 = cur.X, Y1 = cur.Y, Z1 = cur.Z;
+    const HFq2 D = X1 - x2 * Z1, E = Y1 - y2 * Z1, F = D.sqr(), G = E.sqr(), H = D * F, I = X1 * F, J = H + Z1 * G - (I + I);
+    cur.X = D * J; cur.Y = E * (I - J) - (H * Y1); cur.Z = Z1 * H;
+    c.ell_0 = xi * (E * x2 - D * y2); c.ell_VV = E.neg(); c.ell_VW = D;
+}
+static Fq12 line_mul(const Fq12 &f, const EllCoeffs &c, const HFq &px, const HFq &py) {
+    // mul_by_024(ell_0, PY*ell_VW, PX*ell_VV): the sparse factor is (c0 = (ell_0, 0, ell_VV'), c1 = (0, ell_VW', 0))  (fp12_2over3over2.tcc:244-248)
+    const Fq12 a{Fq6{c.ell_0, HFq2::zero(), scale(c.ell_VV, px)}, Fq6{HFq2::zero(), scale(c.ell_VW, py), HFq2::zero()}};
+    return mul(f, a);
+}
+// product of Miller loops over (P_i, Q_i), affine inputs, none at infinity
+static Fq12 multi_miller(const std::vector<HG1Affine> &Ps, const std::vector<HG2Affine> &Qs) {
+    const unsigned __int128 loop = ((unsigned __int128)1 << 64) | 0x9d797039be763ba8ull;   // 29793968203157093288 = 6z+2 (alt_bn128_init.cpp:324)
+    const Frob &F = frob();
+    const size_t n = Ps.size();
+    std::vector<G2Proj> R(n);
+    for (size_t k = 0; k < n; k++) R[k] = G2Proj{Qs[k].x, Qs[k].y, HFq2::one()};
+    Fq12 f = Fq12::one();
+    EllCoeffs c;
+    for (int i = 63; i >= 0; i--) {            // bit 64 is the MSB and is skipped
+        f = sqr(f);
+        for (size_t k = 0; k < n; k++) { doubling_step(R[k], c); f = line_mul(f, c, Ps[k].x, Ps[k].y); }
+        if ((loop >> i) & 1)
+            for (size_t k = 0; k < n; k++) { addition_step(Qs[k].x, Qs[k].y, R[k], c); f = line_mul(f, c, Ps[k].x, Ps[k].y); }
+    }
+    for (size_t k = 0; k < n; k++) {
+        // Q1 = pi(Q), Q2 = -pi^2(Q)  (alt_bn128_G2::mul_by_q: x^q * xi^((q-1)/3), y^q * xi^((q-1)/2); alt_bn128_g2.cpp)
+        const HFq2 q1x = conj2(Qs[k].x) * F.g2, q1y = conj2(Qs[k].y) * F.g3;
+        const HFq2 q2x = conj2(q1x) * F.g2, q2y = (conj2(q1y) * F.g3).neg();
+        addition_step(q1x, q1y, R[k], c); f = line_mul(f, c, Ps[k].x, Ps[k].y);
+        addition_step(q2x, q2y, R[k], c); f = line_mul(f, c, Ps[k].x, Ps[k].y);
+    }
+    return f;
+}
+
+// ---- verification key ---------------------------------------------------------------------------------------------------
+static bool fq_sqrt(const HFq &a, HFq &out) {
+    uint64_t e[4]; memcpy(e, FqTag::MOD, 32); e[0] += 1;
+    for (int i = 0; i < 4; i++) e[i] = (e[i] >> 2) | (i < 3 ? e[i + 1] << 62 : 0);
+    out = a.pow(e);
+    return out.sqr() == a;
+}
+static bool fq2_sqrt(const HFq2 &a, HFq2 &out) {
+    HFq t;
+    if (a.c1.is_zero()) {
+        if (fq_sqrt(a.c0, t)) { out = HFq2{t, HFq::zero()}; return true; }
+        if (fq_sqrt(a.c0.neg(), t)) { out = HFq2{HFq::zero(), t}; return true; }
+        return false;
+    }
+    HFq n;
+    if (!fq_sqrt(a.c0.sqr() + a.c1.sqr(), n)) return false;
+    const HFq half = HFq::from_u64(2).inverse();
+    HFq x0;
+    if (!fq_sqrt((a.c0 + n) * half, x0) && !fq_sqrt((a.c0 - n) * half, x0)) return false;
+    out = HFq2{x0, a.c1 * x0.dbl().inverse()};
+    return out.sqr() == a;
+}
+static bool lsb(const HFq &x) { uint64_t c[4]; x.to_canonical(c); return c[0] & 1; }
+
+struct VerificationKey {
+    Fq12 alpha_beta;
+    HG2Affine gamma_g2, delta_g2;
+    std::vector<HG1Affine> gamma_abc;        // [0] = first, then one per public input
+    bool ok = false;
+};
+struct VkReader {
+    const std::string &d; size_t p = 0; bool fail = false;
+    explicit VkReader(const std::string &s) : d(s) {}
+    HFq dec_fq() {
+        size_t b = p;
+        while (p < d.size() && d[p] >= '0' && d[p] <= '9') p++;
+        HFq v = HFq::zero();
+        if (p == b || !HFq::from_dec(d.data() + b, p - b, v)) fail = true;
+        if (p < d.size()) p++;           // separator
+        return v;
+    }
+    uint64_t dec_u64() {
+        uint64_t v = 0; size_t b = p;
+        while (p < d.size() && d[p] >= '0' && d[p] <= '9') v = v * 10 + (uint64_t)(d[p++] - '0');
+        if (p == b) fail = true;
+        if (p < d.size()) p++;
+        return v;
+    }
+    void expect(char c) { if (p < d.size() && d[p] == c) p++; else fail = true; }
+    HG1Affine g1() {          // alt_bn128_g1.cpp:420-465
+        if (p + 34 > d.size()) { fail = true; return HG1Affine::inf(); }
+        const bool inf = d[p] == '1', ybit = d[p + 33] == '1';
+        HFq x; memcpy(x.v, d.data() + p + 1, 32); p += 34;
+        if (inf) return HG1Affine::inf();
+        HFq y;
+        if (!fq_sqrt(x.sqr() * x + HFq::from_u64(3), y)) { fail = true; return HG1Affine::inf(); }
+        if (lsb(y) != ybit) y = y.neg();
+        return HG1Affine{x, y};
+    }
+    HG2Affine g2() {          // alt_bn128_g2.cpp:433-478
+        if (p + 66 > d.size()) { fail = true; return HG2Affine::inf(); }
+        const bool inf = d[p] == '1', ybit = d[p + 65] == '1';
+        HFq2 x; memcpy(x.c0.v, d.data() + p + 1, 32); memcpy(x.c1.v, d.data() + p + 33, 32); p += 66;
+        if (inf) return HG2Affine::inf();
+        HFq2 y;
+        if (!fq2_sqrt(x.sqr() * x + twist_b(), y)) { fail = true; return HG2Affine::inf(); }
+        if (lsb(y.c0) != ybit) y = y.neg();
+        return HG2Affine{x, y};
+    }
+};
+// vk grammar (r1cs_gg_ppzksnark.tcc:99-108, accumulation_vector.tcc:63-69, sparse_vector.tcc:272-288)
+static VerificationKey parse_vk(const std::string &data) {
+    VerificationKey vk;
+    VkReader r(data);
+    HFq2 *slots[6] = {&vk.alpha_beta.c0.c0, &vk.alpha_beta.c0.c1, &vk.alpha_beta.c0.c2, &vk.alpha_beta.c1.c0, &vk.alpha_beta.c1.c1, &vk.alpha_beta.c1.c2};
+    for (auto *s : slots) { s->c0 = r.dec_fq(); s->c1 = r.dec_fq(); }
+    vk.gamma_g2 = r.g2(); r.expect('\n');
+    vk.delta_g2 = r.g2(); r.expect('\n');
+    vk.gamma_abc.push_back(r.g1()); r.expect('\n');
+    r.dec_u64();                                   // domain size
+    const uint64_t k = r.dec_u64();
+    if (k > 64) r.fail = true;
+    for (uint64_t i = 0; i < k && !r.fail; i++) r.dec_u64();
+    const uint64_t k2 = r.dec_u64();
+    if (k2 != k) r.fail = true;
+    for (uint64_t i = 0; i < k && !r.fail; i++) { vk.gamma_abc.push_back(r.g1()); r.expect('\n'); }
+    vk.ok = !r.fail;
+    return vk;
+}
+
+static std::mutex g_vk_mu;
+static VerificationKey g_vk[4];
+static std::string g_vk_dir[4];
+static const char *NAMES[4] = {"mint", "send", "deposit", "redeem"};
+static std::string key_dir_now() { return zkw::key_dir(); }
+
+static bool hex_fq(const char *s, HFq &out) {      // 64 lowercase hex chars, big-endian (libsnarkBigintFromBytes, mintcgo.cpp:36-48)
+    uint64_t v[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 64; i++) {
+        const char ch = s[i];
+        int d;
+        if (ch >= '0' && ch <= '9') d = ch - '0'; else if (ch >= 'a' && ch <= 'f') d = ch - 'a' + 10; else return false;
+        v[3 - i / 16] |= (uint64_t)d << (4 * (15 - i % 16));
+    }
+    if (HFq::geq_mod(v)) return false;
+    out = HFq::from_canonical(v);
+    return true;
+}
+// pack_bit_vector_into_field_element_vector (field_utils.tcc:79-103): chunks of 253 bits, bit j of a chunk -> 2^j
+static std::vector<HFr> pack_bits(const std::vector<bool> &bits) {
+    std::vector<HFr> out;
+    for (size_t c = 0; c * 253 < bits.size(); c++) {
+        uint64_t x[4] = {0, 0, 0, 0};
+        for (size_t k = 0; k < 253 && c * 253 + k < bits.size(); k++) if (bits[c * 253 + k]) x[k >> 6] |= (uint64_t)1 << (k & 63);
+        out.push_back(HFr::from_canonical(x));
+    }
+    return out;
+}
+static void push_blob(std::vector<bool> &b, const uint8_t *blob, size_t nbytes) {
+    for (size_t i = 0; i < nbytes * 8; i++) b.push_back((blob[i >> 3] >> (7 - (i & 7))) & 1);
+}
+static void push_u64(std::vector<bool> &b, uint64_t v) { uint8_t le[8]; for (int i = 0; i < 8; i++) le[i] = (uint8_t)(v >> (8 * i)); push_blob(b, le, 8); }
+
+static bool verify(int circuit, const char *proof, const std::vector<bool> &input_bits) {
+    std::lock_guard<std::mutex> lk(g_vk_mu);
+    const std::string dir = key_dir_now();
+    if (!g_vk[circuit].ok || g_vk_dir[circuit] != dir) {
+        std::ifstream fh(dir + "/" + NAMES[circuit] + "vk.txt", std::ios::binary);
+        std::string data((std::istreambuf_iterator<char>(fh)), std::istreambuf_iterator<char>());
+        g_vk[circuit] = parse_vk(data);
+        g_vk_dir[circuit] = dir;
+        if (!g_vk[circuit].ok) { fprintf(stderr, "zkb200: cannot read verification key %s/%svk.txt\n", dir.c_str(), NAMES[circuit]); return false; }
+    }
+    const VerificationKey &vk = g_vk[circuit];
+    if (!proof || strnlen(proof, 512) < 512) return false;
+    HFq c[8];
+    for (int i = 0; i < 8; i++) if (!hex_fq(proof + 64 * i, c[i])) return false;
+    const HG1Affine A{c[0], c[1]}, Cp{c[6], c[7]};
+    const HG2Affine B{HFq2{c[3], c[2]}, HFq2{c[5], c[4]}};            // string order is c1 then c0 (mintcgo.cpp:150-169)
+    // proof.is_well_formed(): every point on its curve
+    const HFq three = HFq::from_u64(3);
+    if (!(A.y.sqr() == A.x.sqr() * A.x + three) || !(Cp.y.sqr() == Cp.x.sqr() * Cp.x + three)) return false;
+    if (!(B.y.sqr() == B.x.sqr() * B.x + twist_b())) return false;
+    const std::vector<HFr> inputs = pack_bits(input_bits);
+    if (inputs.size() + 1 != vk.gamma_abc.size()) return false;
+    HG1 acc = HG1::from_affine(vk.gamma_abc[0]);
+    for (size_t i = 0; i < inputs.size(); i++) {
+        uint64_t k[4]; inputs[i].to_canonical(k);
+        acc = acc.add(HG1::from_affine(vk.gamma_abc[i + 1]).mul(k));
+    }
+    const HG1Affine acc_a = acc.to_affine();
+    // e(A, B) == alpha_beta * e(acc, gamma) * e(C, delta)   <=>   FE( ML(A,B) * conj(ML(acc,gamma) * ML(C,delta)) ) == alpha_beta
+    std::vector<HG1Affine> Ps; std::vector<HG2Affine> Qs;
+    if (!acc_a.is_inf()) { Ps.push_back(acc_a); Qs.push_back(vk.gamma_g2); }
+    Ps.push_back(Cp); Qs.push_back(vk.delta_g2);
+    const Fq12 l = multi_miller({A}, {B}), r = multi_miller(Ps, Qs);
+    return final_exponentiation(mul(l, r.conj())) == vk.alpha_beta;
+}
+} // namespace
+
+bool verifyMintproof(char *data, char *cmtA_old_string, char *sn_old_string, char *cmtA_string, uint64_t value_s) {
+    uint8_t a[32], b[32], c[32];
+    zkw::parse_hex_blob(cmtA_old_string, a, 32); zkw::parse_hex_blob(sn_old_string, b, 32); zkw::parse_hex_blob(cmtA_string, c, 32);
+    std::vector<bool> bits; push_blob(bits, a, 32); push_blob(bits, b, 32); push_blob(bits, c, 32); push_u64(bits, value_s);
+    const bool ok = verify(ZKB200_MINT, data, bits);
+    printf(ok ? "Verifying mint proof successfully!!!\n" : "Verifying mint proof unsuccessfully!!!\n");
+    return ok;
+}
+bool verifyRedeemproof(char *data, char *cmtA_old_string, char *sn_old_string, char *cmtA_string, uint64_t value_s) {
+    uint8_t a[32], b[32], c[32];
+    zkw::parse_hex_blob(cmtA_old_string, a, 32); zkw::parse_hex_blob(sn_old_string, b, 32); zkw::parse_hex_blob(cmtA_string, c, 32);
+    std::vector<bool> bits; push_blob(bits, a, 32); push_blob(bits, b, 32); push_blob(bits, c, 32); push_u64(bits, value_s);
+    const bool ok = verify(ZKB200_REDEEM, data, bits);
+    printf(ok ? "Verifying redeem proof successfully!!!\n" : "Verifying redeem proof unsuccessfully!!!\n");
+    return ok;
+}
+bool verifySendproof(char *data, char *cmtA_old_string, char *sn_old_string, char *cmtS_string, char *cmtA_new_string) {
+    uint8_t a[32], b[32], c[32], d[32];
+    zkw::parse_hex_blob(cmtA_old_string, a, 32); zkw::parse_hex_blob(sn_old_string, b, 32); zkw::parse_hex_blob(cmtS_string, c, 32);
+    zkw::parse_hex_blob(cmtA_new_string, d, 32);
+    std::vector<bool> bits; push_blob(bits, a, 32); push_blob(bits, b, 32); push_blob(bits, c, 32); push_blob(bits, d, 32);
+    const bool ok = verify(ZKB200_SEND, data, bits);
+    printf(ok ? "Verifying send proof successfully!!!\n" : "Verifying send proof unsuccessfully!!!\n");
+    return ok;
+}
+bool verifyDepositproof(char *data, char *RT, char *pk, char *cmtb_old, char *snold, char *cmtb, char *sns) {
+    uint8_t rt[32], p[20], a[32], b[32], c[32], d[32];
+    zkw::parse_hex_blob(RT, rt, 32); zkw::parse_hex_blob(pk, p, 20); zkw::parse_hex_blob(cmtb_old, a, 32); zkw::parse_hex_blob(snold, b, 32);
+    zkw::parse_hex_blob(cmtb, c, 32); zkw::parse_hex_blob(sns, d, 32);
+    std::vector<bool> bits; push_blob(bits, rt, 32); push_blob(bits, p, 20); push_blob(bits, a, 32); push_blob(bits, b, 32); push_blob(bits, c, 32);
+    push_blob(bits, d, 32);
+    const bool ok = verify(ZKB200_DEPOSIT, data, bits);
+    printf(ok ? "Verifying deposit proof successfully!!!\n" : "Verifying deposit proof unsuccessfully!!!\n");
+    return ok;
+}

@@ -54,6 +54,9 @@ Assignment deposit_witness(const NoteS &note_s, const Note &note_old, const Note
                            const uint8_t cmtB[32], const uint8_t rt[32], size_t leaf_index, const uint8_t siblings[MERKLE_DEPTH][32],
                            const uint8_t sn_s[32], const uint8_t sk[32]);
 
+// directory of <circuit>{pk,vk}.txt: zkb200_set_key_dir() > $ZKB200_KEY_DIR > /usr/local/prfKey (defined in blockmaze_abi.cu)
+std::string key_dir();
+
 constexpr uint32_t MINT_VARS = 151512, SEND_VARS = 227046, DEPOSIT_VARS = 457127, REDEEM_VARS = 151579;
 
 } // namespace zkw

@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- BlockMaze prover benchmark (contract: one JSON line on rank 0).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload send|mixed1024]
+
+Step (default workload): every GPU proves ONE synthetic `send` transaction (252 286 constraints, the configuration
+BASELINE.json quotes for single-GPU latency).  `value` = proofs/s with the assignment already resident in HBM (GPU pipeline +
+host finish); `e2e` = proofs/s through the BlockMaze cgo surface genSendproof() with host string arguments (native witness
+generation, H2D of the assignment, GPU prover, D2H of the partial sums, hex encoding).  Multi-GPU: independent proofs, one
+process per GPU, no data-path collective (weak scaling); the barrier / max-over-ranks uses torch.distributed.
+--impl reference times the UNMODIFIED libsnark prover (oracle/_ref, -DMULTICORE -fopenmp) on the host cores for the same
+transaction.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+CONSTRAINTS = {"mint": 167270, "send": 252286, "deposit": 503863, "redeem": 167853}
+DOMAIN = {"mint": 196608, "send": 262144, "deposit": 524288, "redeem": 196608}
+IMAD_PER_G1_POINT = 23936          # 16 windows x (11 modmul x 136 IMAD) per point of a 254-bit G1 MSM
+
+
+def shard_batch(seeds, rank, world):
+    """Independent transactions are dealt to the ranks with no inter-GPU traffic.  The transaction type is
+    seed % 4 and deposit proofs cost ~2x a mint, so the deal rotates by seed // 4 to give every rank the same type mix."""
+    return [s for s in seeds if ((s // 4) + s) % world == rank]
+
+
+def reduce_counts_and_time(count, seconds, dist, device="cuda"):
+    """Whole-job units = sum over ranks; time = max over ranks."""
+    if dist is None or not dist.is_initialized():
+        return count, seconds
+    import torch
+    c = torch.tensor([float(count)], device=device)
+    t = torch.tensor([float(seconds)], device=device)
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(round(c.item())), t.item()
+
+
+def key_dir():
+    for d in (os.environ.get("ZKB200_KEY_DIR"), os.path.join(ROOT, "oracle", "_ref", "prfKey"), "/usr/local/prfKey"):
+        if d and os.path.exists(os.path.join(d, "sendpk.txt")):
+            return d
+    raise SystemExit("bench.py: no proving keys found (ZKB200_KEY_DIR, oracle/_ref/prfKey, /usr/local/prfKey)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, windows):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.lines:
+            if not any(a <= t <= b for a, b in windows):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU prover on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import refapi as Rf, bn254_oracle as O
+    import fixtures as F
+    circuit = "send"
+    line = {"impl": "reference", "metric": "proofs_per_sec", "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (libff Fp_model, 254-bit Montgomery)", "data": "synthetic"}
+    if not Rf.available(circuit + "_mt"):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_send_mt.so not built (needs /root/reference at build time)"}))
+        return
+    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+    t0 = time.perf_counter()
+    Rf.load_pk(circuit, os.path.join(key_dir(), circuit + "pk.txt"), mt=True)
+    t_load = time.perf_counter() - t0
+    words = O.fixed_rng_words(42, 64)
+    txs = [F.synthetic(circuit, s) for s in range(args.warmup + args.steps)]
+    for i in range(args.warmup):
+        Rf.prove(circuit, txs[i], words, mt=True)
+    t0 = time.perf_counter()
+    phases = [0.0] * 5
+    for i in range(args.steps):
+        res = Rf.prove(circuit, txs[args.warmup + i], words, mt=True)
+        assert res["rc"] == 0
+        phases = [a + b for a, b in zip(phases, res["timings"])]
+    dt = time.perf_counter() - t0
+    cores = int(os.environ["OMP_NUM_THREADS"])
+    v = args.steps / dt
+    line.update(value=v, ms_per_step=1e3 * dt / args.steps,
+                config={"workload": "send circuit: one Groth16 proof per step (witness + is_satisfied + r1cs_gg_ppzksnark_prover), pk resident",
+                        "constraints": CONSTRAINTS[circuit], "domain": DOMAIN[circuit], "pk_load_s_excluded": round(t_load, 1)},
+                cpu_baseline={"value": v, "unit": "proofs/s", "cores": cores, "kind": "reference",
+                              "sample": "%d send proofs, libsnark -DMULTICORE -fopenmp, OMP_NUM_THREADS=%d; prover phases avg s: qap %.2f A %.2f B %.2f H %.2f L %.2f"
+                                        % (args.steps, cores, *[p / args.steps for p in phases])},
+                e2e={"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="send", choices=["send", "mixed1024"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip per-circuit latency table and NTT roofline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+
+    import blockmaze_b200 as zk
+    from blockmaze_b200 import api
+    from oracle import bn254_oracle as O      # only for the seeded transaction generator's hashing helpers (inputs, not the measured path)
+    import fixtures as F
+    zk.init(local)
+    kd = key_dir()
+    api.set_key_dir(kd)
+
+    def barrier():
+        api.lib.zkb200_device_sync()
+        if dist is not None:
+            dist.barrier()
+
+    circuits = ["send"] if args.workload == "send" else ["mint", "send", "deposit", "redeem"]
+    pks = {c: zk.ProvingKey(os.path.join(kd, c + "pk.txt")) for c in circuits}
+    pk = pks["send"]
+    r, s = O.fr_from_words(O.fixed_rng_words(1000 + rank, 64))
+    sampler = ClockSampler(local)
+    windows = []
+
+    if args.workload == "send":
+        # ---- leg 1: `value` -- assignment resident in HBM -------------------------------------------------------------------------
+        tx0 = F.synthetic("send", rank)
+        w0 = api.witness("send", tx0)
+        res = pk.prove(w0, r, s)
+        assert res["rc"] == 0
+        for _ in range(args.warmup):
+            api.lib.zkb200_flush_l2(); pk.prove(None, r, s)
+        barrier()
+        t0 = time.perf_counter()
+        acc_ms, qap_ms, msm_ms, gpu_ms, launches = [], [], [], [], 0
+        for _ in range(args.steps):
+            api.lib.zkb200_flush_l2()
+            res = pk.prove(None, r, s)
+            gpu_ms.append(res["timings_ms"][0]); qap_ms.append(res["timings_ms"][1]); msm_ms.append(res["timings_ms"][2]); acc_ms.append(res["timings_ms"][4])
+            launches += res["launches"]
+        barrier()
+        t1 = time.perf_counter()
+        windows.append((t0, t1))
+        units, dt = reduce_counts_and_time(args.steps, t1 - t0, dist)
+        # ---- leg 2: `e2e` -- the cgo call a BlockMaze node makes, host string arguments in, proof string out --------------------
+        txs = [F.synthetic("send", rank + world * (i + 1)) for i in range(args.warmup + args.steps)]
+        for i in range(args.warmup):
+            api.gen_proof("send", txs[i])
+        barrier()
+        t2 = time.perf_counter()
+        lat = []
+        for i in range(args.steps):
+            ta = time.perf_counter()
+            proof = api.gen_proof("send", txs[args.warmup + i])
+            lat.append(time.perf_counter() - ta)
+        barrier()
+        t3 = time.perf_counter()
+        windows.append((t2, t3))
+        assert not proof.startswith("0000000000"), "prover returned the default proof for a valid transaction"
+        units_e, dt_e = reduce_counts_and_time(args.steps, t3 - t2, dist)
+        nvars = pk.num_variables
+        workload = ("send circuit (%d constraints, %d variables, QAP domain 2^18): one Groth16 proof per GPU per step; value = resident assignment, "
+                    "e2e = genSendproof() cgo call" % (CONSTRAINTS["send"], nvars))
+        d2h = 4 + sum(128 * (p + 1) * b for p, b in ((24, 4), (24, 4), (24, 4))) + 256 * 25 * 4 + 128 * 19 * 16
+    else:
+        # mixed batch of 1024 synthetic transactions, type = seed mod 4, sharded round-robin over the ranks (strong scaling)
+        names = ["mint", "send", "deposit", "redeem"]
+        mine = shard_batch(list(range(1024)), rank, world)
+        txs = [(names[sd % 4], F.synthetic(names[sd % 4], sd)) for sd in mine]
+        for c in names:
+            api.gen_proof(c, F.synthetic(c, 5000 + rank))
+        barrier()
+        t0 = time.perf_counter()
+        lat = []
+        for c, tx in txs:
+            ta = time.perf_counter(); api.gen_proof(c, tx); lat.append(time.perf_counter() - ta)
+        barrier()
+        t1 = time.perf_counter()
+        windows.append((t0, t1))
+        units, dt = reduce_counts_and_time(len(txs), t1 - t0, dist)
+        units_e, dt_e, launches, acc_ms, qap_ms, msm_ms, gpu_ms = units, dt, 0, [0.0], [0.0], [0.0], [0.0]
+        args.steps = 1
+        nvars = 0
+        workload = "mixed batch of 1024 synthetic mint/send/deposit/redeem transactions (256 each) sharded round-robin over the GPUs, through gen*proof()"
+        d2h = 0
+
+    clocks = sampler.stop(windows)
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        # p50 end-to-end latency per circuit through the cgo surface (BASELINE.json metric, configs[0..3])
+        per = {}
+        for c in ("mint", "send", "deposit", "redeem"):
+            ts = []
+            for i in range(7):
+                tx = F.synthetic(c, 9000 + i)
+                ta = time.perf_counter(); api.gen_proof(c, tx); ts.append(1e3 * (time.perf_counter() - ta))
+            per[c] = round(statistics.median(ts[2:]), 3)
+        extras["p50_latency_ms_per_circuit_e2e"] = per
+        # NTT roofline at a size that does not fit L2 (2^24 x 32 B = 512 MB): algorithmic bytes 64*n per transform
+        ms_ntt = api.lib.zkb200_bench_ntt(24, 1, 5)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        ach = 64.0 * (1 << 24) / (ms_ntt * 1e-3) / 1e9
+        extras["roofline_ntt"] = {"bound": "hbm", "kernel": "ntt_pass_kernel x3 (2^24-point forward NTT)", "achieved": round(ach, 1), "peak": hbm_peak,
+                                  "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": None, "ms": round(ms_ntt, 4),
+                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
+
+    line = None
+    if rank == 0:
+        imad_peak = float(api.lib.zkb200_bench_imad_peak(0))
+        acc_avg = statistics.mean(acc_ms) if acc_ms else 0.0
+        n_h = DOMAIN["send"] - 1
+        ach = IMAD_PER_G1_POINT * n_h / (acc_avg * 1e-3) / 1e12 if acc_avg > 0 else 0.0
+        line = {
+            "metric": "proofs_per_sec", "value": units / dt, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload == "send" else "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload, "l2": "256 MB memset + sync before every timed step (inside the timed region, ~0.06 ms)",
+                       "randomness": "r, s pinned per rank"},
+            "clocks": clocks,
+            "e2e": {"value": units_e / dt_e, "unit": "proofs/s", "h2d_bytes_per_step": nvars * 32, "d2h_bytes_per_step": d2h,
+                    "p50_latency_ms": round(1e3 * statistics.median(lat), 3)},
+            "gpu_launches": launches,
+            "gpu_ms_per_proof": {"total": round(statistics.mean(gpu_ms), 3), "qap_witness_map": round(statistics.mean(qap_ms), 3),
+                                 "msm_H": round(statistics.mean(msm_ms), 3), "msm_H_accumulate_kernel": round(acc_avg, 3)},
+            "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel<Fq> (H query, %d points)" % n_h, "achieved": round(ach, 3), "peak": round(imad_peak, 2),
+                         "unit": "TIMAD/s", "frac": round(ach / imad_peak, 4) if imad_peak else None, "traffic": None,
+                         "note": "integer-multiply roofline (north_star): algorithmic 23936 IMAD/point / CUDA-event kernel time; peak = dependent-free mad.lo.u32 microbenchmark in this run"},
+        }
+        line.update(extras)
+        if world == 1 and not args.no_cpu_baseline and args.workload == "send":
+            line["cpu_baseline"] = cpu_baseline()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def cpu_baseline():
+    """Reference libsnark prover (MULTICORE) on this box's host cores: one send proof, pk load excluded."""
+    code = ("import sys,os,json,time; sys.path.insert(0,%r); sys.path.insert(0,%r)\n"
+            "from oracle import refapi as Rf, bn254_oracle as O; import fixtures as F\n"
+            "os.environ.setdefault('OMP_NUM_THREADS', str(os.cpu_count() or 1))\n"
+            "Rf.load_pk('send', os.path.join(%r,'sendpk.txt'), mt=True)\n"
+            "w=O.fixed_rng_words(42,64); Rf.prove('send',F.synthetic('send',0),w,mt=True)\n"
+            "t=time.perf_counter(); n=3\n"
+            "for i in range(n): Rf.prove('send',F.synthetic('send',1+i),w,mt=True)\n"
+            "dt=time.perf_counter()-t\n"
+            "print('CPUBASE',json.dumps({'value':n/dt,'unit':'proofs/s','cores':int(os.environ['OMP_NUM_THREADS']),'kind':'reference',"
+            "'sample':'3 send proofs after 1 warm-up, unmodified libsnark (-DMULTICORE -fopenmp), witness+is_satisfied+prover, pk load excluded'}))\n"
+            % (ROOT, os.path.join(ROOT, "tests", "golden"), key_dir()))
+    from oracle import refapi as Rf
+    if not Rf.available("send_mt"):
+        return {"value": None, "unit": "proofs/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built on this box"}
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    for l in out.stdout.splitlines():
+        if l.startswith("CPUBASE "):
+            return json.loads(l[8:])
+    return {"value": None, "unit": "proofs/s", "cores": 0, "kind": "reference", "sample": "reference run failed: " + out.stderr[-200:]}
+
+
+if __name__ == "__main__":
+    main()

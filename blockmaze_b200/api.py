@@ -31,8 +31,41 @@ lib.zkb200_bench_ntt.restype = C.c_float
 lib.zkb200_bench_ntt.argtypes = [C.c_int, C.c_int, C.c_int]
 lib.zkb200_bench_msm.restype = C.c_float
 lib.zkb200_bench_msm.argtypes = [C.c_int, C.c_size_t, C.c_int, C.c_int]
+lib.zkb200_flush_l2.restype = None
+lib.zkb200_device_sync.restype = None
 lib.zkb200_bench_imad_peak.restype = C.c_float
 lib.zkb200_bench_imad_peak.argtypes = [C.c_int]
+
+lib.zkb200_set_key_dir.argtypes = [C.c_char_p]
+lib.zkb200_set_random_words.argtypes = [C.c_void_p, C.c_size_t]
+
+# gen<Circuit>proof argument types (SRC/<c>/<c>cgo.hpp) and verify<Circuit>proof argument types
+GEN_SIGS = {
+    "mint": [C.c_uint64, C.c_uint64] + [C.c_char_p] * 6 + [C.c_uint64, C.c_char_p],
+    "redeem": [C.c_uint64, C.c_uint64] + [C.c_char_p] * 6 + [C.c_uint64, C.c_char_p],
+    "send": [C.c_uint64] + [C.c_char_p] * 5 + [C.c_uint64, C.c_char_p, C.c_uint64] + [C.c_char_p] * 5,
+    "deposit": [C.c_uint64, C.c_uint64] + [C.c_char_p] * 8 + [C.c_uint64] + [C.c_char_p] * 4 + [C.c_int, C.c_char_p, C.c_char_p],
+}
+VERIFY_SIGS = {"mint": [C.c_char_p] * 4 + [C.c_uint64], "redeem": [C.c_char_p] * 4 + [C.c_uint64], "send": [C.c_char_p] * 5,
+               "deposit": [C.c_char_p] * 7}
+NUM_VARS = {"mint": 151512, "send": 227046, "deposit": 457127, "redeem": 151579}
+for _c in CIRCUITS:
+    _g = getattr(lib, "gen%sproof" % _c.capitalize())
+    _g.restype = C.c_void_p
+    _g.argtypes = GEN_SIGS[_c]
+    _v = getattr(lib, "verify%sproof" % _c.capitalize())
+    _v.restype = C.c_bool
+    _v.argtypes = VERIFY_SIGS[_c]
+for _h, _sig in (("genCMT", [C.c_uint64, C.c_char_p, C.c_char_p]), ("computePRF", [C.c_char_p] * 2),
+                 ("genCMTS", [C.c_uint64] + [C.c_char_p] * 3), ("computeCRH", [C.c_char_p] * 2), ("genRoot", [C.c_char_p, C.c_int])):
+    getattr(lib, _h).restype = C.c_void_p
+    getattr(lib, _h).argtypes = _sig
+lib.zkb200_witness_mint.restype = C.c_long
+lib.zkb200_witness_mint.argtypes = GEN_SIGS["mint"] + [C.c_int, C.c_void_p, C.c_size_t]
+lib.zkb200_witness_send.restype = C.c_long
+lib.zkb200_witness_send.argtypes = GEN_SIGS["send"] + [C.c_void_p, C.c_size_t]
+lib.zkb200_witness_deposit.restype = C.c_long
+lib.zkb200_witness_deposit.argtypes = GEN_SIGS["deposit"] + [C.c_void_p, C.c_size_t]
 
 DOMAIN_OPS = {"FFT": 0, "iFFT": 1, "cosetFFT": 2, "icosetFFT": 3, "divide_by_Z_on_coset": 4}
 FIELD_OPS = {"mul": 0, "add": 1, "sub": 2, "sqr": 3, "to_mont": 4, "from_mont": 5, "inverse": 6}
@@ -91,6 +124,62 @@ def field_op(field, op, a, b=None):
     return out.raw
 
 
+def _enc(args):
+    return [a.encode() if isinstance(a, str) else a for a in args]
+
+
+def set_key_dir(path):
+    lib.zkb200_set_key_dir(os.fsencode(path))
+
+
+def set_random_words(words):
+    """Pin (r, s): a std::random_device-style 32-bit word stream (empty list = back to the OS entropy source)."""
+    arr = (C.c_uint32 * max(1, len(words)))(*words)
+    lib.zkb200_set_random_words(C.cast(arr, C.c_void_p), len(words))
+
+
+def helper(name, *args):
+    """genCMT / computePRF / genCMTS / computeCRH / genRoot: returns the 64-char hex string."""
+    return C.string_at(getattr(lib, name)(*_enc(args)), 64).decode()
+
+
+def gen_proof(circuit, args):
+    """gen<Circuit>proof through the BlockMaze cgo surface; returns the 512-char proof string."""
+    p = getattr(lib, "gen%sproof" % circuit.capitalize())(*_enc(args))
+    return C.string_at(p, 512).decode()
+
+
+def verify_proof(circuit, proof_hex, args):
+    return bool(getattr(lib, "verify%sproof" % circuit.capitalize())(proof_hex.encode(), *_enc(args)))
+
+
+def verify_args(circuit, gen_args):
+    """The verify<Circuit>proof arguments that go with a gen<Circuit>proof argument list."""
+    a = gen_args
+    if circuit in ("mint", "redeem"):
+        return [a[6], a[2], a[7], a[8]]                       # cmtA_old, sn_old, cmtA, value_s
+    if circuit == "send":
+        return [a[5], a[2], a[4], a[11]]                      # cmtA_old, sn_old, cmtS, cmtA_new
+    rt = "0x" + helper("genRoot", a[14], a[15])
+    return [rt, a[11], a[8], a[2], a[9], a[6]]                # RT, pk, cmtB_old, sn_old, cmtB, sn_s
+
+
+def witness(circuit, args):
+    """Full variable assignment (bytes, num_variables*32) computed by the native host generators."""
+    n = NUM_VARS[circuit]
+    out = C.create_string_buffer(32 * n)
+    ptr = C.cast(out, C.c_void_p)
+    if circuit in ("mint", "redeem"):
+        got = lib.zkb200_witness_mint(*_enc(args), 1 if circuit == "redeem" else 0, ptr, n)
+    elif circuit == "send":
+        got = lib.zkb200_witness_send(*_enc(args), ptr, n)
+    else:
+        got = lib.zkb200_witness_deposit(*_enc(args), ptr, n)
+    if got != n:
+        raise ZkError("witness generation failed (%d)" % got)
+    return out.raw
+
+
 class ProvingKey:
     """A proving key resident on the GPU (zkb200_pk_load)."""
 
@@ -108,10 +197,10 @@ class ProvingKey:
 
     def prove(self, assignment, r, s):
         """assignment: bytes (num_variables*32) or None to reuse the resident one; r, s: ints.
-        Returns dict(rc, proof_hex, parts(384 B), timings_ms[gpu, qap, msm_h, host])."""
+        Returns dict(rc, proof_hex, parts(384 B), timings_ms[gpu, qap, msm_h, host, msm_h_accumulate_kernel])."""
         hexbuf = C.create_string_buffer(513)
         parts = C.create_string_buffer(384)
-        tim = (C.c_float * 4)()
+        tim = (C.c_float * 5)()
         if assignment is not None and len(assignment) != self.num_variables * 32:
             raise ValueError("assignment must be num_variables*32 bytes")
         rc = lib.zkb200_prove(self.handle, assignment, int(r).to_bytes(32, "little"), int(s).to_bytes(32, "little"), hexbuf, parts, tim)

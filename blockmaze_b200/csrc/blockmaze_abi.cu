@@ -197,8 +197,7 @@ char *genDepositproof(uint64_t value, uint64_t value_old, char *sn_old_string, c
     return prove_with(ZKB200_DEPOSIT, deposit_witness(note_s, note_old, note, cmtS, cmtB_old, cmtB, rt, (size_t)first, siblings, sn_s, sk));
 }
 
-// ---- witness-only entry points (parity hooks for the assignment layout) -----------------------------------------------------
-extern "C" {
+// ---- witness-only entry points (parity hooks for the assignment layout; declared extern "C" in zkb200.h) ------------------------
 long zkb200_witness_mint(uint64_t value, uint64_t value_old, const char *sn_old, const char *r_old, const char *sn, const char *r,
                          const char *cmtA_old_s, const char *cmtA_s, uint64_t value_s, const char *sk_s, int redeem, uint8_t *out, size_t cap) {
     Note note_old, note; uint8_t cmtA_old[32], cmtA[32], sk[32];
@@ -245,6 +244,5 @@ long zkb200_witness_deposit(uint64_t value, uint64_t value_old, const char *sn_o
     memcpy(out, a.data(), (size_t)a.num_vars * 32);
     return a.num_vars;
 }
-}
 
-// ---- verification: see verifier.cu -------------------------------------------------------------------------------------------
+// ---- verification: see verifier.cpp -------------------------------------------------------------------------------------------

@@ -156,7 +156,7 @@ int zkb200_prove(void *h, const uint8_t *assignment, const uint8_t r[32], const 
     prove(pk, assignment, rr, ss, pp);
     const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (parts) { put_g1(parts, pp.At); put_g2(parts + 64, pp.Bt_g); put_g1(parts + 192, pp.Bt_h); put_g1(parts + 256, pp.Ht); put_g1(parts + 320, pp.Lt); }
-    if (timings_ms) { timings_ms[0] = pp.gpu_ms; timings_ms[1] = pp.qap_ms; timings_ms[2] = pp.msm_h_ms; timings_ms[3] = (float)(total_ms - pp.gpu_ms); }
+    if (timings_ms) { timings_ms[0] = pp.gpu_ms; timings_ms[1] = pp.qap_ms; timings_ms[2] = pp.msm_h_ms; timings_ms[3] = (float)(total_ms - pp.gpu_ms); timings_ms[4] = pp.acc_h_ms; }
     const std::string hex = pp.satisfied ? proof_hex(pp) : std::string(DEFAULT_PROOF);
     memcpy(proof_hex_out, hex.data(), 512); proof_hex_out[512] = 0;
     return pp.satisfied ? 0 : 1;
@@ -311,6 +311,18 @@ float zkb200_bench_msm(int group, size_t n, int window_bits, int iters) {
     plan.release(); cudaFree(sc); cudaFree(bases);
     return ms / (float)iters;
 }
+
+// write a buffer twice the size of L2 so the next step starts with a cold L2 (bench hygiene)
+void zkb200_flush_l2(void) {
+    if (ensure_device()) return;
+    static void *buf[64];
+    const size_t bytes = 256u << 20;
+    if (!buf[g_device]) ZK_CUDA(cudaMalloc(&buf[g_device], bytes));
+    static int flip = 0;
+    ZK_CUDA(cudaMemset(buf[g_device], ++flip, bytes));
+    ZK_CUDA(cudaDeviceSynchronize());
+}
+void zkb200_device_sync(void) { if (!ensure_device()) ZK_CUDA(cudaDeviceSynchronize()); }
 
 float zkb200_bench_imad_peak(int wide) {
     if (ensure_device()) return -1;

@@ -305,6 +305,7 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2) {
     ZK_CUDA(cudaMalloc(&task_rank, (size_t)task_cap * 4));
     ZK_CUDA(cudaMalloc(&task_span, (size_t)task_cap * 4));
     ZK_CUDA(cudaMalloc(&max_tasks, 4));
+    ZK_CUDA(cudaEventCreate(&ev_acc0)); ZK_CUDA(cudaEventCreate(&ev_acc1));
     const size_t nout = (size_t)(windows + 1) * bpw;
     if (g1) {
         ZK_CUDA(cudaMalloc(&buckets_g1, (size_t)task_cap * sizeof(G1XYZZ)));
@@ -317,9 +318,12 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2) {
         ZK_CUDA(cudaMallocHost(&h_out_g2, nout * sizeof(G2XYZZ)));
     }
 }
+float MsmPlan::last_acc_ms() const { float ms = 0; if (ev_acc0) cudaEventElapsedTime(&ms, ev_acc0, ev_acc1); return ms; }
 void MsmPlan::release() {
     void *ps[] = {counts, offsets, cursors, entries, buckets_g1, buckets_g2, out_g1, out_g2, task_counts, task_off, task_rank, task_span, max_tasks};
     for (void *p : ps) if (p) cudaFree(p);
+    if (ev_acc0) cudaEventDestroy(ev_acc0);
+    if (ev_acc1) cudaEventDestroy(ev_acc1);
     if (h_out_g1) cudaFreeHost(h_out_g1);
     if (h_out_g2) cudaFreeHost(h_out_g2);
     *this = MsmPlan();
@@ -342,8 +346,10 @@ void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, con
     const size_t nout = (size_t)(sh.windows + 1) * p.bpw;
     const uint32_t *toff = (const uint32_t *)p.task_off, *trank = (const uint32_t *)p.task_rank, *tspan = (const uint32_t *)p.task_span;
     if (bases_g1) {
+        ZK_CUDA(cudaEventRecord(p.ev_acc0, st));
         ZK_LAUNCH(msm_accumulate_kernel<Fq>, cdiv(p.task_cap, 128), 128, 0, st, (const G1Affine *)bases_g1, (const uint32_t *)p.offsets,
                   (const uint32_t *)p.entries, toff, p.total, (G1XYZZ *)p.buckets_g1, (uint32_t *)p.task_rank, (uint32_t *)p.task_span);
+        ZK_CUDA(cudaEventRecord(p.ev_acc1, st));
         for (uint32_t k = 0; k < p.combine_passes; k++)
             ZK_LAUNCH(msm_combine_kernel<Fq>, cdiv(p.task_cap, 128), 128, 0, st, (G1XYZZ *)p.buckets_g1, trank, tspan, toff, p.total,
                       (const uint32_t *)p.max_tasks, 1u << k);
@@ -578,6 +584,7 @@ int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const ui
     ZK_CUDA(cudaEventElapsedTime(&out.gpu_ms, pk->ev_t0, pk->ev_t1));
     ZK_CUDA(cudaEventElapsedTime(&out.qap_ms, pk->ev_q0, pk->ev_q1));
     ZK_CUDA(cudaEventElapsedTime(&out.msm_h_ms, pk->ev_h0, pk->ev_h1));
+    out.acc_h_ms = pk->mH.last_acc_ms();
     out.satisfied = (*pk->h_sat_flag == 0);
 
     // host: Horner over the per-window sums, then the proof combination (r1cs_gg_ppzksnark.tcc:487-495)

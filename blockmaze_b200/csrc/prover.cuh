@@ -52,6 +52,8 @@ struct MsmPlan {
     void *buckets_g1 = nullptr, *buckets_g2 = nullptr;   // per-task partial sums
     void *out_g1 = nullptr, *out_g2 = nullptr;           // device partial sums  [(windows+1) * bpw]
     void *h_out_g1 = nullptr, *h_out_g2 = nullptr;       // pinned host copies
+    cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr;    // around the G1 accumulate kernel (roofline measurement)
+    float last_acc_ms() const;
     void init(uint32_t n, int c, uint32_t ones, bool g1, bool g2);
     void release();
 };
@@ -96,7 +98,7 @@ struct ProofPoints {
     zkh::HG1Affine A, C; zkh::HG2Affine B;
     zkh::HG1Affine At, Bt_h, Ht, Lt; zkh::HG2Affine Bt_g;   // the five MSM results (parity hooks)
     bool satisfied = true;
-    float gpu_ms = 0, qap_ms = 0, msm_h_ms = 0;          // CUDA-event timings of the last run
+    float gpu_ms = 0, qap_ms = 0, msm_h_ms = 0, acc_h_ms = 0;   // CUDA-event timings of the last run (acc_h: H accumulate kernel)
 };
 // assignment: num_vars canonical 32-byte LE scalars in HOST memory (copied H2D inside), or nullptr to reuse the
 // assignment already resident on the device (bench "value" leg).

@@ -84,7 +84,7 @@ const char *zkb200_last_error(void);
 /* Replaces r1cs_gg_ppzksnark_prover (r1cs_gg_ppzksnark.tcc:390-506) for a caller-supplied full assignment
  * (primary || auxiliary, num_variables x 32 B) and explicit r, s.  assignment == NULL re-proves the assignment already
  * resident on the GPU.  proof_hex: 513 bytes.  parts (optional, 384 B): the five MSM results At | Bt.g | Bt.h | Ht | Lt.
- * timings_ms (optional, 4 floats): GPU total, QAP witness map, H MSM (CUDA events), host finish.
+ * timings_ms (optional, 5 floats): GPU total, QAP witness map, H MSM, host finish, H-MSM bucket-accumulate kernel (CUDA events).
  * Returns 0 = proof, 1 = constraint system not satisfied (proof_hex = default proof), <0 = error. */
 int zkb200_prove(void *pk, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32], char *proof_hex, uint8_t *parts,
                  float *timings_ms);
@@ -92,6 +92,20 @@ int zkb200_prove(void *pk, const uint8_t *assignment, const uint8_t r[32], const
 int zkb200_qap_witness_map(void *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied);
 /* kernels launched by the last zkb200_prove call */
 int zkb200_last_launches(void);
+
+/* Witness handling: the FULL variable assignment (primary || auxiliary, 32 B canonical each) that the reference obtains by running
+ * its gadgetlib1 circuit (<circuit>_gadget::generate_r1cs_witness, SRC/<c>/circuit/gadget.tcc), computed natively on the host.
+ * Arguments are exactly those of gen<Circuit>proof (redeem != 0 selects the redeem circuit, which shares mint's signature).
+ * Returns the number of variables written, -1 if cap (in elements) is too small, -2 if cmtS is not among the deposit leaves. */
+long zkb200_witness_mint(uint64_t value, uint64_t value_old, const char *sn_old, const char *r_old, const char *sn, const char *r,
+                         const char *cmtA_old, const char *cmtA, uint64_t value_s, const char *sk, int redeem, uint8_t *out, size_t cap);
+long zkb200_witness_send(uint64_t value_A, const char *r_s, const char *sn, const char *r, const char *cmt_s, const char *cmtA, uint64_t value_s,
+                         const char *pk_recv, uint64_t value_A_new, const char *sn_A_new, const char *r_A_new, const char *cmt_A_new,
+                         const char *sk, const char *pk_sender, uint8_t *out, size_t cap);
+long zkb200_witness_deposit(uint64_t value, uint64_t value_old, const char *sn_old, const char *r_old, const char *sn, const char *r,
+                            const char *sns, const char *rs, const char *cmtB_old, const char *cmtB, uint64_t value_s, const char *pk,
+                            const char *sn_A_old, const char *cmtS, const char *cmtarray, int n, const char *RT, const char *sk, uint8_t *out,
+                            size_t cap);
 
 /* Replaces libfqfft::get_evaluation_domain(min_size) + domain->{FFT,iFFT,cosetFFT,icosetFFT,divide_by_Z_on_coset}
  * (get_evaluation_domain.tcc:33-52, basic_radix2_domain.tcc:26-112, step_radix2_domain.tcc:21-248).
@@ -113,6 +127,9 @@ int zkb200_field_op(int field, int op, size_t n, const uint8_t *a, const uint8_t
  * zkb200_bench_msm: dense 254-bit MSM over n synthetic bases (group: 1 = G1, 2 = G2); returns ms per MSM. */
 float zkb200_bench_ntt(int logn, int batch, int iters);
 float zkb200_bench_msm(int group, size_t n, int window_bits, int iters);
+/* bench hygiene: overwrite a 256 MB scratch buffer (2x L2) and synchronise; plain cudaDeviceSynchronize */
+void zkb200_flush_l2(void);
+void zkb200_device_sync(void);
 /* dependent-free 32-bit multiply-add throughput of the GPU in 1e12 IMAD/s (the MSM roofline denominator) */
 float zkb200_bench_imad_peak(int wide);
 

@@ -1,0 +1,156 @@
+"""GPU parity tests of the two hot kernels through the C-ABI: device field layer, evaluation-domain transforms (NTT),
+multi-scalar multiplication.  Bit-exact against the oracle (small sizes), the reference itself (oracle/_ref, large sizes)
+and size-independent properties at sweep sizes."""
+import os
+import random
+
+import pytest
+
+from oracle import bn254_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def fb(v):
+    return b"".join(int(x).to_bytes(32, "little") for x in v)
+
+
+def fl(b):
+    return [int.from_bytes(b[i:i + 32], "little") for i in range(0, len(b), 32)]
+
+
+def g1b(p):
+    return bytes(64) if p is None else p[0].to_bytes(32, "little") + p[1].to_bytes(32, "little")
+
+
+@pytest.mark.parametrize("name,p", [("fr", O.R_MOD), ("fq", O.Q_MOD)])
+def test_field_layer_montgomery_bit_exact(zk, name, p):
+    """8x32-bit limb Montgomery arithmetic == Python integers on raw Montgomery representatives (fp.tcc:23-190 semantics)."""
+    rng = random.Random(7)
+    edge = [0, 1, 2, p - 1, p - 2, (1 << 253), (1 << 254) % p, 0xFFFFFFFF, 1 << 32, (1 << 224) - 1, (1 << 256) % p]
+    a = edge + [rng.randrange(p) for _ in range(20000)]
+    b = list(reversed(edge)) + [rng.randrange(p) for _ in range(20000)]
+    Ri = pow(1 << 256, -1, p)
+    assert fl(zk.field_op(name, "mul", fb(a), fb(b))) == [x * y * Ri % p for x, y in zip(a, b)]
+    assert fl(zk.field_op(name, "sqr", fb(a))) == [x * x * Ri % p for x in a]
+    assert fl(zk.field_op(name, "add", fb(a), fb(b))) == [(x + y) % p for x, y in zip(a, b)]
+    assert fl(zk.field_op(name, "sub", fb(a), fb(b))) == [(x - y) % p for x, y in zip(a, b)]
+    assert fl(zk.field_op(name, "to_mont", fb(a))) == [x * (1 << 256) % p for x in a]
+    assert fl(zk.field_op(name, "from_mont", fb(a))) == [x * Ri % p for x in a]
+    inv = fl(zk.field_op(name, "inverse", fb(a[:128])))
+    assert inv == [(pow(x * Ri % p, -1, p) * (1 << 256) % p if x else 0) for x in a[:128]]
+
+
+def test_field_layer_against_reference(zk, ref):
+    rng = random.Random(3)
+    a = [rng.randrange(O.Q_MOD) for _ in range(512)]
+    b = [rng.randrange(O.Q_MOD) for _ in range(512)]
+    am, bm = ref.to_mont("fq", a), ref.to_mont("fq", b)
+    prod = fl(zk.field_op("fq", "mul", fb(am), fb(bm)))
+    assert prod == ref.to_mont("fq", ref.field_op("fq", "mul", a, b))
+
+
+@pytest.mark.parametrize("ms", [2, 4, 8, 12, 24, 100, 768, 1024, 2048, 3000, 5000, 1 << 13, 3 << 12])
+def test_domain_ops_against_oracle(zk, ms):
+    """FFT/iFFT/cosetFFT/icosetFFT/divide_by_Z_on_coset for basic and step domains, incl. the rounding rule of the selector."""
+    rng = random.Random(ms)
+    dom = O.get_evaluation_domain(ms)
+    assert zk.domain_size(ms) == (dom.m, dom.kind)
+    v = [rng.randrange(O.R_MOD) for _ in range(dom.m)]
+    v[0], v[-1] = 0, O.R_MOD - 1
+    for op, f in (("FFT", dom.FFT), ("iFFT", dom.iFFT), ("cosetFFT", lambda x: dom.cosetFFT(x, 5)), ("icosetFFT", lambda x: dom.icosetFFT(x, 5)),
+                  ("divide_by_Z_on_coset", dom.divide_by_Z_on_coset)):
+        assert fl(zk.domain_op(ms, op, fb(v))) == f(v), (ms, op)
+
+
+@pytest.mark.parametrize("ms", [1 << 16, 196608, 1 << 18, 167275, 1 << 19])
+def test_domain_ops_against_reference_at_circuit_sizes(zk, ref, ms):
+    """The four circuits' domains (mint/redeem: step 2^17+2^16; send 2^18; deposit 2^19) against libfqfft itself."""
+    m, kind = zk.domain_size(ms)
+    assert (m, kind) == ref.domain_size(ms)
+    rng = random.Random(ms)
+    raw = fb([rng.getrandbits(253) for _ in range(m)])
+    for op in ("FFT", "iFFT", "cosetFFT", "icosetFFT", "divide_by_Z_on_coset"):
+        assert zk.domain_op(ms, op, raw) == ref.domain_op_bytes(ms, op, raw), (ms, op)
+
+
+@pytest.mark.parametrize("logn", [20, 22])
+def test_ntt_properties_at_sweep_sizes(zk, logn):
+    """Size-independent properties where the oracle is too slow: iFFT(FFT(a)) = a, icosetFFT(cosetFFT(a)) = a, linearity,
+    and FFT of a delta = all-ones / of the constant polynomial = n*delta."""
+    n = 1 << logn
+    rng = random.Random(logn)
+    raw = b"".join(rng.getrandbits(253).to_bytes(32, "little") for _ in range(n))
+    ev = zk.domain_op(n, "FFT", raw)
+    assert zk.domain_op(n, "iFFT", ev) == raw
+    assert zk.domain_op(n, "icosetFFT", zk.domain_op(n, "cosetFFT", raw)) == raw
+    delta = (1).to_bytes(32, "little") + bytes(32 * (n - 1))
+    assert zk.domain_op(n, "FFT", delta) == (1).to_bytes(32, "little") * n
+    ones = (1).to_bytes(32, "little") * n
+    assert zk.domain_op(n, "iFFT", ones) == delta
+    # spot-check against naive evaluation at a few domain points
+    a = fl(raw[:32 * 64]) + [0] * 0
+    sparse = raw[:32 * 64] + bytes(32 * (n - 64))
+    evs = zk.domain_op(n, "FFT", sparse)
+    w = O.get_root_of_unity(n)
+    for i in (0, 1, 12345, n // 2 + 3, n - 1):
+        x = pow(w, i, O.R_MOD)
+        assert int.from_bytes(evs[32 * i:32 * i + 32], "little") == sum(c * pow(x, k, O.R_MOD) for k, c in enumerate(a)) % O.R_MOD
+
+
+def _points(n):
+    pts, P = [], O.G1_ONE
+    for _ in range(n):
+        P = O.G1.add(P, O.G1_ONE)
+        pts.append(O.G1.to_affine(P))
+    return pts
+
+
+def test_msm_g1_edge_cases_against_oracle(zk):
+    """Empty input, single point, zero / one scalars, r-1, repeated points (doubling inside a bucket), P and -P (cancellation
+    to infinity), infinity among the bases -- the cases multi_exp_with_mixed_addition special-cases (multiexp.tcc:443-496)."""
+    pts = _points(40)
+    J = [O.G1.from_affine(p) for p in pts]
+    inf = bytes(64)
+    assert zk.msm_g1(b"", b"") == inf
+    assert zk.msm_g1(g1b(pts[0]), fb([0])) == inf
+    assert zk.msm_g1(g1b(pts[0]), fb([1])) == g1b(pts[0])
+    assert zk.msm_g1(g1b(pts[3]), fb([O.R_MOD - 1])) == g1b(O.G1.to_affine(O.G1.neg(J[3])))
+    neg = (pts[5][0], O.Q_MOD - pts[5][1])
+    assert zk.msm_g1(g1b(pts[5]) + g1b(neg), fb([7, 7])) == inf
+    assert zk.msm_g1(g1b(pts[5]) * 3, fb([5, 5, 5])) == g1b(O.G1.to_affine(O.G1.mul(15, J[5])))
+    assert zk.msm_g1(g1b(pts[5]) + inf + g1b(pts[6]), fb([2, 99, 1])) == g1b(O.G1.to_affine(O.G1.add(O.G1.mul(2, J[5]), J[6])))
+    rng = random.Random(2)
+    for c in (0, 4, 7, 13, 16):
+        sc = [rng.choice([0, 1, 2, rng.getrandbits(33), rng.randrange(O.R_MOD), O.R_MOD - 1, (1 << 253) + 5]) for _ in pts]
+        exp = O.G1.to_affine(O.G1.multi_exp_with_mixed_addition(J, sc))
+        assert zk.msm_g1(b"".join(map(g1b, pts)), fb(sc), c) == g1b(exp), c
+
+
+@pytest.mark.parametrize("n", [1, 33, 1000, 1 << 14, 1 << 16])
+def test_msm_g1_g2_against_reference(zk, ref, n):
+    rng = random.Random(n)
+    b1, b2 = ref.g1_bases_bytes(n, 12345), ref.g2_bases_bytes(n, 777)
+    sc = [rng.randrange(O.R_MOD) for _ in range(n)]
+    for i in range(0, n, 3):
+        sc[i] = rng.choice([0, 1, rng.getrandbits(33), O.R_MOD - 1])
+    s = fb(sc)
+    assert zk.msm_g1(b1, s) == ref.msm_g1_bytes(b1, s, 1)[0]
+    assert zk.msm_g2(b2, s) == ref.msm_g2_bytes(b2, s, 1)[0]
+
+
+def test_msm_linearity_at_sweep_size(zk, ref):
+    """MSM(s) + MSM(t) == MSM(s + t) and MSM(k*s) == k*MSM(s) at 2^18 points: a size the CPU reference takes seconds for."""
+    n = 1 << 18
+    rng = random.Random(1)
+    b1 = ref.g1_bases_bytes(n, 31337)
+    s = [rng.getrandbits(253) for _ in range(n)]
+    t = [rng.getrandbits(253) for _ in range(n)]
+    ps, pt = zk.msm_g1(b1, fb(s)), zk.msm_g1(b1, fb(t))
+    pst = zk.msm_g1(b1, fb([(x + y) % O.R_MOD for x, y in zip(s, t)]))
+    A, B = ref.g1_from(ps), ref.g1_from(pt)
+    assert O.G1.to_affine(O.G1.add(O.G1.from_affine(A), O.G1.from_affine(B))) == ref.g1_from(pst)
+    k = 0xDEADBEEFCAFE
+    pk = zk.msm_g1(b1, fb([x * k % O.R_MOD for x in s]))
+    assert ref.g1_mul(A, k) == ref.g1_from(pk)
+    assert ps == ref.msm_g1_bytes(b1, fb(s), 0, chunks=0, mt=True)[0]

@@ -1,0 +1,127 @@
+"""CPU-side checks of the product library (no compute on a GPU): the C-ABI loads and exports every symbol the header
+declares, the byte-level helpers / witness generators / verifier (all host code) agree with the reference."""
+import ctypes as C
+import hashlib
+import json
+import os
+import re
+import zlib
+
+import pytest
+
+import fixtures as F
+from oracle import bn254_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+CIRCUITS = ("mint", "send", "deposit", "redeem")
+
+
+@pytest.fixture(scope="module")
+def api():
+    import blockmaze_b200.api as api      # loading the library needs no GPU; compute entry points are not called here
+    return api
+
+
+def test_cabi_exports_every_declared_symbol(api):
+    header = open(os.path.join(ROOT, "include", "zkb200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = set(re.findall(r"\b(\w+)\s*\(", header)) - {"defined", "if"}
+    names = {n for n in names if re.match(r"(zkb200_|gen|verify|compute)", n)}
+    assert len(names) >= 30
+    for n in sorted(names):
+        assert hasattr(api.lib, n), "libzkb200.so does not export " + n
+
+
+def test_helpers_known_answers(api):
+    z = lambda s: "0x" + s.rjust(64, "0")
+    sn_old = api.helper("computePRF", z("1"), z("123456"))
+    assert sn_old == "4a31770fe5354a1a9632ebe1481e108cd82ce514ac094c57b5ffdfaea8ac138a"
+    sn = api.helper("computePRF", z("1"), z("123"))
+    assert sn == "59416ca7b4d0fdcb61dd7fb063db35e9a0a96dd9fecf20a8027aed2d6c4f4006"
+    assert api.helper("genCMT", 6, "0x" + sn_old, z("123456")) == "53996012d011396f7a4953c80ee64d5a1b8b7ed676bbea7886b698c09aa991db"
+    assert api.helper("genCMT", 13, "0x" + sn, z("123")) == "dbc961ea0d748198f21ea3267534e064eaaea65733dbd362fed93b4748991c27"
+
+
+def test_helpers_against_oracle_restatement(api):
+    import random
+    rng = random.Random(4)
+    for _ in range(20):
+        a, b, c = (bytes(rng.getrandbits(8) for _ in range(32)) for _ in range(3))
+        pk = bytes(rng.getrandbits(8) for _ in range(20))
+        v = rng.getrandbits(64)
+        assert api.helper("computePRF", O.arg_hex(a), O.arg_hex(b)) == O.blob_hex(O.compute_prf(a, b))
+        assert api.helper("computeCRH", O.arg_hex(pk), O.arg_hex(b)) == O.blob_hex(O.compute_crh(pk, b))
+        assert api.helper("genCMT", v, O.arg_hex(a), O.arg_hex(b)) == O.blob_hex(O.note_cm(v, a, b))
+        assert api.helper("genCMTS", v, O.arg_hex(pk), O.arg_hex(b), O.arg_hex(c)) == O.blob_hex(O.notes_cm(v, pk, b, c))
+
+
+def test_hex_parsing_quirks(api):
+    """uint256S semantics (uint256.h:200-226): optional 0x, short strings are right-aligned, parsing stops at the first non-hex."""
+    one = api.helper("computePRF", "1", "0x123456")
+    assert one == api.helper("computePRF", "0x" + "1".rjust(64, "0"), "0x" + "123456".rjust(64, "0"))
+    assert api.helper("computePRF", "  0X1", "123456zz") == one
+
+
+def test_gen_root_matches_full_tree(api):
+    import random
+    rng = random.Random(8)
+    for n in (0, 1, 2, 3, 16, 255, 256):
+        leaves = [bytes(rng.getrandbits(8) for _ in range(32)) for _ in range(n)]
+        level = leaves + [bytes(32)] * (256 - n)
+        while len(level) > 1:
+            level = [O.sha256_compress(level[i], level[i + 1]) for i in range(0, len(level), 2)]
+        assert api.helper("genRoot", "".join(O.arg_hex(x) for x in leaves), n) == O.blob_hex(level[0])
+
+
+@pytest.mark.parametrize("circuit", CIRCUITS)
+def test_witness_equals_reference_golden(api, circuit):
+    """Native witness generator == assignment produced by the reference gadgets for the reference's own fixture."""
+    g = json.load(open(os.path.join(GOLD, circuit + ".json")))
+    w = api.witness(circuit, g["args"])
+    assert hashlib.sha256(w).hexdigest() == g["assignment_sha256"]
+    assert w == zlib.decompress(open(os.path.join(GOLD, circuit + "_assignment.bin.z"), "rb").read())
+
+
+@pytest.mark.parametrize("circuit", CIRCUITS)
+def test_witness_equals_reference_on_synthetic_transactions(api, ref, circuit):
+    if not ref.available(circuit):
+        pytest.skip("reference circuit harness not built")
+    for seed in range(4):
+        args = F.synthetic(circuit, seed)
+        theirs, sat = ref.witness(circuit, args)
+        assert sat
+        assert api.witness(circuit, args) == theirs
+
+
+def test_deposit_witness_leaf_positions(api, ref):
+    """Merkle path handling: cmtS at the first, a middle and the last of 256 leaves, and with fewer leaves than the tree holds."""
+    if not ref.available("deposit"):
+        pytest.skip("reference circuit harness not built")
+    import random
+    for n, idx in ((256, 0), (256, 255), (256, 100), (5, 4), (1, 0)):
+        rng = random.Random(n * 1000 + idx)
+        leaves = [bytes(rng.getrandbits(8) for _ in range(32)) for _ in range(n)]
+        args = F.deposit_fixture(leaves=leaves, index=idx)
+        theirs, sat = ref.witness("deposit", args)
+        assert sat and api.witness("deposit", args) == theirs
+
+
+@pytest.mark.parametrize("circuit", CIRCUITS)
+def test_verifier_accepts_reference_proofs_and_rejects_tampering(api, ref, circuit):
+    """verify*proof needs only the vk file (1.3 KB); golden proofs come from the reference prover."""
+    vk = os.path.join(ref.KEY_DIR, circuit + "vk.txt")
+    if not os.path.exists(vk):
+        pytest.skip("reference keys not present")
+    api.set_key_dir(ref.KEY_DIR)
+    g = json.load(open(os.path.join(GOLD, circuit + ".json")))
+    va = api.verify_args(circuit, g["args"])
+    assert api.verify_proof(circuit, g["proof_hex"], va)
+    h = g["proof_hex"]
+    assert not api.verify_proof(circuit, h[:200] + ("1" if h[200] != "1" else "2") + h[201:], va)      # not on the curve any more
+    assert not api.verify_proof(circuit, h[:384] + h[:128], va)                                           # C := A, a valid point
+    bad = list(va)
+    bad[1] = bad[1][:-1] + ("1" if bad[1][-1] != "1" else "2")
+    assert not api.verify_proof(circuit, h, bad)
+    assert not api.verify_proof(circuit, "0" * 63 + "1" + "0" * 63 + "2" + h[128:], va)                  # default-proof style A
+    assert not api.verify_proof(circuit, "zz" + h[2:], va)

@@ -204,11 +204,12 @@ def main():
             api.gen_proof("send", txs[i])
         barrier()
         t2 = time.perf_counter()
-        lat = []
+        lat, brk = [], []
         for i in range(args.steps):
             ta = time.perf_counter()
             proof = api.gen_proof("send", txs[args.warmup + i])
             lat.append(time.perf_counter() - ta)
+            brk.append(api.last_breakdown_ms())
         barrier()
         t3 = time.perf_counter()
         windows.append((t2, t3))
@@ -234,7 +235,7 @@ def main():
         t1 = time.perf_counter()
         windows.append((t0, t1))
         units, dt = reduce_counts_and_time(len(txs), t1 - t0, dist)
-        units_e, dt_e, launches, acc_ms, qap_ms, msm_ms, gpu_ms = units, dt, 0, [0.0], [0.0], [0.0], [0.0]
+        units_e, dt_e, launches, acc_ms, qap_ms, msm_ms, gpu_ms, brk = units, dt, 0, [0.0], [0.0], [0.0], [0.0], []
         args.steps = 1
         nvars = 0
         workload = "mixed batch of 1024 synthetic mint/send/deposit/redeem transactions (256 each) sharded round-robin over the GPUs, through gen*proof()"
@@ -246,6 +247,8 @@ def main():
         # p50 end-to-end latency per circuit through the cgo surface (BASELINE.json metric, configs[0..3])
         per = {}
         for c in ("mint", "send", "deposit", "redeem"):
+            if not os.path.exists(os.path.join(kd, c + "pk.txt")):
+                continue
             ts = []
             for i in range(7):
                 tx = F.synthetic(c, 9000 + i)
@@ -279,7 +282,8 @@ def main():
                        "randomness": "r, s pinned per rank"},
             "clocks": clocks,
             "e2e": {"value": units_e / dt_e, "unit": "proofs/s", "h2d_bytes_per_step": nvars * 32, "d2h_bytes_per_step": d2h,
-                    "p50_latency_ms": round(1e3 * statistics.median(lat), 3)},
+                    "p50_latency_ms": round(1e3 * statistics.median(lat), 3),
+                    "breakdown_ms": {k: round(statistics.median(b[k] for b in brk), 3) for k in brk[0]} if args.workload == "send" else None},
             "gpu_launches": launches,
             "gpu_ms_per_proof": {"total": round(statistics.mean(gpu_ms), 3), "qap_witness_map": round(statistics.mean(qap_ms), 3),
                                  "msm_H": round(statistics.mean(msm_ms), 3), "msm_H_accumulate_kernel": round(acc_avg, 3)},

@@ -31,6 +31,7 @@ lib.zkb200_bench_ntt.restype = C.c_float
 lib.zkb200_bench_ntt.argtypes = [C.c_int, C.c_int, C.c_int]
 lib.zkb200_bench_msm.restype = C.c_float
 lib.zkb200_bench_msm.argtypes = [C.c_int, C.c_size_t, C.c_int, C.c_int]
+lib.zkb200_last_breakdown_ms.argtypes = [C.POINTER(C.c_double)]
 lib.zkb200_flush_l2.restype = None
 lib.zkb200_device_sync.restype = None
 lib.zkb200_bench_imad_peak.restype = C.c_float
@@ -147,6 +148,13 @@ def gen_proof(circuit, args):
     """gen<Circuit>proof through the BlockMaze cgo surface; returns the 512-char proof string."""
     p = getattr(lib, "gen%sproof" % circuit.capitalize())(*_enc(args))
     return C.string_at(p, 512).decode()
+
+
+def last_breakdown_ms():
+    """Host witness generation, zkb200_prove total, of which GPU, host finish -- of the last gen_proof call."""
+    out = (C.c_double * 4)()
+    lib.zkb200_last_breakdown_ms(out)
+    return dict(zip(("witness", "prove", "gpu", "host_finish"), [round(float(x), 3) for x in out]))
 
 
 def verify_proof(circuit, proof_hex, args):

@@ -3,6 +3,7 @@
 // SRC/{mint,send,deposit,redeem}/*cgo.cpp; the proving itself runs on the GPU against proving keys that are parsed once per
 // process and stay resident (the reference re-reads and re-parses the key file inside every gen*proof call,
 // mintcgo.cpp:299-302).
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -21,6 +22,8 @@ static std::string g_key_dir;
 static std::vector<uint32_t> g_words;
 static size_t g_word_pos = 0;
 static void *g_pk[4] = {nullptr, nullptr, nullptr, nullptr};
+static double g_last_ms[4] = {0, 0, 0, 0};      // witness generation, prove call, of which GPU, host finish (last gen*proof)
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const char *CIRCUIT_NAMES[4] = {"mint", "send", "deposit", "redeem"};
 
 std::string zkw::key_dir() {
@@ -76,14 +79,24 @@ static char *dup_hex(const std::string &s, size_t cap) {       // `new char[cap]
     memcpy(p, s.data(), s.size() < cap - 1 ? s.size() : cap - 1);
     return p;
 }
-static char *prove_with(int circuit, const Assignment &a) {
+template <class Fn> static char *prove_timed(int circuit, Fn make) {
+    const double t0 = now_ms();
+    const Assignment a = make();
+    g_last_ms[0] = now_ms() - t0;
+    extern char *zk_prove_with(int, const Assignment &);
+    return zk_prove_with(circuit, a);
+}
+char *zk_prove_with(int circuit, const Assignment &a) {
     std::lock_guard<std::mutex> lk(g_abi_mu);
     void *pk = circuit_pk(circuit);
     uint64_t r[4], s[4];
     next_random_fr(r); next_random_fr(s);                      // r first, then s (r1cs_gg_ppzksnark.tcc:418-419)
     char *p = new char[1153];                                  // the reference returns new char[1153] with 512 hex chars (mintcgo.cpp:316-320)
     memset(p, 0, 1153);
-    const int rc = zkb200_prove(pk, a.data(), (const uint8_t *)r, (const uint8_t *)s, p, nullptr, nullptr);
+    float tm[5] = {0, 0, 0, 0, 0};
+    const double t0 = now_ms();
+    const int rc = zkb200_prove(pk, a.data(), (const uint8_t *)r, (const uint8_t *)s, p, nullptr, tm);
+    g_last_ms[1] = now_ms() - t0; g_last_ms[2] = tm[0]; g_last_ms[3] = tm[3];
     if (rc == 1) printf("can not generate %s proof\n", CIRCUIT_NAMES[circuit]);      // mintcgo.cpp:209
     return p;
 }
@@ -141,7 +154,7 @@ char *genMintproof(uint64_t value, uint64_t value_old, char *sn_old_string, char
     Note note_old, note; uint8_t cmtA_old[32], cmtA[32], sk[32];
     parse_note(note_old, value_old, sn_old_string, r_old_string); parse_note(note, value, sn_string, r_string);
     parse_hex_blob(cmtA_old_string, cmtA_old, 32); parse_hex_blob(cmtA_string, cmtA, 32); parse_hex_blob(sk_string, sk, 32);
-    return prove_with(ZKB200_MINT, mint_witness(note_old, note, cmtA_old, cmtA, value_s, sk));
+    return prove_timed(ZKB200_MINT, [&] { return mint_witness(note_old, note, cmtA_old, cmtA, value_s, sk); });
 }
 char *genRedeemproof(uint64_t value, uint64_t value_old, char *sn_old_string, char *r_old_string, char *sn_string, char *r_string,
                      char *cmtA_old_string, char *cmtA_string, uint64_t value_s, char *sk_string) {
@@ -149,7 +162,7 @@ char *genRedeemproof(uint64_t value, uint64_t value_old, char *sn_old_string, ch
     parse_note(note_old, value_old, sn_old_string, r_old_string); parse_note(note, value, sn_string, r_string);
     parse_hex_blob(cmtA_old_string, cmtA_old, 32); parse_hex_blob(cmtA_string, cmtA, 32); parse_hex_blob(sk_string, sk, 32);
     printf("Trying to generate redeem proof...\n");            // redeemcgo.cpp:310
-    return prove_with(ZKB200_REDEEM, redeem_witness(note_old, note, cmtA_old, cmtA, value_s, sk));
+    return prove_timed(ZKB200_REDEEM, [&] { return redeem_witness(note_old, note, cmtA_old, cmtA, value_s, sk); });
 }
 char *genSendproof(uint64_t value_A, char *r_s_string, char *sn_string, char *r_string, char *cmt_s_string, char *cmtA_string, uint64_t value_s,
                    char *pk_recv_string, uint64_t value_A_new, char *sn_A_new, char *r_A_new, char *cmt_A_new, char *sk_string,
@@ -161,7 +174,7 @@ char *genSendproof(uint64_t value_A, char *r_s_string, char *sn_string, char *r_
     parse_hex_blob(cmt_s_string, cmtS, 32); parse_hex_blob(cmtA_string, cmtA, 32); parse_hex_blob(cmt_A_new, cmtAnew, 32);
     parse_hex_blob(sk_string, sk, 32); parse_hex_blob(pk_sender_string, pk_sender, 20);
     printf("Trying to generate send proof...\n");              // sendcgo.cpp:352
-    return prove_with(ZKB200_SEND, send_witness(note_old, notes, note_new, cmtA, cmtS, cmtAnew, sk, pk_sender));
+    return prove_timed(ZKB200_SEND, [&] { return send_witness(note_old, notes, note_new, cmtA, cmtS, cmtAnew, sk, pk_sender); });
 }
 char *genDepositproof(uint64_t value, uint64_t value_old, char *sn_old_string, char *r_old_string, char *sn_string, char *r_string,
                       char *sns_string, char *rs_string, char *cmtB_old_string, char *cmtB_string, uint64_t value_s, char *pk_string,
@@ -194,8 +207,10 @@ char *genDepositproof(uint64_t value, uint64_t value_old, char *sn_old_string, c
     eff.insert(eff.end(), leaves.begin() + (last + 1) * 32, leaves.end());
     uint8_t siblings[MERKLE_DEPTH][32], rt[32];
     merkle_path((const uint8_t(*)[32])eff.data(), eff.size() / 32, (size_t)first, siblings, rt);
-    return prove_with(ZKB200_DEPOSIT, deposit_witness(note_s, note_old, note, cmtS, cmtB_old, cmtB, rt, (size_t)first, siblings, sn_s, sk));
+    return prove_timed(ZKB200_DEPOSIT, [&] { return deposit_witness(note_s, note_old, note, cmtS, cmtB_old, cmtB, rt, (size_t)first, siblings, sn_s, sk); });
 }
+
+void zkb200_last_breakdown_ms(double out[4]) { for (int i = 0; i < 4; i++) out[i] = g_last_ms[i]; }
 
 // ---- witness-only entry points (parity hooks for the assignment layout; declared extern "C" in zkb200.h) ------------------------
 long zkb200_witness_mint(uint64_t value, uint64_t value_old, const char *sn_old, const char *r_old, const char *sn, const char *r,

@@ -125,7 +125,7 @@ int zkb200_pk_info(void *h, uint64_t info[8], double seconds[3]) {
     if (!pk) return -1;
     info[0] = pk->num_vars; info[1] = pk->num_inputs; info[2] = pk->num_constraints; info[3] = pk->dom->m; info[4] = pk->dom->step ? 1 : 0;
     info[5] = (uint64_t)pk->a.nnz + pk->b.nnz + pk->c.nnz; info[6] = pk->ncoef; info[7] = pk->nB;
-    if (seconds) { seconds[0] = pk->load_seconds; seconds[1] = pk->parse_seconds; seconds[2] = pk->decompress_seconds; }
+    if (seconds) { seconds[0] = pk->load_seconds; seconds[1] = pk->parse_seconds; seconds[2] = pk->decompress_seconds + pk->expand_seconds; }
     return 0;
 }
 
@@ -152,6 +152,7 @@ int zkb200_prove(void *h, const uint8_t *assignment, const uint8_t r[32], const 
     std::lock_guard<std::mutex> lk(g_mu);
     uint64_t rr[4], ss[4]; memcpy(rr, r, 32); memcpy(ss, s, 32);
     ProofPoints pp;
+    pp.want_parts = parts != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
     prove(pk, assignment, rr, ss, pp);
     const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -215,7 +216,7 @@ static int msm_host_entry(size_t n, const uint8_t *bases, const uint8_t *scalars
     ZK_CUDA(cudaMemcpy(d_scalars, scalars, n * 32, cudaMemcpyHostToDevice));
     const size_t nf = n * sizeof(AffT) / 32;
     if (nf) to_mont_generic_kernel<Fq><<<(unsigned)((nf + 255) / 256), 256>>>((Fq *)d_bases, nf);
-    MsmPlan plan; plan.init((uint32_t)n, c, 1024, !g2, g2);
+    MsmPlan plan; plan.init((uint32_t)n, c, 1024, !g2, g2, false);
     msm_run(0, plan, ScalarRef{d_scalars, nullptr, 0, 0}, nullptr, g2 ? nullptr : d_bases, g2 ? d_bases : nullptr);
     ZK_CUDA(cudaStreamSynchronize(0));
     if constexpr (sizeof(AffT) == 64) result = msm_finish_g1(plan); else result = msm_finish_g2(plan);
@@ -277,7 +278,7 @@ float zkb200_bench_ntt(int logn, int batch, int iters) {
 
 float zkb200_bench_msm(int group, size_t n, int window_bits, int iters) {
     if (ensure_device()) return -1;
-    const int c = window_bits > 0 ? window_bits : default_window(n);
+    const int c = window_bits > 0 ? window_bits : (window_bits < 0 ? -window_bits : default_window(n));
     uint32_t *sc; ZK_CUDA(cudaMalloc(&sc, n * 32));
     fill_scalars_kernel<<<(unsigned)((n + 255) / 256), 256>>>(sc, n, 11);
     void *bases;
@@ -297,7 +298,9 @@ float zkb200_bench_msm(int group, size_t n, int window_bits, int iters) {
         gen_bases_kernel<Fq2><<<(unsigned)((n + 127) / 128), 128>>>(g, (G2Affine *)bases, n);
     }
     ZK_CUDA(cudaDeviceSynchronize());
-    MsmPlan plan; plan.init((uint32_t)n, c, 0, group == 1, group == 2);
+    const bool expanded = window_bits < 0;          // negative window_bits: fixed-base (expanded) layout with |window_bits| bits
+    MsmPlan plan; plan.init((uint32_t)n, c, 0, group == 1, group == 2, expanded);
+    if (expanded) { void *e = msm_expand_bases(bases, (uint32_t)n, c, group == 2); ZK_CUDA(cudaDeviceSynchronize()); cudaFree(bases); bases = e; }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     msm_run(0, plan, ScalarRef{sc, nullptr, 0, 0}, nullptr, group == 1 ? bases : nullptr, group == 2 ? bases : nullptr);
     ZK_CUDA(cudaDeviceSynchronize());

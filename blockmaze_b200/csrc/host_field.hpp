@@ -156,10 +156,18 @@ template <class F> struct HPoint {
         r.ZZZ = ZZZ * o.ZZZ * PPP;
         return r;
     }
-    // k = canonical integer (4 x 64 little-endian)
+    // k = canonical integer (4 x 64 little-endian); fixed 4-bit windows: 252 doublings + <= 64 additions
     HPoint mul(const uint64_t k[4]) const {
+        HPoint tab[16];
+        tab[0] = inf(); tab[1] = *this;
+        for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? tab[i - 1].add(*this) : tab[i >> 1].dbl();
         HPoint r = inf();
-        for (int i = 255; i >= 0; i--) { r = r.dbl(); if ((k[i >> 6] >> (i & 63)) & 1) r = r.add(*this); }
+        bool started = false;
+        for (int i = 63; i >= 0; i--) {
+            const unsigned d = (unsigned)((k[i >> 4] >> ((i & 15) * 4)) & 15);
+            if (started) { r = r.dbl().dbl().dbl().dbl(); }
+            if (d) { r = started ? r.add(tab[d]) : tab[d]; started = true; }
+        }
         return r;
     }
     HAffine<F> to_affine() const {

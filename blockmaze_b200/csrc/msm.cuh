@@ -3,14 +3,19 @@
 // Replaces libff::multi_exp<.., BDLO12> and its 0/1 pre-filter (libff/algebra/scalar_multiplication/multiexp.tcc:165-282,
 // 443-496) and libsnark's kc_multi_exp_with_mixed_addition (libsnark/knowledge_commitment/kc_multiexp.tcc:21-89).
 // The result is the same group element; the schedule is GPU-shaped:
-//   1. digits   : every scalar is cut into signed c-bit digits d_k in [-2^(c-1), 2^(c-1)].  Digit (k, |d|) selects bucket
-//                 k*2^(c-1) + |d| - 1.  Scalars equal to 0 are dropped; scalars equal to 1 (45 % of a BlockMaze witness) are
-//                 spread round-robin over a separate range of "ones" buckets instead of all landing in bucket (0,1).
-//   2. count / scan / scatter : a counting sort of (bucket -> point index | sign) built from global atomics.
+//   1. digits   : every scalar is cut into signed c-bit digits d_k in [-2^(c-1), 2^(c-1)].  Scalars equal to 0 are dropped;
+//                 scalars equal to 1 (45 % of a BlockMaze witness) are spread round-robin over a separate range of "ones"
+//                 buckets instead of all landing in bucket (0, 1).
+//                 Two bucket layouts:
+//                   windowed : digit (k, |d|) -> bucket k*2^(c-1) + |d| - 1, base i            (bases given per call)
+//                   expanded : digit (k, |d|) -> bucket |d| - 1,             base k*n + i      (bases fixed in a proving key:
+//                              2^(c*k) * P_i is precomputed once, so all windows share ONE bucket set and no Horner
+//                              recombination is left -- fewer buckets to reduce, nothing to do on the host)
+//   2. count / scan / scatter : a counting sort of (bucket -> base index | sign) built from global atomics.
 //   3. accumulate : buckets are cut into tasks of <= 48 entries; one thread per task does XYZZ += affine mixed additions
-//                   (8M+2S) and a few segmented pairwise passes fold the tasks of oversized buckets.
-//   4. reduce  : per window, sum_j (j+1)*B_j by segmented running sums + a shared-memory tree; ones buckets are summed.
-//   5. the per-window partial sums (a few dozen points) go back to the host, which does the final Horner combination.
+//                   (8M+2S); tasks of one bucket are then folded (small spans by one thread, oversized buckets by a CTA tree).
+//   4. reduce  : per bucket region, sum_j (j+1)*B_j by segmented running sums + a shared-memory tree; ones buckets are summed.
+//   5. the partial sums (a few dozen points) go back to the host.
 #pragma once
 #include <cuda_runtime.h>
 #include "ec.cuh"
@@ -20,12 +25,17 @@ namespace zk {
 struct MsmShape {
     int c;               // window bits
     int windows;         // ceil(255 / c)
-    uint32_t nb;         // buckets per window = 2^(c-1)
+    uint32_t nb;         // buckets per region = 2^(c-1)
     uint32_t ones;       // number of "ones" buckets
-    uint32_t total;      // windows*nb + ones
+    uint32_t regions;    // bucket regions: 1 if expanded, else `windows`
+    uint32_t total;      // regions*nb + ones
+    uint32_t n;          // number of points
+    int expanded;
 };
-static inline MsmShape msm_shape(int c, uint32_t ones) {
-    MsmShape s; s.c = c; s.windows = (255 + c - 1) / c; s.nb = 1u << (c - 1); s.ones = ones; s.total = s.windows * s.nb + ones; return s;
+static inline MsmShape msm_shape(uint32_t n, int c, uint32_t ones, int expanded) {
+    MsmShape s; s.c = c; s.windows = (255 + c - 1) / c; s.nb = 1u << (c - 1); s.ones = ones; s.n = n; s.expanded = expanded;
+    s.regions = expanded ? 1u : (uint32_t)s.windows; s.total = s.regions * s.nb + ones;
+    return s;
 }
 
 __device__ __forceinline__ void ld_scalar(const uint32_t *p, uint32_t s[8]) {
@@ -34,13 +44,13 @@ __device__ __forceinline__ void ld_scalar(const uint32_t *p, uint32_t s[8]) {
     s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
 }
 
-// Visit the non-zero signed digits of the canonical scalar s.  f(bucket, negative)
+// Visit the non-zero signed digits of the canonical scalar s of point i.  f(bucket, entry)   entry = base index | sign << 31
 template <class Fn>
-__device__ __forceinline__ void msm_for_digits(const uint32_t s[8], const MsmShape &sh, uint32_t point_idx, Fn f) {
+__device__ __forceinline__ void msm_for_digits(const uint32_t s[8], const MsmShape &sh, uint32_t i, Fn f) {
     uint32_t orv = s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7];
     if (orv == 0) {
         if (s[0] == 0) return;
-        if (s[0] == 1 && sh.ones) { f(sh.windows * sh.nb + (point_idx % sh.ones), false); return; }
+        if (s[0] == 1 && sh.ones) { f(sh.regions * sh.nb + (i % sh.ones), i); return; }
     }
     uint32_t carry = 0;
     const uint32_t mask = (1u << sh.c) - 1;
@@ -54,13 +64,16 @@ __device__ __forceinline__ void msm_for_digits(const uint32_t s[8], const MsmSha
         }
         v = (v & mask) + carry;
         carry = 0;
-        bool neg = false;
-        if (v > sh.nb) { v = (1u << sh.c) - v; neg = true; carry = 1; }
-        if (v != 0) f((uint32_t)k * sh.nb + v - 1, neg);
+        uint32_t neg = 0;
+        if (v > sh.nb) { v = (1u << sh.c) - v; neg = 0x80000000u; carry = 1; }
+        if (v != 0) {
+            if (sh.expanded) f(v - 1, ((uint32_t)k * sh.n + i) | neg);
+            else f((uint32_t)k * sh.nb + v - 1, i | neg);
+        }
     }
 }
 
-// scalar source: scalars[(map ? map[i] : i + offset)], 8 words each, canonical (or Montgomery if from_mont)
+// scalar source: scalars[(map ? map[i] : i + offset)], 8 words each, canonical (or Montgomery if `montgomery`)
 struct ScalarSrc {
     const uint32_t *scalars;
     const uint32_t *map;
@@ -78,45 +91,58 @@ __device__ __forceinline__ void msm_load_scalar(const ScalarSrc &src, uint32_t i
 }
 
 // skip[i] != 0 marks a base that is the point at infinity (its scalar is ignored)
-static __global__ void msm_count_kernel(ScalarSrc src, const uint8_t *skip, uint32_t n, MsmShape sh, uint32_t *counts) {
+static __global__ void msm_count_kernel(ScalarSrc src, const uint8_t *skip, MsmShape sh, uint32_t *counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= sh.n) return;
     if (skip && skip[i]) return;
     uint32_t s[8];
     msm_load_scalar(src, i, s);
-    msm_for_digits(s, sh, i, [&](uint32_t bucket, bool) { atomicAdd(counts + bucket, 1u); });
+    msm_for_digits(s, sh, i, [&](uint32_t bucket, uint32_t) { atomicAdd(counts + bucket, 1u); });
 }
-static __global__ void msm_scatter_kernel(ScalarSrc src, const uint8_t *skip, uint32_t n, MsmShape sh, const uint32_t *offsets, uint32_t *cursors,
-                                   uint32_t *entries) {
+static __global__ void msm_scatter_kernel(ScalarSrc src, const uint8_t *skip, MsmShape sh, const uint32_t *offsets, uint32_t *cursors,
+                                          uint32_t *entries) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= sh.n) return;
     if (skip && skip[i]) return;
     uint32_t s[8];
     msm_load_scalar(src, i, s);
-    msm_for_digits(s, sh, i, [&](uint32_t bucket, bool neg) {
+    msm_for_digits(s, sh, i, [&](uint32_t bucket, uint32_t entry) {
         uint32_t pos = atomicAdd(cursors + bucket, 1u);
-        entries[offsets[bucket] + pos] = i | (neg ? 0x80000000u : 0u);
+        entries[offsets[bucket] + pos] = entry;
     });
 }
 
-// exclusive scan of `n` counts by one CTA of 1024 threads (n up to a few million): offsets[n] = total
-static __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t *counts, uint32_t *offsets, uint32_t n) {
-    __shared__ uint32_t part[1024];
-    const uint32_t per = (n + 1023) / 1024;
-    const uint32_t lo = threadIdx.x * per, hi = min(lo + per, n);
+// exclusive scan of `n` counts by one CTA of 32 warps; every warp owns a contiguous slice and reads it coalesced.  offsets[n] = total
+static __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ offsets, uint32_t n) {
+    __shared__ uint32_t warp_off[33];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t per = (((n + 31) / 32) + 31) / 32 * 32;
+    const uint32_t lo = min(warp * per, n), hi = min(lo + per, n);
     uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; i++) sum += counts[i];
-    part[threadIdx.x] = sum;
+    for (uint32_t i = lo + lane; i < hi; i += 32) sum += counts[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (lane == 0) warp_off[warp] = sum;
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        uint32_t v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
+    if (warp == 0) {
+        uint32_t v = warp_off[lane], incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
+        warp_off[lane] = incl - v;
+        if (lane == 31) warp_off[32] = incl;
     }
-    uint32_t run = part[threadIdx.x] - sum;
-    for (uint32_t i = lo; i < hi; i++) { offsets[i] = run; run += counts[i]; }
-    if (threadIdx.x == 1023) offsets[n] = part[1023];
+    __syncthreads();
+    uint32_t run = warp_off[warp];
+    for (uint32_t base = lo; base < hi; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t v = i < hi ? counts[i] : 0;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
+        if (i < hi) offsets[i] = run + incl - v;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (threadIdx.x == 0) offsets[n] = warp_off[32];
 }
 
 template <class F> __device__ __forceinline__ Affine<F> ld_affine(const Affine<F> *p) {
@@ -145,29 +171,44 @@ template <class F> __device__ __forceinline__ XYZZ<F> ld_xyzz(const XYZZ<F> *p) 
     return v;
 }
 
-// ---- bucket accumulation, load-balanced ------------------------------------------------------------------------------
+// ---- fixed-base expansion (proving-key load time) --------------------------------------------------------------------------
+// out[k*n + i] = 2^(c*k) * in[i] in affine form, k < windows.  One thread per point.
+template <class F>
+static __global__ void __launch_bounds__(128) msm_expand_bases_kernel(const Affine<F> *__restrict__ in, uint32_t n, int c, int windows,
+                                                                      Affine<F> *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Affine<F> p = in[i];
+    out[i] = p;
+    XYZZ<F> cur = XYZZ<F>::from_affine(p);
+    for (int k = 1; k < windows; k++) {
+        for (int j = 0; j < c; j++) cur = cur.dbl();
+        out[(size_t)k * n + i] = cur.to_affine();
+    }
+}
+
+// ---- bucket accumulation, load-balanced ------------------------------------------------------------------------------------
 // Bucket sizes are wildly uneven in practice (the top window of a 254-bit scalar has only 2-3 live bits, so a handful of
 // buckets hold n/4 points each; witness scalars repeat), so buckets are cut into TASKS of at most MSM_TASK entries:
 //   task_count : tasks_b = ceil(count_b / MSM_TASK), scanned into task_off[]
 //   accumulate : one thread per task sums its <= MSM_TASK points (XYZZ += affine) into partial[task]
-//   combine    : log2(max tasks per bucket) segmented pairwise passes fold partial[] so that partial[task_off[b]] = bucket b
+//   fold       : partial[task_off[b]] = sum of the bucket's partials -- by one thread when the span is small, by a whole
+//                CTA (strided sums + shared-memory tree) for the few oversized buckets, which are queued in heavy[]
 constexpr uint32_t MSM_TASK = 48;
+constexpr uint32_t MSM_FOLD_SMALL = 8;
+constexpr uint32_t MSM_HEAVY_MAX = 1024;
 
-static __global__ void msm_task_count_kernel(const uint32_t *__restrict__ offsets, uint32_t total_buckets, uint32_t *__restrict__ task_counts,
-                                             uint32_t *__restrict__ max_tasks) {
+static __global__ void msm_task_count_kernel(const uint32_t *__restrict__ offsets, uint32_t total_buckets, uint32_t *__restrict__ task_counts) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= total_buckets) return;
     const uint32_t cnt = offsets[b + 1] - offsets[b];
-    const uint32_t t = (cnt + MSM_TASK - 1) / MSM_TASK;
-    task_counts[b] = t;
-    if (t > 1) atomicMax(max_tasks, t);
+    task_counts[b] = (cnt + MSM_TASK - 1) / MSM_TASK;
 }
 
 template <class F>
 static __global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ offsets,
-                                                             const uint32_t *__restrict__ entries, const uint32_t *__restrict__ task_off,
-                                                             uint32_t total_buckets, XYZZ<F> *__restrict__ partial,
-                                                             uint32_t *__restrict__ task_rank, uint32_t *__restrict__ task_span) {
+                                                                    const uint32_t *__restrict__ entries, const uint32_t *__restrict__ task_off,
+                                                                    uint32_t total_buckets, XYZZ<F> *__restrict__ partial) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= task_off[total_buckets]) return;
     // bucket of task t: last b with task_off[b] <= t
@@ -183,22 +224,43 @@ static __global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine
         acc.add_affine(p);
     }
     st_xyzz(partial + t, acc);
-    task_rank[t] = rank;
-    task_span[t] = __ldg(task_off + b + 1) - __ldg(task_off + b);
 }
-// pass with stride s: partial[t] += partial[t + s] when rank % 2s == 0 and rank + s < span
+// one thread per bucket: fold short spans in place, queue long ones
 template <class F>
-static __global__ void __launch_bounds__(128) msm_combine_kernel(XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ task_rank,
-                                                          const uint32_t *__restrict__ task_span, const uint32_t *__restrict__ task_off,
-                                                          uint32_t total_buckets, const uint32_t *__restrict__ max_tasks, uint32_t s) {
-    if (s >= *max_tasks) return;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= task_off[total_buckets]) return;
-    const uint32_t rank = task_rank[t];
-    if ((rank & (2 * s - 1)) != 0 || rank + s >= task_span[t]) return;
-    XYZZ<F> a = ld_xyzz(partial + t);
-    a.add(ld_xyzz(partial + t + s));
-    st_xyzz(partial + t, a);
+static __global__ void __launch_bounds__(128) msm_fold_small_kernel(XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ task_off,
+                                                                    uint32_t total_buckets, uint32_t *__restrict__ heavy /* [0] = count */) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total_buckets) return;
+    const uint32_t t0 = task_off[b], span = task_off[b + 1] - t0;
+    if (span <= 1) return;
+    if (span > MSM_FOLD_SMALL) {
+        const uint32_t slot = atomicAdd(heavy, 1u);
+        if (slot < MSM_HEAVY_MAX) { heavy[1 + slot] = b; return; }      // (overflow: fall through and fold serially -- still correct)
+    }
+    XYZZ<F> a = ld_xyzz(partial + t0);
+    for (uint32_t k = 1; k < span; k++) a.add(ld_xyzz(partial + t0 + k));
+    st_xyzz(partial + t0, a);
+}
+constexpr int MSM_HEAVY_THREADS = 128;
+template <class F>
+static __global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_fold_heavy_kernel(XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ task_off,
+                                                                                  const uint32_t *__restrict__ heavy) {
+    extern __shared__ uint32_t fold_sm[];
+    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(fold_sm);
+    const uint32_t cnt = min(heavy[0], MSM_HEAVY_MAX);
+    for (uint32_t h = blockIdx.x; h < cnt; h += gridDim.x) {
+        const uint32_t b = heavy[1 + h], t0 = task_off[b], span = task_off[b + 1] - t0;
+        XYZZ<F> a = XYZZ<F>::inf();
+        for (uint32_t k = threadIdx.x; k < span; k += MSM_HEAVY_THREADS) a.add(ld_xyzz(partial + t0 + k));
+        sm[threadIdx.x] = a;
+        __syncthreads();
+        for (int d = MSM_HEAVY_THREADS / 2; d > 0; d >>= 1) {
+            if ((int)threadIdx.x < d) { XYZZ<F> x = sm[threadIdx.x]; x.add(sm[threadIdx.x + d]); sm[threadIdx.x] = x; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) st_xyzz(partial + t0, sm[0]);
+        __syncthreads();
+    }
 }
 template <class F> __device__ __forceinline__ XYZZ<F> msm_bucket(const XYZZ<F> *partial, const uint32_t *task_off, uint32_t b) {
     const uint32_t t0 = __ldg(task_off + b);
@@ -206,20 +268,21 @@ template <class F> __device__ __forceinline__ XYZZ<F> msm_bucket(const XYZZ<F> *
     return ld_xyzz(partial + t0);
 }
 
-// Per window w (blockIdx.y) and segment block (blockIdx.x): every thread owns `seg` consecutive buckets [lo, lo+seg) and computes
+// Per bucket region (blockIdx.y) and CTA (blockIdx.x): every thread owns `seg` consecutive buckets [lo, lo+seg) and computes
 //   S = sum_j B_j   and   T = sum_j (j - lo + 1) * B_j     by the running-sum trick, then contributes  T + lo * S.
-// The CTA's contributions are tree-summed in shared memory; one XYZZ per (window, blockIdx.x) is written.
-// For blockIdx.y == windows the "ones" buckets are summed with weight 1.
-constexpr int MSM_RED_THREADS = 64;
+// The CTA's contributions are tree-summed in shared memory; one XYZZ per (region, blockIdx.x) is written.
+// For blockIdx.y == regions the "ones" buckets are summed with weight 1.
+constexpr int MSM_RED_THREADS = 128;
 template <class F>
-static __global__ void __launch_bounds__(MSM_RED_THREADS) msm_reduce_kernel(const XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ task_off, MsmShape sh,
-                                                                     uint32_t seg, uint32_t blocks_per_window, XYZZ<F> *__restrict__ out) {
+static __global__ void __launch_bounds__(MSM_RED_THREADS) msm_reduce_kernel(const XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ task_off,
+                                                                            MsmShape sh, uint32_t seg, uint32_t blocks_per_region,
+                                                                            XYZZ<F> *__restrict__ out) {
     extern __shared__ uint32_t red_sm[];
     XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(red_sm);
     const uint32_t w = blockIdx.y;
-    const bool ones = (w == (uint32_t)sh.windows);
+    const bool ones = (w == sh.regions);
     const uint32_t count = ones ? sh.ones : sh.nb;
-    const uint32_t base = w * sh.nb;                              // ones region starts at windows*nb as well
+    const uint32_t base = w * sh.nb;                              // the ones region starts at regions*nb as well
     const uint32_t lo = (blockIdx.x * MSM_RED_THREADS + threadIdx.x) * seg;
     XYZZ<F> S = XYZZ<F>::inf(), T = XYZZ<F>::inf();
     if (lo < count) {
@@ -229,7 +292,7 @@ static __global__ void __launch_bounds__(MSM_RED_THREADS) msm_reduce_kernel(cons
             if (!ones) T.add(S);
         }
         if (ones) T = S;
-        else if (lo) T.add(S.mul_small(lo));
+        else if (lo && !S.is_inf()) T.add(S.mul_small(lo));
     }
     sm[threadIdx.x] = T;
     __syncthreads();
@@ -237,7 +300,7 @@ static __global__ void __launch_bounds__(MSM_RED_THREADS) msm_reduce_kernel(cons
         if ((int)threadIdx.x < d) { XYZZ<F> a = sm[threadIdx.x]; a.add(sm[threadIdx.x + d]); sm[threadIdx.x] = a; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) st_xyzz(out + (size_t)w * blocks_per_window + blockIdx.x, sm[0]);
+    if (threadIdx.x == 0) st_xyzz(out + (size_t)w * blocks_per_region + blockIdx.x, sm[0]);
 }
 
 } // namespace zk

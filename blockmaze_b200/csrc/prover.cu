@@ -287,9 +287,11 @@ static void decompress_vec(const std::vector<C> &v, A **out, uint8_t **skip, boo
 
 // =====================================================================================================================
 // MSM
-void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2) {
-    n = n_; c = c_; windows = (255 + c - 1) / c; nb = 1u << (c - 1); ones = ones_; total = windows * nb + ones;
-    seg = 16; if (seg > nb) seg = nb;
+void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool expanded_) {
+    n = n_; c = c_; windows = (255 + c - 1) / c; nb = 1u << (c - 1); ones = ones_; expanded = expanded_;
+    regions = expanded ? 1u : (uint32_t)windows;
+    total = regions * nb + ones;
+    seg = 4; if (seg > nb) seg = nb;
     const uint32_t widest = nb > ones ? nb : ones;
     bpw = cdiv(cdiv(widest, seg), MSM_RED_THREADS);
     ZK_CUDA(cudaMalloc(&counts, (size_t)(total + 1) * 4));
@@ -298,15 +300,11 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2) {
     entries_cap = (size_t)n * windows + 16;
     ZK_CUDA(cudaMalloc(&entries, entries_cap * 4));
     task_cap = total + (uint32_t)(((size_t)n * windows) / MSM_TASK) + 1;
-    combine_passes = 0;
-    for (uint32_t p = cdiv(n ? n : 1, MSM_TASK); p > 1; p = (p + 1) / 2) combine_passes++;
     ZK_CUDA(cudaMalloc(&task_counts, (size_t)(total + 1) * 4));
     ZK_CUDA(cudaMalloc(&task_off, (size_t)(total + 1) * 4));
-    ZK_CUDA(cudaMalloc(&task_rank, (size_t)task_cap * 4));
-    ZK_CUDA(cudaMalloc(&task_span, (size_t)task_cap * 4));
-    ZK_CUDA(cudaMalloc(&max_tasks, 4));
+    ZK_CUDA(cudaMalloc(&heavy, (size_t)(MSM_HEAVY_MAX + 1) * 4));
     ZK_CUDA(cudaEventCreate(&ev_acc0)); ZK_CUDA(cudaEventCreate(&ev_acc1));
-    const size_t nout = (size_t)(windows + 1) * bpw;
+    const size_t nout = (size_t)(regions + 1) * bpw;
     if (g1) {
         ZK_CUDA(cudaMalloc(&buckets_g1, (size_t)task_cap * sizeof(G1XYZZ)));
         ZK_CUDA(cudaMalloc(&out_g1, nout * sizeof(G1XYZZ)));
@@ -320,7 +318,7 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2) {
 }
 float MsmPlan::last_acc_ms() const { float ms = 0; if (ev_acc0) cudaEventElapsedTime(&ms, ev_acc0, ev_acc1); return ms; }
 void MsmPlan::release() {
-    void *ps[] = {counts, offsets, cursors, entries, buckets_g1, buckets_g2, out_g1, out_g2, task_counts, task_off, task_rank, task_span, max_tasks};
+    void *ps[] = {counts, offsets, cursors, entries, buckets_g1, buckets_g2, out_g1, out_g2, task_counts, task_off, heavy};
     for (void *p : ps) if (p) cudaFree(p);
     if (ev_acc0) cudaEventDestroy(ev_acc0);
     if (ev_acc1) cudaEventDestroy(ev_acc1);
@@ -329,50 +327,57 @@ void MsmPlan::release() {
     *this = MsmPlan();
 }
 
+// out[k*n + i] = 2^(c*k) * in[i]  (device -> device), the fixed-base table of an `expanded` plan
+void *msm_expand_bases(const void *bases, uint32_t n, int c, bool g2) {
+    const int windows = (255 + c - 1) / c;
+    void *out;
+    const size_t pt = g2 ? sizeof(G2Affine) : sizeof(G1Affine);
+    ZK_CUDA(cudaMalloc(&out, (size_t)windows * (n ? n : 1) * pt));
+    if (n) {
+        if (g2) msm_expand_bases_kernel<Fq2><<<cdiv(n, 128), 128>>>((const G2Affine *)bases, n, c, windows, (G2Affine *)out);
+        else msm_expand_bases_kernel<Fq><<<cdiv(n, 128), 128>>>((const G1Affine *)bases, n, c, windows, (G1Affine *)out);
+        ZK_CUDA(cudaGetLastError());
+    }
+    return out;
+}
+
+template <class F>
+static void msm_points(cudaStream_t st, MsmPlan &p, const MsmShape &sh, const Affine<F> *bases, XYZZ<F> *partial, XYZZ<F> *out, void *h_out, bool timed) {
+    const uint32_t *toff = (const uint32_t *)p.task_off;
+    ZK_CUDA(cudaMemsetAsync(p.heavy, 0, 4, st));
+    if (timed) ZK_CUDA(cudaEventRecord(p.ev_acc0, st));
+    ZK_LAUNCH(msm_accumulate_kernel<F>, cdiv(p.task_cap, 128), 128, 0, st, bases, (const uint32_t *)p.offsets, (const uint32_t *)p.entries, toff, p.total,
+              partial);
+    if (timed) ZK_CUDA(cudaEventRecord(p.ev_acc1, st));
+    ZK_LAUNCH(msm_fold_small_kernel<F>, cdiv(p.total, 128), 128, 0, st, partial, toff, p.total, (uint32_t *)p.heavy);
+    ZK_LAUNCH(msm_fold_heavy_kernel<F>, 64, MSM_HEAVY_THREADS, MSM_HEAVY_THREADS * sizeof(XYZZ<F>), st, partial, toff, (const uint32_t *)p.heavy);
+    const dim3 rgrid(p.bpw, sh.regions + 1);
+    ZK_LAUNCH(msm_reduce_kernel<F>, rgrid, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(XYZZ<F>), st, (const XYZZ<F> *)partial, toff, sh, p.seg, p.bpw, out);
+    ZK_CUDA(cudaMemcpyAsync(h_out, out, (size_t)(sh.regions + 1) * p.bpw * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+}
+
 void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, const void *bases_g1, const void *bases_g2) {
-    const MsmShape sh = msm_shape(p.c, p.ones);
+    const MsmShape sh = msm_shape(p.n, p.c, p.ones, p.expanded ? 1 : 0);
     ScalarSrc src{(const uint32_t *)sc.scalars, sc.map, sc.offset, sc.montgomery};
     ZK_CUDA(cudaMemsetAsync(p.counts, 0, (size_t)(p.total + 1) * 4, st));
     ZK_CUDA(cudaMemsetAsync(p.cursors, 0, (size_t)(p.total + 1) * 4, st));
-    if (p.n) ZK_LAUNCH(msm_count_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, p.n, sh, (uint32_t *)p.counts);
+    if (p.n) ZK_LAUNCH(msm_count_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (uint32_t *)p.counts);
     ZK_LAUNCH(msm_scan_kernel, 1, 1024, 0, st, (const uint32_t *)p.counts, (uint32_t *)p.offsets, p.total);
-    if (p.n) ZK_LAUNCH(msm_scatter_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, p.n, sh, (const uint32_t *)p.offsets, (uint32_t *)p.cursors,
-                       (uint32_t *)p.entries);
-    ZK_CUDA(cudaMemsetAsync(p.max_tasks, 0, 4, st));
-    ZK_LAUNCH(msm_task_count_kernel, cdiv(p.total, 256), 256, 0, st, (const uint32_t *)p.offsets, p.total, (uint32_t *)p.task_counts,
-              (uint32_t *)p.max_tasks);
+    if (p.n) ZK_LAUNCH(msm_scatter_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (const uint32_t *)p.offsets, (uint32_t *)p.cursors, (uint32_t *)p.entries);
+    ZK_LAUNCH(msm_task_count_kernel, cdiv(p.total, 256), 256, 0, st, (const uint32_t *)p.offsets, p.total, (uint32_t *)p.task_counts);
     ZK_LAUNCH(msm_scan_kernel, 1, 1024, 0, st, (const uint32_t *)p.task_counts, (uint32_t *)p.task_off, p.total);
-    const dim3 rgrid(p.bpw, sh.windows + 1);
-    const size_t nout = (size_t)(sh.windows + 1) * p.bpw;
-    const uint32_t *toff = (const uint32_t *)p.task_off, *trank = (const uint32_t *)p.task_rank, *tspan = (const uint32_t *)p.task_span;
-    if (bases_g1) {
-        ZK_CUDA(cudaEventRecord(p.ev_acc0, st));
-        ZK_LAUNCH(msm_accumulate_kernel<Fq>, cdiv(p.task_cap, 128), 128, 0, st, (const G1Affine *)bases_g1, (const uint32_t *)p.offsets,
-                  (const uint32_t *)p.entries, toff, p.total, (G1XYZZ *)p.buckets_g1, (uint32_t *)p.task_rank, (uint32_t *)p.task_span);
-        ZK_CUDA(cudaEventRecord(p.ev_acc1, st));
-        for (uint32_t k = 0; k < p.combine_passes; k++)
-            ZK_LAUNCH(msm_combine_kernel<Fq>, cdiv(p.task_cap, 128), 128, 0, st, (G1XYZZ *)p.buckets_g1, trank, tspan, toff, p.total,
-                      (const uint32_t *)p.max_tasks, 1u << k);
-        ZK_LAUNCH(msm_reduce_kernel<Fq>, rgrid, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(G1XYZZ), st, (const G1XYZZ *)p.buckets_g1, toff, sh, p.seg,
-                  p.bpw, (G1XYZZ *)p.out_g1);
-        ZK_CUDA(cudaMemcpyAsync(p.h_out_g1, p.out_g1, nout * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, st));
-    }
-    if (bases_g2) {
-        ZK_LAUNCH(msm_accumulate_kernel<Fq2>, cdiv(p.task_cap, 128), 128, 0, st, (const G2Affine *)bases_g2, (const uint32_t *)p.offsets,
-                  (const uint32_t *)p.entries, toff, p.total, (G2XYZZ *)p.buckets_g2, (uint32_t *)p.task_rank, (uint32_t *)p.task_span);
-        for (uint32_t k = 0; k < p.combine_passes; k++)
-            ZK_LAUNCH(msm_combine_kernel<Fq2>, cdiv(p.task_cap, 128), 128, 0, st, (G2XYZZ *)p.buckets_g2, trank, tspan, toff, p.total,
-                      (const uint32_t *)p.max_tasks, 1u << k);
-        ZK_LAUNCH(msm_reduce_kernel<Fq2>, rgrid, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(G2XYZZ), st, (const G2XYZZ *)p.buckets_g2, toff, sh, p.seg,
-                  p.bpw, (G2XYZZ *)p.out_g2);
-        ZK_CUDA(cudaMemcpyAsync(p.h_out_g2, p.out_g2, nout * sizeof(G2XYZZ), cudaMemcpyDeviceToHost, st));
-    }
+    if (bases_g1) msm_points<Fq>(st, p, sh, (const G1Affine *)bases_g1, (G1XYZZ *)p.buckets_g1, (G1XYZZ *)p.out_g1, p.h_out_g1, true);
+    if (bases_g2) msm_points<Fq2>(st, p, sh, (const G2Affine *)bases_g2, (G2XYZZ *)p.buckets_g2, (G2XYZZ *)p.out_g2, p.h_out_g2, false);
 }
 
 template <class P> static P msm_finish(const MsmPlan &p, const void *h_out) {
     const P *part = (const P *)h_out;
     P acc = P::inf();
-    for (int w = p.windows - 1; w >= 0; w--) {
+    if (p.expanded) {
+        for (uint32_t b = 0; b < 2 * p.bpw; b++) acc = acc.add(part[b]);       // the single bucket region, then the ones region
+        return acc;
+    }
+    for (int w = p.windows - 1; w >= 0; w--) {                                  // windowed layout: Horner over the per-window sums
         for (int i = 0; i < p.c; i++) acc = acc.dbl();
         for (uint32_t b = 0; b < p.bpw; b++) acc = acc.add(part[(size_t)w * p.bpw + b]);
     }
@@ -393,12 +398,7 @@ static void upload_csr(const zkpk::Csr &h, DeviceCsr &d) {
     ZK_CUDA(cudaMemcpy(d.col, h.col.data(), (size_t)d.nnz * 4, cudaMemcpyHostToDevice));
     ZK_CUDA(cudaMemcpy(d.coef, h.coef.data(), (size_t)d.nnz * 4, cudaMemcpyHostToDevice));
 }
-static int pick_window(uint32_t n) {       // dense 254-bit scalars: about log2(n) - 4, clamped
-    int c = ilog2_ceil(n ? n : 1) - 4;
-    if (c < 6) c = 6;
-    if (c > 16) c = 16;
-    return c;
-}
+constexpr int MSM_C = 16;                  // window bits of the resident (expanded) MSMs: 16 windows, 32768 buckets
 
 template <class A> static A fetch_point(const void *dev, size_t idx) {
     A a; ZK_CUDA(cudaMemcpy(&a, (const char *)dev + idx * sizeof(A), sizeof(A), cudaMemcpyDeviceToHost)); return a;
@@ -442,20 +442,46 @@ DevicePk *pk_load(const char *path, int device, std::string &err) {
     decompress_vec<zkpk::CompressedG2, G2Affine>(fixed2, &f2, nullptr, true, d_bad, k);
     pk->alpha_g1 = fetch_point<HG1Affine>(f1, 0); pk->beta_g1 = fetch_point<HG1Affine>(f1, 1); pk->delta_g1 = fetch_point<HG1Affine>(f1, 2);
     pk->beta_g2 = fetch_point<HG2Affine>(f2, 0); pk->delta_g2 = fetch_point<HG2Affine>(f2, 1);
-    cudaFree(f1); cudaFree(f2);
     uint32_t bad = 0; ZK_CUDA(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost)); cudaFree(d_bad);
     pk->decompress_seconds = now_s() - t2;
     if (bad) { err = "proving key holds " + std::to_string(bad) + " x-coordinates that are not on the curve"; pk_free(pk); return nullptr; }
     pk->nA = (uint32_t)P.A.size(); pk->nB = (uint32_t)P.B_g1.size(); pk->nH = (uint32_t)P.H.size(); pk->nL = (uint32_t)P.L.size();
+    // The zero-knowledge terms r*delta_g1, s*(delta_g2, delta_g1), -(r*s)*delta_g1 ride along in the A, B, L MSMs: delta is appended as
+    // one more base (decompress_vec left room), its scalar sits after the assignment in w_can = [1 | w | r | s | -rs].
+    const uint32_t nw1 = (uint32_t)pk->num_vars + 1;                 // index of r in w_can; s = nw1 + 1; -rs = nw1 + 2
+    const G1Affine d1 = fetch_point<G1Affine>(f1, 2); const G2Affine d2 = fetch_point<G2Affine>(f2, 1);
+    const uint8_t zero8 = 0;
+    ZK_CUDA(cudaMemcpy((G1Affine *)pk->A + pk->nA, &d1, sizeof d1, cudaMemcpyHostToDevice)); ZK_CUDA(cudaMemcpy(pk->A_skip + pk->nA, &zero8, 1, cudaMemcpyHostToDevice));
+    ZK_CUDA(cudaMemcpy((G1Affine *)pk->B1 + pk->nB, &d1, sizeof d1, cudaMemcpyHostToDevice)); ZK_CUDA(cudaMemcpy(pk->B_skip + pk->nB, &zero8, 1, cudaMemcpyHostToDevice));
+    ZK_CUDA(cudaMemcpy((G2Affine *)pk->B2 + pk->nB, &d2, sizeof d2, cudaMemcpyHostToDevice));
+    ZK_CUDA(cudaMemcpy((G1Affine *)pk->L + pk->nL, &d1, sizeof d1, cudaMemcpyHostToDevice)); ZK_CUDA(cudaMemcpy(pk->L_skip + pk->nL, &zero8, 1, cudaMemcpyHostToDevice));
     // a B entry whose G1 half is infinity but G2 half is not cannot be expressed with one skip flag; libsnark never emits one
-    ZK_CUDA(cudaMalloc(&pk->B_idx, (size_t)(pk->nB + 1) * 4));
-    ZK_CUDA(cudaMemcpy(pk->B_idx, P.B_idx.data(), (size_t)pk->nB * 4, cudaMemcpyHostToDevice));
+    std::vector<uint32_t> bidx(P.B_idx); bidx.push_back(nw1 + 1);
+    ZK_CUDA(cudaMalloc(&pk->B_idx, bidx.size() * 4));
+    ZK_CUDA(cudaMemcpy(pk->B_idx, bidx.data(), bidx.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<uint32_t> lidx(pk->nL + 1);
+    for (uint32_t i = 0; i < pk->nL; i++) lidx[i] = (uint32_t)pk->num_inputs + 1 + i;
+    lidx[pk->nL] = nw1 + 2;
+    ZK_CUDA(cudaMalloc(&pk->L_idx, lidx.size() * 4));
+    ZK_CUDA(cudaMemcpy(pk->L_idx, lidx.data(), lidx.size() * 4, cudaMemcpyHostToDevice));
+    pk->nA += 1; pk->nB += 1; pk->nL += 1;
+    cudaFree(f1); cudaFree(f2);
+    // fixed-base tables: 2^(16k) * P for every window k, so each MSM needs a single bucket set and no Horner step
+    const double t3 = now_s();
+    { void *e;
+      e = msm_expand_bases(pk->A, pk->nA, MSM_C, false); cudaFree(pk->A); pk->A = e;
+      e = msm_expand_bases(pk->B1, pk->nB, MSM_C, false); cudaFree(pk->B1); pk->B1 = e;
+      e = msm_expand_bases(pk->B2, pk->nB, MSM_C, true); cudaFree(pk->B2); pk->B2 = e;
+      e = msm_expand_bases(pk->H, pk->nH, MSM_C, false); cudaFree(pk->H); pk->H = e;
+      e = msm_expand_bases(pk->L, pk->nL, MSM_C, false); cudaFree(pk->L); pk->L = e;
+      ZK_CUDA(cudaDeviceSynchronize()); }
+    pk->expand_seconds = now_s() - t3;
 
     upload_csr(P.a, pk->a); upload_csr(P.b, pk->b); upload_csr(P.c, pk->c);
     pk->ncoef = (uint32_t)P.coef_dict.size();
     pk->coef_dict = dev_const(P.coef_dict.data(), P.coef_dict.size());
 
-    const size_t nw = pk->num_vars + 1, m = pk->dom->m;
+    const size_t nw = pk->num_vars + 4, m = pk->dom->m;            // [1 | w | r | s | -rs]
     ZK_CUDA(cudaMalloc(&pk->w_can, nw * 32)); ZK_CUDA(cudaMalloc(&pk->w_mont, nw * 32));
     ZK_CUDA(cudaMemset(pk->w_can, 0, nw * 32));
     const uint64_t one_can[4] = {1, 0, 0, 0};
@@ -466,10 +492,10 @@ DevicePk *pk_load(const char *path, int device, std::string &err) {
     ZK_CUDA(cudaMalloc(&pk->sat_flag, 4)); ZK_CUDA(cudaMallocHost(&pk->h_sat_flag, 4));
 
     // witness MSMs: ~97 % of the scalars are 0/1 and nearly all others are <= 64 bits, so small windows; H is dense
-    pk->mA.init(pk->nA, 11, 4096, true, false);
-    pk->mB.init(pk->nB, 11, 4096, true, true);
-    pk->mL.init(pk->nL, 11, 4096, true, false);
-    pk->mH.init(pk->nH, pick_window(pk->nH), 0, true, false);
+    pk->mA.init(pk->nA, MSM_C, 4096, true, false, true);
+    pk->mB.init(pk->nB, MSM_C, 4096, true, true, true);
+    pk->mL.init(pk->nL, MSM_C, 4096, true, false, true);
+    pk->mH.init(pk->nH, MSM_C, 0, true, false, true);
 
     ZK_CUDA(cudaStreamCreateWithFlags(&pk->s_main, cudaStreamNonBlocking)); ZK_CUDA(cudaStreamCreateWithFlags(&pk->s_a, cudaStreamNonBlocking));
     ZK_CUDA(cudaStreamCreateWithFlags(&pk->s_b, cudaStreamNonBlocking)); ZK_CUDA(cudaStreamCreateWithFlags(&pk->s_l, cudaStreamNonBlocking));
@@ -486,7 +512,7 @@ void pk_free(DevicePk *pk) {
     if (!pk) return;
     cudaSetDevice(pk->device);
     cudaDeviceSynchronize();
-    void *ps[] = {pk->A, pk->B1, pk->B2, pk->H, pk->L, pk->A_skip, pk->B_skip, pk->H_skip, pk->L_skip, pk->B_idx, pk->a.rowptr, pk->a.col, pk->a.coef,
+    void *ps[] = {pk->A, pk->B1, pk->B2, pk->H, pk->L, pk->A_skip, pk->B_skip, pk->H_skip, pk->L_skip, pk->B_idx, pk->L_idx, pk->a.rowptr, pk->a.col, pk->a.coef,
                   pk->b.rowptr, pk->b.col, pk->b.coef, pk->c.rowptr, pk->c.col, pk->c.coef, pk->coef_dict, pk->w_can, pk->w_mont, pk->bufA, pk->bufB,
                   pk->bufC, pk->tmp, pk->sat_flag};
     for (void *p : ps) if (p) cudaFree(p);
@@ -503,11 +529,15 @@ void pk_free(DevicePk *pk) {
 
 // =====================================================================================================================
 // the per-proof pipeline
-static void upload_assignment(DevicePk *pk, const uint8_t *assignment, cudaStream_t st) {
+static void upload_assignment(DevicePk *pk, const uint8_t *assignment, const uint64_t *zk_scalars /* r, s, -rs or null */, cudaStream_t st) {
     const size_t n = pk->num_vars;
+    char *pin = (char *)pk->h_w_pinned;
+    if (zk_scalars) memcpy(pin + n * 32, zk_scalars, 96);
     if (assignment) {
-        memcpy(pk->h_w_pinned, assignment, n * 32);
-        ZK_CUDA(cudaMemcpyAsync((char *)pk->w_can + 32, pk->h_w_pinned, n * 32, cudaMemcpyHostToDevice, st));
+        memcpy(pin, assignment, n * 32);
+        ZK_CUDA(cudaMemcpyAsync((char *)pk->w_can + 32, pin, n * 32 + (zk_scalars ? 96 : 0), cudaMemcpyHostToDevice, st));
+    } else if (zk_scalars) {
+        ZK_CUDA(cudaMemcpyAsync((char *)pk->w_can + 32 + n * 32, pin + n * 32, 96, cudaMemcpyHostToDevice, st));
     }
     ZK_CUDA(cudaMemcpyAsync(pk->w_mont, pk->w_can, (n + 1) * 32, cudaMemcpyDeviceToDevice, st));
     ZK_LAUNCH(to_mont_kernel, cdiv(n + 1, 256), 256, 0, st, (Fr *)pk->w_mont, (uint32_t)(n + 1));
@@ -543,7 +573,7 @@ static void qap_pipeline(DevicePk *pk, cudaStream_t st) {
 int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied) {
     device_init(pk->device);
     cudaStream_t st = pk->s_main;
-    upload_assignment(pk, assignment, st);
+    upload_assignment(pk, assignment, nullptr, st);
     qap_pipeline(pk, st);
     const uint32_t m = pk->dom->m;
     ZK_LAUNCH(from_mont_kernel, cdiv(m, 256), 256, 0, st, (const Fr *)pk->tmp, (Fr *)pk->bufB, m);
@@ -560,16 +590,20 @@ int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const ui
     device_init(pk->device);
     g_launches = 0;
     cudaStream_t st = pk->s_main;
+    uint64_t zks[12];
+    memcpy(zks, r, 32); memcpy(zks + 4, s, 32);
+    (HFr::from_canonical(r) * HFr::from_canonical(s)).neg().to_canonical(zks + 8);          // -(r*s) mod r
     ZK_CUDA(cudaEventRecord(pk->ev_t0, st));
-    upload_assignment(pk, assignment, st);
+    upload_assignment(pk, assignment, zks, st);
     ZK_CUDA(cudaEventRecord(pk->ev_w, st));
     ZK_CUDA(cudaStreamWaitEvent(pk->s_a, pk->ev_w, 0));
     ZK_CUDA(cudaStreamWaitEvent(pk->s_b, pk->ev_w, 0));
     ZK_CUDA(cudaStreamWaitEvent(pk->s_l, pk->ev_w, 0));
-    // A, B, L queries: scalars are the canonical padded assignment [1 | w]  (r1cs_gg_ppzksnark.tcc:437-484)
+    // A, B, L queries: scalars are the canonical padded assignment [1 | w]  (r1cs_gg_ppzksnark.tcc:437-484); the trailing delta base of
+    // each query picks up r, s, -rs, so the MSM results already are  eA + r*delta,  eB + s*delta,  eL - rs*delta.
     msm_run(pk->s_a, pk->mA, ScalarRef{pk->w_can, nullptr, 0, 0}, pk->A_skip, pk->A, nullptr);
     msm_run(pk->s_b, pk->mB, ScalarRef{pk->w_can, pk->B_idx, 0, 0}, pk->B_skip, pk->B1, pk->B2);
-    msm_run(pk->s_l, pk->mL, ScalarRef{pk->w_can, nullptr, (uint32_t)pk->num_inputs + 1, 0}, pk->L_skip, pk->L, nullptr);
+    msm_run(pk->s_l, pk->mL, ScalarRef{pk->w_can, pk->L_idx, 0, 0}, pk->L_skip, pk->L, nullptr);
     ZK_CUDA(cudaEventRecord(pk->ev_a, pk->s_a)); ZK_CUDA(cudaEventRecord(pk->ev_b, pk->s_b)); ZK_CUDA(cudaEventRecord(pk->ev_l, pk->s_l));
     // H: QAP witness map, then the dense MSM over coefficients_for_H[0 .. m-1)
     ZK_CUDA(cudaEventRecord(pk->ev_q0, st));
@@ -587,15 +621,21 @@ int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const ui
     out.acc_h_ms = pk->mH.last_acc_ms();
     out.satisfied = (*pk->h_sat_flag == 0);
 
-    // host: Horner over the per-window sums, then the proof combination (r1cs_gg_ppzksnark.tcc:487-495)
-    const HG1 eA = msm_finish_g1(pk->mA), eB1 = msm_finish_g1(pk->mB), eH = msm_finish_g1(pk->mH), eL = msm_finish_g1(pk->mL);
-    const HG2 eB2 = msm_finish_g2(pk->mB);
-    out.At = eA.to_affine(); out.Bt_h = eB1.to_affine(); out.Ht = eH.to_affine(); out.Lt = eL.to_affine(); out.Bt_g = eB2.to_affine();
-    uint64_t rs[4]; (HFr::from_canonical(r) * HFr::from_canonical(s)).to_canonical(rs);
-    const HG1 gA = HG1::from_affine(pk->alpha_g1).add(eA).add(g1_mul(pk->delta_g1, r));
-    const HG1 g1B = HG1::from_affine(pk->beta_g1).add(eB1).add(g1_mul(pk->delta_g1, s));
-    const HG2 g2B = HG2::from_affine(pk->beta_g2).add(eB2).add(HG2::from_affine(pk->delta_g2).mul(s));
-    const HG1 gC = eH.add(eL).add(gA.mul(s)).add(g1B.mul(r)).add(g1_mul(pk->delta_g1, rs).neg());
+    // host: add up the handful of partial sums per MSM, then the proof combination (r1cs_gg_ppzksnark.tcc:487-495)
+    const HG1 eAr = msm_finish_g1(pk->mA), eB1s = msm_finish_g1(pk->mB), eH = msm_finish_g1(pk->mH), eLrs = msm_finish_g1(pk->mL);
+    const HG2 eB2s = msm_finish_g2(pk->mB);
+    if (out.want_parts) {
+        // the five plain MSM values of the reference (parity hooks): strip the folded zero-knowledge terms again
+        const HG1 rd = g1_mul(pk->delta_g1, r).neg(), sd = g1_mul(pk->delta_g1, s).neg();
+        uint64_t rs[4]; (HFr::from_canonical(r) * HFr::from_canonical(s)).to_canonical(rs);
+        out.At = eAr.add(rd).to_affine(); out.Bt_h = eB1s.add(sd).to_affine(); out.Ht = eH.to_affine();
+        out.Lt = eLrs.add(g1_mul(pk->delta_g1, rs)).to_affine();
+        out.Bt_g = eB2s.add(HG2::from_affine(pk->delta_g2).mul(s).neg()).to_affine();
+    }
+    const HG1 gA = HG1::from_affine(pk->alpha_g1).add(eAr);
+    const HG1 g1B = HG1::from_affine(pk->beta_g1).add(eB1s);
+    const HG2 g2B = HG2::from_affine(pk->beta_g2).add(eB2s);
+    const HG1 gC = eH.add(eLrs).add(gA.mul(s)).add(g1B.mul(r));
     out.A = gA.to_affine(); out.B = g2B.to_affine(); out.C = gC.to_affine();
     return 0;
 }

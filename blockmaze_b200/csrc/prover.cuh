@@ -47,21 +47,24 @@ struct MsmPlan {
     uint32_t ones_bpw = 0;
     void *counts = nullptr, *offsets = nullptr, *cursors = nullptr, *entries = nullptr;
     size_t entries_cap = 0;
-    void *task_counts = nullptr, *task_off = nullptr, *task_rank = nullptr, *task_span = nullptr, *max_tasks = nullptr;
-    uint32_t task_cap = 0, combine_passes = 0;
+    bool expanded = false;      // bases hold 2^(c*k)*P for every window k: one bucket region, no Horner
+    uint32_t regions = 0;
+    void *task_counts = nullptr, *task_off = nullptr, *heavy = nullptr;
+    uint32_t task_cap = 0;
     void *buckets_g1 = nullptr, *buckets_g2 = nullptr;   // per-task partial sums
     void *out_g1 = nullptr, *out_g2 = nullptr;           // device partial sums  [(windows+1) * bpw]
     void *h_out_g1 = nullptr, *h_out_g2 = nullptr;       // pinned host copies
     cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr;    // around the G1 accumulate kernel (roofline measurement)
     float last_acc_ms() const;
-    void init(uint32_t n, int c, uint32_t ones, bool g1, bool g2);
+    void init(uint32_t n, int c, uint32_t ones, bool g1, bool g2, bool expanded);
     void release();
 };
 struct ScalarRef { const void *scalars; const uint32_t *map; uint32_t offset; int montgomery; };
 // sort digits (count / scan / scatter) then accumulate+reduce for G1 and/or G2 bases; results land in plan.h_out_* after
 // the stream is synchronised.
 void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, const void *bases_g1, const void *bases_g2);
-zkh::HG1 msm_finish_g1(const MsmPlan &p);      // host: per-window sums -> Horner
+void *msm_expand_bases(const void *bases, uint32_t n, int c, bool g2);   // device table out[k*n+i] = 2^(c*k) * bases[i]
+zkh::HG1 msm_finish_g1(const MsmPlan &p);      // host: add the partial sums (windowed layout: Horner over windows)
 zkh::HG2 msm_finish_g2(const MsmPlan &p);
 
 // ---- proving key resident on one GPU -------------------------------------------------------------------------------------
@@ -74,7 +77,7 @@ struct DevicePk {
     void *A = nullptr, *B1 = nullptr, *B2 = nullptr, *H = nullptr, *L = nullptr;
     uint8_t *A_skip = nullptr, *B_skip = nullptr, *H_skip = nullptr, *L_skip = nullptr;
     uint32_t nA = 0, nB = 0, nH = 0, nL = 0;
-    uint32_t *B_idx = nullptr;
+    uint32_t *B_idx = nullptr, *L_idx = nullptr;
     zkh::HG1Affine alpha_g1, beta_g1, delta_g1;
     zkh::HG2Affine beta_g2, delta_g2;
     DeviceCsr a, b, c;
@@ -88,7 +91,7 @@ struct DevicePk {
     cudaStream_t s_main = nullptr, s_a = nullptr, s_b = nullptr, s_l = nullptr;
     cudaEvent_t ev_w = nullptr, ev_a = nullptr, ev_b = nullptr, ev_l = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_q0 = nullptr, ev_q1 = nullptr,
                 ev_h0 = nullptr, ev_h1 = nullptr;
-    double load_seconds = 0, parse_seconds = 0, decompress_seconds = 0;
+    double load_seconds = 0, parse_seconds = 0, decompress_seconds = 0, expand_seconds = 0;
 };
 
 DevicePk *pk_load(const char *path, int device, std::string &err);
@@ -98,6 +101,7 @@ struct ProofPoints {
     zkh::HG1Affine A, C; zkh::HG2Affine B;
     zkh::HG1Affine At, Bt_h, Ht, Lt; zkh::HG2Affine Bt_g;   // the five MSM results (parity hooks)
     bool satisfied = true;
+    bool want_parts = false;                            // also compute the five plain MSM values (costs four host scalar multiplications)
     float gpu_ms = 0, qap_ms = 0, msm_h_ms = 0, acc_h_ms = 0;   // CUDA-event timings of the last run (acc_h: H accumulate kernel)
 };
 // assignment: num_vars canonical 32-byte LE scalars in HOST memory (copied H2D inside), or nullptr to reuse the

@@ -77,7 +77,7 @@ void zkb200_set_random_words(const uint32_t *words, size_t n_words);
 void *zkb200_pk_load(const char *path);
 void zkb200_pk_free(void *pk);
 /* info[0..7] = num_variables, num_inputs, num_constraints, domain m, domain kind (0 basic_radix2, 1 step_radix2),
- * nnz(A)+nnz(B)+nnz(C), distinct coefficients, B_query entries.  seconds[0..2] = total load, parse, GPU decompression. */
+ * nnz(A)+nnz(B)+nnz(C), distinct coefficients, B_query entries.  seconds[0..2] = total load, parse, GPU decompression + fixed-base table expansion. */
 int zkb200_pk_info(void *pk, uint64_t info[8], double seconds[3]);
 const char *zkb200_last_error(void);
 
@@ -90,6 +90,8 @@ int zkb200_prove(void *pk, const uint8_t *assignment, const uint8_t r[32], const
                  float *timings_ms);
 /* Replaces r1cs_to_qap_witness_map (r1cs_to_qap.tcc:205-334): out_H receives (m+1) x 32 B coefficients_for_H. */
 int zkb200_qap_witness_map(void *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied);
+/* milliseconds of the last gen*proof call: host witness generation, zkb200_prove total, of which GPU (CUDA events), host finish */
+void zkb200_last_breakdown_ms(double out[4]);
 /* kernels launched by the last zkb200_prove call */
 int zkb200_last_launches(void);
 
@@ -124,7 +126,9 @@ int zkb200_field_op(int field, int op, size_t n, const uint8_t *a, const uint8_t
 
 /* Device-resident benchmarks (inputs generated / kept in HBM, timed with CUDA events on the launching stream).
  * zkb200_bench_ntt: `iters` forward size-2^logn transforms over a buffer of `batch` independent vectors; returns ms per transform.
- * zkb200_bench_msm: dense 254-bit MSM over n synthetic bases (group: 1 = G1, 2 = G2); returns ms per MSM. */
+ * zkb200_bench_msm: dense 254-bit MSM over n synthetic bases (group: 1 = G1, 2 = G2); returns ms per MSM.  window_bits > 0:
+ * windowed layout (bases as given, Horner on the host); window_bits < 0: fixed-base layout with |window_bits| bits (the table
+ * 2^(c*k)*P is built once outside the timed region, as for a resident proving key); 0: default windowed. */
 float zkb200_bench_ntt(int logn, int batch, int iters);
 float zkb200_bench_msm(int group, size_t n, int window_bits, int iters);
 /* bench hygiene: overwrite a 256 MB scratch buffer (2x L2) and synchronise; plain cudaDeviceSynchronize */

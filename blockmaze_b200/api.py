@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzkb200.so")
+LIB_PATH = os.environ.get("ZKB200_LIB") or os.path.join(_HERE, "libzkb200.so")
 CIRCUITS = ("mint", "send", "deposit", "redeem")
 
 if not os.path.exists(LIB_PATH):

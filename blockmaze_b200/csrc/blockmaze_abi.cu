@@ -79,24 +79,22 @@ static char *dup_hex(const std::string &s, size_t cap) {       // `new char[cap]
     memcpy(p, s.data(), s.size() < cap - 1 ? s.size() : cap - 1);
     return p;
 }
+// gen*proof core: the witness is generated straight into the proving key's pinned staging buffer (no intermediate copy), then proved
 template <class Fn> static char *prove_timed(int circuit, Fn make) {
-    const double t0 = now_ms();
-    const Assignment a = make();
-    g_last_ms[0] = now_ms() - t0;
-    extern char *zk_prove_with(int, const Assignment &);
-    return zk_prove_with(circuit, a);
-}
-char *zk_prove_with(int circuit, const Assignment &a) {
     std::lock_guard<std::mutex> lk(g_abi_mu);
     void *pk = circuit_pk(circuit);
+    uint64_t *ext = reinterpret_cast<uint64_t *>(zkp::pinned_assignment((zkp::DevicePk *)pk)) - 4;      // variable 0 (ONE) sits in the pad slot
+    const double t0 = now_ms();
+    const Assignment a = make(ext);
+    g_last_ms[0] = now_ms() - t0;
     uint64_t r[4], s[4];
     next_random_fr(r); next_random_fr(s);                      // r first, then s (r1cs_gg_ppzksnark.tcc:418-419)
     char *p = new char[1153];                                  // the reference returns new char[1153] with 512 hex chars (mintcgo.cpp:316-320)
     memset(p, 0, 1153);
     float tm[5] = {0, 0, 0, 0, 0};
-    const double t0 = now_ms();
+    const double t1 = now_ms();
     const int rc = zkb200_prove(pk, a.data(), (const uint8_t *)r, (const uint8_t *)s, p, nullptr, tm);
-    g_last_ms[1] = now_ms() - t0; g_last_ms[2] = tm[0]; g_last_ms[3] = tm[3];
+    g_last_ms[1] = now_ms() - t1; g_last_ms[2] = tm[0]; g_last_ms[3] = tm[3];
     if (rc == 1) printf("can not generate %s proof\n", CIRCUIT_NAMES[circuit]);      // mintcgo.cpp:209
     return p;
 }
@@ -154,7 +152,7 @@ char *genMintproof(uint64_t value, uint64_t value_old, char *sn_old_string, char
     Note note_old, note; uint8_t cmtA_old[32], cmtA[32], sk[32];
     parse_note(note_old, value_old, sn_old_string, r_old_string); parse_note(note, value, sn_string, r_string);
     parse_hex_blob(cmtA_old_string, cmtA_old, 32); parse_hex_blob(cmtA_string, cmtA, 32); parse_hex_blob(sk_string, sk, 32);
-    return prove_timed(ZKB200_MINT, [&] { return mint_witness(note_old, note, cmtA_old, cmtA, value_s, sk); });
+    return prove_timed(ZKB200_MINT, [&](uint64_t *ext) { return mint_witness(note_old, note, cmtA_old, cmtA, value_s, sk, ext); });
 }
 char *genRedeemproof(uint64_t value, uint64_t value_old, char *sn_old_string, char *r_old_string, char *sn_string, char *r_string,
                      char *cmtA_old_string, char *cmtA_string, uint64_t value_s, char *sk_string) {
@@ -162,7 +160,7 @@ char *genRedeemproof(uint64_t value, uint64_t value_old, char *sn_old_string, ch
     parse_note(note_old, value_old, sn_old_string, r_old_string); parse_note(note, value, sn_string, r_string);
     parse_hex_blob(cmtA_old_string, cmtA_old, 32); parse_hex_blob(cmtA_string, cmtA, 32); parse_hex_blob(sk_string, sk, 32);
     printf("Trying to generate redeem proof...\n");            // redeemcgo.cpp:310
-    return prove_timed(ZKB200_REDEEM, [&] { return redeem_witness(note_old, note, cmtA_old, cmtA, value_s, sk); });
+    return prove_timed(ZKB200_REDEEM, [&](uint64_t *ext) { return redeem_witness(note_old, note, cmtA_old, cmtA, value_s, sk, ext); });
 }
 char *genSendproof(uint64_t value_A, char *r_s_string, char *sn_string, char *r_string, char *cmt_s_string, char *cmtA_string, uint64_t value_s,
                    char *pk_recv_string, uint64_t value_A_new, char *sn_A_new, char *r_A_new, char *cmt_A_new, char *sk_string,
@@ -174,7 +172,7 @@ char *genSendproof(uint64_t value_A, char *r_s_string, char *sn_string, char *r_
     parse_hex_blob(cmt_s_string, cmtS, 32); parse_hex_blob(cmtA_string, cmtA, 32); parse_hex_blob(cmt_A_new, cmtAnew, 32);
     parse_hex_blob(sk_string, sk, 32); parse_hex_blob(pk_sender_string, pk_sender, 20);
     printf("Trying to generate send proof...\n");              // sendcgo.cpp:352
-    return prove_timed(ZKB200_SEND, [&] { return send_witness(note_old, notes, note_new, cmtA, cmtS, cmtAnew, sk, pk_sender); });
+    return prove_timed(ZKB200_SEND, [&](uint64_t *ext) { return send_witness(note_old, notes, note_new, cmtA, cmtS, cmtAnew, sk, pk_sender, ext); });
 }
 char *genDepositproof(uint64_t value, uint64_t value_old, char *sn_old_string, char *r_old_string, char *sn_string, char *r_string,
                       char *sns_string, char *rs_string, char *cmtB_old_string, char *cmtB_string, uint64_t value_s, char *pk_string,
@@ -207,7 +205,7 @@ char *genDepositproof(uint64_t value, uint64_t value_old, char *sn_old_string, c
     eff.insert(eff.end(), leaves.begin() + (last + 1) * 32, leaves.end());
     uint8_t siblings[MERKLE_DEPTH][32], rt[32];
     merkle_path((const uint8_t(*)[32])eff.data(), eff.size() / 32, (size_t)first, siblings, rt);
-    return prove_timed(ZKB200_DEPOSIT, [&] { return deposit_witness(note_s, note_old, note, cmtS, cmtB_old, cmtB, rt, (size_t)first, siblings, sn_s, sk); });
+    return prove_timed(ZKB200_DEPOSIT, [&](uint64_t *ext) { return deposit_witness(note_s, note_old, note, cmtS, cmtB_old, cmtB, rt, (size_t)first, siblings, sn_s, sk, ext); });
 }
 
 void zkb200_last_breakdown_ms(double out[4]) { for (int i = 0; i < 4; i++) out[i] = g_last_ms[i]; }

@@ -61,7 +61,8 @@ template <class F> struct XYZZ {
         return r;
     }
     // madd-2008-s: this += affine
-    ZK_EC void add_affine(const Affine<F> &a) {
+    ZK_EC void add_affine(const Affine<F> &a) { add_affine_inl(a); }
+    ZK_HD void add_affine_inl(const Affine<F> &a) {
         if (a.is_inf()) return;
         if (is_inf()) { X = a.x; Y = a.y; ZZ = F::one(); ZZZ = F::one(); return; }
         F U2 = a.x * ZZ, S2 = a.y * ZZZ;

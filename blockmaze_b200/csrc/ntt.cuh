@@ -47,14 +47,14 @@ __device__ __forceinline__ void st_fr(Fr *p, const Fr &r) {
     q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
 
-constexpr int NTT_THREADS = 512;
-constexpr int NTT_TILE_LOG = 11;          // 2048 elements * 32 B = 64 KB of shared memory per CTA
+constexpr int NTT_MAX_THREADS = 512;
+constexpr int NTT_TILE_LOG = 11;          // at most 2048 elements * 32 B = 64 KB of shared memory per CTA; 4 elements per thread
 
 // One pass = stages s0+1 .. s0+k of the decimation-in-time schedule over `n = 2^logn` elements.
 //   set  = the 2^k elements that differ only in index bits [s0, s0+k)
 //   tile = G = 2^logG sets with consecutive low bits, so global accesses are G*32-byte contiguous runs
 template <bool FIRST>
-static __global__ void __launch_bounds__(NTT_THREADS)
+static __global__ void __launch_bounds__(NTT_MAX_THREADS, 2)
 ntt_pass_kernel(const Fr *__restrict__ src, Fr *__restrict__ dst, const Fr *__restrict__ tw,
                 int logn, int s0, int k, int logG, PowMul pre, PowMul post, int last) {
     extern __shared__ uint32_t sm[];
@@ -62,7 +62,8 @@ ntt_pass_kernel(const Fr *__restrict__ src, Fr *__restrict__ dst, const Fr *__re
     const uint32_t set0 = blockIdx.x << logG;
     const uint32_t lowmask = (1u << s0) - 1;
 
-    for (int e = threadIdx.x; e < N; e += NTT_THREADS) {
+    const int nthreads = blockDim.x;
+    for (int e = threadIdx.x; e < N; e += nthreads) {
         int t, g;
         if (FIRST) { t = e & ((1 << k) - 1); g = e >> k; } else { g = e & ((1 << logG) - 1); t = e >> logG; }
         const uint32_t set = set0 + g;
@@ -84,7 +85,7 @@ ntt_pass_kernel(const Fr *__restrict__ src, Fr *__restrict__ dst, const Fr *__re
     for (int q = 1; q <= k; q++) {
         __syncthreads();
         const int hq = 1 << (q - 1);
-        for (int u = threadIdx.x; u < half; u += NTT_THREADS) {
+        for (int u = threadIdx.x; u < half; u += nthreads) {
             const int g = u >> (k - 1), tt = u & ((1 << (k - 1)) - 1);
             const int tlow = tt & (hq - 1);
             const int t = ((tt >> (q - 1)) << q) | tlow;
@@ -102,7 +103,7 @@ ntt_pass_kernel(const Fr *__restrict__ src, Fr *__restrict__ dst, const Fr *__re
     }
     __syncthreads();
 
-    for (int e = threadIdx.x; e < N; e += NTT_THREADS) {
+    for (int e = threadIdx.x; e < N; e += nthreads) {
         int t, g;
         if (FIRST) { t = e & ((1 << k) - 1); g = e >> k; } else { g = e & ((1 << logG) - 1); t = e >> logG; }
         const uint32_t set = set0 + g;
@@ -124,7 +125,10 @@ static inline int ntt_plan_passes(int logn, NttPass out[4]) {
     int s0 = 0;
     for (int p = 0; p < np; p++) {
         int k = (logn - s0 + (np - p) - 1) / (np - p);
-        int logG = NTT_TILE_LOG - k;
+        // tile = 2^(k+logG) elements: as large as 2048 for big transforms (long contiguous runs), but small enough that a
+        // circuit-sized transform still spreads over >= 2 CTAs per SM (2^18: 512 CTAs of 512 elements)
+        int tile = logn - 9; if (tile > NTT_TILE_LOG) tile = NTT_TILE_LOG; if (tile < k) tile = k;
+        int logG = tile - k;
         if (logG < 0) logG = 0;
         if (k + logG > logn) logG = logn - k;
         if (p > 0 && logG > s0) logG = s0;
@@ -143,10 +147,11 @@ static inline void ntt_launch(cudaStream_t st, const Fr *src, Fr *dst, const Fr 
         const size_t smem = (size_t)N * 32;
         const unsigned blocks = 1u << (logn - ps[p].k - ps[p].logG);
         const int last = (p == np - 1);
+        int threads = N / 4; if (threads < 32) threads = 32; if (threads > NTT_MAX_THREADS) threads = NTT_MAX_THREADS;
         if (p == 0)
-            ntt_pass_kernel<true><<<blocks, NTT_THREADS, smem, st>>>(src, dst, tw, logn, ps[p].s0, ps[p].k, ps[p].logG, pre, post, last);
+            ntt_pass_kernel<true><<<blocks, threads, smem, st>>>(src, dst, tw, logn, ps[p].s0, ps[p].k, ps[p].logG, pre, post, last);
         else
-            ntt_pass_kernel<false><<<blocks, NTT_THREADS, smem, st>>>(dst, dst, tw, logn, ps[p].s0, ps[p].k, ps[p].logG, pre, post, last);
+            ntt_pass_kernel<false><<<blocks, threads, smem, st>>>(dst, dst, tw, logn, ps[p].s0, ps[p].k, ps[p].logG, pre, post, last);
     }
 }
 static inline void ntt_init_attrs() {

@@ -177,10 +177,12 @@ void domain_op(cudaStream_t st, const Domain &d, int op, void *data, void *tmp) 
 // =====================================================================================================================
 // sparse A.w / B.w / C.w  (linear_combination::evaluate, libsnark/relations/variable.tcc:262; r1cs_to_qap.tcc:227-236,281-285)
 // one thread per constraint row; coefficient dictionary index 0 = +1, 1 = -1 (no multiplication)
-__global__ void spmv_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const uint32_t *__restrict__ coef,
-                            const Fr *__restrict__ dict, const Fr *__restrict__ w, Fr *__restrict__ out, uint32_t rows) {
+struct SpmvArgs { const uint32_t *rowptr[3], *col[3], *coef[3]; Fr *out[3]; };
+__global__ void spmv_kernel(SpmvArgs A, const Fr *__restrict__ dict, const Fr *__restrict__ w, uint32_t rows) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
+    const uint32_t *__restrict__ rowptr = A.rowptr[blockIdx.y], *__restrict__ col = A.col[blockIdx.y], *__restrict__ coef = A.coef[blockIdx.y];
+    Fr *__restrict__ out = A.out[blockIdx.y];
     Fr acc = Fr::zero();
     for (uint32_t k = rowptr[i], e = rowptr[i + 1]; k < e; k++) {
         const uint32_t ci = __ldg(coef + k);
@@ -486,7 +488,7 @@ DevicePk *pk_load(const char *path, int device, std::string &err) {
     ZK_CUDA(cudaMemset(pk->w_can, 0, nw * 32));
     const uint64_t one_can[4] = {1, 0, 0, 0};
     ZK_CUDA(cudaMemcpy(pk->w_can, one_can, 32, cudaMemcpyHostToDevice));
-    ZK_CUDA(cudaMallocHost(&pk->h_w_pinned, nw * 32));
+    ZK_CUDA(cudaMallocHost(&pk->h_w_pinned, (nw + 1) * 32));
     ZK_CUDA(cudaMalloc(&pk->bufA, m * 32)); ZK_CUDA(cudaMalloc(&pk->bufB, m * 32)); ZK_CUDA(cudaMalloc(&pk->bufC, m * 32));
     ZK_CUDA(cudaMalloc(&pk->tmp, m * 32));
     ZK_CUDA(cudaMalloc(&pk->sat_flag, 4)); ZK_CUDA(cudaMallocHost(&pk->h_sat_flag, 4));
@@ -497,8 +499,12 @@ DevicePk *pk_load(const char *path, int device, std::string &err) {
     pk->mL.init(pk->nL, MSM_C, 4096, true, false, true);
     pk->mH.init(pk->nH, MSM_C, 0, true, false, true);
 
-    ZK_CUDA(cudaStreamCreateWithFlags(&pk->s_main, cudaStreamNonBlocking)); ZK_CUDA(cudaStreamCreateWithFlags(&pk->s_a, cudaStreamNonBlocking));
-    ZK_CUDA(cudaStreamCreateWithFlags(&pk->s_b, cudaStreamNonBlocking)); ZK_CUDA(cudaStreamCreateWithFlags(&pk->s_l, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    ZK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));          // the QAP map + H MSM chain is the critical path
+    ZK_CUDA(cudaStreamCreateWithPriority(&pk->s_main, cudaStreamNonBlocking, prio_hi));
+    ZK_CUDA(cudaStreamCreateWithPriority(&pk->s_a, cudaStreamNonBlocking, prio_lo));
+    ZK_CUDA(cudaStreamCreateWithPriority(&pk->s_b, cudaStreamNonBlocking, prio_lo));
+    ZK_CUDA(cudaStreamCreateWithPriority(&pk->s_l, cudaStreamNonBlocking, prio_lo));
     cudaEvent_t *evs[] = {&pk->ev_w, &pk->ev_a, &pk->ev_b, &pk->ev_l};
     for (auto *e : evs) ZK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     cudaEvent_t *tev[] = {&pk->ev_t0, &pk->ev_t1, &pk->ev_q0, &pk->ev_q1, &pk->ev_h0, &pk->ev_h1};
@@ -507,6 +513,8 @@ DevicePk *pk_load(const char *path, int device, std::string &err) {
     pk->load_seconds = now_s() - t0;
     return pk;
 }
+
+uint8_t *pinned_assignment(DevicePk *pk) { return (uint8_t *)pk->h_w_pinned + 32; }
 
 void pk_free(DevicePk *pk) {
     if (!pk) return;
@@ -531,10 +539,10 @@ void pk_free(DevicePk *pk) {
 // the per-proof pipeline
 static void upload_assignment(DevicePk *pk, const uint8_t *assignment, const uint64_t *zk_scalars /* r, s, -rs or null */, cudaStream_t st) {
     const size_t n = pk->num_vars;
-    char *pin = (char *)pk->h_w_pinned;
+    char *pin = (char *)pk->h_w_pinned + 32;            // [pad | assignment | r | s | -rs]
     if (zk_scalars) memcpy(pin + n * 32, zk_scalars, 96);
     if (assignment) {
-        memcpy(pin, assignment, n * 32);
+        if ((const char *)assignment != pin) memcpy(pin, assignment, n * 32);
         ZK_CUDA(cudaMemcpyAsync((char *)pk->w_can + 32, pin, n * 32 + (zk_scalars ? 96 : 0), cudaMemcpyHostToDevice, st));
     } else if (zk_scalars) {
         ZK_CUDA(cudaMemcpyAsync((char *)pk->w_can + 32 + n * 32, pin + n * 32, 96, cudaMemcpyHostToDevice, st));
@@ -552,9 +560,8 @@ static void qap_pipeline(DevicePk *pk, cudaStream_t st) {
     ZK_CUDA(cudaMemsetAsync(A + nc, 0, (size_t)(m - nc) * 32, st));
     ZK_CUDA(cudaMemsetAsync(B + nc, 0, (size_t)(m - nc) * 32, st));
     ZK_CUDA(cudaMemsetAsync(C + nc, 0, (size_t)(m - nc) * 32, st));
-    ZK_LAUNCH(spmv_kernel, cdiv(nc, 128), 128, 0, st, pk->a.rowptr, pk->a.col, pk->a.coef, dict, w, A, nc);
-    ZK_LAUNCH(spmv_kernel, cdiv(nc, 128), 128, 0, st, pk->b.rowptr, pk->b.col, pk->b.coef, dict, w, B, nc);
-    ZK_LAUNCH(spmv_kernel, cdiv(nc, 128), 128, 0, st, pk->c.rowptr, pk->c.col, pk->c.coef, dict, w, C, nc);
+    SpmvArgs sa{{pk->a.rowptr, pk->b.rowptr, pk->c.rowptr}, {pk->a.col, pk->b.col, pk->c.col}, {pk->a.coef, pk->b.coef, pk->c.coef}, {A, B, C}};
+    ZK_LAUNCH(spmv_kernel, dim3(cdiv(nc, 128), 3), 128, 0, st, sa, dict, w, nc);
     ZK_CUDA(cudaMemsetAsync(pk->sat_flag, 0, 4, st));
     ZK_LAUNCH(sat_check_kernel, cdiv(nc, 256), 256, 0, st, A, B, C, nc, pk->sat_flag);
     ZK_CUDA(cudaMemcpyAsync(pk->h_sat_flag, pk->sat_flag, 4, cudaMemcpyDeviceToHost, st));

@@ -110,6 +110,9 @@ int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const ui
 // QAP witness map only; writes (m+1)*32 bytes canonical to host `out_H`
 int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied);
 
+// pinned host staging buffer shaped [pad(32 B) | assignment | r | s | -rs]: build the assignment at +32 and pass that pointer to
+// prove() to skip the staging copy
+uint8_t *pinned_assignment(DevicePk *pk);
 void device_init(int device);
 std::string proof_hex(const ProofPoints &p);           // mintcgo.cpp:112-187 layout
 int launches_last_prove();                             // number of kernels launched by the last prove() call

@@ -122,9 +122,14 @@ namespace {
 typedef std::vector<int32_t> Refs;        // >= 0: variable index (0 = constant ONE); -1: the constant 0 (e.g. an IV bit that is 0)
 
 struct Tape {
-    std::vector<uint64_t> v;
+    std::vector<uint64_t> own;
+    uint64_t *v, *ext;
     uint32_t next = 1, cap;
-    explicit Tape(uint32_t nvars) : v(((size_t)nvars + 1) * 4, 0), cap(nvars) { v[0] = 1; }
+    Tape(uint32_t nvars, uint64_t *ext_) : ext(ext_), cap(nvars) {
+        const size_t words = ((size_t)nvars + 1) * 4;
+        if (ext) { v = ext; memset(v, 0, words * 8); } else { own.assign(words, 0); v = own.data(); }
+        v[0] = 1;
+    }
     uint32_t alloc(uint32_t n = 1) { uint32_t r = next; next += n; return r; }
     Refs alloc_refs(uint32_t n) { uint32_t b = alloc(n); Refs r(n); for (uint32_t i = 0; i < n; i++) r[i] = (int32_t)(b + i); return r; }
     uint64_t get(int32_t ref) const { return ref < 0 ? 0 : v[(size_t)ref * 4]; }
@@ -330,15 +335,15 @@ struct LessCmp {
 };
 
 static Assignment finish(Tape &t) {
-    Assignment a; a.num_vars = t.cap; a.tape = std::move(t.v); return a;
+    Assignment a; a.num_vars = t.cap; a.ext = t.ext; if (!t.ext) a.tape = std::move(t.own); return a;
 }
 } // namespace
 
 // =====================================================================================================================
 // mint  (SRC/mint/circuit/gadget.tcc:71-162 allocation order; :194-246 witness order)
 static Assignment mint_like(bool redeem, const Note &note_old, const Note &note, const uint8_t cmtA_old_d[32], const uint8_t cmtA_d[32],
-                            uint64_t value_s_v, const uint8_t sk_d[32]) {
-    Tape t(redeem ? REDEEM_VARS : MINT_VARS);
+                            uint64_t value_s_v, const uint8_t sk_d[32], uint64_t *ext) {
+    Tape t(redeem ? REDEEM_VARS : MINT_VARS, ext);
     const uint32_t packed = t.alloc(4);
     Refs cmtA_old = t.alloc_refs(256), sn_old = t.alloc_refs(256), cmtA = t.alloc_refs(256), value_s = t.alloc_refs(64);
     const Refs unpacked = concat({cmtA_old, sn_old, cmtA, value_s});
@@ -371,18 +376,18 @@ static Assignment mint_like(bool redeem, const Note &note_old, const Note &note,
     delete cmp;
     return finish(t);
 }
-Assignment mint_witness(const Note &note_old, const Note &note, const uint8_t cmtA_old[32], const uint8_t cmtA[32], uint64_t value_s, const uint8_t sk[32]) {
-    return mint_like(false, note_old, note, cmtA_old, cmtA, value_s, sk);
+Assignment mint_witness(const Note &note_old, const Note &note, const uint8_t cmtA_old[32], const uint8_t cmtA[32], uint64_t value_s, const uint8_t sk[32], uint64_t *ext) {
+    return mint_like(false, note_old, note, cmtA_old, cmtA, value_s, sk, ext);
 }
-Assignment redeem_witness(const Note &note_old, const Note &note, const uint8_t cmtA_old[32], const uint8_t cmtA[32], uint64_t value_s, const uint8_t sk[32]) {
-    return mint_like(true, note_old, note, cmtA_old, cmtA, value_s, sk);
+Assignment redeem_witness(const Note &note_old, const Note &note, const uint8_t cmtA_old[32], const uint8_t cmtA[32], uint64_t value_s, const uint8_t sk[32], uint64_t *ext) {
+    return mint_like(true, note_old, note, cmtA_old, cmtA, value_s, sk, ext);
 }
 
 // =====================================================================================================================
 // send  (SRC/send/circuit/gadget.tcc constructor / generate_r1cs_witness; note.tcc; less_cmp.tcc; commitment.tcc)
 Assignment send_witness(const Note &note_old, const NoteS &note_s, const Note &note, const uint8_t cmtA_old_d[32], const uint8_t cmtS_d[32],
-                        const uint8_t cmtA_d[32], const uint8_t sk_d[32], const uint8_t pk_sender_d[20]) {
-    Tape t(SEND_VARS);
+                        const uint8_t cmtA_d[32], const uint8_t sk_d[32], const uint8_t pk_sender_d[20], uint64_t *ext) {
+    Tape t(SEND_VARS, ext);
     const uint32_t packed = t.alloc(5);
     Refs cmtA_old = t.alloc_refs(256), sn_old = t.alloc_refs(256), cmtS = t.alloc_refs(256), cmtA = t.alloc_refs(256);
     const Refs unpacked = concat({cmtA_old, sn_old, cmtS, cmtA});
@@ -426,9 +431,9 @@ Assignment send_witness(const Note &note_old, const NoteS &note_s, const Note &n
 // deposit  (SRC/deposit/circuit/gadget.tcc, merkle.tcc, note.tcc; libsnark merkle_tree_check_read_gadget.tcc:32-125)
 Assignment deposit_witness(const NoteS &note_s, const Note &note_old, const Note &note, const uint8_t cmtS_d[32], const uint8_t cmtB_old_d[32],
                            const uint8_t cmtB_d[32], const uint8_t rt_d[32], size_t leaf_index, const uint8_t siblings[MERKLE_DEPTH][32],
-                           const uint8_t sn_s_d[32], const uint8_t sk_d[32]) {
+                           const uint8_t sn_s_d[32], const uint8_t sk_d[32], uint64_t *ext) {
     const int D = MERKLE_DEPTH;
-    Tape t(DEPOSIT_VARS);
+    Tape t(DEPOSIT_VARS, ext);
     const uint32_t packed = t.alloc(6);
     Refs root = t.alloc_refs(256), pk_recv = t.alloc_refs(160), cmtB_old = t.alloc_refs(256), sn_old = t.alloc_refs(256), cmtB = t.alloc_refs(256),
          sn_s = t.alloc_refs(256);

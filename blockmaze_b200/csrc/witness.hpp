@@ -33,26 +33,28 @@ void merkle_path(const uint8_t (*leaves)[32], size_t n, size_t index, uint8_t si
 // ---- full assignments -----------------------------------------------------------------------------------------------------
 struct Assignment {
     std::vector<uint64_t> tape;       // (num_vars + 1) x 4 limbs, variable i at tape[4*i..], variable 0 = constant ONE
+    uint64_t *ext = nullptr;          // caller-provided storage of the same shape (e.g. pinned host memory) used instead of `tape`
     uint32_t num_vars = 0;
-    const uint8_t *data() const { return reinterpret_cast<const uint8_t *>(tape.data() + 4); }   // num_vars x 32 B canonical LE
+    const uint8_t *data() const { return reinterpret_cast<const uint8_t *>((ext ? ext : tape.data()) + 4); }   // num_vars x 32 B canonical LE
 };
+// Every generator takes an optional `ext` buffer of (num_vars + 1) * 4 uint64 to build the assignment in place.
 
 struct Note { uint64_t value; uint8_t sn[32]; uint8_t r[32]; };
 struct NoteS { uint64_t value; uint8_t pk[20]; uint8_t r[32]; uint8_t sn_old[32]; };
 
 // mint_gadget::generate_r1cs_witness (SRC/mint/circuit/gadget.tcc:194-246)
 Assignment mint_witness(const Note &note_old, const Note &note, const uint8_t cmtA_old[32], const uint8_t cmtA[32], uint64_t value_s,
-                        const uint8_t sk[32]);
+                        const uint8_t sk[32], uint64_t *ext = nullptr);
 // redeem_gadget::generate_r1cs_witness (SRC/redeem/circuit/gadget.tcc)
 Assignment redeem_witness(const Note &note_old, const Note &note, const uint8_t cmtA_old[32], const uint8_t cmtA[32], uint64_t value_s,
-                          const uint8_t sk[32]);
+                          const uint8_t sk[32], uint64_t *ext = nullptr);
 // send_gadget::generate_r1cs_witness (SRC/send/circuit/gadget.tcc)
 Assignment send_witness(const Note &note_old, const NoteS &note_s, const Note &note, const uint8_t cmtA_old[32], const uint8_t cmtS[32],
-                        const uint8_t cmtA[32], const uint8_t sk[32], const uint8_t pk_sender[20]);
+                        const uint8_t cmtA[32], const uint8_t sk[32], const uint8_t pk_sender[20], uint64_t *ext = nullptr);
 // deposit_gadget::generate_r1cs_witness (SRC/deposit/circuit/gadget.tcc); path as produced by merkle_path()
 Assignment deposit_witness(const NoteS &note_s, const Note &note_old, const Note &note, const uint8_t cmtS[32], const uint8_t cmtB_old[32],
                            const uint8_t cmtB[32], const uint8_t rt[32], size_t leaf_index, const uint8_t siblings[MERKLE_DEPTH][32],
-                           const uint8_t sn_s[32], const uint8_t sk[32]);
+                           const uint8_t sn_s[32], const uint8_t sk[32], uint64_t *ext = nullptr);
 
 // directory of <circuit>{pk,vk}.txt: zkb200_set_key_dir() > $ZKB200_KEY_DIR > /usr/local/prfKey (defined in blockmaze_abi.cu)
 std::string key_dir();

@@ -137,10 +137,11 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="send", choices=["send", "mixed1024"])
+    ap.add_argument("--workload", default="send", choices=["send", "mixed1024", "sweep", "msm_split"])
+    ap.add_argument("--logn", type=int, default=24, help="msm_split: log2 of the total number of points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip per-circuit latency table and NTT roofline")
     args = ap.parse_args()
@@ -170,6 +171,14 @@ def main():
         api.lib.zkb200_device_sync()
         if dist is not None:
             dist.barrier()
+
+    if args.workload == "sweep":
+        if rank == 0:
+            print(json.dumps(kernel_sweep(api)))
+        return
+    if args.workload == "msm_split":
+        msm_split(args, api, dist, rank, world, barrier)
+        return
 
     circuits = ["send"] if args.workload == "send" else ["mint", "send", "deposit", "redeem"]
     pks = {c: zk.ProvingKey(os.path.join(kd, c + "pk.txt")) for c in circuits}
@@ -299,6 +308,90 @@ def main():
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line))
+
+
+def kernel_sweep(api):
+    """BASELINE.json configs[4]: BN254 G1/G2 MSM and Fr NTT at 2^16..2^24 on one GPU, next to libff multi_exp / libfqfft FFT on the host
+    cores (CPU legs up to 2^20: beyond that they take minutes)."""
+    import ctypes as C
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    imad = float(api.lib.zkb200_bench_imad_peak(0))
+    cpu = None
+    try:
+        from oracle import refapi as Rf
+        if Rf.available("kernels_mt"):
+            os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+            cpu = Rf.lib("kernels_mt")
+            cpu.ref_fft_seconds.restype = C.c_double
+            cpu.ref_msm_g1_seconds.restype = C.c_double
+    except Exception:
+        cpu = None
+    rows = []
+    for lg in (16, 18, 20, 22, 24):
+        n = 1 << lg
+        row = {"log2_n": lg}
+        ms = float(api.lib.zkb200_bench_ntt(lg, 1, 5))
+        row["ntt_ms"] = round(ms, 4)
+        row["ntt_GBps"] = round(64.0 * n / (ms * 1e-3) / 1e9, 1)
+        row["ntt_frac_of_hbm"] = round(row["ntt_GBps"] / hbm, 4)
+        ms = float(api.lib.zkb200_bench_msm(1, n, 0, 2))
+        row["msm_g1_ms"] = round(ms, 3)
+        row["msm_g1_TIMADps"] = round(IMAD_PER_G1_POINT * n / (ms * 1e-3) / 1e12, 3)
+        row["msm_g1_frac_of_imad"] = round(row["msm_g1_TIMADps"] / imad, 4)
+        ms = float(api.lib.zkb200_bench_msm(1, n, -16, 2))
+        row["msm_g1_fixed_base_ms"] = round(ms, 3)
+        row["msm_g1_fixed_base_frac_of_imad"] = round(IMAD_PER_G1_POINT * n / (ms * 1e-3) / 1e12 / imad, 4)
+        if lg <= 22:
+            ms = float(api.lib.zkb200_bench_msm(2, n, 0, 2))
+            row["msm_g2_ms"] = round(ms, 3)
+            row["msm_g2_frac_of_imad"] = round(3 * IMAD_PER_G1_POINT * n / (ms * 1e-3) / 1e12 / imad, 4)
+        if cpu is not None and lg <= 20:
+            row["cpu_fft_s"] = round(cpu.ref_fft_seconds(C.c_size_t(n), 1), 4)
+            row["cpu_msm_g1_s"] = round(cpu.ref_msm_g1_seconds(C.c_size_t(n), C.c_size_t(0)), 3)
+        rows.append(row)
+    return {"metric": "kernel_sweep", "unit": "ms", "n_gpus": 1, "data": "synthetic (splitmix64 scalars < 2^253, bases k_i*G)",
+            "peaks": {"hbm_GBps": hbm, "imad_T_per_s": round(imad, 2), "cpu_threads": int(os.environ.get("OMP_NUM_THREADS", "0") or 0)},
+            "algorithmic": {"ntt_bytes_per_element": 64, "imad_per_g1_point": IMAD_PER_G1_POINT, "imad_per_g2_point": 3 * IMAD_PER_G1_POINT},
+            "rows": rows}
+
+
+def msm_split(args, api, dist, rank, world, barrier):
+    """BASELINE.json configs[4], second half: ONE large G1 MSM split by point range over the GPUs; every GPU returns one partial point
+    and rank 0 adds them on the host (no collective on the data path; the 64-byte points travel through the rendezvous gather)."""
+    from oracle import bn254_oracle as O        # host-side point addition of <= 8 partial points (test-infrastructure arithmetic)
+    n = 1 << args.logn
+    per = n // world
+    first, count = rank * per, (per if rank < world - 1 else n - per * (world - 1))
+    import ctypes as C
+    out = C.create_string_buffer(64)
+    api.lib.zkb200_bench_msm_slice(1, first, count, 0, 1, out)          # warm-up, also builds the slice
+    barrier()
+    t0 = time.perf_counter()
+    ms = float(api.lib.zkb200_bench_msm_slice(1, first, count, 0, max(1, args.steps // 4), out))
+    barrier()
+    units, tmax = reduce_counts_and_time(count, ms * 1e-3, dist)
+    pts = [out.raw]
+    if dist is not None:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, out.raw)
+        pts = gathered
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        acc = O.G1.zero()
+        for b in pts:
+            if any(b):
+                acc = O.G1.add(acc, O.G1.from_affine((int.from_bytes(b[:32], "little"), int.from_bytes(b[32:], "little"))))
+        aff = O.G1.to_affine(acc)
+        print(json.dumps({"metric": "msm_points_per_sec", "value": units / tmax, "unit": "points/s", "n_gpus": world, "ms_per_step": 1e3 * tmax,
+                          "higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "u32",
+                          "config": {"workload": "single G1 MSM of 2^%d points split by point range, one partial point per GPU summed on the host" % args.logn},
+                          "result_x": "%064x" % (aff[0] if aff else 0)}))
 
 
 def cpu_baseline():

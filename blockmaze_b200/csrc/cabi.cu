@@ -43,20 +43,20 @@ template <class F> __global__ void field_op_kernel(const F *a, const F *b, F *ou
     out[i] = z;
 }
 
-__global__ void fill_scalars_kernel(uint32_t *out, size_t n, uint64_t seed) {      // splitmix64 stream, reduced below 2^253
+__global__ void fill_scalars_kernel(uint32_t *out, size_t n, uint64_t seed, size_t first = 0) {      // splitmix64 stream, reduced below 2^253
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     for (int w = 0; w < 4; w++) {
-        uint64_t z = seed + (i * 4 + w + 1) * 0x9E3779B97F4A7C15ull;
+        uint64_t z = seed + ((first + i) * 4 + w + 1) * 0x9E3779B97F4A7C15ull;
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
         out[i * 8 + 2 * w] = (uint32_t)z; out[i * 8 + 2 * w + 1] = (uint32_t)(z >> 32);
     }
     out[i * 8 + 7] &= 0x1fffffffu;
 }
-template <class F> __global__ void gen_bases_kernel(Affine<F> gen, Affine<F> *out, size_t n) {   // P_i = (i+1) * 0x9E3779B97F4A7C15 * G (mod 2^64 scalar)
+template <class F> __global__ void gen_bases_kernel(Affine<F> gen, Affine<F> *out, size_t n, size_t first = 0) {   // P_i = ((i+1) * 0x9E3779B97F4A7C15 mod 2^64 | 1) * G
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint64_t k = (i + 1) * 0x9E3779B97F4A7C15ull | 1ull;
+    uint64_t k = (first + i + 1) * 0x9E3779B97F4A7C15ull | 1ull;
     uint32_t kk[8] = {(uint32_t)k, (uint32_t)(k >> 32), 0, 0, 0, 0, 0, 0};
     XYZZ<F> g = XYZZ<F>::from_affine(gen), r = XYZZ<F>::inf();
     for (int b = 63; b >= 0; b--) { r = r.dbl(); if ((kk[b >> 5] >> (b & 31)) & 1) r.add(g); }
@@ -276,18 +276,20 @@ float zkb200_bench_ntt(int logn, int batch, int iters) {
     return ms / (float)(iters * batch);
 }
 
-float zkb200_bench_msm(int group, size_t n, int window_bits, int iters) {
+// slice [first, first+n) of the synthetic MSM problem (bases P_i, scalars s_i are functions of the GLOBAL index i), so that a single
+// large MSM can be split by point range over several GPUs: every rank calls this with its slice and the partial points are added.
+float zkb200_bench_msm_slice(int group, size_t first, size_t n, int window_bits, int iters, uint8_t *out_point) {
     if (ensure_device()) return -1;
     const int c = window_bits > 0 ? window_bits : (window_bits < 0 ? -window_bits : default_window(n));
-    uint32_t *sc; ZK_CUDA(cudaMalloc(&sc, n * 32));
-    fill_scalars_kernel<<<(unsigned)((n + 255) / 256), 256>>>(sc, n, 11);
+    uint32_t *sc; ZK_CUDA(cudaMalloc(&sc, (n + 1) * 32));
+    if (n) fill_scalars_kernel<<<(unsigned)((n + 255) / 256), 256>>>(sc, n, 11, first);
     void *bases;
     if (group == 1) {
-        ZK_CUDA(cudaMalloc(&bases, n * sizeof(G1Affine)));
+        ZK_CUDA(cudaMalloc(&bases, (n + 1) * sizeof(G1Affine)));
         G1Affine g; g.x = Fq::one(); g.y = Fq::one() + Fq::one();
-        gen_bases_kernel<Fq><<<(unsigned)((n + 127) / 128), 128>>>(g, (G1Affine *)bases, n);
+        if (n) gen_bases_kernel<Fq><<<(unsigned)((n + 127) / 128), 128>>>(g, (G1Affine *)bases, n, first);
     } else {
-        ZK_CUDA(cudaMalloc(&bases, n * sizeof(G2Affine)));
+        ZK_CUDA(cudaMalloc(&bases, (n + 1) * sizeof(G2Affine)));
         // G2 generator (alt_bn128_init.cpp:265-269), Montgomery form computed on the host
         const char *gs[4] = {"10857046999023057135944570762232829481370756359578518086990519993285655852781",
                              "11559732032986387107991004021392285783925812861821192530917403151452391805634",
@@ -295,7 +297,7 @@ float zkb200_bench_msm(int group, size_t n, int window_bits, int iters) {
                              "4082367875863433681332203403145435568316851327593401208105741076214120093531"};
         zkh::HFq v[4]; for (int i = 0; i < 4; i++) zkh::HFq::from_dec(gs[i], strlen(gs[i]), v[i]);
         G2Affine g; memcpy(&g, v, 128);
-        gen_bases_kernel<Fq2><<<(unsigned)((n + 127) / 128), 128>>>(g, (G2Affine *)bases, n);
+        if (n) gen_bases_kernel<Fq2><<<(unsigned)((n + 127) / 128), 128>>>(g, (G2Affine *)bases, n, first);
     }
     ZK_CUDA(cudaDeviceSynchronize());
     const bool expanded = window_bits < 0;          // negative window_bits: fixed-base (expanded) layout with |window_bits| bits
@@ -311,9 +313,11 @@ float zkb200_bench_msm(int group, size_t n, int window_bits, int iters) {
     ZK_CUDA(cudaEventSynchronize(e1));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (out_point) { if (group == 1) put_g1(out_point, msm_finish_g1(plan).to_affine()); else put_g2(out_point, msm_finish_g2(plan).to_affine()); }
     plan.release(); cudaFree(sc); cudaFree(bases);
-    return ms / (float)iters;
+    return ms / (float)(iters > 0 ? iters : 1);
 }
+float zkb200_bench_msm(int group, size_t n, int window_bits, int iters) { return zkb200_bench_msm_slice(group, 0, n, window_bits, iters, nullptr); }
 
 // write a buffer twice the size of L2 so the next step starts with a cold L2 (bench hygiene)
 void zkb200_flush_l2(void) {

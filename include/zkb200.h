@@ -131,6 +131,10 @@ int zkb200_field_op(int field, int op, size_t n, const uint8_t *a, const uint8_t
  * 2^(c*k)*P is built once outside the timed region, as for a resident proving key); 0: default windowed. */
 float zkb200_bench_ntt(int logn, int batch, int iters);
 float zkb200_bench_msm(int group, size_t n, int window_bits, int iters);
+/* The same synthetic problem restricted to points [first, first+n): bases and scalars are functions of the GLOBAL index, so a single
+ * large MSM splits by point range over several GPUs (one partial point per GPU, added on the host).  out_point
+ * (64 B G1 / 128 B G2, may be NULL) receives the partial sum.  Also returns the points/scalars to the host for cross-checks when small. */
+float zkb200_bench_msm_slice(int group, size_t first, size_t n, int window_bits, int iters, uint8_t *out_point);
 /* bench hygiene: overwrite a 256 MB scratch buffer (2x L2) and synchronise; plain cudaDeviceSynchronize */
 void zkb200_flush_l2(void);
 void zkb200_device_sync(void);

@@ -74,6 +74,37 @@ long ref_domain_op(size_t min_size, int op, uint8_t *data, size_t n) {
     } catch (...) { return -1; }
 }
 
+// wall time of `reps` in-place forward FFTs of the domain over random-ish data already converted to Fr (conversion excluded)
+double ref_fft_seconds(size_t min_size, int reps) {
+    ensure_init();
+    try {
+        auto d = libfqfft::get_evaluation_domain<FrT>(min_size);
+        std::vector<FrT> a(d->m);
+        FrT x = FrT(12345), g = FrT(7);
+        for (size_t i = 0; i < d->m; i++) { a[i] = x; x = x * g + FrT::one(); }
+        struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); double t0 = ts.tv_sec + 1e-9 * ts.tv_nsec;
+        for (int r = 0; r < reps; r++) d->FFT(a);
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return (ts.tv_sec + 1e-9 * ts.tv_nsec - t0) / reps;
+    } catch (...) { return -1; }
+}
+// wall time of one multi_exp<G1, BDLO12> over n synthetic bases (running-sum points) and pseudo-random 254-bit scalars
+double ref_msm_g1_seconds(size_t n, size_t chunks) {
+    ensure_init();
+    std::vector<G1T> b(n); std::vector<FrT> s(n);
+    G1T d = FrT(31337) * G1T::one(), acc = d;
+    for (size_t i = 0; i < n; i++) { b[i] = acc; acc = acc + d; }
+    G1T::batch_to_special_all_non_zeros(b);
+    FrT x = FrT(12345), g = FrT(7);
+    for (size_t i = 0; i < n; i++) { s[i] = x; x = x * x + g; }
+    if (chunks == 0) chunks = ref_threads();
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); double t0 = ts.tv_sec + 1e-9 * ts.tv_nsec;
+    G1T r = libff::multi_exp<G1T, FrT, libff::multi_exp_method_BDLO12>(b.begin(), b.end(), s.begin(), s.end(), chunks);
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    volatile bool z = r.is_zero(); (void)z;
+    return ts.tv_sec + 1e-9 * ts.tv_nsec - t0;
+}
+
 // domain element idx and vanishing polynomial at t (for the libfqfft-style property tests)
 long ref_domain_element(size_t min_size, size_t idx, uint8_t *out) {
     ensure_init();

@@ -154,3 +154,20 @@ def test_msm_linearity_at_sweep_size(zk, ref):
     pk = zk.msm_g1(b1, fb([x * k % O.R_MOD for x in s]))
     assert ref.g1_mul(A, k) == ref.g1_from(pk)
     assert ps == ref.msm_g1_bytes(b1, fb(s), 0, chunks=0, mt=True)[0]
+
+
+def test_msm_point_range_split_adds_up(zk):
+    """A single MSM split by point range: the partial points of the slices add up to the full result."""
+    import ctypes as C
+    n, c = 50000, 12
+    full, a, b = (C.create_string_buffer(64) for _ in range(3))
+    zk.lib.zkb200_bench_msm_slice(1, 0, n, c, 1, full)
+    zk.lib.zkb200_bench_msm_slice(1, 0, 20000, c, 1, a)
+    zk.lib.zkb200_bench_msm_slice(1, 20000, n - 20000, c, 1, b)
+    pt = lambda r: (int.from_bytes(r[:32], "little"), int.from_bytes(r[32:], "little"))
+    s = O.G1.to_affine(O.G1.add(O.G1.from_affine(pt(a.raw)), O.G1.from_affine(pt(b.raw))))
+    assert s == pt(full.raw) and O.G1.on_curve(s)
+    # the fixed-base (expanded) layout gives the same point as the windowed one
+    fb = C.create_string_buffer(64)
+    zk.lib.zkb200_bench_msm_slice(1, 0, n, -16, 1, fb)
+    assert fb.raw == full.raw

@@ -26,6 +26,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 CONSTRAINTS = {"mint": 167270, "send": 252286, "deposit": 503863, "redeem": 167853}
 DOMAIN = {"mint": 196608, "send": 262144, "deposit": 524288, "redeem": 196608}
+WORKLOADS = {"send": "send circuit (252286 constraints, QAP domain 2^18): one Groth16 proof per step per GPU",
+             "mixed1024": "mixed batch of 1024 synthetic mint/send/deposit/redeem transactions sharded over the GPUs"}
 IMAD_PER_G1_POINT = 23936          # 16 windows x (11 modmul x 136 IMAD) per point of a 254-bit G1 MSM
 
 
@@ -125,7 +127,7 @@ def reference_arm(args, rank, world):
     cores = int(os.environ["OMP_NUM_THREADS"])
     v = args.steps / dt
     line.update(value=v, ms_per_step=1e3 * dt / args.steps,
-                config={"workload": "send circuit: one Groth16 proof per step (witness + is_satisfied + r1cs_gg_ppzksnark_prover), pk resident",
+                config={"workload": WORKLOADS["send"], "detail": "reference path per step: gadget construction + witness + is_satisfied + r1cs_gg_ppzksnark_prover, pk resident",
                         "constraints": CONSTRAINTS[circuit], "domain": DOMAIN[circuit], "pk_load_s_excluded": round(t_load, 1)},
                 cpu_baseline={"value": v, "unit": "proofs/s", "cores": cores, "kind": "reference",
                               "sample": "%d send proofs, libsnark -DMULTICORE -fopenmp, OMP_NUM_THREADS=%d; prover phases avg s: qap %.2f A %.2f B %.2f H %.2f L %.2f"
@@ -287,7 +289,7 @@ def main():
             "metric": "proofs_per_sec", "value": units / dt, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload == "send" else "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload, "l2": "256 MB memset + sync before every timed step (inside the timed region, ~0.06 ms)",
+            "config": {"workload": WORKLOADS[args.workload], "detail": workload, "l2": "256 MB memset + sync before every timed step (inside the timed region, ~0.06 ms)",
                        "randomness": "r, s pinned per rank"},
             "clocks": clocks,
             "e2e": {"value": units_e / dt_e, "unit": "proofs/s", "h2d_bytes_per_step": nvars * 32, "d2h_bytes_per_step": d2h,

@@ -63,6 +63,8 @@ template <class F> __global__ void gen_bases_kernel(Affine<F> gen, Affine<F> *ou
     out[i] = r.to_affine();
 }
 
+// Dependent-free mad.lo.u32 streams (8 independent accumulators per thread).  SASS check: the `wide == 0` path is a run of
+// `IMAD Rk, Ra, Rb, Rk`; ptxas strength-reduces the loop-invariant mad.wide variant to IADD3, so only wide == 0 is a valid peak.
 __global__ void imad_peak_kernel(uint32_t *out, int iters, int wide) {
     uint32_t a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 3;
     uint64_t w0 = a, w1 = b, w2 = a ^ b, w3 = a + b, w4 = 5, w5 = 7, w6 = 11, w7 = 13;

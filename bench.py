@@ -292,7 +292,7 @@ def main():
             "config": {"workload": WORKLOADS[args.workload], "detail": workload, "l2": "256 MB memset + sync before every timed step (inside the timed region, ~0.06 ms)",
                        "randomness": "r, s pinned per rank"},
             "clocks": clocks,
-            "e2e": {"value": units_e / dt_e, "unit": "proofs/s", "h2d_bytes_per_step": nvars * 32, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": units_e / dt_e, "unit": "proofs/s", "h2d_bytes_per_step": (nvars + 1) * 8 + 40 * 8 if nvars else 0, "d2h_bytes_per_step": d2h,
                     "p50_latency_ms": round(1e3 * statistics.median(lat), 3),
                     "breakdown_ms": {k: round(statistics.median(b[k] for b in brk), 3) for k in brk[0]} if args.workload == "send" else None},
             "gpu_launches": launches,

@@ -83,7 +83,7 @@ static char *dup_hex(const std::string &s, size_t cap) {       // `new char[cap]
 template <class Fn> static char *prove_timed(int circuit, Fn make) {
     std::lock_guard<std::mutex> lk(g_abi_mu);
     void *pk = circuit_pk(circuit);
-    uint64_t *ext = reinterpret_cast<uint64_t *>(zkp::pinned_assignment((zkp::DevicePk *)pk)) - 4;      // variable 0 (ONE) sits in the pad slot
+    uint64_t *ext = zkb200_compact_staging(pk);                // pinned: the generator writes the compact assignment in place
     const double t0 = now_ms();
     const Assignment a = make(ext);
     g_last_ms[0] = now_ms() - t0;
@@ -93,7 +93,7 @@ template <class Fn> static char *prove_timed(int circuit, Fn make) {
     memset(p, 0, 1153);
     float tm[5] = {0, 0, 0, 0, 0};
     const double t1 = now_ms();
-    const int rc = zkb200_prove(pk, a.data(), (const uint8_t *)r, (const uint8_t *)s, p, nullptr, tm);
+    const int rc = zkb200_prove_compact(pk, a.lo(), a.wide.data(), a.wide.size(), (const uint8_t *)r, (const uint8_t *)s, p, tm);
     g_last_ms[1] = now_ms() - t1; g_last_ms[2] = tm[0]; g_last_ms[3] = tm[3];
     if (rc == 1) printf("can not generate %s proof\n", CIRCUIT_NAMES[circuit]);      // mintcgo.cpp:209
     return p;
@@ -197,8 +197,8 @@ char *genDepositproof(uint64_t value, uint64_t value_old, char *sn_old_string, c
         char *p = new char[1153]; memset(p, 0, 1153);
         uint64_t zero[4] = {0, 0, 0, 0};
         std::lock_guard<std::mutex> lk(g_abi_mu);
-        Assignment bad; bad.num_vars = DEPOSIT_VARS; bad.tape.assign(((size_t)DEPOSIT_VARS + 1) * 4, 0);
-        zkb200_prove(circuit_pk(ZKB200_DEPOSIT), bad.data(), (const uint8_t *)zero, (const uint8_t *)zero, p, nullptr, nullptr);
+        std::vector<uint64_t> bad((size_t)DEPOSIT_VARS + 1, 0); bad[0] = 1;      // all-zero assignment: unsatisfied -> default proof
+        zkb200_prove_compact(circuit_pk(ZKB200_DEPOSIT), bad.data(), nullptr, 0, (const uint8_t *)zero, (const uint8_t *)zero, p, nullptr);
         return p;
     }
     std::vector<uint8_t> eff(leaves.begin(), leaves.begin() + (first + 1) * 32);
@@ -218,7 +218,7 @@ long zkb200_witness_mint(uint64_t value, uint64_t value_old, const char *sn_old,
     parse_hex_blob(cmtA_old_s, cmtA_old, 32); parse_hex_blob(cmtA_s, cmtA, 32); parse_hex_blob(sk_s, sk, 32);
     Assignment a = redeem ? redeem_witness(note_old, note, cmtA_old, cmtA, value_s, sk) : mint_witness(note_old, note, cmtA_old, cmtA, value_s, sk);
     if (cap < a.num_vars) return -1;
-    memcpy(out, a.data(), (size_t)a.num_vars * 32);
+    a.expand(out);
     return a.num_vars;
 }
 long zkb200_witness_send(uint64_t value_A, const char *r_s, const char *sn, const char *r, const char *cmt_s, const char *cmtA_s, uint64_t value_s,
@@ -231,7 +231,7 @@ long zkb200_witness_send(uint64_t value_A, const char *r_s, const char *sn, cons
     parse_hex_blob(sk_s, sk, 32); parse_hex_blob(pk_sender_s, pk_sender, 20);
     Assignment a = send_witness(note_old, notes, note_new, cmtA, cmtS, cmtAnew, sk, pk_sender);
     if (cap < a.num_vars) return -1;
-    memcpy(out, a.data(), (size_t)a.num_vars * 32);
+    a.expand(out);
     return a.num_vars;
 }
 long zkb200_witness_deposit(uint64_t value, uint64_t value_old, const char *sn_old, const char *r_old, const char *sn, const char *r, const char *sns,
@@ -254,7 +254,7 @@ long zkb200_witness_deposit(uint64_t value, uint64_t value_old, const char *sn_o
     merkle_path((const uint8_t(*)[32])eff.data(), eff.size() / 32, (size_t)first, siblings, rt);
     Assignment a = deposit_witness(note_s, note_old, note, cmtS, cmtB_old, cmtB, rt, (size_t)first, siblings, sn_s, sk);
     if (cap < a.num_vars) return -1;
-    memcpy(out, a.data(), (size_t)a.num_vars * 32);
+    a.expand(out);
     return a.num_vars;
 }
 

@@ -148,7 +148,18 @@ static const char *DEFAULT_PROOF =   // (G1::one, G2::one, G1::one): r1cs_gg_ppz
     "0000000000000000000000000000000000000000000000000000000000000001"
     "0000000000000000000000000000000000000000000000000000000000000002";
 
+static int prove_any(void *h, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint8_t r[32], const uint8_t s[32],
+                     char *proof_hex_out, uint8_t *parts, float *timings_ms);
 int zkb200_prove(void *h, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32], char *proof_hex_out, uint8_t *parts, float *timings_ms) {
+    return prove_any(h, assignment, nullptr, nullptr, 0, r, s, proof_hex_out, parts, timings_ms);
+}
+int zkb200_prove_compact(void *h, const uint64_t *lo, const void *wide, size_t nwide, const uint8_t r[32], const uint8_t s[32], char *proof_hex_out,
+                         float *timings_ms) {
+    return prove_any(h, nullptr, lo, (const WideIn *)wide, (uint32_t)nwide, r, s, proof_hex_out, nullptr, timings_ms);
+}
+uint64_t *zkb200_compact_staging(void *h) { return h ? compact_staging((DevicePk *)h) : nullptr; }
+static int prove_any(void *h, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint8_t r[32], const uint8_t s[32],
+                     char *proof_hex_out, uint8_t *parts, float *timings_ms) {
     DevicePk *pk = (DevicePk *)h;
     if (!pk) return -1;
     std::lock_guard<std::mutex> lk(g_mu);
@@ -156,7 +167,7 @@ int zkb200_prove(void *h, const uint8_t *assignment, const uint8_t r[32], const 
     ProofPoints pp;
     pp.want_parts = parts != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
-    prove(pk, assignment, rr, ss, pp);
+    if (lo) prove_compact(pk, lo, wide, nwide, rr, ss, pp); else prove(pk, assignment, rr, ss, pp);
     const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (parts) { put_g1(parts, pp.At); put_g2(parts + 64, pp.Bt_g); put_g1(parts + 192, pp.Bt_h); put_g1(parts + 256, pp.Ht); put_g1(parts + 320, pp.Lt); }
     if (timings_ms) { timings_ms[0] = pp.gpu_ms; timings_ms[1] = pp.qap_ms; timings_ms[2] = pp.msm_h_ms; timings_ms[3] = (float)(total_ms - pp.gpu_ms); timings_ms[4] = pp.acc_h_ms; }

@@ -400,6 +400,7 @@ static void upload_csr(const zkpk::Csr &h, DeviceCsr &d) {
     ZK_CUDA(cudaMemcpy(d.col, h.col.data(), (size_t)d.nnz * 4, cudaMemcpyHostToDevice));
     ZK_CUDA(cudaMemcpy(d.coef, h.coef.data(), (size_t)d.nnz * 4, cudaMemcpyHostToDevice));
 }
+constexpr uint32_t MAX_WIDE = 64;
 constexpr int MSM_C = 16;                  // window bits of the resident (expanded) MSMs: 16 windows, 32768 buckets
 
 template <class A> static A fetch_point(const void *dev, size_t idx) {
@@ -489,6 +490,8 @@ DevicePk *pk_load(const char *path, int device, std::string &err) {
     const uint64_t one_can[4] = {1, 0, 0, 0};
     ZK_CUDA(cudaMemcpy(pk->w_can, one_can, 32, cudaMemcpyHostToDevice));
     ZK_CUDA(cudaMallocHost(&pk->h_w_pinned, (nw + 1) * 32));
+    ZK_CUDA(cudaMalloc(&pk->w_lo, nw * 8)); ZK_CUDA(cudaMalloc(&pk->w_wide, MAX_WIDE * sizeof(WideIn)));
+    ZK_CUDA(cudaMallocHost(&pk->h_wide_pinned, MAX_WIDE * sizeof(WideIn)));
     ZK_CUDA(cudaMalloc(&pk->bufA, m * 32)); ZK_CUDA(cudaMalloc(&pk->bufB, m * 32)); ZK_CUDA(cudaMalloc(&pk->bufC, m * 32));
     ZK_CUDA(cudaMalloc(&pk->tmp, m * 32));
     ZK_CUDA(cudaMalloc(&pk->sat_flag, 4)); ZK_CUDA(cudaMallocHost(&pk->h_sat_flag, 4));
@@ -515,6 +518,7 @@ DevicePk *pk_load(const char *path, int device, std::string &err) {
 }
 
 uint8_t *pinned_assignment(DevicePk *pk) { return (uint8_t *)pk->h_w_pinned + 32; }
+uint64_t *compact_staging(DevicePk *pk) { return (uint64_t *)pk->h_w_pinned; }
 
 void pk_free(DevicePk *pk) {
     if (!pk) return;
@@ -522,7 +526,8 @@ void pk_free(DevicePk *pk) {
     cudaDeviceSynchronize();
     void *ps[] = {pk->A, pk->B1, pk->B2, pk->H, pk->L, pk->A_skip, pk->B_skip, pk->H_skip, pk->L_skip, pk->B_idx, pk->L_idx, pk->a.rowptr, pk->a.col, pk->a.coef,
                   pk->b.rowptr, pk->b.col, pk->b.coef, pk->c.rowptr, pk->c.col, pk->c.coef, pk->coef_dict, pk->w_can, pk->w_mont, pk->bufA, pk->bufB,
-                  pk->bufC, pk->tmp, pk->sat_flag};
+                  pk->bufC, pk->tmp, pk->sat_flag, pk->w_lo, pk->w_wide};
+    if (pk->h_wide_pinned) cudaFreeHost(pk->h_wide_pinned);
     for (void *p : ps) if (p) cudaFree(p);
     if (pk->h_w_pinned) cudaFreeHost(pk->h_w_pinned);
     if (pk->h_sat_flag) cudaFreeHost(pk->h_sat_flag);
@@ -549,6 +554,37 @@ static void upload_assignment(DevicePk *pk, const uint8_t *assignment, const uin
     }
     ZK_CUDA(cudaMemcpyAsync(pk->w_mont, pk->w_can, (n + 1) * 32, cudaMemcpyDeviceToDevice, st));
     ZK_LAUNCH(to_mont_kernel, cdiv(n + 1, 256), 256, 0, st, (Fr *)pk->w_mont, (uint32_t)(n + 1));
+}
+
+// compact upload: w_can[i] = lo[i] (zero-extended), w_mont[i] = lo[i] * R, then the few wide values (and r, s, -rs) are patched in
+__global__ void expand_assignment_kernel(const uint64_t *__restrict__ lo, uint32_t count, Fr *__restrict__ w_can, Fr *__restrict__ w_mont) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t x = lo[i];
+    Fr c = Fr::zero(); c.v[0] = (uint32_t)x; c.v[1] = (uint32_t)(x >> 32);
+    st_fr(w_can + i, c);
+    st_fr(w_mont + i, x <= 1 ? (x ? Fr::one() : c) : c.to_mont());
+}
+__global__ void patch_wide_kernel(const WideIn *__restrict__ wide, uint32_t nwide, uint32_t mont_limit, Fr *__restrict__ w_can, Fr *__restrict__ w_mont) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nwide) return;
+    Fr c; memcpy(c.v, wide[k].v, 32);
+    st_fr(w_can + wide[k].idx, c);
+    if (wide[k].idx < mont_limit) st_fr(w_mont + wide[k].idx, c.to_mont());
+}
+static void upload_compact(DevicePk *pk, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t *zk_scalars, cudaStream_t st) {
+    const uint32_t n = (uint32_t)pk->num_vars;
+    uint64_t *pin = (uint64_t *)pk->h_w_pinned;
+    if (lo != pin) memcpy(pin, lo, (size_t)(n + 1) * 8);
+    WideIn *pw = (WideIn *)pk->h_wide_pinned;
+    if (nwide > MAX_WIDE - 3) nwide = MAX_WIDE - 3;                  // (circuits here have <= 10)
+    memcpy(pw, wide, nwide * sizeof(WideIn));
+    for (int k = 0; k < 3; k++) { pw[nwide + k].idx = n + 1 + k; pw[nwide + k].pad = 0; memcpy(pw[nwide + k].v, zk_scalars + 4 * k, 32); }
+    nwide += 3;
+    ZK_CUDA(cudaMemcpyAsync(pk->w_lo, pin, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    ZK_CUDA(cudaMemcpyAsync(pk->w_wide, pw, nwide * sizeof(WideIn), cudaMemcpyHostToDevice, st));
+    ZK_LAUNCH(expand_assignment_kernel, cdiv(n + 1, 256), 256, 0, st, (const uint64_t *)pk->w_lo, n + 1, (Fr *)pk->w_can, (Fr *)pk->w_mont);
+    ZK_LAUNCH(patch_wide_kernel, 1, 64, 0, st, (const WideIn *)pk->w_wide, nwide, n + 1, (Fr *)pk->w_can, (Fr *)pk->w_mont);
 }
 
 // r1cs_to_qap_witness_map (r1cs_to_qap.tcc:205-334) on stream st.  Result: coefficients_for_H[0..m) in pk->tmp (Montgomery form).
@@ -593,7 +629,16 @@ int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int
 
 static HG1 g1_mul(const HG1Affine &p, const uint64_t k[4]) { return HG1::from_affine(p).mul(k); }
 
+static int prove_staged(DevicePk *pk, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4],
+                        const uint64_t s[4], ProofPoints &out);
 int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const uint64_t s[4], ProofPoints &out) {
+    return prove_staged(pk, assignment, nullptr, nullptr, 0, r, s, out);
+}
+int prove_compact(DevicePk *pk, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4], const uint64_t s[4], ProofPoints &out) {
+    return prove_staged(pk, nullptr, lo, wide, nwide, r, s, out);
+}
+static int prove_staged(DevicePk *pk, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4],
+                        const uint64_t s[4], ProofPoints &out) {
     device_init(pk->device);
     g_launches = 0;
     cudaStream_t st = pk->s_main;
@@ -601,7 +646,8 @@ int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const ui
     memcpy(zks, r, 32); memcpy(zks + 4, s, 32);
     (HFr::from_canonical(r) * HFr::from_canonical(s)).neg().to_canonical(zks + 8);          // -(r*s) mod r
     ZK_CUDA(cudaEventRecord(pk->ev_t0, st));
-    upload_assignment(pk, assignment, zks, st);
+    if (lo) upload_compact(pk, lo, wide, nwide, zks, st);
+    else upload_assignment(pk, assignment, zks, st);
     ZK_CUDA(cudaEventRecord(pk->ev_w, st));
     ZK_CUDA(cudaStreamWaitEvent(pk->s_a, pk->ev_w, 0));
     ZK_CUDA(cudaStreamWaitEvent(pk->s_b, pk->ev_w, 0));

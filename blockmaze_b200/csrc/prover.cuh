@@ -85,6 +85,8 @@ struct DevicePk {
     // per-proof work buffers
     void *w_can = nullptr, *w_mont = nullptr;            // (num_vars + 1) scalars: [1 | assignment]
     void *h_w_pinned = nullptr;
+    void *w_lo = nullptr, *w_wide = nullptr;              // device: compact assignment staging
+    void *h_wide_pinned = nullptr;
     void *bufA = nullptr, *bufB = nullptr, *bufC = nullptr, *tmp = nullptr;   // m Fr each
     uint32_t *sat_flag = nullptr; uint32_t *h_sat_flag = nullptr;
     MsmPlan mA, mB, mH, mL;
@@ -107,6 +109,11 @@ struct ProofPoints {
 // assignment: num_vars canonical 32-byte LE scalars in HOST memory (copied H2D inside), or nullptr to reuse the
 // assignment already resident on the device (bench "value" leg).
 int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const uint64_t s[4], ProofPoints &out);
+// Compact form (witness.hpp): lo[0..num_vars] = low 64 bits per variable (lo[0] = 1), wide = the few values above 64 bits.
+// Uploads 8 B per variable; lo may be compact_staging(pk) itself to skip the staging copy.
+struct WideIn { uint32_t idx; uint32_t pad; uint64_t v[4]; };
+int prove_compact(DevicePk *pk, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4], const uint64_t s[4], ProofPoints &out);
+uint64_t *compact_staging(DevicePk *pk);                // pinned, (num_vars + 1) uint64
 // QAP witness map only; writes (m+1)*32 bytes canonical to host `out_H`
 int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied);
 

@@ -123,18 +123,23 @@ typedef std::vector<int32_t> Refs;        // >= 0: variable index (0 = constant 
 
 struct Tape {
     std::vector<uint64_t> own;
+    std::vector<WideValue> wide;
     uint64_t *v, *ext;
     uint32_t next = 1, cap;
     Tape(uint32_t nvars, uint64_t *ext_) : ext(ext_), cap(nvars) {
-        const size_t words = ((size_t)nvars + 1) * 4;
+        const size_t words = (size_t)nvars + 1;
         if (ext) { v = ext; memset(v, 0, words * 8); } else { own.assign(words, 0); v = own.data(); }
         v[0] = 1;
     }
     uint32_t alloc(uint32_t n = 1) { uint32_t r = next; next += n; return r; }
     Refs alloc_refs(uint32_t n) { uint32_t b = alloc(n); Refs r(n); for (uint32_t i = 0; i < n; i++) r[i] = (int32_t)(b + i); return r; }
-    uint64_t get(int32_t ref) const { return ref < 0 ? 0 : v[(size_t)ref * 4]; }
-    void set(uint32_t idx, uint64_t x) { uint64_t *p = &v[(size_t)idx * 4]; p[0] = x; p[1] = p[2] = p[3] = 0; }
-    void set4(uint32_t idx, const uint64_t x[4]) { memcpy(&v[(size_t)idx * 4], x, 32); }
+    uint64_t get(int32_t ref) const { return ref < 0 ? 0 : v[ref]; }
+    void set(uint32_t idx, uint64_t x) { v[idx] = x; }
+    void set4(uint32_t idx, const uint64_t x[4]) {                  // values that may exceed 64 bits (packed inputs, 2^64+B-A, inverses)
+        v[idx] = x[0];
+        for (size_t k = 0; k < wide.size(); k++) if (wide[k].idx == idx) { wide.erase(wide.begin() + k); break; }
+        if (x[1] | x[2] | x[3]) { WideValue w; w.idx = idx; w.pad = 0; memcpy(w.v, x, 32); wide.push_back(w); }
+    }
     void setref(int32_t ref, uint64_t x) { if (ref > 0) set((uint32_t)ref, x); }     // writes to ONE / constants are dropped
 };
 
@@ -335,7 +340,7 @@ struct LessCmp {
 };
 
 static Assignment finish(Tape &t) {
-    Assignment a; a.num_vars = t.cap; a.ext = t.ext; if (!t.ext) a.tape = std::move(t.own); return a;
+    Assignment a; a.num_vars = t.cap; a.ext = t.ext; a.wide = std::move(t.wide); if (!t.ext) a.own = std::move(t.own); return a;
 }
 } // namespace
 

@@ -31,13 +31,24 @@ void merkle_root(const uint8_t (*leaves)[32], size_t n, uint8_t out[32]);
 void merkle_path(const uint8_t (*leaves)[32], size_t n, size_t index, uint8_t siblings[MERKLE_DEPTH][32], uint8_t root[32]);
 
 // ---- full assignments -----------------------------------------------------------------------------------------------------
+// Compact form: ~97 % of a BlockMaze assignment is 0/1 and all but a handful of values fit 64 bits, so the assignment is kept as one
+// uint64 per variable (`lo`) plus a short list of values wider than 64 bits.  This is what travels to the GPU (8 B instead of 32 B
+// per variable); expand() produces the canonical 32-byte form of the C-ABI.
+struct WideValue { uint32_t idx; uint32_t pad; uint64_t v[4]; };      // idx = variable index (1-based, 0 is the constant ONE)
 struct Assignment {
-    std::vector<uint64_t> tape;       // (num_vars + 1) x 4 limbs, variable i at tape[4*i..], variable 0 = constant ONE
-    uint64_t *ext = nullptr;          // caller-provided storage of the same shape (e.g. pinned host memory) used instead of `tape`
+    std::vector<uint64_t> own;        // (num_vars + 1) low words, variable i at [i], variable 0 = constant ONE
+    uint64_t *ext = nullptr;          // caller-provided storage of the same shape (e.g. pinned host memory) used instead of `own`
+    std::vector<WideValue> wide;
     uint32_t num_vars = 0;
-    const uint8_t *data() const { return reinterpret_cast<const uint8_t *>((ext ? ext : tape.data()) + 4); }   // num_vars x 32 B canonical LE
+    const uint64_t *lo() const { return ext ? ext : own.data(); }
+    void expand(uint8_t *out) const {                                  // num_vars x 32 B canonical little-endian
+        const uint64_t *l = lo();
+        uint64_t *o = reinterpret_cast<uint64_t *>(out);
+        for (uint32_t i = 1; i <= num_vars; i++) { o[4 * (i - 1)] = l[i]; o[4 * (i - 1) + 1] = o[4 * (i - 1) + 2] = o[4 * (i - 1) + 3] = 0; }
+        for (const WideValue &w : wide) memcpy(o + 4 * (size_t)(w.idx - 1), w.v, 32);
+    }
 };
-// Every generator takes an optional `ext` buffer of (num_vars + 1) * 4 uint64 to build the assignment in place.
+// Every generator takes an optional `ext` buffer of (num_vars + 1) uint64 to build the low words in place.
 
 struct Note { uint64_t value; uint8_t sn[32]; uint8_t r[32]; };
 struct NoteS { uint64_t value; uint8_t pk[20]; uint8_t r[32]; uint8_t sn_old[32]; };

@@ -88,6 +88,12 @@ const char *zkb200_last_error(void);
  * Returns 0 = proof, 1 = constraint system not satisfied (proof_hex = default proof), <0 = error. */
 int zkb200_prove(void *pk, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32], char *proof_hex, uint8_t *parts,
                  float *timings_ms);
+/* Same prover fed with the COMPACT assignment the native witness generators produce: lo[0..num_variables] = low 64 bits of every
+ * variable (lo[0] = 1, the constant ONE), wide = nwide records {uint32 idx; uint32 pad; uint64 v[4]} for the few values above 64 bits.
+ * 8 instead of 32 bytes per variable cross PCIe.  lo may be zkb200_compact_staging(pk) (pinned) to skip the staging copy. */
+int zkb200_prove_compact(void *pk, const uint64_t *lo, const void *wide, size_t nwide, const uint8_t r[32], const uint8_t s[32], char *proof_hex,
+                         float *timings_ms);
+uint64_t *zkb200_compact_staging(void *pk);
 /* Replaces r1cs_to_qap_witness_map (r1cs_to_qap.tcc:205-334): out_H receives (m+1) x 32 B coefficients_for_H. */
 int zkb200_qap_witness_map(void *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied);
 /* milliseconds of the last gen*proof call: host witness generation, zkb200_prove total, of which GPU (CUDA events), host finish */

@@ -299,7 +299,8 @@ def main():
             "gpu_ms_per_proof": {"total": round(statistics.mean(gpu_ms), 3), "qap_witness_map": round(statistics.mean(qap_ms), 3),
                                  "msm_H": round(statistics.mean(msm_ms), 3), "msm_H_accumulate_kernel": round(acc_avg, 3)},
             "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel<Fq> (H query, %d points)" % n_h, "achieved": round(ach, 3), "peak": round(imad_peak, 2),
-                         "unit": "TIMAD/s", "frac": round(ach / imad_peak, 4) if imad_peak else None, "traffic": None,
+                         "unit": "TIMAD/s", "frac": round(ach / imad_peak, 4) if imad_peak else None,
+                         "traffic": {"dram_bytes_per_launch": 522112768, "source": "profiles/r01_notes.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of this launch)"},
                          "note": "integer-multiply roofline (north_star): algorithmic 23936 IMAD/point / CUDA-event kernel time; peak = dependent-free mad.lo.u32 microbenchmark in this run"},
         }
         line.update(extras)

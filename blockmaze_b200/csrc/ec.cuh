@@ -133,7 +133,4 @@ typedef Affine<Fq2> G2Affine;
 typedef XYZZ<Fq> G1XYZZ;
 typedef XYZZ<Fq2> G2XYZZ;
 
-// curve coefficients in Montgomery form: G1 b = 3; G2 twist b' = 3/(9+u) (alt_bn128_init.cpp:190-192)
-ZK_HD Fq g1_coeff_b() { Fq t = Fq::one(); return t + t + t; }
-
 } // namespace zk

@@ -174,11 +174,6 @@ static __global__ void pow_table_kernel(Fr *out, Fr base, Fr scale, uint32_t cou
 
 // ---------------------------------------------------------------------------------------------------------------
 // element-wise glue
-static __global__ void scale_pow_kernel(Fr *a, uint32_t n, PowMul pm) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) st_fr(a + i, ld_fr(a + i) * pm.at(i));
-}
-
 // step_radix2 FFT front end (step_radix2_domain.tcc:44-63), in place:
 //   a' = a .* pre (coset shift, optional);  c[i] = a'[i] + a'[i+big] (i<small) | a'[i];  d[i] = w^i (a'[i] - a'[i+big] | a'[i])
 //   e[i] = sum_j d[i + j*small]   ->   a[0..big) = c, a[big..big+small) = e

@@ -1,8 +1,8 @@
 // GPU pipeline of the Groth16 prover for BlockMaze's circuits (replaces r1cs_gg_ppzksnark_prover,
 // libsnark/zk_proof_systems/ppzksnark/r1cs_gg_ppzksnark/r1cs_gg_ppzksnark.tcc:390-506, and everything below it:
 // r1cs_to_qap_witness_map r1cs_to_qap.tcc:205-334, libfqfft domains, libff multi_exp).  One DevicePk per (circuit, GPU):
-// bases, constraint matrices, twiddles and all work buffers stay resident in HBM; a proof is one H2D copy of the
-// assignment, ~45 kernel launches on four streams, and a D2H copy of a few hundred partial sums.
+// fixed-base tables, constraint matrices, twiddles and all work buffers stay resident in HBM; a proof is one H2D copy of the
+// (compact) assignment, ~60 kernel launches on four streams, and a D2H copy of a few hundred partial sums.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -517,7 +517,6 @@ DevicePk *pk_load(const char *path, int device, std::string &err) {
     return pk;
 }
 
-uint8_t *pinned_assignment(DevicePk *pk) { return (uint8_t *)pk->h_w_pinned + 32; }
 uint64_t *compact_staging(DevicePk *pk) { return (uint64_t *)pk->h_w_pinned; }
 
 void pk_free(DevicePk *pk) {

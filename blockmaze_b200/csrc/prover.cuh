@@ -44,7 +44,6 @@ struct MsmPlan {
     int c = 0, windows = 0;
     uint32_t nb = 0, ones = 0, total = 0;
     uint32_t seg = 0, bpw = 0;  // reduce: buckets per thread, CTAs per window
-    uint32_t ones_bpw = 0;
     void *counts = nullptr, *offsets = nullptr, *cursors = nullptr, *entries = nullptr;
     size_t entries_cap = 0;
     bool expanded = false;      // bases hold 2^(c*k)*P for every window k: one bucket region, no Horner
@@ -117,9 +116,6 @@ uint64_t *compact_staging(DevicePk *pk);                // pinned, (num_vars + 1
 // QAP witness map only; writes (m+1)*32 bytes canonical to host `out_H`
 int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied);
 
-// pinned host staging buffer shaped [pad(32 B) | assignment | r | s | -rs]: build the assignment at +32 and pass that pointer to
-// prove() to skip the staging copy
-uint8_t *pinned_assignment(DevicePk *pk);
 void device_init(int device);
 std::string proof_hex(const ProofPoints &p);           // mintcgo.cpp:112-187 layout
 int launches_last_prove();                             // number of kernels launched by the last prove() call

@@ -70,6 +70,8 @@ lib.zkb200_witness_send.argtypes = GEN_SIGS["send"] + [C.c_void_p, C.c_size_t]
 lib.zkb200_witness_deposit.restype = C.c_long
 lib.zkb200_witness_deposit.argtypes = GEN_SIGS["deposit"] + [C.c_void_p, C.c_size_t]
 
+lib.zkb200_keygen.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_char_p, C.POINTER(C.c_double)]
+
 DOMAIN_OPS = {"FFT": 0, "iFFT": 1, "cosetFFT": 2, "icosetFFT": 3, "divide_by_Z_on_coset": 4}
 FIELD_OPS = {"mul": 0, "add": 1, "sub": 2, "sqr": 3, "to_mont": 4, "from_mont": 5, "inverse": 6}
 
@@ -188,6 +190,16 @@ def witness(circuit, args):
     if got != n:
         raise ZkError("witness generation failed (%d)" % got)
     return out.raw
+
+
+def keygen(cs_source_pk, out_pk, out_vk, words=()):
+    """Generate a fresh key pair for the constraint system embedded in `cs_source_pk` (zkb200_keygen).  Returns phase seconds."""
+    arr = (C.c_uint32 * max(1, len(words)))(*words)
+    secs = (C.c_double * 3)()
+    rc = lib.zkb200_keygen(os.fsencode(cs_source_pk), C.cast(arr, C.c_void_p), len(words), os.fsencode(out_pk), os.fsencode(out_vk), secs)
+    if rc != 0:
+        raise ZkError("zkb200_keygen failed (%d)" % rc)
+    return [float(x) for x in secs]
 
 
 class ProvingKey:

@@ -315,6 +315,16 @@ static bool verify(int circuit, const char *proof, const std::vector<bool> &inpu
 }
 } // namespace
 
+// e(P, Q) as libff's alt_bn128_reduced_pairing computes it; out = the 12 Fq coefficients in the order operator<< prints them
+// (c0.c0.c0, c0.c0.c1, c0.c1.c0, ... c1.c2.c1).  Used by the key generator for alpha_g1_beta_g2.
+namespace zkv {
+void reduced_pairing(const HG1Affine &P, const HG2Affine &Q, HFq out[12]) {
+    const Fq12 f = final_exponentiation(multi_miller({P}, {Q}));
+    const HFq2 *c[6] = {&f.c0.c0, &f.c0.c1, &f.c0.c2, &f.c1.c0, &f.c1.c1, &f.c1.c2};
+    for (int i = 0; i < 6; i++) { out[2 * i] = c[i]->c0; out[2 * i + 1] = c[i]->c1; }
+}
+} // namespace zkv
+
 bool verifyMintproof(char *data, char *cmtA_old_string, char *sn_old_string, char *cmtA_string, uint64_t value_s) {
     uint8_t a[32], b[32], c[32];
     zkw::parse_hex_blob(cmtA_old_string, a, 32); zkw::parse_hex_blob(sn_old_string, b, 32); zkw::parse_hex_blob(cmtA_string, c, 32);

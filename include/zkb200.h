@@ -115,6 +115,14 @@ long zkb200_witness_deposit(uint64_t value, uint64_t value_old, const char *sn_o
                             const char *sn_A_old, const char *cmtS, const char *cmtarray, int n, const char *RT, const char *sk, uint8_t *out,
                             size_t cap);
 
+/* Replaces r1cs_gg_ppzksnark_generator + the *_key tools (r1cs_gg_ppzksnark.tcc:211-388, SRC/<c>/getpvk.cpp) for the constraint system
+ * embedded in an existing proving-key file: draws t, alpha, beta, gamma, delta and the two generator scalars from `words` (same
+ * consumption as Fr::random_element; n_words = 0: OS entropy), evaluates the QAP at t on the host and does the ~2.3 M fixed-base
+ * scalar multiplications on the GPU, then writes pk / vk files in the reference's format.  seconds[0..2] = host QAP evaluation,
+ * GPU fixed-base phase, file encoding.  Returns 0 on success. */
+int zkb200_keygen(const char *cs_source_pk_path, const uint32_t *words, size_t n_words, const char *out_pk_path, const char *out_vk_path,
+                  double seconds[3]);
+
 /* Replaces libfqfft::get_evaluation_domain(min_size) + domain->{FFT,iFFT,cosetFFT,icosetFFT,divide_by_Z_on_coset}
  * (get_evaluation_domain.tcc:33-52, basic_radix2_domain.tcc:26-112, step_radix2_domain.tcc:21-248).
  * op: 0 FFT, 1 iFFT, 2 cosetFFT (g = 5), 3 icosetFFT, 4 divide_by_Z_on_coset.  data: n = domain size elements, in place.

@@ -135,3 +135,34 @@ def test_reference_verifier_accepts_gpu_proof(zk, ref):
     L.verifyMintproof.argtypes = [C.c_char_p] * 4 + [C.c_uint64]
     va = zk.verify_args("mint", args)
     assert L.verifyMintproof(proof.encode(), *[x.encode() if isinstance(x, str) else x for x in va])
+
+
+@pytest.mark.parametrize("circuit", CIRCUITS)
+def test_keygen_byte_identical_to_reference_key_tool(zk, circuit, tmp_path):
+    """SURVEY.md 8(f) rank 4.  With the random word stream pinned, zkb200_keygen writes the same pk/vk bytes as the reference's
+    <circuit>_key tool run under LD_PRELOAD=libfixed_rng.so with the same seed (sha256 + size recorded in tests/golden/keygen.json by
+    tests/golden/make_keygen_golden.py); the constraint system comes from the key file that travels with the repo."""
+    gk = json.load(open(os.path.join(GOLD, "keygen.json")))[circuit]
+    pk_out, vk_out = str(tmp_path / "pk.txt"), str(tmp_path / "vk.txt")
+    secs = zk.keygen(os.path.join(key_dir(), circuit + "pk.txt"), pk_out, vk_out, O.fixed_rng_words(gk["seed"], 512))
+    pk_bytes, vk_bytes = open(pk_out, "rb").read(), open(vk_out, "rb").read()
+    assert len(pk_bytes) == gk["pk_size"] and len(vk_bytes) == gk["vk_size"]
+    assert hashlib.sha256(vk_bytes).hexdigest() == gk["vk_sha256"]
+    assert hashlib.sha256(pk_bytes).hexdigest() == gk["pk_sha256"]
+    assert sum(secs) < 60
+
+
+def test_keygen_keys_prove_and_verify(zk, tmp_path):
+    """A key pair generated on the GPU with fresh randomness is usable end to end: prove with it, verify with its vk."""
+    d = tmp_path / "keys"
+    d.mkdir()
+    zk.keygen(os.path.join(key_dir(), "mintpk.txt"), str(d / "mintpk.txt"), str(d / "mintvk.txt"))
+    zk.set_key_dir(str(d))
+    try:
+        args = F.synthetic("mint", 21)
+        proof = zk.gen_proof("mint", args)
+        assert zk.verify_proof("mint", proof, zk.verify_args("mint", args))
+        other = F.synthetic("mint", 22)
+        assert not zk.verify_proof("mint", proof, zk.verify_args("mint", other))
+    finally:
+        zk.set_key_dir(key_dir())

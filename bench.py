@@ -21,6 +21,24 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+
+# The cgo layer printf()s what the reference prints ("Trying to generate send proof..."): send the process's stdout to stderr and keep
+# the real stdout for the one JSON line of the contract.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    if _REAL_STDOUT is None:
+        print(json.dumps(obj), flush=True)
+    else:
+        os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
@@ -28,7 +46,15 @@ CONSTRAINTS = {"mint": 167270, "send": 252286, "deposit": 503863, "redeem": 1678
 DOMAIN = {"mint": 196608, "send": 262144, "deposit": 524288, "redeem": 196608}
 WORKLOADS = {"send": "send circuit (252286 constraints, QAP domain 2^18): one Groth16 proof per step per GPU",
              "mixed1024": "mixed batch of 1024 synthetic mint/send/deposit/redeem transactions sharded over the GPUs"}
-IMAD_PER_G1_POINT = 23936          # 16 windows x (11 modmul x 136 IMAD) per point of a 254-bit G1 MSM
+IMAD_PER_G1_POINT = 23936          # 16 windows x (11 modmul x 136 wide multiply-adds) per point of a 254-bit G1 MSM
+MODMUL_PER_G1_ADD = 10             # what msm_accumulate_kernel really issues: XYZZ += affine is 8M + 2S (ec.cuh)
+
+
+def imad_peaks(api):
+    """Measured in this run (cabi.cu imad_peak_kernel): 32-bit IMAD, carry-chained wide IMAD (SURVEY.md 8d's denominator: the
+    field multiplication is made of IMAD.WIDE.U32.X, which issues at half the IMAD rate), whole modular multiplications."""
+    return {"imad32_T": float(api.lib.zkb200_bench_imad_peak(0)), "imad_wide_T": float(api.lib.zkb200_bench_imad_peak(1)),
+            "modmul_G": 1e3 * float(api.lib.zkb200_bench_imad_peak(2))}
 
 
 def shard_batch(seeds, rank, world):
@@ -107,7 +133,7 @@ def reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": "proofs_per_sec", "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (libff Fp_model, 254-bit Montgomery)", "data": "synthetic"}
     if not Rf.available(circuit + "_mt"):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_send_mt.so not built (needs /root/reference at build time)"}))
+        emit(({"impl": "reference", "unavailable": "oracle/_ref/libref_send_mt.so not built (needs /root/reference at build time)"}))
         return
     os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
     t0 = time.perf_counter()
@@ -133,7 +159,7 @@ def reference_arm(args, rank, world):
                               "sample": "%d send proofs, libsnark -DMULTICORE -fopenmp, OMP_NUM_THREADS=%d; prover phases avg s: qap %.2f A %.2f B %.2f H %.2f L %.2f"
                                         % (args.steps, cores, *[p / args.steps for p in phases])},
                 e2e={"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)
-    print(json.dumps(line))
+    emit((line))
 
 
 def main():
@@ -147,6 +173,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip per-circuit latency table and NTT roofline")
     args = ap.parse_args()
+    capture_stdout()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 
@@ -176,7 +203,7 @@ def main():
 
     if args.workload == "sweep":
         if rank == 0:
-            print(json.dumps(kernel_sweep(api)))
+            emit((kernel_sweep(api)))
         return
     if args.workload == "msm_split":
         msm_split(args, api, dist, rank, world, barrier)
@@ -189,46 +216,69 @@ def main():
     sampler = ClockSampler(local)
     windows = []
 
+    from concurrent.futures import ThreadPoolExecutor
+    depth = pk.lanes                       # proofs in flight per GPU (zkb200.h "lanes")
+
     if args.workload == "send":
-        # ---- leg 1: `value` -- assignment resident in HBM -------------------------------------------------------------------------
         tx0 = F.synthetic("send", rank)
         w0 = api.witness("send", tx0)
+        # ---- sequential pass (one proof at a time, L2 flushed before each): per-kernel CUDA-event times for the rooflines ----------
         res = pk.prove(w0, r, s)
         assert res["rc"] == 0
-        for _ in range(args.warmup):
-            api.lib.zkb200_flush_l2(); pk.prove(None, r, s)
-        barrier()
-        t0 = time.perf_counter()
-        acc_ms, qap_ms, msm_ms, gpu_ms, launches = [], [], [], [], 0
-        for _ in range(args.steps):
+        acc_ms, qap_ms, msm_ms, gpu_ms = [], [], [], []
+        for i in range(args.warmup + min(args.steps, 30)):
             api.lib.zkb200_flush_l2()
             res = pk.prove(None, r, s)
-            gpu_ms.append(res["timings_ms"][0]); qap_ms.append(res["timings_ms"][1]); msm_ms.append(res["timings_ms"][2]); acc_ms.append(res["timings_ms"][4])
-            launches += res["launches"]
+            if i >= args.warmup:
+                gpu_ms.append(res["timings_ms"][0]); qap_ms.append(res["timings_ms"][1]); msm_ms.append(res["timings_ms"][2]); acc_ms.append(res["timings_ms"][4])
+        # ---- leg 1: `value` -- assignment resident in HBM, `depth` proofs in flight ------------------------------------------------
+        lanes = [pk.lane_acquire() for _ in range(depth)]
+        for ln in lanes:                     # make the assignment resident on every lane
+            pk.submit(ln, w0, r, s)
+        for ln in lanes:
+            assert pk.collect(ln)["rc"] == 0
+        for i in range(args.warmup):
+            pk.submit(lanes[i % depth], None, r, s); pk.collect(lanes[i % depth])
+        barrier()
+        t0 = time.perf_counter()
+        launches = 0
+        for i in range(args.steps):
+            ln = lanes[i % depth]
+            if i >= depth:
+                launches += pk.collect(ln)["launches"]
+            pk.submit(ln, None, r, s)
+        for i in range(args.steps, args.steps + min(depth, args.steps)):
+            launches += pk.collect(lanes[i % depth])["launches"]
         barrier()
         t1 = time.perf_counter()
+        for ln in lanes:
+            pk.lane_release(ln)
         windows.append((t0, t1))
         units, dt = reduce_counts_and_time(args.steps, t1 - t0, dist)
-        # ---- leg 2: `e2e` -- the cgo call a BlockMaze node makes, host string arguments in, proof string out --------------------
+        # ---- leg 2: `e2e` -- the cgo call a BlockMaze node makes, host string arguments in, proof string out; `depth` caller threads
+        #      (goroutines in geth), each call synchronous --------------------------------------------------------------------------
         txs = [F.synthetic("send", rank + world * (i + 1)) for i in range(args.warmup + args.steps)]
-        for i in range(args.warmup):
-            api.gen_proof("send", txs[i])
+        lat, brk = [], []
+        for i in range(args.warmup + min(args.steps, 30)):          # single caller: latency and its breakdown
+            ta = time.perf_counter()
+            proof = api.gen_proof("send", txs[i])
+            if i >= args.warmup:
+                lat.append(time.perf_counter() - ta)
+                brk.append(api.last_breakdown_ms())
+        pool = ThreadPoolExecutor(depth)
+        list(pool.map(lambda tx: api.gen_proof("send", tx), txs[:args.warmup]))
         barrier()
         t2 = time.perf_counter()
-        lat, brk = [], []
-        for i in range(args.steps):
-            ta = time.perf_counter()
-            proof = api.gen_proof("send", txs[args.warmup + i])
-            lat.append(time.perf_counter() - ta)
-            brk.append(api.last_breakdown_ms())
+        proofs = list(pool.map(lambda tx: api.gen_proof("send", tx), txs[args.warmup:]))
         barrier()
         t3 = time.perf_counter()
+        pool.shutdown()
         windows.append((t2, t3))
-        assert not proof.startswith("0000000000"), "prover returned the default proof for a valid transaction"
+        assert all(not p_.startswith("0000000000") for p_ in proofs + [proof]), "prover returned the default proof for a valid transaction"
         units_e, dt_e = reduce_counts_and_time(args.steps, t3 - t2, dist)
         nvars = pk.num_variables
-        workload = ("send circuit (%d constraints, %d variables, QAP domain 2^18): one Groth16 proof per GPU per step; value = resident assignment, "
-                    "e2e = genSendproof() cgo call" % (CONSTRAINTS["send"], nvars))
+        workload = ("send circuit (%d constraints, %d variables, QAP domain 2^18): one Groth16 proof per step per GPU, %d proofs in flight; value = resident "
+                    "assignment through submit/collect, e2e = genSendproof() cgo calls from %d caller threads" % (CONSTRAINTS["send"], nvars, depth, depth))
         d2h = 4 + sum(128 * (p + 1) * b for p, b in ((24, 4), (24, 4), (24, 4))) + 256 * 25 * 4 + 128 * 19 * 16
     else:
         # mixed batch of 1024 synthetic transactions, type = seed mod 4, sharded round-robin over the ranks (strong scaling)
@@ -237,19 +287,25 @@ def main():
         txs = [(names[sd % 4], F.synthetic(names[sd % 4], sd)) for sd in mine]
         for c in names:
             api.gen_proof(c, F.synthetic(c, 5000 + rank))
+        lat = []
+
+        def one(ctx):
+            ta = time.perf_counter(); api.gen_proof(ctx[0], ctx[1]); return time.perf_counter() - ta
+        pool = ThreadPoolExecutor(depth)
+        list(pool.map(one, [(c, F.synthetic(c, 6000 + rank)) for c in names] * 2))
         barrier()
         t0 = time.perf_counter()
-        lat = []
-        for c, tx in txs:
-            ta = time.perf_counter(); api.gen_proof(c, tx); lat.append(time.perf_counter() - ta)
+        lat = list(pool.map(one, txs))
         barrier()
         t1 = time.perf_counter()
+        pool.shutdown()
         windows.append((t0, t1))
         units, dt = reduce_counts_and_time(len(txs), t1 - t0, dist)
         units_e, dt_e, launches, acc_ms, qap_ms, msm_ms, gpu_ms, brk = units, dt, 0, [0.0], [0.0], [0.0], [0.0], []
         args.steps = 1
         nvars = 0
-        workload = "mixed batch of 1024 synthetic mint/send/deposit/redeem transactions (256 each) sharded round-robin over the GPUs, through gen*proof()"
+        workload = ("mixed batch of 1024 synthetic mint/send/deposit/redeem transactions (256 each) sharded round-robin over the GPUs, through gen*proof() "
+                    "from %d caller threads per GPU" % depth)
         d2h = 0
 
     clocks = sampler.stop(windows)
@@ -278,30 +334,45 @@ def main():
         extras["roofline_ntt"] = {"bound": "hbm", "kernel": "ntt_pass_kernel x3 (2^24-point forward NTT)", "achieved": round(ach, 1), "peak": hbm_peak,
                                   "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": None, "ms": round(ms_ntt, 4),
                                   "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
+        mm_peak = 1e3 * float(api.lib.zkb200_bench_imad_peak(2))
+        mm_rate = 12.0 * (1 << 24) / (ms_ntt * 1e-3) / 1e9          # (n/2) * log2(n) butterflies, one modular multiplication each
+        extras["roofline_ntt"]["integer_bound"] = {
+            "modmul_G_per_s": round(mm_rate, 2), "modmul_peak_G_per_s": round(mm_peak, 2), "frac": round(mm_rate / mm_peak, 4) if mm_peak else None,
+            "what": "a 254-bit NTT is bound by the integer-multiply pipe, not HBM: 12 modular multiplications per 64 algorithmic bytes "
+                    "cap it at modmul_peak * 64 / 12 bytes/s (about 0.36 TB/s), 5.6 % of the HBM peak"}
 
     line = None
     if rank == 0:
-        imad_peak = float(api.lib.zkb200_bench_imad_peak(0))
+        pk_ = imad_peaks(api)
+        imad_peak = pk_["imad_wide_T"]
         acc_avg = statistics.mean(acc_ms) if acc_ms else 0.0
         n_h = DOMAIN["send"] - 1
         ach = IMAD_PER_G1_POINT * n_h / (acc_avg * 1e-3) / 1e12 if acc_avg > 0 else 0.0
+        modmul_rate = MODMUL_PER_G1_ADD * 16 * n_h / (acc_avg * 1e-3) / 1e9 if acc_avg > 0 else 0.0
         line = {
             "metric": "proofs_per_sec", "value": units / dt, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload == "send" else "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "detail": workload, "l2": "256 MB memset + sync before every timed step (inside the timed region, ~0.06 ms)",
+            "config": {"workload": WORKLOADS[args.workload], "detail": workload, "l2": "no flush in the timed loops: every proof streams ~0.6 GB of fixed-base tables (all 16 windows of the H, A, B, L queries), "
+                             "5x the 126 MB L2; the sequential pass behind gpu_ms_per_proof and the rooflines flushes L2 (256 MB memset) before every proof",
+                       "proofs_in_flight": depth,
                        "randomness": "r, s pinned per rank"},
             "clocks": clocks,
             "e2e": {"value": units_e / dt_e, "unit": "proofs/s", "h2d_bytes_per_step": (nvars + 1) * 8 + 40 * 8 if nvars else 0, "d2h_bytes_per_step": d2h,
                     "p50_latency_ms": round(1e3 * statistics.median(lat), 3),
                     "breakdown_ms": {k: round(statistics.median(b[k] for b in brk), 3) for k in brk[0]} if args.workload == "send" else None},
             "gpu_launches": launches,
-            "gpu_ms_per_proof": {"total": round(statistics.mean(gpu_ms), 3), "qap_witness_map": round(statistics.mean(qap_ms), 3),
+            "gpu_ms_per_proof": {"what": "one proof at a time, CUDA events", "total": round(statistics.mean(gpu_ms), 3), "qap_witness_map": round(statistics.mean(qap_ms), 3),
                                  "msm_H": round(statistics.mean(msm_ms), 3), "msm_H_accumulate_kernel": round(acc_avg, 3)},
             "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel<Fq> (H query, %d points)" % n_h, "achieved": round(ach, 3), "peak": round(imad_peak, 2),
                          "unit": "TIMAD/s", "frac": round(ach / imad_peak, 4) if imad_peak else None,
                          "traffic": {"dram_bytes_per_launch": 522112768, "source": "profiles/r01_notes.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of this launch)"},
-                         "note": "integer-multiply roofline (north_star): algorithmic 23936 IMAD/point / CUDA-event kernel time; peak = dependent-free mad.lo.u32 microbenchmark in this run"},
+                         "issued": {"modmul_G_per_s": round(modmul_rate, 2), "modmul_peak_G_per_s": round(pk_["modmul_G"], 2),
+                                    "frac": round(modmul_rate / pk_["modmul_G"], 4) if pk_["modmul_G"] else None,
+                                    "what": "modular multiplications the kernel really issues (10 per mixed addition, 16 per point) against a kernel of back-to-back ff.cuh multiplications"},
+                         "peaks": {k: round(v, 2) for k, v in pk_.items()},
+                         "note": "integer-multiply roofline (SURVEY.md 8d): algorithmic 23936 wide multiply-adds per point / CUDA-event kernel time; "
+                                 "peak = carry-chained mad.lo.cc/madc.hi.cc (IMAD.WIDE.U32.X) microbenchmark in this run"},
         }
         line.update(extras)
         if world == 1 and not args.no_cpu_baseline and args.workload == "send":
@@ -310,7 +381,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        emit((line))
 
 
 def kernel_sweep(api):
@@ -323,7 +394,7 @@ def kernel_sweep(api):
     except OSError:
         pass
     hbm = peaks.get("hbm_gbs", 6650.0)
-    imad = float(api.lib.zkb200_bench_imad_peak(0))
+    imad = float(api.lib.zkb200_bench_imad_peak(1))
     cpu = None
     try:
         from oracle import refapi as Rf
@@ -391,7 +462,7 @@ def msm_split(args, api, dist, rank, world, barrier):
             if any(b):
                 acc = O.G1.add(acc, O.G1.from_affine((int.from_bytes(b[:32], "little"), int.from_bytes(b[32:], "little"))))
         aff = O.G1.to_affine(acc)
-        print(json.dumps({"metric": "msm_points_per_sec", "value": units / tmax, "unit": "points/s", "n_gpus": world, "ms_per_step": 1e3 * tmax,
+        emit(({"metric": "msm_points_per_sec", "value": units / tmax, "unit": "points/s", "n_gpus": world, "ms_per_step": 1e3 * tmax,
                           "higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "u32",
                           "config": {"workload": "single G1 MSM of 2^%d points split by point range, one partial point per GPU summed on the host" % args.logn},
                           "result_x": "%064x" % (aff[0] if aff else 0)}))

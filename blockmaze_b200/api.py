@@ -70,6 +70,12 @@ lib.zkb200_witness_send.argtypes = GEN_SIGS["send"] + [C.c_void_p, C.c_size_t]
 lib.zkb200_witness_deposit.restype = C.c_long
 lib.zkb200_witness_deposit.argtypes = GEN_SIGS["deposit"] + [C.c_void_p, C.c_size_t]
 
+lib.zkb200_pk_lanes.argtypes = [C.c_void_p]
+lib.zkb200_lane_acquire.argtypes = [C.c_void_p]
+lib.zkb200_lane_release.argtypes = [C.c_void_p, C.c_int]
+lib.zkb200_lane_release.restype = None
+lib.zkb200_prove_submit.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p]
+lib.zkb200_prove_collect.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.POINTER(C.c_float)]
 lib.zkb200_keygen.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_char_p, C.POINTER(C.c_double)]
 
 DOMAIN_OPS = {"FFT": 0, "iFFT": 1, "cosetFFT": 2, "icosetFFT": 3, "divide_by_Z_on_coset": 4}
@@ -219,16 +225,44 @@ class ProvingKey:
 
     def prove(self, assignment, r, s):
         """assignment: bytes (num_variables*32) or None to reuse the resident one; r, s: ints.
-        Returns dict(rc, proof_hex, parts(384 B), timings_ms[gpu, qap, msm_h, host, msm_h_accumulate_kernel])."""
+        Returns dict(rc, proof_hex, parts(384 B), timings_ms[gpu, qap, msm_h, host, msm_h_accumulate_kernel, A done, B done, L done])."""
         hexbuf = C.create_string_buffer(513)
         parts = C.create_string_buffer(384)
-        tim = (C.c_float * 5)()
+        tim = (C.c_float * 8)()
         if assignment is not None and len(assignment) != self.num_variables * 32:
             raise ValueError("assignment must be num_variables*32 bytes")
         rc = lib.zkb200_prove(self.handle, assignment, int(r).to_bytes(32, "little"), int(s).to_bytes(32, "little"), hexbuf, parts, tim)
         if rc < 0:
             raise ZkError(last_error())
         return dict(rc=rc, proof_hex=hexbuf.value.decode(), parts=parts.raw, timings_ms=list(tim), launches=lib.zkb200_last_launches())
+
+    # ---- proofs in flight (zkb200.h "lanes"): submit enqueues the copy and all kernels, collect waits and assembles the proof
+    @property
+    def lanes(self):
+        return int(lib.zkb200_pk_lanes(self.handle))
+
+    def lane_acquire(self):
+        return int(lib.zkb200_lane_acquire(self.handle))
+
+    def lane_release(self, lane):
+        lib.zkb200_lane_release(self.handle, lane)
+
+    def submit(self, lane, assignment, r, s):
+        """assignment: bytes or None to reuse what the lane holds.  The lane must be held (lane_acquire) and idle."""
+        if assignment is not None and len(assignment) != self.num_variables * 32:
+            raise ValueError("assignment must be num_variables*32 bytes")
+        if lib.zkb200_prove_submit(self.handle, lane, assignment, int(r).to_bytes(32, "little"), int(s).to_bytes(32, "little")) != 0:
+            raise ZkError("lane %d is not held or has a proof pending" % lane)
+
+    def collect(self, lane, want_parts=False):
+        hexbuf = C.create_string_buffer(513)
+        parts = C.create_string_buffer(384) if want_parts else None
+        tim = (C.c_float * 8)()
+        rc = lib.zkb200_prove_collect(self.handle, lane, hexbuf, parts, tim)
+        if rc < 0:
+            raise ZkError("lane %d has nothing to collect" % lane)
+        return dict(rc=rc, proof_hex=hexbuf.value.decode(), parts=parts.raw if parts else None, timings_ms=list(tim),
+                    launches=lib.zkb200_last_launches())
 
     def qap_witness_map(self, assignment):
         out = C.create_string_buffer((self.domain_size + 1) * 32)

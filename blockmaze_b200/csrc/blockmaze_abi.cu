@@ -22,7 +22,7 @@ static std::string g_key_dir;
 static std::vector<uint32_t> g_words;
 static size_t g_word_pos = 0;
 static void *g_pk[4] = {nullptr, nullptr, nullptr, nullptr};
-static double g_last_ms[4] = {0, 0, 0, 0};      // witness generation, prove call, of which GPU, host finish (last gen*proof)
+static thread_local double g_last_ms[4] = {0, 0, 0, 0};      // witness generation, prove call, of which GPU, host finish (last gen*proof of this thread)
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const char *CIRCUIT_NAMES[4] = {"mint", "send", "deposit", "redeem"};
 
@@ -79,22 +79,25 @@ static char *dup_hex(const std::string &s, size_t cap) {       // `new char[cap]
     memcpy(p, s.data(), s.size() < cap - 1 ? s.size() : cap - 1);
     return p;
 }
-// gen*proof core: the witness is generated straight into the proving key's pinned staging buffer (no intermediate copy), then proved
+// gen*proof core: take a free lane of the resident key, generate the witness straight into that lane's pinned staging buffer (no
+// intermediate copy), prove on it.  Only the key lookup and the random draws are serialised: concurrent callers overlap.
 template <class Fn> static char *prove_timed(int circuit, Fn make) {
-    std::lock_guard<std::mutex> lk(g_abi_mu);
-    void *pk = circuit_pk(circuit);
-    uint64_t *ext = zkb200_compact_staging(pk);                // pinned: the generator writes the compact assignment in place
+    void *pk;
+    { std::lock_guard<std::mutex> lk(g_abi_mu); pk = circuit_pk(circuit); }
+    const int lane = zkb200_lane_acquire(pk);
+    uint64_t *ext = zkb200_lane_staging(pk, lane);             // pinned: the generator writes the compact assignment in place
     const double t0 = now_ms();
     const Assignment a = make(ext);
     g_last_ms[0] = now_ms() - t0;
     uint64_t r[4], s[4];
-    next_random_fr(r); next_random_fr(s);                      // r first, then s (r1cs_gg_ppzksnark.tcc:418-419)
+    { std::lock_guard<std::mutex> lk(g_abi_mu); next_random_fr(r); next_random_fr(s); }      // r first, then s (r1cs_gg_ppzksnark.tcc:418-419)
     char *p = new char[1153];                                  // the reference returns new char[1153] with 512 hex chars (mintcgo.cpp:316-320)
     memset(p, 0, 1153);
-    float tm[5] = {0, 0, 0, 0, 0};
+    float tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const double t1 = now_ms();
     const int rc = zkb200_prove_compact(pk, a.lo(), a.wide.data(), a.wide.size(), (const uint8_t *)r, (const uint8_t *)s, p, tm);
     g_last_ms[1] = now_ms() - t1; g_last_ms[2] = tm[0]; g_last_ms[3] = tm[3];
+    zkb200_lane_release(pk, lane);
     if (rc == 1) printf("can not generate %s proof\n", CIRCUIT_NAMES[circuit]);      // mintcgo.cpp:209
     return p;
 }
@@ -196,9 +199,10 @@ char *genDepositproof(uint64_t value, uint64_t value_old, char *sn_old_string, c
         printf("can not generate deposit proof\n");
         char *p = new char[1153]; memset(p, 0, 1153);
         uint64_t zero[4] = {0, 0, 0, 0};
-        std::lock_guard<std::mutex> lk(g_abi_mu);
+        void *pk;
+        { std::lock_guard<std::mutex> lk(g_abi_mu); pk = circuit_pk(ZKB200_DEPOSIT); }
         std::vector<uint64_t> bad((size_t)DEPOSIT_VARS + 1, 0); bad[0] = 1;      // all-zero assignment: unsatisfied -> default proof
-        zkb200_prove_compact(circuit_pk(ZKB200_DEPOSIT), bad.data(), nullptr, 0, (const uint8_t *)zero, (const uint8_t *)zero, p, nullptr);
+        zkb200_prove_compact(pk, bad.data(), nullptr, 0, (const uint8_t *)zero, (const uint8_t *)zero, p, nullptr);
         return p;
     }
     std::vector<uint8_t> eff(leaves.begin(), leaves.begin() + (first + 1) * 32);

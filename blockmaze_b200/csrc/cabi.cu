@@ -65,41 +65,50 @@ template <class F> __global__ void gen_bases_kernel(Affine<F> gen, Affine<F> *ou
 
 // Dependent-free mad.lo.u32 streams (8 independent accumulators per thread).  SASS check: the `wide == 0` path is a run of
 // `IMAD Rk, Ra, Rb, Rk`; ptxas strength-reduces the loop-invariant mad.wide variant to IADD3, so only wide == 0 is a valid peak.
-__global__ void imad_peak_kernel(uint32_t *out, int iters, int wide) {
-    uint32_t a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 3;
-    uint64_t w0 = a, w1 = b, w2 = a ^ b, w3 = a + b, w4 = 5, w5 = 7, w6 = 11, w7 = 13;
-    uint32_t x0 = a, x1 = b, x2 = a ^ b, x3 = a + b, x4 = 5, x5 = 7, x6 = 11, x7 = 13;
-    if (wide) {
+// Integer-multiply peaks of the device (roofline denominators; same kernels as scripts/ubench/imad.cu):
+//   mode 0  32x32->32 multiply-add (IMAD),        dependent-free mad.lo.u32 chains
+//   mode 1  32x32->64 multiply-add (IMAD.WIDE.X), carry-chained mad.lo.cc/madc.hi.cc pairs exactly as the field multiplication
+//           issues them (ptxas fuses each pair into one IMAD.WIDE.U32.X)
+//   mode 2  whole 254-bit Montgomery multiplications (Fq), one dependent chain per thread
+__global__ void imad_peak_kernel(uint32_t *out, int iters, int mode) {
+    const uint32_t a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 3;
+    uint32_t r = 0;
+    if (mode == 0) {
+        uint32_t x[8] = {a, a * 3, a ^ b, a + b, a * 5, a * 7, a * 11, a * 13};
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) asm volatile("mad.lo.u32 %0, %0, %1, %0;" : "+r"(x[k]) : "r"(b));
+        }
+        for (int k = 0; k < 8; k++) r ^= x[k];
+    } else if (mode == 1) {
+        uint32_t v[18];
+        for (int k = 0; k < 18; k++) v[k] = a * (k + 1);
         for (int i = 0; i < iters; i++) {
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w0) : "r"(a), "r"(b));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w1) : "r"(a), "r"(b));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w2) : "r"(a), "r"(b));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w3) : "r"(a), "r"(b));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w4) : "r"(a), "r"(b));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w5) : "r"(a), "r"(b));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w6) : "r"(a), "r"(b));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w7) : "r"(a), "r"(b));
+                asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(v[0]) : "r"(v[16]), "r"(b));
+                asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(v[1]) : "r"(v[16]), "r"(b));
+#pragma unroll
+                for (int k = 2; k < 16; k += 2) {
+                    asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(v[k]) : "r"(v[17]), "r"(b));
+                    asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(v[k + 1]) : "r"(v[17]), "r"(b));
+                }
+                asm volatile("addc.u32 %0, %0, 0;" : "+r"(v[16]));
+                v[17] ^= v[3];
             }
         }
-        out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)(w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7);
+        for (int k = 0; k < 18; k++) r ^= v[k];
     } else {
-        for (int i = 0; i < iters; i++) {
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x0) : "r"(a), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x1) : "r"(a), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x2) : "r"(a), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x3) : "r"(a), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x4) : "r"(a), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x5) : "r"(a), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x6) : "r"(a), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x7) : "r"(a), "r"(b));
-            }
-        }
-        out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+        Fq x = Fq::one(), y;
+        for (int k = 0; k < 8; k++) y.v[k] = Fq::r2().v[k] ^ (threadIdx.x & 0xff);
+        y.v[7] &= 0x0fffffff;
+        x.v[0] += blockIdx.x;
+        for (int i = 0; i < iters * 64; i++) x = Fq::mul_impl(x, y);
+        for (int k = 0; k < 8; k++) r ^= x.v[k];
     }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 // every exported function below is declared extern "C" in include/zkb200.h, which fixes its linkage
 
@@ -148,8 +157,27 @@ static const char *DEFAULT_PROOF =   // (G1::one, G2::one, G1::one): r1cs_gg_ppz
     "0000000000000000000000000000000000000000000000000000000000000001"
     "0000000000000000000000000000000000000000000000000000000000000002";
 
+// proof bytes, parity hooks and timings of a collected proof
+static int finish_outputs(ProofPoints &pp, double host_ms, char *proof_hex_out, uint8_t *parts, float *timings_ms) {
+    if (parts) { put_g1(parts, pp.At); put_g2(parts + 64, pp.Bt_g); put_g1(parts + 192, pp.Bt_h); put_g1(parts + 256, pp.Ht); put_g1(parts + 320, pp.Lt); }
+    if (timings_ms) { timings_ms[0] = pp.gpu_ms; timings_ms[1] = pp.qap_ms; timings_ms[2] = pp.msm_h_ms; timings_ms[3] = (float)host_ms; timings_ms[4] = pp.acc_h_ms;
+                      timings_ms[5] = pp.a_done_ms; timings_ms[6] = pp.b_done_ms; timings_ms[7] = pp.l_done_ms; }
+    const std::string hex = pp.satisfied ? proof_hex(pp) : std::string(DEFAULT_PROOF);
+    memcpy(proof_hex_out, hex.data(), 512); proof_hex_out[512] = 0;
+    return pp.satisfied ? 0 : 1;
+}
 static int prove_any(void *h, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint8_t r[32], const uint8_t s[32],
-                     char *proof_hex_out, uint8_t *parts, float *timings_ms);
+                     char *proof_hex_out, uint8_t *parts, float *timings_ms) {
+    DevicePk *pk = (DevicePk *)h;
+    if (!pk) return -1;
+    uint64_t rr[4], ss[4]; memcpy(rr, r, 32); memcpy(ss, s, 32);
+    ProofPoints pp;
+    pp.want_parts = parts != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (lo) prove_compact(pk, lo, wide, nwide, rr, ss, pp); else prove(pk, assignment, rr, ss, pp);
+    const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return finish_outputs(pp, total_ms - pp.gpu_ms, proof_hex_out, parts, timings_ms);
+}
 int zkb200_prove(void *h, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32], char *proof_hex_out, uint8_t *parts, float *timings_ms) {
     return prove_any(h, assignment, nullptr, nullptr, 0, r, s, proof_hex_out, parts, timings_ms);
 }
@@ -157,28 +185,42 @@ int zkb200_prove_compact(void *h, const uint64_t *lo, const void *wide, size_t n
                          float *timings_ms) {
     return prove_any(h, nullptr, lo, (const WideIn *)wide, (uint32_t)nwide, r, s, proof_hex_out, nullptr, timings_ms);
 }
-uint64_t *zkb200_compact_staging(void *h) { return h ? compact_staging((DevicePk *)h) : nullptr; }
-static int prove_any(void *h, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint8_t r[32], const uint8_t s[32],
-                     char *proof_hex_out, uint8_t *parts, float *timings_ms) {
+int zkb200_pk_lanes(void *h) { return h ? ((DevicePk *)h)->nlanes : 0; }
+int zkb200_lane_acquire(void *h) { return h ? lane_acquire((DevicePk *)h)->index : -1; }
+static Lane *held_lane(void *h, int lane) {
     DevicePk *pk = (DevicePk *)h;
-    if (!pk) return -1;
-    std::lock_guard<std::mutex> lk(g_mu);
+    if (!pk || lane < 0 || lane >= pk->nlanes || !pk->lanes[lane]->busy) return nullptr;
+    return pk->lanes[lane];
+}
+void zkb200_lane_release(void *h, int lane) { if (Lane *ln = held_lane(h, lane)) lane_release((DevicePk *)h, ln); }
+uint64_t *zkb200_lane_staging(void *h, int lane) { Lane *ln = held_lane(h, lane); return ln ? compact_staging(ln) : nullptr; }
+int zkb200_prove_submit(void *h, int lane, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32]) {
+    Lane *ln = held_lane(h, lane);
+    if (!ln || ln->pending) return -1;
     uint64_t rr[4], ss[4]; memcpy(rr, r, 32); memcpy(ss, s, 32);
+    prove_submit((DevicePk *)h, ln, assignment, nullptr, nullptr, 0, rr, ss);
+    return 0;
+}
+int zkb200_prove_submit_compact(void *h, int lane, const uint64_t *lo, const void *wide, size_t nwide, const uint8_t r[32], const uint8_t s[32]) {
+    Lane *ln = held_lane(h, lane);
+    if (!ln || ln->pending || !lo) return -1;
+    uint64_t rr[4], ss[4]; memcpy(rr, r, 32); memcpy(ss, s, 32);
+    prove_submit((DevicePk *)h, ln, nullptr, lo, (const WideIn *)wide, (uint32_t)nwide, rr, ss);
+    return 0;
+}
+int zkb200_prove_collect(void *h, int lane, char *proof_hex_out, uint8_t *parts, float *timings_ms) {
+    Lane *ln = held_lane(h, lane);
+    if (!ln || !ln->pending) return -1;
     ProofPoints pp;
     pp.want_parts = parts != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
-    if (lo) prove_compact(pk, lo, wide, nwide, rr, ss, pp); else prove(pk, assignment, rr, ss, pp);
-    const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (parts) { put_g1(parts, pp.At); put_g2(parts + 64, pp.Bt_g); put_g1(parts + 192, pp.Bt_h); put_g1(parts + 256, pp.Ht); put_g1(parts + 320, pp.Lt); }
-    if (timings_ms) { timings_ms[0] = pp.gpu_ms; timings_ms[1] = pp.qap_ms; timings_ms[2] = pp.msm_h_ms; timings_ms[3] = (float)(total_ms - pp.gpu_ms); timings_ms[4] = pp.acc_h_ms; }
-    const std::string hex = pp.satisfied ? proof_hex(pp) : std::string(DEFAULT_PROOF);
-    memcpy(proof_hex_out, hex.data(), 512); proof_hex_out[512] = 0;
-    return pp.satisfied ? 0 : 1;
+    if (prove_collect((DevicePk *)h, ln, pp)) return -1;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return finish_outputs(pp, ms, proof_hex_out, parts, timings_ms);
 }
 int zkb200_qap_witness_map(void *h, const uint8_t *assignment, uint8_t *out_H, int *satisfied) {
     DevicePk *pk = (DevicePk *)h;
     if (!pk) return -1;
-    std::lock_guard<std::mutex> lk(g_mu);
     return qap_witness_map(pk, assignment, out_H, satisfied);
 }
 int zkb200_last_launches(void) { return launches_last_prove(); }
@@ -344,22 +386,23 @@ void zkb200_flush_l2(void) {
 }
 void zkb200_device_sync(void) { if (!ensure_device()) ZK_CUDA(cudaDeviceSynchronize()); }
 
-float zkb200_bench_imad_peak(int wide) {
+float zkb200_bench_imad_peak(int mode) {
     if (ensure_device()) return -1;
     cudaDeviceProp prop; cudaGetDeviceProperties(&prop, g_device);
-    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = mode == 2 ? 32 : 4096;
     uint32_t *out; ZK_CUDA(cudaMalloc(&out, (size_t)blocks * threads * 4));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    imad_peak_kernel<<<blocks, threads>>>(out, 64, wide);
+    imad_peak_kernel<<<blocks, threads>>>(out, 2, mode);
     ZK_CUDA(cudaDeviceSynchronize());
     cudaEventRecord(e0, 0);
-    imad_peak_kernel<<<blocks, threads>>>(out, iters, wide);
+    imad_peak_kernel<<<blocks, threads>>>(out, iters, mode);
     cudaEventRecord(e1, 0);
     ZK_CUDA(cudaEventSynchronize(e1));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    // per thread and iteration: 64 IMAD (mode 0), 64 wide multiply-adds (mode 1), 64 modular multiplications (mode 2)
     const double ops = (double)blocks * threads * iters * 64.0;
-    return (float)(ops / (ms * 1e-3) / 1e12);
+    return (float)(ops / (ms * 1e-3) / 1e12);             // tera-ops per second
 }
 
 

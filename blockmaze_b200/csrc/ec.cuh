@@ -78,6 +78,23 @@ template <class F> struct XYZZ {
         ZZ = ZZ * PP;
         ZZZ = ZZZ * PPP;
     }
+    // the same mixed addition with every field multiplication inlined (G1 accumulate kernel variant, see msm.cuh)
+    template <class M> ZK_HD void add_affine_with(const Affine<F> &a, M mul) {
+        if (a.is_inf()) return;
+        if (is_inf()) { X = a.x; Y = a.y; ZZ = F::one(); ZZZ = F::one(); return; }
+        F U2 = mul(a.x, ZZ), S2 = mul(a.y, ZZZ);
+        F Pp = U2 - X, R = S2 - Y;
+        if (Pp.is_zero()) {
+            if (R.is_zero()) *this = dbl_affine(a); else *this = inf();
+            return;
+        }
+        F PP = mul(Pp, Pp), PPP = mul(Pp, PP), Q = mul(X, PP);
+        F X3 = mul(R, R) - PPP - Q.dbl();
+        Y = mul(R, Q - X3) - mul(Y, PPP);
+        X = X3;
+        ZZ = mul(ZZ, PP);
+        ZZZ = mul(ZZZ, PPP);
+    }
     // add-2008-s: this += other
     ZK_EC void add(const XYZZ &o) {
         if (o.is_inf()) return;

@@ -12,8 +12,9 @@
 //                              2^(c*k) * P_i is precomputed once, so all windows share ONE bucket set and no Horner
 //                              recombination is left -- fewer buckets to reduce, nothing to do on the host)
 //   2. count / scan / scatter : a counting sort of (bucket -> base index | sign) built from global atomics.
-//   3. accumulate : buckets are cut into tasks of <= 48 entries; one thread per task does XYZZ += affine mixed additions
-//                   (8M+2S); tasks of one bucket are then folded (small spans by one thread, oversized buckets by a CTA tree).
+//   3. accumulate : the sorted entry list is cut into equal ranges, one per thread of a single resident wave; a thread does
+//                   XYZZ += affine mixed additions (8M+2S) and emits one piece per bucket it touches; the pieces of a bucket
+//                   are then folded (small spans by one thread, oversized buckets by a CTA tree).
 //   4. reduce  : per bucket region, sum_j (j+1)*B_j by segmented running sums + a shared-memory tree; ones buckets are summed.
 //   5. the partial sums (a few dozen points) go back to the host.
 #pragma once
@@ -189,59 +190,88 @@ static __global__ void __launch_bounds__(128) msm_expand_bases_kernel(const Affi
 
 // ---- bucket accumulation, load-balanced ------------------------------------------------------------------------------------
 // Bucket sizes are wildly uneven in practice (the top window of a 254-bit scalar has only 2-3 live bits, so a handful of
-// buckets hold n/4 points each; witness scalars repeat), so buckets are cut into TASKS of at most MSM_TASK entries:
-//   task_count : tasks_b = ceil(count_b / MSM_TASK), scanned into task_off[]
-//   accumulate : one thread per task sums its <= MSM_TASK points (XYZZ += affine) into partial[task]
-//   fold       : partial[task_off[b]] = sum of the bucket's partials -- by one thread when the span is small, by a whole
-//                CTA (strided sums + shared-memory tree) for the few oversized buckets, which are queued in heavy[]
-constexpr uint32_t MSM_TASK = 48;
+// buckets hold n/4 points each; witness scalars repeat), and the kernel is bound by the integer-multiply pipe, so what matters
+// is that every resident thread gets the same number of mixed additions.  The SORTED ENTRY LIST -- not the bucket list -- is
+// therefore cut into equal ranges of L = ceil(entries / T) entries, T = the threads of exactly one resident wave:
+//   accumulate : thread t sums entries [t*L, (t+1)*L) (XYZZ += affine); whenever the range crosses into the next bucket it
+//                stores the finished piece and starts over.  The piece of bucket b made by thread t lives in slot t + b
+//                (both only grow along the list, so slots never collide).
+//   fold       : bucket b owns the pieces of threads off[b]/L .. (off[b+1]-1)/L; they are summed into the first slot -- by
+//                one thread when the span is small, by a whole CTA (strided sums + shared-memory tree) for the few oversized
+//                buckets, which are queued in heavy[]
+constexpr uint32_t MSM_MIN_RANGE = 16;
 constexpr uint32_t MSM_FOLD_SMALL = 8;
 constexpr uint32_t MSM_HEAVY_MAX = 1024;
 
-static __global__ void msm_task_count_kernel(const uint32_t *__restrict__ offsets, uint32_t total_buckets, uint32_t *__restrict__ task_counts) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= total_buckets) return;
-    const uint32_t cnt = offsets[b + 1] - offsets[b];
-    task_counts[b] = (cnt + MSM_TASK - 1) / MSM_TASK;
+__host__ __device__ __forceinline__ uint32_t msm_range_len(uint32_t total_entries, uint32_t threads) {
+    const uint32_t L = (total_entries + threads - 1) / threads;
+    return L < MSM_MIN_RANGE ? MSM_MIN_RANGE : L;
 }
 
 #ifndef ZK_ACC_MINBLOCKS
 #define ZK_ACC_MINBLOCKS 1
 #endif
+#ifndef ZK_ACC_INLINE_MUL
+#define ZK_ACC_INLINE_MUL 1      // G1: also inline the ten field multiplications of the mixed addition (30 KB loop body, 118 registers;
+                                 // measured 10 % faster than calling the shared copy: no argument shuffling on the multiply pipe)
+#endif
 #ifndef ZK_ACC_INLINE_ADD
-#define ZK_ACC_INLINE_ADD 1      // G1: keep the accumulator in registers across the task loop (measured 5 % faster; 108 registers)
+#define ZK_ACC_INLINE_ADD 1      // G1: keep the accumulator in registers across the range loop (measured 5 % faster; 108 registers)
 #endif
 template <class F>
 static __global__ void __launch_bounds__(128, ZK_ACC_MINBLOCKS) msm_accumulate_kernel(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ offsets,
-                                                                    const uint32_t *__restrict__ entries, const uint32_t *__restrict__ task_off,
-                                                                    uint32_t total_buckets, XYZZ<F> *__restrict__ partial) {
+                                                                    const uint32_t *__restrict__ entries, uint32_t total_buckets, uint32_t threads,
+                                                                    XYZZ<F> *__restrict__ partial) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= task_off[total_buckets]) return;
-    // bucket of task t: last b with task_off[b] <= t
+    const uint32_t total = __ldg(offsets + total_buckets), L = msm_range_len(total, threads);
+    const uint32_t e0 = t * L, e1 = min(e0 + L, total);
+    if (t >= threads || e0 >= total) return;
+    // bucket of entry e0: the last b with offsets[b] <= e0 (among equal offsets that is the non-empty one)
     uint32_t lo = 0, hi = total_buckets;
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(task_off + mid) <= t) lo = mid; else hi = mid; }
-    const uint32_t b = lo, rank = t - __ldg(task_off + b);
-    const uint32_t e0 = offsets[b] + rank * MSM_TASK, e1 = min(e0 + MSM_TASK, offsets[b + 1]);
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(offsets + mid) <= e0) lo = mid; else hi = mid; }
+    uint32_t b = lo, next = __ldg(offsets + b + 1);
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t e = e0; e < e1; e++) {
+        if (e == next) {
+            st_xyzz(partial + t + b, acc);
+            acc = XYZZ<F>::inf();
+            b++; next = __ldg(offsets + b + 1);
+            if (next <= e) {                       // a run of empty buckets (sparse witness MSMs): search, do not walk
+                lo = b; hi = total_buckets;
+                while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(offsets + mid) <= e) lo = mid; else hi = mid; }
+                b = lo; next = __ldg(offsets + b + 1);
+            }
+        }
         const uint32_t ent = __ldg(entries + e);
         Affine<F> p = ld_affine(bases + (ent & 0x7fffffffu));
         if (ent & 0x80000000u) p.y = p.y.neg();
-#if ZK_ACC_INLINE_ADD
+#if ZK_ACC_INLINE_MUL
+        if constexpr (sizeof(F) == 32) acc.add_affine_with(p, [](const F &x, const F &y) { return F::mul_impl(x, y); }); else acc.add_affine(p);
+#elif ZK_ACC_INLINE_ADD
         if (sizeof(F) == 32) acc.add_affine_inl(p); else acc.add_affine(p);
 #else
         acc.add_affine(p);
 #endif
     }
-    st_xyzz(partial + t, acc);
+    st_xyzz(partial + t + b, acc);
+}
+// slots of bucket b: first slot and number of pieces (0 for an empty bucket)
+__device__ __forceinline__ uint32_t msm_bucket_span(const uint32_t *__restrict__ offsets, uint32_t L, uint32_t b, uint32_t &slot0) {
+    const uint32_t o0 = __ldg(offsets + b), o1 = __ldg(offsets + b + 1);
+    if (o1 == o0) return 0;
+    const uint32_t t0 = o0 / L;
+    slot0 = t0 + b;
+    return (o1 - 1) / L - t0 + 1;
 }
 // one thread per bucket: fold short spans in place, queue long ones
 template <class F>
-static __global__ void __launch_bounds__(128) msm_fold_small_kernel(XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ task_off,
-                                                                    uint32_t total_buckets, uint32_t *__restrict__ heavy /* [0] = count */) {
+static __global__ void __launch_bounds__(128) msm_fold_small_kernel(XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ offsets,
+                                                                    uint32_t total_buckets, uint32_t threads, uint32_t *__restrict__ heavy /* [0] = count */) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= total_buckets) return;
-    const uint32_t t0 = task_off[b], span = task_off[b + 1] - t0;
+    const uint32_t L = msm_range_len(__ldg(offsets + total_buckets), threads);
+    uint32_t t0 = 0;
+    const uint32_t span = msm_bucket_span(offsets, L, b, t0);
     if (span <= 1) return;
     if (span > MSM_FOLD_SMALL) {
         const uint32_t slot = atomicAdd(heavy, 1u);
@@ -253,13 +283,15 @@ static __global__ void __launch_bounds__(128) msm_fold_small_kernel(XYZZ<F> *__r
 }
 constexpr int MSM_HEAVY_THREADS = 128;
 template <class F>
-static __global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_fold_heavy_kernel(XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ task_off,
-                                                                                  const uint32_t *__restrict__ heavy) {
+static __global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_fold_heavy_kernel(XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ offsets,
+                                                                                  uint32_t total_buckets, uint32_t threads, const uint32_t *__restrict__ heavy) {
     extern __shared__ uint32_t fold_sm[];
     XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(fold_sm);
     const uint32_t cnt = min(heavy[0], MSM_HEAVY_MAX);
+    const uint32_t L = msm_range_len(__ldg(offsets + total_buckets), threads);
     for (uint32_t h = blockIdx.x; h < cnt; h += gridDim.x) {
-        const uint32_t b = heavy[1 + h], t0 = task_off[b], span = task_off[b + 1] - t0;
+        uint32_t t0 = 0;
+        const uint32_t span = msm_bucket_span(offsets, L, heavy[1 + h], t0);
         XYZZ<F> a = XYZZ<F>::inf();
         for (uint32_t k = threadIdx.x; k < span; k += MSM_HEAVY_THREADS) a.add(ld_xyzz(partial + t0 + k));
         sm[threadIdx.x] = a;
@@ -272,9 +304,9 @@ static __global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_fold_heavy_kerne
         __syncthreads();
     }
 }
-template <class F> __device__ __forceinline__ XYZZ<F> msm_bucket(const XYZZ<F> *partial, const uint32_t *task_off, uint32_t b) {
-    const uint32_t t0 = __ldg(task_off + b);
-    if (__ldg(task_off + b + 1) == t0) return XYZZ<F>::inf();
+template <class F> __device__ __forceinline__ XYZZ<F> msm_bucket(const XYZZ<F> *partial, const uint32_t *offsets, uint32_t L, uint32_t b) {
+    uint32_t t0 = 0;
+    if (msm_bucket_span(offsets, L, b, t0) == 0) return XYZZ<F>::inf();
     return ld_xyzz(partial + t0);
 }
 
@@ -284,8 +316,8 @@ template <class F> __device__ __forceinline__ XYZZ<F> msm_bucket(const XYZZ<F> *
 // For blockIdx.y == regions the "ones" buckets are summed with weight 1.
 constexpr int MSM_RED_THREADS = 128;
 template <class F>
-static __global__ void __launch_bounds__(MSM_RED_THREADS) msm_reduce_kernel(const XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ task_off,
-                                                                            MsmShape sh, uint32_t seg, uint32_t blocks_per_region,
+static __global__ void __launch_bounds__(MSM_RED_THREADS) msm_reduce_kernel(const XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ offsets,
+                                                                            uint32_t threads, MsmShape sh, uint32_t seg, uint32_t blocks_per_region,
                                                                             XYZZ<F> *__restrict__ out) {
     extern __shared__ uint32_t red_sm[];
     XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(red_sm);
@@ -294,11 +326,12 @@ static __global__ void __launch_bounds__(MSM_RED_THREADS) msm_reduce_kernel(cons
     const uint32_t count = ones ? sh.ones : sh.nb;
     const uint32_t base = w * sh.nb;                              // the ones region starts at regions*nb as well
     const uint32_t lo = (blockIdx.x * MSM_RED_THREADS + threadIdx.x) * seg;
+    const uint32_t L = msm_range_len(__ldg(offsets + sh.total), threads);
     XYZZ<F> S = XYZZ<F>::inf(), T = XYZZ<F>::inf();
     if (lo < count) {
         const uint32_t hi = min(lo + seg, count);
         for (uint32_t j = hi; j-- > lo;) {
-            S.add(msm_bucket(partial, task_off, base + j));
+            S.add(msm_bucket(partial, offsets, L, base + j));
             if (!ones) T.add(S);
         }
         if (ones) T = S;

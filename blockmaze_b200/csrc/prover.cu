@@ -4,9 +4,12 @@
 // fixed-base tables, constraint matrices, twiddles and all work buffers stay resident in HBM; a proof is one H2D copy of the
 // (compact) assignment, ~60 kernel launches on four streams, and a D2H copy of a few hundred partial sums.
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <mutex>
+#include <thread>
 #include "prover.cuh"
 #include "pk_format.hpp"
 #include "ntt.cuh"
@@ -16,7 +19,8 @@ namespace zkp {
 using namespace zk;
 using zkh::HFr; using zkh::HFq; using zkh::HFq2; using zkh::HG1; using zkh::HG2; using zkh::HG1Affine; using zkh::HG2Affine;
 
-static int g_launches = 0;
+static thread_local int g_launches = 0;     // kernels launched by this thread since the last prove_submit() began
+static int g_last_launches = 0;
 #define ZK_LAUNCH(kernel, grid, block, smem, stream, ...) do { kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); g_launches++; } while (0)
 
 void cuda_check(cudaError_t e, const char *what) {
@@ -25,7 +29,7 @@ void cuda_check(cudaError_t e, const char *what) {
         abort();
     }
 }
-int launches_last_prove() { return g_launches; }
+int launches_last_prove() { return g_last_launches; }
 
 static inline Fr to_dev(const HFr &x) { Fr r; memcpy(r.v, x.v, 32); return r; }
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -127,29 +131,33 @@ static PowMul pm_none() { return PowMul{nullptr, nullptr, 0}; }
 static PowMul pm_const(const void *c) { return PowMul{(const Fr *)c, nullptr, 0}; }
 static PowMul pm_two(const void *lo, const void *hi) { return PowMul{(const Fr *)lo, (const Fr *)hi, 10}; }
 
-static void ntt(cudaStream_t st, const void *src, void *dst, const void *tw, int logn, PowMul pre, PowMul post) {
-    if (logn == 0) { ZK_CUDA(cudaMemcpyAsync(dst, src, 32, cudaMemcpyDeviceToDevice, st)); return; }
+static void ntt(cudaStream_t st, const void *src, void *dst, const void *tw, int logn, PowMul pre, PowMul post, int batch = 1, size_t stride = 0) {
+    if (logn == 0) {
+        for (int b = 0; b < batch; b++) ZK_CUDA(cudaMemcpyAsync((Fr *)dst + b * stride, (const Fr *)src + b * stride, 32, cudaMemcpyDeviceToDevice, st));
+        return;
+    }
     NttPass ps[4]; g_launches += ntt_plan_passes(logn, ps);
-    ntt_launch(st, (const Fr *)src, (Fr *)dst, (const Fr *)tw, logn, pre, post);
+    ntt_launch(st, (const Fr *)src, (Fr *)dst, (const Fr *)tw, logn, pre, post, batch, stride);
 }
 
 // inverse transform src -> dst (dst != src), coefficient i additionally multiplied by `post` (e.g. g^i for the coset shift
 // that follows, or g^-i for icosetFFT).  For the basic domain the 1/m factor must be folded into `post` by the caller.
-static void domain_ifft(cudaStream_t st, const Domain &d, void *src, void *dst, PowMul post_basic, PowMul post_step) {
+// `batch` independent vectors, `stride` elements apart in src and in dst, go through every launch together.
+static void domain_ifft(cudaStream_t st, const Domain &d, void *src, void *dst, PowMul post_basic, PowMul post_step, int batch = 1, size_t stride = 0) {
     Fr *s = (Fr *)src, *t = (Fr *)dst;
-    if (!d.step) { ntt(st, s, t, d.tw_big_i, d.log_big, pm_none(), post_basic); return; }
-    ntt(st, s, t, d.tw_big_i, d.log_big, pm_none(), pm_const(d.c_big_inv));
-    ntt(st, s + d.big, t + d.big, d.tw_small_i, d.log_small, pm_none(), pm_const(d.c_small_inv));
-    ZK_LAUNCH(step_ifft_post_kernel, cdiv(d.small, 128), 128, 0, st, t, (const Fr *)d.tw_step_f, (const Fr *)d.tw_step_i, d.big, d.small,
-              to_dev(d.over_two), post_step);
+    if (!d.step) { ntt(st, s, t, d.tw_big_i, d.log_big, pm_none(), post_basic, batch, stride); return; }
+    ntt(st, s, t, d.tw_big_i, d.log_big, pm_none(), pm_const(d.c_big_inv), batch, stride);
+    ntt(st, s + d.big, t + d.big, d.tw_small_i, d.log_small, pm_none(), pm_const(d.c_small_inv), batch, stride);
+    ZK_LAUNCH(step_ifft_post_kernel, dim3(cdiv(d.small, 128), batch), 128, 0, st, t, (const Fr *)d.tw_step_f, (const Fr *)d.tw_step_i, d.big, d.small,
+              to_dev(d.over_two), post_step, stride);
 }
 // forward transform src -> dst (dst != src; src is clobbered for the step domain), input coefficient i first multiplied by `pre`
-static void domain_fft(cudaStream_t st, const Domain &d, void *src, void *dst, PowMul pre) {
+static void domain_fft(cudaStream_t st, const Domain &d, void *src, void *dst, PowMul pre, int batch = 1, size_t stride = 0) {
     Fr *s = (Fr *)src, *t = (Fr *)dst;
-    if (!d.step) { ntt(st, s, t, d.tw_big_f, d.log_big, pre, pm_none()); return; }
-    ZK_LAUNCH(step_fft_pre_kernel, cdiv(d.small, 128), 128, 0, st, s, (const Fr *)d.tw_step_f, d.big, d.small, pre);
-    ntt(st, s, t, d.tw_big_f, d.log_big, pm_none(), pm_none());
-    ntt(st, s + d.big, t + d.big, d.tw_small_f, d.log_small, pm_none(), pm_none());
+    if (!d.step) { ntt(st, s, t, d.tw_big_f, d.log_big, pre, pm_none(), batch, stride); return; }
+    ZK_LAUNCH(step_fft_pre_kernel, dim3(cdiv(d.small, 128), batch), 128, 0, st, s, (const Fr *)d.tw_step_f, d.big, d.small, pre, stride);
+    ntt(st, s, t, d.tw_big_f, d.log_big, pm_none(), pm_none(), batch, stride);
+    ntt(st, s + d.big, t + d.big, d.tw_small_f, d.log_small, pm_none(), pm_none(), batch, stride);
 }
 
 void domain_op(cudaStream_t st, const Domain &d, int op, void *data, void *tmp) {
@@ -176,22 +184,36 @@ void domain_op(cudaStream_t st, const Domain &d, int op, void *data, void *tmp) 
 
 // =====================================================================================================================
 // sparse A.w / B.w / C.w  (linear_combination::evaluate, libsnark/relations/variable.tcc:262; r1cs_to_qap.tcc:227-236,281-285)
-// one thread per constraint row; coefficient dictionary index 0 = +1, 1 = -1 (no multiplication)
+// SPMV_G lanes per constraint row (97 % of the rows have <= 4 terms, but the packing constraints of the SHA-256 gadgets have
+// 33-65 and would serialise a whole warp behind one lane); partial sums meet in a shuffle tree.  Coefficient dictionary
+// index 0 = +1, 1 = -1 (no multiplication).
+#ifndef ZK_SPMV_G
+#define ZK_SPMV_G 4
+#endif
+constexpr int SPMV_G = ZK_SPMV_G;
 struct SpmvArgs { const uint32_t *rowptr[3], *col[3], *coef[3]; Fr *out[3]; };
-__global__ void spmv_kernel(SpmvArgs A, const Fr *__restrict__ dict, const Fr *__restrict__ w, uint32_t rows) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows) return;
+__global__ void __launch_bounds__(128) spmv_kernel(SpmvArgs A, const Fr *__restrict__ dict, const Fr *__restrict__ w, uint32_t rows) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = tid / SPMV_G, sub = tid % SPMV_G;
     const uint32_t *__restrict__ rowptr = A.rowptr[blockIdx.y], *__restrict__ col = A.col[blockIdx.y], *__restrict__ coef = A.coef[blockIdx.y];
-    Fr *__restrict__ out = A.out[blockIdx.y];
     Fr acc = Fr::zero();
-    for (uint32_t k = rowptr[i], e = rowptr[i + 1]; k < e; k++) {
-        const uint32_t ci = __ldg(coef + k);
-        Fr x = ldg_fr(w + __ldg(col + k));
-        if (ci == 0) acc = acc + x;
-        else if (ci == 1) acc = acc - x;
-        else acc = acc + x * ldg_fr(dict + ci);
+    if (i < rows) {
+        for (uint32_t k = __ldg(rowptr + i) + sub, e = __ldg(rowptr + i + 1); k < e; k += SPMV_G) {
+            const uint32_t ci = __ldg(coef + k);
+            Fr x = ldg_fr(w + __ldg(col + k));
+            if (ci == 0) acc = acc + x;
+            else if (ci == 1) acc = acc - x;
+            else acc = acc + x * ldg_fr(dict + ci);
+        }
     }
-    st_fr(out + i, acc);
+#pragma unroll
+    for (int d = SPMV_G / 2; d > 0; d >>= 1) {
+        Fr o;
+#pragma unroll
+        for (int q = 0; q < 8; q++) o.v[q] = __shfl_down_sync(0xffffffffu, acc.v[q], d, SPMV_G);
+        acc = acc + o;
+    }
+    if (i < rows && sub == 0) st_fr(A.out[blockIdx.y] + i, acc);
 }
 // the extra rows  aA[num_constraints + i] = (1, w_1 .. w_inputs)[i]  (r1cs_to_qap.tcc:227-230)
 __global__ void input_rows_kernel(const Fr *w, Fr *outA, uint32_t nc, uint32_t count) {
@@ -301,26 +323,32 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool e
     ZK_CUDA(cudaMalloc(&cursors, (size_t)(total + 1) * 4));
     entries_cap = (size_t)n * windows + 16;
     ZK_CUDA(cudaMalloc(&entries, entries_cap * 4));
-    task_cap = total + (uint32_t)(((size_t)n * windows) / MSM_TASK) + 1;
-    ZK_CUDA(cudaMalloc(&task_counts, (size_t)(total + 1) * 4));
-    ZK_CUDA(cudaMalloc(&task_off, (size_t)(total + 1) * 4));
-    ZK_CUDA(cudaMalloc(&heavy, (size_t)(MSM_HEAVY_MAX + 1) * 4));
+    ZK_CUDA(cudaMalloc(&heavy, (size_t)(MSM_HEAVY_MAX + 1) * 4)); ZK_CUDA(cudaMalloc(&heavy_g2, (size_t)(MSM_HEAVY_MAX + 1) * 4));
+    ZK_CUDA(cudaEventCreateWithFlags(&ev_sorted, cudaEventDisableTiming));
+    // one resident wave of the accumulate kernel: every thread then gets the same share of the sorted entries
+    int dev = 0, sms = 0, occ1 = 0, occ2 = 0;
+    ZK_CUDA(cudaGetDevice(&dev)); ZK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, msm_accumulate_kernel<Fq>, 128, 0));
+    ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, msm_accumulate_kernel<Fq2>, 128, 0));
+    acc_threads_g1 = (uint32_t)(sms * (occ1 > 0 ? occ1 : 1) * 128);
+    acc_threads_g2 = (uint32_t)(sms * (occ2 > 0 ? occ2 : 1) * 128);
     ZK_CUDA(cudaEventCreate(&ev_acc0)); ZK_CUDA(cudaEventCreate(&ev_acc1));
     const size_t nout = (size_t)(regions + 1) * bpw;
     if (g1) {
-        ZK_CUDA(cudaMalloc(&buckets_g1, (size_t)task_cap * sizeof(G1XYZZ)));
+        ZK_CUDA(cudaMalloc(&buckets_g1, (size_t)(acc_threads_g1 + total + 1) * sizeof(G1XYZZ)));
         ZK_CUDA(cudaMalloc(&out_g1, nout * sizeof(G1XYZZ)));
         ZK_CUDA(cudaMallocHost(&h_out_g1, nout * sizeof(G1XYZZ)));
     }
     if (g2) {
-        ZK_CUDA(cudaMalloc(&buckets_g2, (size_t)task_cap * sizeof(G2XYZZ)));
+        ZK_CUDA(cudaMalloc(&buckets_g2, (size_t)(acc_threads_g2 + total + 1) * sizeof(G2XYZZ)));
         ZK_CUDA(cudaMalloc(&out_g2, nout * sizeof(G2XYZZ)));
         ZK_CUDA(cudaMallocHost(&h_out_g2, nout * sizeof(G2XYZZ)));
     }
 }
 float MsmPlan::last_acc_ms() const { float ms = 0; if (ev_acc0) cudaEventElapsedTime(&ms, ev_acc0, ev_acc1); return ms; }
 void MsmPlan::release() {
-    void *ps[] = {counts, offsets, cursors, entries, buckets_g1, buckets_g2, out_g1, out_g2, task_counts, task_off, heavy};
+    void *ps[] = {counts, offsets, cursors, entries, buckets_g1, buckets_g2, out_g1, out_g2, heavy, heavy_g2};
+    if (ev_sorted) cudaEventDestroy(ev_sorted);
     for (void *p : ps) if (p) cudaFree(p);
     if (ev_acc0) cudaEventDestroy(ev_acc0);
     if (ev_acc1) cudaEventDestroy(ev_acc1);
@@ -345,20 +373,21 @@ void *msm_expand_bases(const void *bases, uint32_t n, int c, bool g2) {
 
 template <class F>
 static void msm_points(cudaStream_t st, MsmPlan &p, const MsmShape &sh, const Affine<F> *bases, XYZZ<F> *partial, XYZZ<F> *out, void *h_out, bool timed) {
-    const uint32_t *toff = (const uint32_t *)p.task_off;
-    ZK_CUDA(cudaMemsetAsync(p.heavy, 0, 4, st));
+    const uint32_t *off = (const uint32_t *)p.offsets;
+    const uint32_t T = sizeof(F) == 32 ? p.acc_threads_g1 : p.acc_threads_g2;
+    uint32_t *heavy = (uint32_t *)(sizeof(F) == 32 ? p.heavy : p.heavy_g2);
+    ZK_CUDA(cudaMemsetAsync(heavy, 0, 4, st));
     if (timed) ZK_CUDA(cudaEventRecord(p.ev_acc0, st));
-    ZK_LAUNCH(msm_accumulate_kernel<F>, cdiv(p.task_cap, 128), 128, 0, st, bases, (const uint32_t *)p.offsets, (const uint32_t *)p.entries, toff, p.total,
-              partial);
+    ZK_LAUNCH(msm_accumulate_kernel<F>, T / 128, 128, 0, st, bases, off, (const uint32_t *)p.entries, p.total, T, partial);
     if (timed) ZK_CUDA(cudaEventRecord(p.ev_acc1, st));
-    ZK_LAUNCH(msm_fold_small_kernel<F>, cdiv(p.total, 128), 128, 0, st, partial, toff, p.total, (uint32_t *)p.heavy);
-    ZK_LAUNCH(msm_fold_heavy_kernel<F>, 64, MSM_HEAVY_THREADS, MSM_HEAVY_THREADS * sizeof(XYZZ<F>), st, partial, toff, (const uint32_t *)p.heavy);
+    ZK_LAUNCH(msm_fold_small_kernel<F>, cdiv(p.total, 128), 128, 0, st, partial, off, p.total, T, heavy);
+    ZK_LAUNCH(msm_fold_heavy_kernel<F>, 64, MSM_HEAVY_THREADS, MSM_HEAVY_THREADS * sizeof(XYZZ<F>), st, partial, off, p.total, T, (const uint32_t *)heavy);
     const dim3 rgrid(p.bpw, sh.regions + 1);
-    ZK_LAUNCH(msm_reduce_kernel<F>, rgrid, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(XYZZ<F>), st, (const XYZZ<F> *)partial, toff, sh, p.seg, p.bpw, out);
+    ZK_LAUNCH(msm_reduce_kernel<F>, rgrid, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(XYZZ<F>), st, (const XYZZ<F> *)partial, off, T, sh, p.seg, p.bpw, out);
     ZK_CUDA(cudaMemcpyAsync(h_out, out, (size_t)(sh.regions + 1) * p.bpw * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
 }
 
-void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, const void *bases_g1, const void *bases_g2) {
+void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, const void *bases_g1, const void *bases_g2, cudaStream_t st_g2) {
     const MsmShape sh = msm_shape(p.n, p.c, p.ones, p.expanded ? 1 : 0);
     ScalarSrc src{(const uint32_t *)sc.scalars, sc.map, sc.offset, sc.montgomery};
     ZK_CUDA(cudaMemsetAsync(p.counts, 0, (size_t)(p.total + 1) * 4, st));
@@ -366,10 +395,10 @@ void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, con
     if (p.n) ZK_LAUNCH(msm_count_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (uint32_t *)p.counts);
     ZK_LAUNCH(msm_scan_kernel, 1, 1024, 0, st, (const uint32_t *)p.counts, (uint32_t *)p.offsets, p.total);
     if (p.n) ZK_LAUNCH(msm_scatter_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (const uint32_t *)p.offsets, (uint32_t *)p.cursors, (uint32_t *)p.entries);
-    ZK_LAUNCH(msm_task_count_kernel, cdiv(p.total, 256), 256, 0, st, (const uint32_t *)p.offsets, p.total, (uint32_t *)p.task_counts);
-    ZK_LAUNCH(msm_scan_kernel, 1, 1024, 0, st, (const uint32_t *)p.task_counts, (uint32_t *)p.task_off, p.total);
+    // the G2 half of a knowledge-commitment query shares the digit sort and then runs beside the G1 half on its own stream
+    if (bases_g2 && st_g2) { ZK_CUDA(cudaEventRecord(p.ev_sorted, st)); ZK_CUDA(cudaStreamWaitEvent(st_g2, p.ev_sorted, 0)); }
+    if (bases_g2) msm_points<Fq2>(st_g2 ? st_g2 : st, p, sh, (const G2Affine *)bases_g2, (G2XYZZ *)p.buckets_g2, (G2XYZZ *)p.out_g2, p.h_out_g2, false);
     if (bases_g1) msm_points<Fq>(st, p, sh, (const G1Affine *)bases_g1, (G1XYZZ *)p.buckets_g1, (G1XYZZ *)p.out_g1, p.h_out_g1, true);
-    if (bases_g2) msm_points<Fq2>(st, p, sh, (const G2Affine *)bases_g2, (G2XYZZ *)p.buckets_g2, (G2XYZZ *)p.out_g2, p.h_out_g2, false);
 }
 
 template <class P> static P msm_finish(const MsmPlan &p, const void *h_out) {
@@ -405,6 +434,83 @@ constexpr int MSM_C = 16;                  // window bits of the resident (expan
 
 template <class A> static A fetch_point(const void *dev, size_t idx) {
     A a; ZK_CUDA(cudaMemcpy(&a, (const char *)dev + idx * sizeof(A), sizeof(A), cudaMemcpyDeviceToHost)); return a;
+}
+
+struct LaneSync { std::mutex mu; std::condition_variable cv; };
+
+static Lane *lane_create(const DevicePk *pk, int index) {
+    Lane *ln = new Lane();
+    ln->index = index;
+    const size_t nw = pk->num_vars + 4, m = pk->dom->m;            // [1 | w | r | s | -rs]
+    ZK_CUDA(cudaMalloc(&ln->w_can, nw * 32)); ZK_CUDA(cudaMalloc(&ln->w_mont, nw * 32));
+    ZK_CUDA(cudaMemset(ln->w_can, 0, nw * 32));
+    const uint64_t one_can[4] = {1, 0, 0, 0};
+    ZK_CUDA(cudaMemcpy(ln->w_can, one_can, 32, cudaMemcpyHostToDevice));
+    ZK_CUDA(cudaMallocHost(&ln->h_w_pinned, (nw + 1) * 32));
+    ZK_CUDA(cudaMalloc(&ln->w_lo, nw * 8)); ZK_CUDA(cudaMalloc(&ln->w_wide, MAX_WIDE * sizeof(WideIn)));
+    ZK_CUDA(cudaMallocHost(&ln->h_wide_pinned, MAX_WIDE * sizeof(WideIn)));
+    ZK_CUDA(cudaMalloc(&ln->bufA, 3 * m * 32));                     // A | B | C contiguous: the three transforms of a stage share one launch
+    ln->bufB = (char *)ln->bufA + m * 32; ln->bufC = (char *)ln->bufA + 2 * m * 32;
+    ZK_CUDA(cudaMalloc(&ln->tmp, 3 * m * 32));
+    ZK_CUDA(cudaMalloc(&ln->sat_flag, 4)); ZK_CUDA(cudaMallocHost(&ln->h_sat_flag, 4));
+    // witness MSMs: ~97 % of the scalars are 0/1 and nearly all others are <= 64 bits; H is dense
+    ln->mA.init(pk->nA, MSM_C, 4096, true, false, true);
+    ln->mB.init(pk->nB, MSM_C, 4096, true, true, true);
+    ln->mL.init(pk->nL, MSM_C, 4096, true, false, true);
+    ln->mH.init(pk->nH, MSM_C, 0, true, false, true);
+    int prio_lo = 0, prio_hi = 0;
+    ZK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));          // the QAP map + H MSM chain is the critical path
+    if (const char *e = getenv("ZKB200_SIDE_PRIO")) { if (atoi(e) == 1) { const int t = prio_lo; prio_lo = prio_hi; prio_hi = t; } else if (atoi(e) == 2) prio_lo = prio_hi; }
+    ZK_CUDA(cudaStreamCreateWithPriority(&ln->s_main, cudaStreamNonBlocking, prio_hi));
+    ZK_CUDA(cudaStreamCreateWithPriority(&ln->s_a, cudaStreamNonBlocking, prio_lo));
+    ZK_CUDA(cudaStreamCreateWithPriority(&ln->s_b, cudaStreamNonBlocking, prio_lo));
+    ZK_CUDA(cudaStreamCreateWithPriority(&ln->s_l, cudaStreamNonBlocking, prio_lo));
+    ZK_CUDA(cudaStreamCreateWithPriority(&ln->s_b2, cudaStreamNonBlocking, prio_lo));
+    ZK_CUDA(cudaEventCreateWithFlags(&ln->ev_w, cudaEventDisableTiming));
+    cudaEvent_t *tev[] = {&ln->ev_t0, &ln->ev_t1, &ln->ev_q0, &ln->ev_q1, &ln->ev_h0, &ln->ev_h1, &ln->ev_a, &ln->ev_b, &ln->ev_l, &ln->ev_b2};
+    for (auto *e : tev) ZK_CUDA(cudaEventCreate(e));
+    return ln;
+}
+static void lane_destroy(Lane *ln) {
+    void *ps[] = {ln->w_can, ln->w_mont, ln->bufA, ln->tmp, ln->sat_flag, ln->w_lo, ln->w_wide};
+    for (void *p : ps) if (p) cudaFree(p);
+    if (ln->h_wide_pinned) cudaFreeHost(ln->h_wide_pinned);
+    if (ln->h_w_pinned) cudaFreeHost(ln->h_w_pinned);
+    if (ln->h_sat_flag) cudaFreeHost(ln->h_sat_flag);
+    ln->mA.release(); ln->mB.release(); ln->mH.release(); ln->mL.release();
+    cudaStream_t ss[] = {ln->s_main, ln->s_a, ln->s_b, ln->s_l, ln->s_b2};
+    for (auto st : ss) if (st) cudaStreamDestroy(st);
+    cudaEvent_t es[] = {ln->ev_w, ln->ev_a, ln->ev_b, ln->ev_l, ln->ev_b2, ln->ev_t0, ln->ev_t1, ln->ev_q0, ln->ev_q1, ln->ev_h0, ln->ev_h1};
+    for (auto e : es) if (e) cudaEventDestroy(e);
+    delete ln;
+}
+Lane *lane_acquire(DevicePk *pk) {
+    LaneSync *sy = (LaneSync *)pk->sync;
+    std::unique_lock<std::mutex> lk(sy->mu);
+    for (;;) {
+        for (int i = 0; i < pk->nlanes; i++) if (!pk->lanes[i]->busy) { pk->lanes[i]->busy = true; return pk->lanes[i]; }
+        sy->cv.wait(lk);
+    }
+}
+Lane *lane_try(DevicePk *pk, int index) {
+    if (index < 0 || index >= pk->nlanes) return nullptr;
+    LaneSync *sy = (LaneSync *)pk->sync;
+    std::lock_guard<std::mutex> lk(sy->mu);
+    if (pk->lanes[index]->busy) return nullptr;
+    pk->lanes[index]->busy = true;
+    return pk->lanes[index];
+}
+void lane_release(DevicePk *pk, Lane *ln) {
+    LaneSync *sy = (LaneSync *)pk->sync;
+    { std::lock_guard<std::mutex> lk(sy->mu); ln->busy = false; }
+    sy->cv.notify_one();
+}
+Lane *lane_of_staging(DevicePk *pk, const void *p) {
+    for (int i = 0; i < pk->nlanes; i++) {
+        const char *base = (const char *)pk->lanes[i]->h_w_pinned;
+        if ((const char *)p >= base && (const char *)p < base + (pk->num_vars + 5) * 32) return pk->lanes[i];
+    }
+    return nullptr;
 }
 
 DevicePk *pk_load(const char *path, int device, std::string &err) {
@@ -484,75 +590,46 @@ DevicePk *pk_load(const char *path, int device, std::string &err) {
     pk->ncoef = (uint32_t)P.coef_dict.size();
     pk->coef_dict = dev_const(P.coef_dict.data(), P.coef_dict.size());
 
-    const size_t nw = pk->num_vars + 4, m = pk->dom->m;            // [1 | w | r | s | -rs]
-    ZK_CUDA(cudaMalloc(&pk->w_can, nw * 32)); ZK_CUDA(cudaMalloc(&pk->w_mont, nw * 32));
-    ZK_CUDA(cudaMemset(pk->w_can, 0, nw * 32));
-    const uint64_t one_can[4] = {1, 0, 0, 0};
-    ZK_CUDA(cudaMemcpy(pk->w_can, one_can, 32, cudaMemcpyHostToDevice));
-    ZK_CUDA(cudaMallocHost(&pk->h_w_pinned, (nw + 1) * 32));
-    ZK_CUDA(cudaMalloc(&pk->w_lo, nw * 8)); ZK_CUDA(cudaMalloc(&pk->w_wide, MAX_WIDE * sizeof(WideIn)));
-    ZK_CUDA(cudaMallocHost(&pk->h_wide_pinned, MAX_WIDE * sizeof(WideIn)));
-    ZK_CUDA(cudaMalloc(&pk->bufA, m * 32)); ZK_CUDA(cudaMalloc(&pk->bufB, m * 32)); ZK_CUDA(cudaMalloc(&pk->bufC, m * 32));
-    ZK_CUDA(cudaMalloc(&pk->tmp, m * 32));
-    ZK_CUDA(cudaMalloc(&pk->sat_flag, 4)); ZK_CUDA(cudaMallocHost(&pk->h_sat_flag, 4));
-
-    // witness MSMs: ~97 % of the scalars are 0/1 and nearly all others are <= 64 bits, so small windows; H is dense
-    pk->mA.init(pk->nA, MSM_C, 4096, true, false, true);
-    pk->mB.init(pk->nB, MSM_C, 4096, true, true, true);
-    pk->mL.init(pk->nL, MSM_C, 4096, true, false, true);
-    pk->mH.init(pk->nH, MSM_C, 0, true, false, true);
-
-    int prio_lo = 0, prio_hi = 0;
-    ZK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));          // the QAP map + H MSM chain is the critical path
-    ZK_CUDA(cudaStreamCreateWithPriority(&pk->s_main, cudaStreamNonBlocking, prio_hi));
-    ZK_CUDA(cudaStreamCreateWithPriority(&pk->s_a, cudaStreamNonBlocking, prio_lo));
-    ZK_CUDA(cudaStreamCreateWithPriority(&pk->s_b, cudaStreamNonBlocking, prio_lo));
-    ZK_CUDA(cudaStreamCreateWithPriority(&pk->s_l, cudaStreamNonBlocking, prio_lo));
-    cudaEvent_t *evs[] = {&pk->ev_w, &pk->ev_a, &pk->ev_b, &pk->ev_l};
-    for (auto *e : evs) ZK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-    cudaEvent_t *tev[] = {&pk->ev_t0, &pk->ev_t1, &pk->ev_q0, &pk->ev_q1, &pk->ev_h0, &pk->ev_h1};
-    for (auto *e : tev) ZK_CUDA(cudaEventCreate(e));
+    int nl = 3;                                                    // proofs in flight per key
+    if (const char *e = getenv("ZKB200_LANES")) nl = atoi(e);
+    if (nl < 1) nl = 1;
+    if (nl > MAX_LANES) nl = MAX_LANES;
+    pk->sync = new LaneSync();
+    for (int i = 0; i < nl; i++) { pk->lanes[i] = lane_create(pk, i); pk->nlanes = i + 1; }
     ZK_CUDA(cudaDeviceSynchronize());
     pk->load_seconds = now_s() - t0;
     return pk;
 }
 
-uint64_t *compact_staging(DevicePk *pk) { return (uint64_t *)pk->h_w_pinned; }
+uint64_t *compact_staging(Lane *ln) { return (uint64_t *)ln->h_w_pinned; }
 
 void pk_free(DevicePk *pk) {
     if (!pk) return;
     cudaSetDevice(pk->device);
     cudaDeviceSynchronize();
     void *ps[] = {pk->A, pk->B1, pk->B2, pk->H, pk->L, pk->A_skip, pk->B_skip, pk->H_skip, pk->L_skip, pk->B_idx, pk->L_idx, pk->a.rowptr, pk->a.col, pk->a.coef,
-                  pk->b.rowptr, pk->b.col, pk->b.coef, pk->c.rowptr, pk->c.col, pk->c.coef, pk->coef_dict, pk->w_can, pk->w_mont, pk->bufA, pk->bufB,
-                  pk->bufC, pk->tmp, pk->sat_flag, pk->w_lo, pk->w_wide};
-    if (pk->h_wide_pinned) cudaFreeHost(pk->h_wide_pinned);
+                  pk->b.rowptr, pk->b.col, pk->b.coef, pk->c.rowptr, pk->c.col, pk->c.coef, pk->coef_dict};
     for (void *p : ps) if (p) cudaFree(p);
-    if (pk->h_w_pinned) cudaFreeHost(pk->h_w_pinned);
-    if (pk->h_sat_flag) cudaFreeHost(pk->h_sat_flag);
-    pk->mA.release(); pk->mB.release(); pk->mH.release(); pk->mL.release();
+    for (int i = 0; i < pk->nlanes; i++) lane_destroy(pk->lanes[i]);
     if (pk->dom) { pk->dom->release(); delete pk->dom; }
-    cudaStream_t ss[] = {pk->s_main, pk->s_a, pk->s_b, pk->s_l};
-    for (auto s : ss) if (s) cudaStreamDestroy(s);
-    cudaEvent_t es[] = {pk->ev_w, pk->ev_a, pk->ev_b, pk->ev_l, pk->ev_t0, pk->ev_t1, pk->ev_q0, pk->ev_q1, pk->ev_h0, pk->ev_h1};
-    for (auto e : es) if (e) cudaEventDestroy(e);
+    delete (LaneSync *)pk->sync;
     delete pk;
 }
 
 // =====================================================================================================================
 // the per-proof pipeline
-static void upload_assignment(DevicePk *pk, const uint8_t *assignment, const uint64_t *zk_scalars /* r, s, -rs or null */, cudaStream_t st) {
+static void upload_assignment(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64_t *zk_scalars /* r, s, -rs or null */, cudaStream_t st) {
     const size_t n = pk->num_vars;
-    char *pin = (char *)pk->h_w_pinned + 32;            // [pad | assignment | r | s | -rs]
+    char *pin = (char *)ln->h_w_pinned + 32;            // [pad | assignment | r | s | -rs]
     if (zk_scalars) memcpy(pin + n * 32, zk_scalars, 96);
     if (assignment) {
         if ((const char *)assignment != pin) memcpy(pin, assignment, n * 32);
-        ZK_CUDA(cudaMemcpyAsync((char *)pk->w_can + 32, pin, n * 32 + (zk_scalars ? 96 : 0), cudaMemcpyHostToDevice, st));
-    } else if (zk_scalars) {
-        ZK_CUDA(cudaMemcpyAsync((char *)pk->w_can + 32 + n * 32, pin + n * 32, 96, cudaMemcpyHostToDevice, st));
+        ZK_CUDA(cudaMemcpyAsync((char *)ln->w_can + 32, pin, n * 32 + (zk_scalars ? 96 : 0), cudaMemcpyHostToDevice, st));
+        ZK_CUDA(cudaMemcpyAsync(ln->w_mont, ln->w_can, (n + 1) * 32, cudaMemcpyDeviceToDevice, st));
+        ZK_LAUNCH(to_mont_kernel, cdiv(n + 1, 256), 256, 0, st, (Fr *)ln->w_mont, (uint32_t)(n + 1));
+    } else if (zk_scalars) {                            // resident assignment: only r, s, -rs change
+        ZK_CUDA(cudaMemcpyAsync((char *)ln->w_can + 32 + n * 32, pin + n * 32, 96, cudaMemcpyHostToDevice, st));
     }
-    ZK_CUDA(cudaMemcpyAsync(pk->w_mont, pk->w_can, (n + 1) * 32, cudaMemcpyDeviceToDevice, st));
-    ZK_LAUNCH(to_mont_kernel, cdiv(n + 1, 256), 256, 0, st, (Fr *)pk->w_mont, (uint32_t)(n + 1));
 }
 
 // compact upload: w_can[i] = lo[i] (zero-extended), w_mont[i] = lo[i] * R, then the few wide values (and r, s, -rs) are patched in
@@ -571,111 +648,120 @@ __global__ void patch_wide_kernel(const WideIn *__restrict__ wide, uint32_t nwid
     st_fr(w_can + wide[k].idx, c);
     if (wide[k].idx < mont_limit) st_fr(w_mont + wide[k].idx, c.to_mont());
 }
-static void upload_compact(DevicePk *pk, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t *zk_scalars, cudaStream_t st) {
+static void upload_compact(DevicePk *pk, Lane *ln, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t *zk_scalars, cudaStream_t st) {
     const uint32_t n = (uint32_t)pk->num_vars;
-    uint64_t *pin = (uint64_t *)pk->h_w_pinned;
+    uint64_t *pin = (uint64_t *)ln->h_w_pinned;
     if (lo != pin) memcpy(pin, lo, (size_t)(n + 1) * 8);
-    WideIn *pw = (WideIn *)pk->h_wide_pinned;
+    WideIn *pw = (WideIn *)ln->h_wide_pinned;
     if (nwide > MAX_WIDE - 3) nwide = MAX_WIDE - 3;                  // (circuits here have <= 10)
-    memcpy(pw, wide, nwide * sizeof(WideIn));
+    if (nwide) memcpy(pw, wide, nwide * sizeof(WideIn));
     for (int k = 0; k < 3; k++) { pw[nwide + k].idx = n + 1 + k; pw[nwide + k].pad = 0; memcpy(pw[nwide + k].v, zk_scalars + 4 * k, 32); }
     nwide += 3;
-    ZK_CUDA(cudaMemcpyAsync(pk->w_lo, pin, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-    ZK_CUDA(cudaMemcpyAsync(pk->w_wide, pw, nwide * sizeof(WideIn), cudaMemcpyHostToDevice, st));
-    ZK_LAUNCH(expand_assignment_kernel, cdiv(n + 1, 256), 256, 0, st, (const uint64_t *)pk->w_lo, n + 1, (Fr *)pk->w_can, (Fr *)pk->w_mont);
-    ZK_LAUNCH(patch_wide_kernel, 1, 64, 0, st, (const WideIn *)pk->w_wide, nwide, n + 1, (Fr *)pk->w_can, (Fr *)pk->w_mont);
+    ZK_CUDA(cudaMemcpyAsync(ln->w_lo, pin, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    ZK_CUDA(cudaMemcpyAsync(ln->w_wide, pw, nwide * sizeof(WideIn), cudaMemcpyHostToDevice, st));
+    ZK_LAUNCH(expand_assignment_kernel, cdiv(n + 1, 256), 256, 0, st, (const uint64_t *)ln->w_lo, n + 1, (Fr *)ln->w_can, (Fr *)ln->w_mont);
+    ZK_LAUNCH(patch_wide_kernel, 1, 64, 0, st, (const WideIn *)ln->w_wide, nwide, n + 1, (Fr *)ln->w_can, (Fr *)ln->w_mont);
 }
 
-// r1cs_to_qap_witness_map (r1cs_to_qap.tcc:205-334) on stream st.  Result: coefficients_for_H[0..m) in pk->tmp (Montgomery form).
-static void qap_pipeline(DevicePk *pk, cudaStream_t st) {
+// r1cs_to_qap_witness_map (r1cs_to_qap.tcc:205-334) on stream st.  Result: coefficients_for_H[0..m) in ln->tmp (Montgomery form).
+static void qap_pipeline(DevicePk *pk, Lane *ln, cudaStream_t st) {
     const Domain &d = *pk->dom;
     const uint32_t nc = (uint32_t)pk->num_constraints, m = d.m;
-    const Fr *w = (const Fr *)pk->w_mont, *dict = (const Fr *)pk->coef_dict;
-    Fr *A = (Fr *)pk->bufA, *B = (Fr *)pk->bufB, *C = (Fr *)pk->bufC, *T = (Fr *)pk->tmp;
+    const Fr *w = (const Fr *)ln->w_mont, *dict = (const Fr *)pk->coef_dict;
+    Fr *A = (Fr *)ln->bufA, *B = (Fr *)ln->bufB, *C = (Fr *)ln->bufC, *T = (Fr *)ln->tmp;
     ZK_CUDA(cudaMemsetAsync(A + nc, 0, (size_t)(m - nc) * 32, st));
     ZK_CUDA(cudaMemsetAsync(B + nc, 0, (size_t)(m - nc) * 32, st));
     ZK_CUDA(cudaMemsetAsync(C + nc, 0, (size_t)(m - nc) * 32, st));
     SpmvArgs sa{{pk->a.rowptr, pk->b.rowptr, pk->c.rowptr}, {pk->a.col, pk->b.col, pk->c.col}, {pk->a.coef, pk->b.coef, pk->c.coef}, {A, B, C}};
-    ZK_LAUNCH(spmv_kernel, dim3(cdiv(nc, 128), 3), 128, 0, st, sa, dict, w, nc);
-    ZK_CUDA(cudaMemsetAsync(pk->sat_flag, 0, 4, st));
-    ZK_LAUNCH(sat_check_kernel, cdiv(nc, 256), 256, 0, st, A, B, C, nc, pk->sat_flag);
-    ZK_CUDA(cudaMemcpyAsync(pk->h_sat_flag, pk->sat_flag, 4, cudaMemcpyDeviceToHost, st));
+    ZK_LAUNCH(spmv_kernel, dim3(cdiv((size_t)nc * SPMV_G, 128), 3), 128, 0, st, sa, dict, w, nc);
+    ZK_CUDA(cudaMemsetAsync(ln->sat_flag, 0, 4, st));
+    ZK_LAUNCH(sat_check_kernel, cdiv(nc, 256), 256, 0, st, A, B, C, nc, ln->sat_flag);
+    ZK_CUDA(cudaMemcpyAsync(ln->h_sat_flag, ln->sat_flag, 4, cudaMemcpyDeviceToHost, st));
     ZK_LAUNCH(input_rows_kernel, 1, 64, 0, st, w, A, nc, (uint32_t)pk->num_inputs + 1);
     // iFFT then cosetFFT of each of A, B, C: coefficient i is multiplied by g^i (and 1/m for the basic domain) on the way
-    Fr *bufs[3] = {A, B, C};
-    for (Fr *X : bufs) {
-        domain_ifft(st, d, X, T, pm_none(), pm_two(d.g_lo, d.g_hi));
-        if (!d.step) domain_fft(st, d, T, X, pm_two(d.g_lo, d.g_hi_ninv));
-        else domain_fft(st, d, T, X, pm_none());
-    }
+    domain_ifft(st, d, A, T, pm_none(), pm_two(d.g_lo, d.g_hi), 3, m);
+    if (!d.step) domain_fft(st, d, T, A, pm_two(d.g_lo, d.g_hi_ninv), 3, m);
+    else domain_fft(st, d, T, A, pm_none(), 3, m);
     ZK_LAUNCH(qap_pointwise_kernel, cdiv(m, 256), 256, 0, st, A, B, C, m, d.big, d.compr, (const Fr *)d.zt, to_dev(d.z1));
     domain_ifft(st, d, A, T, pm_two(d.gi_lo, d.gi_hi_ninv), pm_two(d.gi_lo, d.gi_hi));
 }
 
 int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied) {
     device_init(pk->device);
-    cudaStream_t st = pk->s_main;
-    upload_assignment(pk, assignment, nullptr, st);
-    qap_pipeline(pk, st);
+    Lane *ln = lane_acquire(pk);
+    cudaStream_t st = ln->s_main;
+    upload_assignment(pk, ln, assignment, nullptr, st);
+    qap_pipeline(pk, ln, st);
     const uint32_t m = pk->dom->m;
-    ZK_LAUNCH(from_mont_kernel, cdiv(m, 256), 256, 0, st, (const Fr *)pk->tmp, (Fr *)pk->bufB, m);
-    ZK_CUDA(cudaMemcpyAsync(out_H, pk->bufB, (size_t)m * 32, cudaMemcpyDeviceToHost, st));
+    ZK_LAUNCH(from_mont_kernel, cdiv(m, 256), 256, 0, st, (const Fr *)ln->tmp, (Fr *)ln->bufB, m);
+    ZK_CUDA(cudaMemcpyAsync(out_H, ln->bufB, (size_t)m * 32, cudaMemcpyDeviceToHost, st));
     ZK_CUDA(cudaStreamSynchronize(st));
     memset(out_H + (size_t)m * 32, 0, 32);          // coefficients_for_H[m] = 0 (no ZK patch: d1 = d2 = d3 = 0)
-    if (satisfied) *satisfied = (*pk->h_sat_flag == 0);
+    if (satisfied) *satisfied = (*ln->h_sat_flag == 0);
+    lane_release(pk, ln);
     return 0;
 }
 
 static HG1 g1_mul(const HG1Affine &p, const uint64_t k[4]) { return HG1::from_affine(p).mul(k); }
 
-static int prove_staged(DevicePk *pk, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4],
-                        const uint64_t s[4], ProofPoints &out);
-int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const uint64_t s[4], ProofPoints &out) {
-    return prove_staged(pk, assignment, nullptr, nullptr, 0, r, s, out);
-}
-int prove_compact(DevicePk *pk, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4], const uint64_t s[4], ProofPoints &out) {
-    return prove_staged(pk, nullptr, lo, wide, nwide, r, s, out);
-}
-static int prove_staged(DevicePk *pk, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4],
-                        const uint64_t s[4], ProofPoints &out) {
+void prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4],
+                  const uint64_t s[4]) {
     device_init(pk->device);
     g_launches = 0;
-    cudaStream_t st = pk->s_main;
+    cudaStream_t st = ln->s_main;
+    memcpy(ln->r, r, 32); memcpy(ln->s, s, 32);
     uint64_t zks[12];
     memcpy(zks, r, 32); memcpy(zks + 4, s, 32);
     (HFr::from_canonical(r) * HFr::from_canonical(s)).neg().to_canonical(zks + 8);          // -(r*s) mod r
-    ZK_CUDA(cudaEventRecord(pk->ev_t0, st));
-    if (lo) upload_compact(pk, lo, wide, nwide, zks, st);
-    else upload_assignment(pk, assignment, zks, st);
-    ZK_CUDA(cudaEventRecord(pk->ev_w, st));
-    ZK_CUDA(cudaStreamWaitEvent(pk->s_a, pk->ev_w, 0));
-    ZK_CUDA(cudaStreamWaitEvent(pk->s_b, pk->ev_w, 0));
-    ZK_CUDA(cudaStreamWaitEvent(pk->s_l, pk->ev_w, 0));
-    // A, B, L queries: scalars are the canonical padded assignment [1 | w]  (r1cs_gg_ppzksnark.tcc:437-484); the trailing delta base of
-    // each query picks up r, s, -rs, so the MSM results already are  eA + r*delta,  eB + s*delta,  eL - rs*delta.
-    msm_run(pk->s_a, pk->mA, ScalarRef{pk->w_can, nullptr, 0, 0}, pk->A_skip, pk->A, nullptr);
-    msm_run(pk->s_b, pk->mB, ScalarRef{pk->w_can, pk->B_idx, 0, 0}, pk->B_skip, pk->B1, pk->B2);
-    msm_run(pk->s_l, pk->mL, ScalarRef{pk->w_can, pk->L_idx, 0, 0}, pk->L_skip, pk->L, nullptr);
-    ZK_CUDA(cudaEventRecord(pk->ev_a, pk->s_a)); ZK_CUDA(cudaEventRecord(pk->ev_b, pk->s_b)); ZK_CUDA(cudaEventRecord(pk->ev_l, pk->s_l));
-    // H: QAP witness map, then the dense MSM over coefficients_for_H[0 .. m-1)
-    ZK_CUDA(cudaEventRecord(pk->ev_q0, st));
-    qap_pipeline(pk, st);
-    ZK_CUDA(cudaEventRecord(pk->ev_q1, st));
-    ZK_CUDA(cudaEventRecord(pk->ev_h0, st));
-    msm_run(st, pk->mH, ScalarRef{pk->tmp, nullptr, 0, 1}, pk->H_skip, pk->H, nullptr);
-    ZK_CUDA(cudaEventRecord(pk->ev_h1, st));
-    ZK_CUDA(cudaStreamWaitEvent(st, pk->ev_a, 0)); ZK_CUDA(cudaStreamWaitEvent(st, pk->ev_b, 0)); ZK_CUDA(cudaStreamWaitEvent(st, pk->ev_l, 0));
-    ZK_CUDA(cudaEventRecord(pk->ev_t1, st));
-    ZK_CUDA(cudaStreamSynchronize(st));
-    ZK_CUDA(cudaEventElapsedTime(&out.gpu_ms, pk->ev_t0, pk->ev_t1));
-    ZK_CUDA(cudaEventElapsedTime(&out.qap_ms, pk->ev_q0, pk->ev_q1));
-    ZK_CUDA(cudaEventElapsedTime(&out.msm_h_ms, pk->ev_h0, pk->ev_h1));
-    out.acc_h_ms = pk->mH.last_acc_ms();
-    out.satisfied = (*pk->h_sat_flag == 0);
+    ZK_CUDA(cudaEventRecord(ln->ev_t0, st));
+    if (lo) upload_compact(pk, ln, lo, wide, nwide, zks, st);
+    else upload_assignment(pk, ln, assignment, zks, st);
+    ZK_CUDA(cudaEventRecord(ln->ev_w, st));
+    // H first (it is the critical path and the host needs ~0.2 ms to enqueue the rest): QAP witness map, then the dense MSM over
+    // coefficients_for_H[0 .. m-1)
+    ZK_CUDA(cudaEventRecord(ln->ev_q0, st));
+    qap_pipeline(pk, ln, st);
+    ZK_CUDA(cudaEventRecord(ln->ev_q1, st));
+    ZK_CUDA(cudaEventRecord(ln->ev_h0, st));
+    msm_run(st, ln->mH, ScalarRef{ln->tmp, nullptr, 0, 1}, pk->H_skip, pk->H, nullptr);
+    ZK_CUDA(cudaEventRecord(ln->ev_h1, st));
+    // A, B, L queries on side streams: scalars are the canonical padded assignment [1 | w]  (r1cs_gg_ppzksnark.tcc:437-484); the trailing
+    // delta base of each query picks up r, s, -rs, so the MSM results already are  eA + r*delta,  eB + s*delta,  eL - rs*delta.
+    ZK_CUDA(cudaStreamWaitEvent(ln->s_a, ln->ev_w, 0));
+    ZK_CUDA(cudaStreamWaitEvent(ln->s_b, ln->ev_w, 0));
+    ZK_CUDA(cudaStreamWaitEvent(ln->s_l, ln->ev_w, 0));
+    msm_run(ln->s_b, ln->mB, ScalarRef{ln->w_can, pk->B_idx, 0, 0}, pk->B_skip, pk->B1, pk->B2, ln->s_b2);
+    msm_run(ln->s_a, ln->mA, ScalarRef{ln->w_can, nullptr, 0, 0}, pk->A_skip, pk->A, nullptr);
+    msm_run(ln->s_l, ln->mL, ScalarRef{ln->w_can, pk->L_idx, 0, 0}, pk->L_skip, pk->L, nullptr);
+    ZK_CUDA(cudaEventRecord(ln->ev_a, ln->s_a)); ZK_CUDA(cudaEventRecord(ln->ev_b, ln->s_b)); ZK_CUDA(cudaEventRecord(ln->ev_l, ln->s_l));
+    ZK_CUDA(cudaEventRecord(ln->ev_b2, ln->s_b2));
+    ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_a, 0)); ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_b, 0)); ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_l, 0));
+    ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_b2, 0));
+    ZK_CUDA(cudaEventRecord(ln->ev_t1, st));
+    ln->launches = g_launches;
+    ln->pending = true;
+}
+
+int prove_collect(DevicePk *pk, Lane *ln, ProofPoints &out) {
+    if (!ln->pending) return -1;
+    device_init(pk->device);
+    const uint64_t *r = ln->r, *s = ln->s;
+    ZK_CUDA(cudaStreamSynchronize(ln->s_main));
+    ln->pending = false;
+    ZK_CUDA(cudaEventElapsedTime(&out.gpu_ms, ln->ev_t0, ln->ev_t1));
+    ZK_CUDA(cudaEventElapsedTime(&out.qap_ms, ln->ev_q0, ln->ev_q1));
+    ZK_CUDA(cudaEventElapsedTime(&out.msm_h_ms, ln->ev_h0, ln->ev_h1));
+    out.acc_h_ms = ln->mH.last_acc_ms();
+    ZK_CUDA(cudaEventElapsedTime(&out.a_done_ms, ln->ev_t0, ln->ev_a));
+    { float b1 = 0, b2 = 0; ZK_CUDA(cudaEventElapsedTime(&b1, ln->ev_t0, ln->ev_b)); ZK_CUDA(cudaEventElapsedTime(&b2, ln->ev_t0, ln->ev_b2)); out.b_done_ms = b1 > b2 ? b1 : b2; }
+    ZK_CUDA(cudaEventElapsedTime(&out.l_done_ms, ln->ev_t0, ln->ev_l));
+    out.satisfied = (*ln->h_sat_flag == 0);
+    out.launches = ln->launches;
+    g_last_launches = ln->launches;
 
     // host: add up the handful of partial sums per MSM, then the proof combination (r1cs_gg_ppzksnark.tcc:487-495)
-    const HG1 eAr = msm_finish_g1(pk->mA), eB1s = msm_finish_g1(pk->mB), eH = msm_finish_g1(pk->mH), eLrs = msm_finish_g1(pk->mL);
-    const HG2 eB2s = msm_finish_g2(pk->mB);
+    const HG1 eAr = msm_finish_g1(ln->mA), eB1s = msm_finish_g1(ln->mB), eH = msm_finish_g1(ln->mH), eLrs = msm_finish_g1(ln->mL);
+    const HG2 eB2s = msm_finish_g2(ln->mB);
     if (out.want_parts) {
         // the five plain MSM values of the reference (parity hooks): strip the folded zero-knowledge terms again
         const HG1 rd = g1_mul(pk->delta_g1, r).neg(), sd = g1_mul(pk->delta_g1, s).neg();
@@ -690,6 +776,25 @@ static int prove_staged(DevicePk *pk, const uint8_t *assignment, const uint64_t 
     const HG1 gC = eH.add(eLrs).add(gA.mul(s)).add(g1B.mul(r));
     out.A = gA.to_affine(); out.B = g2B.to_affine(); out.C = gC.to_affine();
     return 0;
+}
+
+int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const uint64_t s[4], ProofPoints &out) {
+    // a null assignment reuses what lane 0 holds (single-lane callers: the parity tests and the bench's sequential leg)
+    Lane *ln = nullptr;
+    if (!assignment) { while (!(ln = lane_try(pk, 0))) std::this_thread::yield(); }
+    else ln = lane_acquire(pk);
+    prove_submit(pk, ln, assignment, nullptr, nullptr, 0, r, s);
+    const int rc = prove_collect(pk, ln, out);
+    lane_release(pk, ln);
+    return rc;
+}
+int prove_compact(DevicePk *pk, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4], const uint64_t s[4], ProofPoints &out) {
+    Lane *own = lane_of_staging(pk, lo);               // the caller generated the witness in a lane it already holds
+    Lane *ln = own ? own : lane_acquire(pk);
+    prove_submit(pk, ln, nullptr, lo, wide, nwide, r, s);
+    const int rc = prove_collect(pk, ln, out);
+    if (!own) lane_release(pk, ln);
+    return rc;
 }
 
 static void hex_fq(const HFq &x, std::string &o) {

@@ -48,9 +48,10 @@ struct MsmPlan {
     size_t entries_cap = 0;
     bool expanded = false;      // bases hold 2^(c*k)*P for every window k: one bucket region, no Horner
     uint32_t regions = 0;
-    void *task_counts = nullptr, *task_off = nullptr, *heavy = nullptr;
-    uint32_t task_cap = 0;
-    void *buckets_g1 = nullptr, *buckets_g2 = nullptr;   // per-task partial sums
+    void *heavy = nullptr, *heavy_g2 = nullptr;          // queues of oversized buckets for the CTA-wide fold
+    cudaEvent_t ev_sorted = nullptr;                     // digit sort done (the G2 half may start on its own stream)
+    uint32_t acc_threads_g1 = 0, acc_threads_g2 = 0;     // threads of one resident wave of the accumulate kernel (multiple of 128)
+    void *buckets_g1 = nullptr, *buckets_g2 = nullptr;   // bucket pieces, slot = thread + bucket  [acc_threads + total + 1]
     void *out_g1 = nullptr, *out_g2 = nullptr;           // device partial sums  [(windows+1) * bpw]
     void *h_out_g1 = nullptr, *h_out_g2 = nullptr;       // pinned host copies
     cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr;    // around the G1 accumulate kernel (roofline measurement)
@@ -61,13 +62,35 @@ struct MsmPlan {
 struct ScalarRef { const void *scalars; const uint32_t *map; uint32_t offset; int montgomery; };
 // sort digits (count / scan / scatter) then accumulate+reduce for G1 and/or G2 bases; results land in plan.h_out_* after
 // the stream is synchronised.
-void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, const void *bases_g1, const void *bases_g2);
+void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, const void *bases_g1, const void *bases_g2, cudaStream_t st_g2 = nullptr);
 void *msm_expand_bases(const void *bases, uint32_t n, int c, bool g2);   // device table out[k*n+i] = 2^(c*k) * bases[i]
 zkh::HG1 msm_finish_g1(const MsmPlan &p);      // host: add the partial sums (windowed layout: Horner over windows)
 zkh::HG2 msm_finish_g2(const MsmPlan &p);
 
 // ---- proving key resident on one GPU -------------------------------------------------------------------------------------
 struct DeviceCsr { uint32_t *rowptr = nullptr, *col = nullptr, *coef = nullptr; uint32_t nnz = 0; };
+// Everything ONE in-flight proof writes: assignment, QAP work vectors, MSM work areas, streams.  A proving key owns a few of
+// these ("lanes") so that independent proofs overlap on the GPU: the latency-bound tails of one proof (bucket reduction, digit
+// sort) run under the integer-bound kernels of the next, and host work (witness generation, proof assembly) overlaps both.
+struct Lane {
+    int index = 0;
+    bool busy = false;
+    void *w_can = nullptr, *w_mont = nullptr;            // (num_vars + 1) scalars: [1 | assignment]
+    void *h_w_pinned = nullptr;
+    void *w_lo = nullptr, *w_wide = nullptr;              // device: compact assignment staging
+    void *h_wide_pinned = nullptr;
+    void *bufA = nullptr, *bufB = nullptr, *bufC = nullptr, *tmp = nullptr;   // m Fr each
+    uint32_t *sat_flag = nullptr; uint32_t *h_sat_flag = nullptr;
+    MsmPlan mA, mB, mH, mL;
+    cudaStream_t s_main = nullptr, s_a = nullptr, s_b = nullptr, s_l = nullptr, s_b2 = nullptr;
+    cudaEvent_t ev_w = nullptr, ev_a = nullptr, ev_b = nullptr, ev_l = nullptr, ev_b2 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_q0 = nullptr, ev_q1 = nullptr,
+                ev_h0 = nullptr, ev_h1 = nullptr;
+    uint64_t r[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0};   // zero-knowledge scalars of the proof in flight
+    int launches = 0;                                    // kernels launched for the proof in flight
+    bool pending = false;                                // submitted, not yet collected
+};
+constexpr int MAX_LANES = 8;
+
 struct DevicePk {
     int device = 0;
     uint64_t num_inputs = 0, num_vars = 0, num_constraints = 0;
@@ -81,22 +104,19 @@ struct DevicePk {
     zkh::HG2Affine beta_g2, delta_g2;
     DeviceCsr a, b, c;
     void *coef_dict = nullptr; uint32_t ncoef = 0;
-    // per-proof work buffers
-    void *w_can = nullptr, *w_mont = nullptr;            // (num_vars + 1) scalars: [1 | assignment]
-    void *h_w_pinned = nullptr;
-    void *w_lo = nullptr, *w_wide = nullptr;              // device: compact assignment staging
-    void *h_wide_pinned = nullptr;
-    void *bufA = nullptr, *bufB = nullptr, *bufC = nullptr, *tmp = nullptr;   // m Fr each
-    uint32_t *sat_flag = nullptr; uint32_t *h_sat_flag = nullptr;
-    MsmPlan mA, mB, mH, mL;
-    cudaStream_t s_main = nullptr, s_a = nullptr, s_b = nullptr, s_l = nullptr;
-    cudaEvent_t ev_w = nullptr, ev_a = nullptr, ev_b = nullptr, ev_l = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_q0 = nullptr, ev_q1 = nullptr,
-                ev_h0 = nullptr, ev_h1 = nullptr;
+    // per-proof state
+    Lane *lanes[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int nlanes = 0;
+    void *sync = nullptr;                                 // mutex + condition variable guarding Lane::busy (opaque here)
     double load_seconds = 0, parse_seconds = 0, decompress_seconds = 0, expand_seconds = 0;
 };
 
-DevicePk *pk_load(const char *path, int device, std::string &err);
+DevicePk *pk_load(const char *path, int device, std::string &err);     // lanes: env ZKB200_LANES (default 3)
 void pk_free(DevicePk *pk);
+Lane *lane_acquire(DevicePk *pk);                       // blocks until a lane is free
+Lane *lane_try(DevicePk *pk, int index);                // lane `index` if it is free, else nullptr
+void lane_release(DevicePk *pk, Lane *ln);
+Lane *lane_of_staging(DevicePk *pk, const void *p);     // the lane whose pinned staging buffer `p` points into, or nullptr
 
 struct ProofPoints {
     zkh::HG1Affine A, C; zkh::HG2Affine B;
@@ -104,20 +124,28 @@ struct ProofPoints {
     bool satisfied = true;
     bool want_parts = false;                            // also compute the five plain MSM values (costs four host scalar multiplications)
     float gpu_ms = 0, qap_ms = 0, msm_h_ms = 0, acc_h_ms = 0;   // CUDA-event timings of the last run (acc_h: H accumulate kernel)
+    float a_done_ms = 0, b_done_ms = 0, l_done_ms = 0;          // when the A, B, L query MSMs (side streams) finished, from the start
+    int launches = 0;
 };
-// assignment: num_vars canonical 32-byte LE scalars in HOST memory (copied H2D inside), or nullptr to reuse the
-// assignment already resident on the device (bench "value" leg).
-int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const uint64_t s[4], ProofPoints &out);
-// Compact form (witness.hpp): lo[0..num_vars] = low 64 bits per variable (lo[0] = 1), wide = the few values above 64 bits.
-// Uploads 8 B per variable; lo may be compact_staging(pk) itself to skip the staging copy.
+// Two halves of one proof on a lane the caller holds.  submit: H2D copy of the assignment + every kernel, asynchronous.
+//   assignment: num_vars canonical 32-byte LE scalars in HOST memory, or
+//   lo/wide   : compact form (witness.hpp): lo[0..num_vars] = low 64 bits per variable (lo[0] = 1), wide = the few values above
+//               64 bits; uploads 8 B per variable; lo may be the lane's own pinned staging (no staging copy), or
+//   neither   : reuse the assignment already resident on the lane (bench "value" leg).
+// collect: waits for the lane's streams, sums the partial points and assembles the proof on the host.
 struct WideIn { uint32_t idx; uint32_t pad; uint64_t v[4]; };
+void prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4],
+                  const uint64_t s[4]);
+int prove_collect(DevicePk *pk, Lane *ln, ProofPoints &out);
+// synchronous conveniences: acquire a lane (or use the one that owns `lo`), submit, collect, release
+int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const uint64_t s[4], ProofPoints &out);
 int prove_compact(DevicePk *pk, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4], const uint64_t s[4], ProofPoints &out);
-uint64_t *compact_staging(DevicePk *pk);                // pinned, (num_vars + 1) uint64
+uint64_t *compact_staging(Lane *ln);                    // pinned, (num_vars + 1) uint64
 // QAP witness map only; writes (m+1)*32 bytes canonical to host `out_H`
 int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied);
 
 void device_init(int device);
 std::string proof_hex(const ProofPoints &p);           // mintcgo.cpp:112-187 layout
-int launches_last_prove();                             // number of kernels launched by the last prove() call
+int launches_last_prove();                             // number of kernels launched by the last collected proof
 
 } // namespace zkp

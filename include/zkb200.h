@@ -84,21 +84,39 @@ const char *zkb200_last_error(void);
 /* Replaces r1cs_gg_ppzksnark_prover (r1cs_gg_ppzksnark.tcc:390-506) for a caller-supplied full assignment
  * (primary || auxiliary, num_variables x 32 B) and explicit r, s.  assignment == NULL re-proves the assignment already
  * resident on the GPU.  proof_hex: 513 bytes.  parts (optional, 384 B): the five MSM results At | Bt.g | Bt.h | Ht | Lt.
- * timings_ms (optional, 5 floats): GPU total, QAP witness map, H MSM, host finish, H-MSM bucket-accumulate kernel (CUDA events).
+ * timings_ms (optional, 8 floats): GPU total, QAP witness map, H MSM, host finish, H-MSM bucket-accumulate kernel, and the times at
+ * which the A, B and L query MSMs (side streams) were done, counted from the start (CUDA events).
  * Returns 0 = proof, 1 = constraint system not satisfied (proof_hex = default proof), <0 = error. */
 int zkb200_prove(void *pk, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32], char *proof_hex, uint8_t *parts,
                  float *timings_ms);
 /* Same prover fed with the COMPACT assignment the native witness generators produce: lo[0..num_variables] = low 64 bits of every
  * variable (lo[0] = 1, the constant ONE), wide = nwide records {uint32 idx; uint32 pad; uint64 v[4]} for the few values above 64 bits.
- * 8 instead of 32 bytes per variable cross PCIe.  lo may be zkb200_compact_staging(pk) (pinned) to skip the staging copy. */
+ * 8 instead of 32 bytes per variable cross PCIe.  lo may be zkb200_lane_staging() of a lane the caller holds (pinned: no staging copy;
+ * the proof then runs on that lane). */
 int zkb200_prove_compact(void *pk, const uint64_t *lo, const void *wide, size_t nwide, const uint8_t r[32], const uint8_t s[32], char *proof_hex,
                          float *timings_ms);
-uint64_t *zkb200_compact_staging(void *pk);
+
+/* Proofs in flight.  A resident proving key owns zkb200_pk_lanes(pk) "lanes" (env ZKB200_LANES, default 3): private copies of every
+ * buffer one proof writes, with their own CUDA streams.  zkb200_prove / zkb200_prove_compact / gen*proof are thread-safe and take a
+ * free lane each, so concurrent callers (goroutines in geth) overlap on the GPU.  A single-threaded caller gets the same overlap by
+ * splitting a proof in two: submit enqueues the copy and every kernel and returns, collect waits and assembles the proof.
+ *   zkb200_lane_acquire  returns a free lane index (blocks while all are busy); zkb200_lane_release gives it back
+ *   zkb200_lane_staging  pinned buffer of num_variables + 1 uint64 for the compact assignment of that lane
+ *   zkb200_prove_submit  assignment (num_variables x 32 B, host) or NULL = the assignment the lane already holds
+ *   zkb200_prove_submit_compact  lo / wide as in zkb200_prove_compact
+ *   zkb200_prove_collect same outputs and return value as zkb200_prove (timings_ms[3], host finish, counts from the call) */
+int zkb200_pk_lanes(void *pk);
+int zkb200_lane_acquire(void *pk);
+void zkb200_lane_release(void *pk, int lane);
+uint64_t *zkb200_lane_staging(void *pk, int lane);
+int zkb200_prove_submit(void *pk, int lane, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32]);
+int zkb200_prove_submit_compact(void *pk, int lane, const uint64_t *lo, const void *wide, size_t nwide, const uint8_t r[32], const uint8_t s[32]);
+int zkb200_prove_collect(void *pk, int lane, char *proof_hex, uint8_t *parts, float *timings_ms);
 /* Replaces r1cs_to_qap_witness_map (r1cs_to_qap.tcc:205-334): out_H receives (m+1) x 32 B coefficients_for_H. */
 int zkb200_qap_witness_map(void *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied);
 /* milliseconds of the last gen*proof call: host witness generation, zkb200_prove total, of which GPU (CUDA events), host finish */
 void zkb200_last_breakdown_ms(double out[4]);
-/* kernels launched by the last zkb200_prove call */
+/* kernels launched for the last collected proof */
 int zkb200_last_launches(void);
 
 /* Witness handling: the FULL variable assignment (primary || auxiliary, 32 B canonical each) that the reference obtains by running
@@ -152,8 +170,10 @@ float zkb200_bench_msm_slice(int group, size_t first, size_t n, int window_bits,
 /* bench hygiene: overwrite a 256 MB scratch buffer (2x L2) and synchronise; plain cudaDeviceSynchronize */
 void zkb200_flush_l2(void);
 void zkb200_device_sync(void);
-/* dependent-free 32-bit multiply-add throughput of the GPU in 1e12 IMAD/s (the MSM roofline denominator) */
-float zkb200_bench_imad_peak(int wide);
+/* integer-multiply peaks of the GPU in 1e12 ops/s (the MSM roofline denominators): mode 0 = 32x32->32 multiply-add (IMAD),
+ * mode 1 = 32x32->64 multiply-add in carry chains (IMAD.WIDE.U32.X, the instruction the field multiplication is made of),
+ * mode 2 = whole 254-bit Montgomery multiplications */
+float zkb200_bench_imad_peak(int mode);
 
 #ifdef __cplusplus
 }

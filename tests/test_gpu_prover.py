@@ -120,6 +120,74 @@ def test_cgo_random_proofs_verify_and_bad_inputs_fail(zk, circuit):
     assert zk.gen_proof(circuit, bad)[:10] == "0000000000"
 
 
+def test_lanes_proofs_in_flight_match_one_at_a_time(pks):
+    """zkb200_prove_submit / zkb200_prove_collect: proofs that overlap on the GPU (one per lane, different r, s and different
+    assignments) are byte-identical to the same proofs made one at a time, and to the reference for the golden (r, s)."""
+    g, w = gold("send")
+    pk = pks("send")
+    w2 = zk_witness_other(w)
+    assert pk.lanes >= 2
+    jobs = [(w, int(g["r"], 16), int(g["s"], 16)), (w2, 12345, 67890), (w, 3, 5), (w2, int(g["s"], 16), int(g["r"], 16))][:pk.lanes + 1]
+    want = [pk.prove(a, r, s) for a, r, s in jobs]
+    assert want[0]["proof_hex"] == g["proof_hex"] and all(x["rc"] == 0 for x in want)
+    lanes = [pk.lane_acquire() for _ in range(pk.lanes)]
+    assert sorted(lanes) == list(range(pk.lanes))
+    try:
+        got = [None] * len(jobs)
+        for i, (a, r, s) in enumerate(jobs):                    # more jobs than lanes: the first lane is reused after its collect
+            ln = lanes[i % len(lanes)]
+            if i >= len(lanes):
+                got[i - len(lanes)] = pk.collect(ln, want_parts=True)
+            pk.submit(ln, a, r, s)
+        for i in range(max(0, len(jobs) - len(lanes)), len(jobs)):
+            got[i] = pk.collect(lanes[i % len(lanes)], want_parts=True)
+        for x, y in zip(want, got):
+            assert x["proof_hex"] == y["proof_hex"] and x["parts"] == y["parts"] and y["rc"] == 0
+        # the assignment stays resident per lane: re-prove without uploading
+        pk.submit(lanes[1], None, 3, 5)
+        assert pk.collect(lanes[1])["proof_hex"] == pk_prove_on_free_lane(pk, jobs[1][0], 3, 5)
+        with pytest.raises(Exception):
+            pk.collect(lanes[0])                                # nothing pending
+    finally:
+        for ln in lanes:
+            pk.lane_release(ln)
+
+
+def zk_witness_other(w):
+    """A second satisfying send assignment: the native witness of a synthetic transaction."""
+    from blockmaze_b200 import api
+    w2 = api.witness("send", F.synthetic("send", 77))
+    assert len(w2) == len(w) and w2 != w
+    return w2
+
+
+def pk_prove_on_free_lane(pk, a, r, s):
+    import threading
+    out = {}
+    t = threading.Thread(target=lambda: out.update(pk.prove(a, r, s)))      # all lanes are held by the caller: this blocks until ...
+    t.start()
+    t.join(0.5)
+    assert t.is_alive()                                                     # ... one is released
+    pk.lane_release(2 if pk.lanes > 2 else 0)
+    t.join(30)
+    assert not t.is_alive()
+    got = pk.lane_acquire()                                                 # take it back so that the caller's bookkeeping stays valid
+    assert got == (2 if pk.lanes > 2 else 0)
+    return out["proof_hex"]
+
+
+def test_cgo_concurrent_callers(zk):
+    """gen*proof from several threads at once (goroutines in geth): calls overlap on the lanes, every proof verifies."""
+    from concurrent.futures import ThreadPoolExecutor
+    zk.set_key_dir(key_dir())
+    jobs = [(c, F.synthetic(c, 40 + i)) for i, c in enumerate(["send", "mint", "send", "redeem", "send", "deposit", "mint", "send", "send", "redeem"])]
+    with ThreadPoolExecutor(4) as pool:
+        proofs = list(pool.map(lambda j: zk.gen_proof(j[0], j[1]), jobs))
+    for (c, args), p in zip(jobs, proofs):
+        assert p[:10] != "0000000000"
+        assert zk.verify_proof(c, p, zk.verify_args(c, args))
+
+
 def test_reference_verifier_accepts_gpu_proof(zk, ref):
     """The UNMODIFIED reference verifier (libzk_mint.so verifyMintproof) accepts a GPU proof.  It reads the hard-coded
     /usr/local/prfKey, so this only runs where that directory exists (the build container)."""

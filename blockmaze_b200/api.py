@@ -70,6 +70,8 @@ lib.zkb200_witness_send.argtypes = GEN_SIGS["send"] + [C.c_void_p, C.c_size_t]
 lib.zkb200_witness_deposit.restype = C.c_long
 lib.zkb200_witness_deposit.argtypes = GEN_SIGS["deposit"] + [C.c_void_p, C.c_size_t]
 
+lib.zkb200_set_isolate_h.argtypes = [C.c_int]
+lib.zkb200_set_isolate_h.restype = None
 lib.zkb200_pk_lanes.argtypes = [C.c_void_p]
 lib.zkb200_lane_acquire.argtypes = [C.c_void_p]
 lib.zkb200_lane_release.argtypes = [C.c_void_p, C.c_int]

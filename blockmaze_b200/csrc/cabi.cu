@@ -224,6 +224,7 @@ int zkb200_qap_witness_map(void *h, const uint8_t *assignment, uint8_t *out_H, i
     return qap_witness_map(pk, assignment, out_H, satisfied);
 }
 int zkb200_last_launches(void) { return launches_last_prove(); }
+void zkb200_set_isolate_h(int on) { set_isolate_h(on != 0); }
 
 // ---- evaluation domains ---------------------------------------------------------------------------------------------------
 static std::map<std::pair<int, uint64_t>, Domain *> g_domains;

@@ -200,7 +200,7 @@ static __global__ void __launch_bounds__(128) msm_expand_bases_kernel(const Affi
 //                one thread when the span is small, by a whole CTA (strided sums + shared-memory tree) for the few oversized
 //                buckets, which are queued in heavy[]
 constexpr uint32_t MSM_MIN_RANGE = 16;
-constexpr uint32_t MSM_FOLD_SMALL = 8;
+constexpr uint32_t MSM_FOLD_SMALL = 16;
 constexpr uint32_t MSM_HEAVY_MAX = 1024;
 
 __host__ __device__ __forceinline__ uint32_t msm_range_len(uint32_t total_entries, uint32_t threads) {

@@ -21,6 +21,7 @@ using zkh::HFr; using zkh::HFq; using zkh::HFq2; using zkh::HG1; using zkh::HG2;
 
 static thread_local int g_launches = 0;     // kernels launched by this thread since the last prove_submit() began
 static int g_last_launches = 0;
+static bool g_isolate_h = false;            // measurement mode, see set_isolate_h()
 #define ZK_LAUNCH(kernel, grid, block, smem, stream, ...) do { kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); g_launches++; } while (0)
 
 void cuda_check(cudaError_t e, const char *what) {
@@ -30,6 +31,7 @@ void cuda_check(cudaError_t e, const char *what) {
     }
 }
 int launches_last_prove() { return g_last_launches; }
+void set_isolate_h(bool on) { g_isolate_h = on; }
 
 static inline Fr to_dev(const HFr &x) { Fr r; memcpy(r.v, x.v, 32); return r; }
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -330,6 +332,7 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool e
     ZK_CUDA(cudaGetDevice(&dev)); ZK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, msm_accumulate_kernel<Fq>, 128, 0));
     ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, msm_accumulate_kernel<Fq2>, 128, 0));
+    if (const char *e = getenv("ZKB200_ACC_CTAS")) { const int v = atoi(e); if (v > 0 && v < occ1) occ1 = v; if (v > 0 && v < occ2) occ2 = v; }
     acc_threads_g1 = (uint32_t)(sms * (occ1 > 0 ? occ1 : 1) * 128);
     acc_threads_g2 = (uint32_t)(sms * (occ2 > 0 ? occ2 : 1) * 128);
     ZK_CUDA(cudaEventCreate(&ev_acc0)); ZK_CUDA(cudaEventCreate(&ev_acc1));
@@ -430,7 +433,12 @@ static void upload_csr(const zkpk::Csr &h, DeviceCsr &d) {
     ZK_CUDA(cudaMemcpy(d.coef, h.coef.data(), (size_t)d.nnz * 4, cudaMemcpyHostToDevice));
 }
 constexpr uint32_t MAX_WIDE = 64;
-constexpr int MSM_C = 16;                  // window bits of the resident (expanded) MSMs: 16 windows, 32768 buckets
+constexpr int MSM_C = 16;                  // window bits of the dense H-query MSM: 16 windows, 32768 buckets
+// Witness queries (A, B, L): 97 % of the scalars are 0 or 1 ("ones" buckets), nearly all others fit 64 bits, so only a few thousand
+// entries reach the windowed buckets.  With 16-bit windows they were scattered over 32768 buckets and the bucket reduction (a chain of
+// ~35 dependent point additions per thread, 8192 threads each doing a 15-bit scalar multiplication) cost 0.3 ms and 14 % of the proof's
+// multiply-pipe work for next to nothing; 8-bit windows leave 128 buckets.  The fixed-base tables double (32 windows) -- HBM is cheap.
+constexpr int MSM_C_SIDE = 8;
 
 template <class A> static A fetch_point(const void *dev, size_t idx) {
     A a; ZK_CUDA(cudaMemcpy(&a, (const char *)dev + idx * sizeof(A), sizeof(A), cudaMemcpyDeviceToHost)); return a;
@@ -454,9 +462,9 @@ static Lane *lane_create(const DevicePk *pk, int index) {
     ZK_CUDA(cudaMalloc(&ln->tmp, 3 * m * 32));
     ZK_CUDA(cudaMalloc(&ln->sat_flag, 4)); ZK_CUDA(cudaMallocHost(&ln->h_sat_flag, 4));
     // witness MSMs: ~97 % of the scalars are 0/1 and nearly all others are <= 64 bits; H is dense
-    ln->mA.init(pk->nA, MSM_C, 4096, true, false, true);
-    ln->mB.init(pk->nB, MSM_C, 4096, true, true, true);
-    ln->mL.init(pk->nL, MSM_C, 4096, true, false, true);
+    ln->mA.init(pk->nA, MSM_C_SIDE, 4096, true, false, true);
+    ln->mB.init(pk->nB, MSM_C_SIDE, 4096, true, true, true);
+    ln->mL.init(pk->nL, MSM_C_SIDE, 4096, true, false, true);
     ln->mH.init(pk->nH, MSM_C, 0, true, false, true);
     int prio_lo = 0, prio_hi = 0;
     ZK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));          // the QAP map + H MSM chain is the critical path
@@ -578,11 +586,11 @@ DevicePk *pk_load(const char *path, int device, std::string &err) {
     // fixed-base tables: 2^(16k) * P for every window k, so each MSM needs a single bucket set and no Horner step
     const double t3 = now_s();
     { void *e;
-      e = msm_expand_bases(pk->A, pk->nA, MSM_C, false); cudaFree(pk->A); pk->A = e;
-      e = msm_expand_bases(pk->B1, pk->nB, MSM_C, false); cudaFree(pk->B1); pk->B1 = e;
-      e = msm_expand_bases(pk->B2, pk->nB, MSM_C, true); cudaFree(pk->B2); pk->B2 = e;
+      e = msm_expand_bases(pk->A, pk->nA, MSM_C_SIDE, false); cudaFree(pk->A); pk->A = e;
+      e = msm_expand_bases(pk->B1, pk->nB, MSM_C_SIDE, false); cudaFree(pk->B1); pk->B1 = e;
+      e = msm_expand_bases(pk->B2, pk->nB, MSM_C_SIDE, true); cudaFree(pk->B2); pk->B2 = e;
       e = msm_expand_bases(pk->H, pk->nH, MSM_C, false); cudaFree(pk->H); pk->H = e;
-      e = msm_expand_bases(pk->L, pk->nL, MSM_C, false); cudaFree(pk->L); pk->L = e;
+      e = msm_expand_bases(pk->L, pk->nL, MSM_C_SIDE, false); cudaFree(pk->L); pk->L = e;
       ZK_CUDA(cudaDeviceSynchronize()); }
     pk->expand_seconds = now_s() - t3;
 
@@ -717,26 +725,33 @@ void prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint6
     if (lo) upload_compact(pk, ln, lo, wide, nwide, zks, st);
     else upload_assignment(pk, ln, assignment, zks, st);
     ZK_CUDA(cudaEventRecord(ln->ev_w, st));
-    // H first (it is the critical path and the host needs ~0.2 ms to enqueue the rest): QAP witness map, then the dense MSM over
-    // coefficients_for_H[0 .. m-1)
+    // A, B, L queries on side streams: scalars are the canonical padded assignment [1 | w]  (r1cs_gg_ppzksnark.tcc:437-484); the trailing
+    // delta base of each query picks up r, s, -rs, so the MSM results already are  eA + r*delta,  eB + s*delta,  eL - rs*delta.
+    auto side_queries = [&]() {
+        ZK_CUDA(cudaStreamWaitEvent(ln->s_a, ln->ev_w, 0));
+        ZK_CUDA(cudaStreamWaitEvent(ln->s_b, ln->ev_w, 0));
+        ZK_CUDA(cudaStreamWaitEvent(ln->s_l, ln->ev_w, 0));
+        msm_run(ln->s_b, ln->mB, ScalarRef{ln->w_can, pk->B_idx, 0, 0}, pk->B_skip, pk->B1, pk->B2, ln->s_b2);
+        msm_run(ln->s_a, ln->mA, ScalarRef{ln->w_can, nullptr, 0, 0}, pk->A_skip, pk->A, nullptr);
+        msm_run(ln->s_l, ln->mL, ScalarRef{ln->w_can, pk->L_idx, 0, 0}, pk->L_skip, pk->L, nullptr);
+        ZK_CUDA(cudaEventRecord(ln->ev_a, ln->s_a)); ZK_CUDA(cudaEventRecord(ln->ev_b, ln->s_b)); ZK_CUDA(cudaEventRecord(ln->ev_l, ln->s_l));
+        ZK_CUDA(cudaEventRecord(ln->ev_b2, ln->s_b2));
+    };
+    auto wait_side = [&]() {
+        ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_a, 0)); ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_b, 0)); ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_l, 0));
+        ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_b2, 0));
+    };
+    // H: QAP witness map, then the dense MSM over coefficients_for_H[0 .. m-1).  This is the critical path, so the QAP map is enqueued
+    // first (the host needs ~0.2 ms to enqueue the side queries).  Measurement mode: H waits for the side queries.
     ZK_CUDA(cudaEventRecord(ln->ev_q0, st));
     qap_pipeline(pk, ln, st);
     ZK_CUDA(cudaEventRecord(ln->ev_q1, st));
+    side_queries();                           // enqueued while the GPU is busy with the QAP map: they run beside it and are mostly done when H starts
+    if (g_isolate_h) wait_side();
     ZK_CUDA(cudaEventRecord(ln->ev_h0, st));
     msm_run(st, ln->mH, ScalarRef{ln->tmp, nullptr, 0, 1}, pk->H_skip, pk->H, nullptr);
     ZK_CUDA(cudaEventRecord(ln->ev_h1, st));
-    // A, B, L queries on side streams: scalars are the canonical padded assignment [1 | w]  (r1cs_gg_ppzksnark.tcc:437-484); the trailing
-    // delta base of each query picks up r, s, -rs, so the MSM results already are  eA + r*delta,  eB + s*delta,  eL - rs*delta.
-    ZK_CUDA(cudaStreamWaitEvent(ln->s_a, ln->ev_w, 0));
-    ZK_CUDA(cudaStreamWaitEvent(ln->s_b, ln->ev_w, 0));
-    ZK_CUDA(cudaStreamWaitEvent(ln->s_l, ln->ev_w, 0));
-    msm_run(ln->s_b, ln->mB, ScalarRef{ln->w_can, pk->B_idx, 0, 0}, pk->B_skip, pk->B1, pk->B2, ln->s_b2);
-    msm_run(ln->s_a, ln->mA, ScalarRef{ln->w_can, nullptr, 0, 0}, pk->A_skip, pk->A, nullptr);
-    msm_run(ln->s_l, ln->mL, ScalarRef{ln->w_can, pk->L_idx, 0, 0}, pk->L_skip, pk->L, nullptr);
-    ZK_CUDA(cudaEventRecord(ln->ev_a, ln->s_a)); ZK_CUDA(cudaEventRecord(ln->ev_b, ln->s_b)); ZK_CUDA(cudaEventRecord(ln->ev_l, ln->s_l));
-    ZK_CUDA(cudaEventRecord(ln->ev_b2, ln->s_b2));
-    ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_a, 0)); ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_b, 0)); ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_l, 0));
-    ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_b2, 0));
+    wait_side();
     ZK_CUDA(cudaEventRecord(ln->ev_t1, st));
     ln->launches = g_launches;
     ln->pending = true;

@@ -146,6 +146,9 @@ int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int
 
 void device_init(int device);
 std::string proof_hex(const ProofPoints &p);           // mintcgo.cpp:112-187 layout
+// measurement mode: the H-query MSM of the next proofs starts only after the A, B, L queries are done, so that the CUDA-event time of
+// its kernels is that of the kernels alone (roofline); costs latency, never used otherwise
+void set_isolate_h(bool on);
 int launches_last_prove();                             // number of kernels launched by the last collected proof
 
 } // namespace zkp

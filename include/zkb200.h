@@ -118,6 +118,9 @@ int zkb200_qap_witness_map(void *pk, const uint8_t *assignment, uint8_t *out_H, 
 void zkb200_last_breakdown_ms(double out[4]);
 /* kernels launched for the last collected proof */
 int zkb200_last_launches(void);
+/* measurement mode (bench.py roofline): when on, a proof's H-query MSM starts only after its A, B, L queries are done, so the CUDA-event
+ * time of the H kernels (timings_ms[2], [4]) is that of the kernels running alone.  Costs latency; off by default. */
+void zkb200_set_isolate_h(int on);
 
 /* Witness handling: the FULL variable assignment (primary || auxiliary, 32 B canonical each) that the reference obtains by running
  * its gadgetlib1 circuit (<circuit>_gadget::generate_r1cs_witness, SRC/<c>/circuit/gadget.tcc), computed natively on the host.

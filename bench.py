@@ -373,7 +373,7 @@ def main():
                                  "msm_H": round(statistics.mean(msm_ms), 3), "msm_H_accumulate_kernel_alone": round(acc_avg, 3)},
             "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel<Fq> (H query, %d points)" % n_h, "achieved": round(ach, 3), "peak": round(imad_peak, 2),
                          "unit": "TIMAD/s", "frac": round(ach / imad_peak, 4) if imad_peak else None,
-                         "traffic": {"dram_bytes_per_launch": 522112768, "source": "profiles/r01_notes.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of this launch)"},
+                         "traffic": {"dram_bytes_per_launch": 501680000, "source": "profiles/r01_notes.md (B) (ncu --set full: dram__bytes_read.sum 487.22 MB + dram__bytes_write.sum 14.46 MB of this launch)"},
                          "issued": {"modmul_G_per_s": round(modmul_rate, 2), "modmul_peak_G_per_s": round(pk_["modmul_G"], 2),
                                     "frac": round(modmul_rate / pk_["modmul_G"], 4) if pk_["modmul_G"] else None,
                                     "what": "modular multiplications the kernel really issues (10 per mixed addition, 16 per point) against a kernel of back-to-back ff.cuh multiplications"},

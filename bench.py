@@ -14,6 +14,7 @@ transaction.
 import argparse
 import json
 import os
+import random
 import statistics
 import subprocess
 import sys
@@ -47,6 +48,7 @@ DOMAIN = {"mint": 196608, "send": 262144, "deposit": 524288, "redeem": 196608}
 WORKLOADS = {"send": "send circuit (252286 constraints, QAP domain 2^18): one Groth16 proof per step per GPU",
              "mixed1024": "mixed batch of 1024 synthetic mint/send/deposit/redeem transactions sharded over the GPUs"}
 IMAD_PER_G1_POINT = 23936          # 16 windows x (11 modmul x 136 wide multiply-adds) per point of a 254-bit G1 MSM
+FR_MODULUS = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 MODMUL_PER_G1_ADD = 10             # what msm_accumulate_kernel really issues: XYZZ += affine is 8M + 2S (ec.cuh)
 
 
@@ -190,8 +192,7 @@ def main():
 
     import blockmaze_b200 as zk
     from blockmaze_b200 import api
-    from oracle import bn254_oracle as O      # only for the seeded transaction generator's hashing helpers (inputs, not the measured path)
-    import fixtures as F
+    from blockmaze_b200 import wallet as F    # seeded transactions built with the library's own cgo helpers (nothing from oracle/ on this arm)
     zk.init(local)
     kd = key_dir()
     api.set_key_dir(kd)
@@ -212,7 +213,8 @@ def main():
     circuits = ["send"] if args.workload == "send" else ["mint", "send", "deposit", "redeem"]
     pks = {c: zk.ProvingKey(os.path.join(kd, c + "pk.txt")) for c in circuits}
     pk = pks["send"]
-    r, s = O.fr_from_words(O.fixed_rng_words(1000 + rank, 64))
+    rng = random.Random(1000 + rank)
+    r, s = rng.randrange(1, FR_MODULUS), rng.randrange(1, FR_MODULUS)      # pinned per rank
     sampler = ClockSampler(local)
     windows = []
 
@@ -444,7 +446,6 @@ def kernel_sweep(api):
 def msm_split(args, api, dist, rank, world, barrier):
     """BASELINE.json configs[4], second half: ONE large G1 MSM split by point range over the GPUs; every GPU returns one partial point
     and rank 0 adds them on the host (no collective on the data path; the 64-byte points travel through the rendezvous gather)."""
-    from oracle import bn254_oracle as O        # host-side point addition of <= 8 partial points (test-infrastructure arithmetic)
     n = 1 << args.logn
     per = n // world
     first, count = rank * per, (per if rank < world - 1 else n - per * (world - 1))
@@ -464,15 +465,11 @@ def msm_split(args, api, dist, rank, world, barrier):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        acc = O.G1.zero()
-        for b in pts:
-            if any(b):
-                acc = O.G1.add(acc, O.G1.from_affine((int.from_bytes(b[:32], "little"), int.from_bytes(b[32:], "little"))))
-        aff = O.G1.to_affine(acc)
+        total = api.g1_sum(pts)                 # one partial point per GPU, summed on the host (zkb200_g1_sum)
         emit(({"metric": "msm_points_per_sec", "value": units / tmax, "unit": "points/s", "n_gpus": world, "ms_per_step": 1e3 * tmax,
                           "higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "u32",
                           "config": {"workload": "single G1 MSM of 2^%d points split by point range, one partial point per GPU summed on the host" % args.logn},
-                          "result_x": "%064x" % (aff[0] if aff else 0)}))
+                          "result_x": "%064x" % int.from_bytes(total[:32], "little")}))
 
 
 def cpu_baseline():

@@ -70,6 +70,7 @@ lib.zkb200_witness_send.argtypes = GEN_SIGS["send"] + [C.c_void_p, C.c_size_t]
 lib.zkb200_witness_deposit.restype = C.c_long
 lib.zkb200_witness_deposit.argtypes = GEN_SIGS["deposit"] + [C.c_void_p, C.c_size_t]
 
+lib.zkb200_g1_sum.argtypes = [C.c_size_t, C.c_char_p, C.c_char_p]
 lib.zkb200_set_isolate_h.argtypes = [C.c_int]
 lib.zkb200_set_isolate_h.restype = None
 lib.zkb200_pk_lanes.argtypes = [C.c_void_p]
@@ -118,6 +119,13 @@ def msm_g1(bases, scalars, window_bits=0):
     out = C.create_string_buffer(64)
     if lib.zkb200_msm_g1(len(scalars) // 32, bytes(bases), bytes(scalars), window_bits, out) != 0:
         raise ZkError(last_error())
+    return out.raw
+
+
+def g1_sum(points):
+    """Host-side sum of affine G1 points (64 B each): the last step of an MSM split by point range over several GPUs."""
+    out = C.create_string_buffer(64)
+    lib.zkb200_g1_sum(len(points), b"".join(points), out)
     return out.raw
 
 

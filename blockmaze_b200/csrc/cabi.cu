@@ -373,6 +373,18 @@ float zkb200_bench_msm_slice(int group, size_t first, size_t n, int window_bits,
     plan.release(); cudaFree(sc); cudaFree(bases);
     return ms / (float)(iters > 0 ? iters : 1);
 }
+// host: sum of n affine G1 points (64 B each, all-zero = infinity) -- the last step of an MSM split by point range over several GPUs
+int zkb200_g1_sum(size_t n, const uint8_t *points, uint8_t out[64]) {
+    zkh::HG1 acc = zkh::HG1::inf();
+    for (size_t i = 0; i < n; i++) {
+        uint64_t c[8]; memcpy(c, points + 64 * i, 64);
+        if (!(c[0] | c[1] | c[2] | c[3] | c[4] | c[5] | c[6] | c[7])) continue;
+        zkh::HG1Affine a{zkh::HFq::from_canonical(c), zkh::HFq::from_canonical(c + 4)};
+        acc = acc.add(zkh::HG1::from_affine(a));
+    }
+    put_g1(out, acc.to_affine());
+    return 0;
+}
 float zkb200_bench_msm(int group, size_t n, int window_bits, int iters) { return zkb200_bench_msm_slice(group, 0, n, window_bits, iters, nullptr); }
 
 // write a buffer twice the size of L2 so the next step starts with a cold L2 (bench hygiene)

@@ -170,6 +170,9 @@ float zkb200_bench_msm(int group, size_t n, int window_bits, int iters);
  * large MSM splits by point range over several GPUs (one partial point per GPU, added on the host).  out_point
  * (64 B G1 / 128 B G2, may be NULL) receives the partial sum.  Also returns the points/scalars to the host for cross-checks when small. */
 float zkb200_bench_msm_slice(int group, size_t first, size_t n, int window_bits, int iters, uint8_t *out_point);
+/* Host-side sum of n affine G1 points (64 B each as in zkb200_msm_g1; all-zero = infinity): the "one partial point per GPU summed on the
+ * host" step of an MSM split by point range. */
+int zkb200_g1_sum(size_t n, const uint8_t *points, uint8_t out[64]);
 /* bench hygiene: overwrite a 256 MB scratch buffer (2x L2) and synchronise; plain cudaDeviceSynchronize */
 void zkb200_flush_l2(void);
 void zkb200_device_sync(void);

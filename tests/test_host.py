@@ -125,3 +125,71 @@ def test_verifier_accepts_reference_proofs_and_rejects_tampering(api, ref, circu
     assert not api.verify_proof(circuit, h, bad)
     assert not api.verify_proof(circuit, "0" * 63 + "1" + "0" * 63 + "2" + h[128:], va)                  # default-proof style A
     assert not api.verify_proof(circuit, "zz" + h[2:], va)
+
+
+def test_wallet_generator_equals_fixture_generator(api):
+    """bench.py builds its transactions with blockmaze_b200.wallet (the library's own cgo helpers); the reference arm and the parity tests
+    use tests/golden/fixtures.py (oracle hashing).  Same seeds must give the same gen*proof argument lists."""
+    from blockmaze_b200 import wallet as W
+    for c in ("mint", "send", "deposit", "redeem"):
+        for seed in (0, 1, 5, 1023):
+            assert W.synthetic(c, seed) == F.synthetic(c, seed)
+    assert W.mint(13, 6, 7, "1", "123456", "123") == F.mint_fixture()
+    assert W.send(14, 22, 8, "1", "123456", "12", "456", "123") == F.send_fixture()
+
+
+def test_g1_sum_on_host(api):
+    """zkb200_g1_sum (the host step of an MSM split by point range) against the oracle's group law, incl. infinity and P + (-P)."""
+    import random
+    rng = random.Random(3)
+    pts = [O.G1.to_affine(O.G1.mul(rng.randrange(1, O.R_MOD), O.G1.from_affine(O.G1_GEN))) for _ in range(5)]
+    enc = lambda p: p[0].to_bytes(32, "little") + p[1].to_bytes(32, "little")
+    acc = O.G1.zero()
+    for p in pts:
+        acc = O.G1.add(acc, O.G1.from_affine(p))
+    assert api.g1_sum([enc(p) for p in pts] + [bytes(64)]) == enc(O.G1.to_affine(acc))
+    neg = (pts[0][0], O.Q_MOD - pts[0][1])
+    assert api.g1_sum([enc(pts[0]), enc(neg)]) == bytes(64)
+    assert api.g1_sum([enc(pts[1]), enc(pts[1])]) == enc(O.G1.to_affine(O.G1.add(O.G1.from_affine(pts[1]), O.G1.from_affine(pts[1]))))
+
+
+def test_equal_range_accumulation_index_math():
+    """Host restatement of the index arithmetic of msm_accumulate_kernel / msm_fold_* (csrc/msm.cuh): the bucket-sorted entry list is cut
+    into equal ranges, thread t stores the piece of bucket b in slot t + b, bucket b later folds slots off[b]/L + b .. (off[b+1]-1)/L + b.
+    Checks that slots never collide, that the fold sees exactly the pieces of its bucket, and that every entry is counted once."""
+    import random
+    rng = random.Random(11)
+    for trial in range(30):
+        nb = rng.choice([5, 64, 300])
+        counts = [rng.choice([0, 0, 1, 2, 7, 40, rng.randrange(0, 3000)]) for _ in range(nb)]
+        off = [0]
+        for c in counts:
+            off.append(off[-1] + c)
+        total, threads = off[-1], rng.choice([128, 256, 1024])
+        L = max(16, -(-total // threads))
+        slots = {}
+        for t in range(threads):
+            e0, e1 = t * L, min(t * L + L, total)
+            if e0 >= total:
+                continue
+            b = max(i for i in range(nb) if off[i] <= e0)           # the kernel's binary search: last b with off[b] <= e0
+            assert off[b + 1] > e0
+            acc, nxt = 0, off[b + 1]
+            for e in range(e0, e1):
+                if e == nxt:
+                    assert (t + b) not in slots
+                    slots[t + b] = (b, acc)
+                    acc = 0
+                    b = max(i for i in range(nb) if off[i] <= e)
+                    nxt = off[b + 1]
+                acc += 1
+            assert (t + b) not in slots
+            slots[t + b] = (b, acc)
+        assert max(slots, default=0) <= threads + nb
+        for b in range(nb):
+            if counts[b] == 0:
+                continue
+            t0, t1 = off[b] // L, (off[b + 1] - 1) // L
+            pieces = [slots.pop(t + b) for t in range(t0, t1 + 1)]
+            assert all(pb == b for pb, _ in pieces) and sum(c for _, c in pieces) == counts[b]
+        assert not slots

@@ -176,7 +176,8 @@ static int prove_any(void *h, const uint8_t *assignment, const uint64_t *lo, con
     const auto t0 = std::chrono::steady_clock::now();
     if (lo) prove_compact(pk, lo, wide, nwide, rr, ss, pp); else prove(pk, assignment, rr, ss, pp);
     const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    return finish_outputs(pp, total_ms - pp.gpu_ms, proof_hex_out, parts, timings_ms);
+    (void)total_ms;
+    return finish_outputs(pp, pp.host_tail_ms, proof_hex_out, parts, timings_ms);
 }
 int zkb200_prove(void *h, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32], char *proof_hex_out, uint8_t *parts, float *timings_ms) {
     return prove_any(h, assignment, nullptr, nullptr, 0, r, s, proof_hex_out, parts, timings_ms);
@@ -216,7 +217,8 @@ int zkb200_prove_collect(void *h, int lane, char *proof_hex_out, uint8_t *parts,
     const auto t0 = std::chrono::steady_clock::now();
     if (prove_collect((DevicePk *)h, ln, pp)) return -1;
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    return finish_outputs(pp, ms, proof_hex_out, parts, timings_ms);
+    (void)ms;
+    return finish_outputs(pp, pp.host_tail_ms, proof_hex_out, parts, timings_ms);
 }
 int zkb200_qap_witness_map(void *h, const uint8_t *assignment, uint8_t *out_H, int *satisfied) {
     DevicePk *pk = (DevicePk *)h;

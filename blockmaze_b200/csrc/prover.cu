@@ -761,7 +761,29 @@ int prove_collect(DevicePk *pk, Lane *ln, ProofPoints &out) {
     if (!ln->pending) return -1;
     device_init(pk->device);
     const uint64_t *r = ln->r, *s = ln->s;
+    // The witness queries finish well before the H query (which waits for the QAP map): everything of the proof combination
+    // (r1cs_gg_ppzksnark.tcc:487-495) that does not involve H -- above all the two 254-bit scalar multiplications s*A and r*B1, 0.2 ms of
+    // host time -- is done while the GPU is still busy with it.
+    ZK_CUDA(cudaEventSynchronize(ln->ev_a)); ZK_CUDA(cudaEventSynchronize(ln->ev_b)); ZK_CUDA(cudaEventSynchronize(ln->ev_b2));
+    ZK_CUDA(cudaEventSynchronize(ln->ev_l));
+    const HG1 eAr = msm_finish_g1(ln->mA), eB1s = msm_finish_g1(ln->mB), eLrs = msm_finish_g1(ln->mL);
+    const HG2 eB2s = msm_finish_g2(ln->mB);
+    const HG1 gA = HG1::from_affine(pk->alpha_g1).add(eAr);
+    const HG1 g1B = HG1::from_affine(pk->beta_g1).add(eB1s);
+    const HG2 g2B = HG2::from_affine(pk->beta_g2).add(eB2s);
+    const HG1 c_part = eLrs.add(gA.mul(s)).add(g1B.mul(r));
+    out.A = gA.to_affine(); out.B = g2B.to_affine();
+    if (out.want_parts) {
+        // the plain MSM values of the reference (parity hooks): strip the folded zero-knowledge terms again
+        const HG1 rd = g1_mul(pk->delta_g1, r).neg(), sd = g1_mul(pk->delta_g1, s).neg();
+        uint64_t rs[4]; (HFr::from_canonical(r) * HFr::from_canonical(s)).to_canonical(rs);
+        out.At = eAr.add(rd).to_affine(); out.Bt_h = eB1s.add(sd).to_affine();
+        out.Lt = eLrs.add(g1_mul(pk->delta_g1, rs)).to_affine();
+        out.Bt_g = eB2s.add(HG2::from_affine(pk->delta_g2).mul(s).neg()).to_affine();
+    }
+
     ZK_CUDA(cudaStreamSynchronize(ln->s_main));
+    const double t_sync = now_s();
     ln->pending = false;
     ZK_CUDA(cudaEventElapsedTime(&out.gpu_ms, ln->ev_t0, ln->ev_t1));
     ZK_CUDA(cudaEventElapsedTime(&out.qap_ms, ln->ev_q0, ln->ev_q1));
@@ -773,23 +795,10 @@ int prove_collect(DevicePk *pk, Lane *ln, ProofPoints &out) {
     out.satisfied = (*ln->h_sat_flag == 0);
     out.launches = ln->launches;
     g_last_launches = ln->launches;
-
-    // host: add up the handful of partial sums per MSM, then the proof combination (r1cs_gg_ppzksnark.tcc:487-495)
-    const HG1 eAr = msm_finish_g1(ln->mA), eB1s = msm_finish_g1(ln->mB), eH = msm_finish_g1(ln->mH), eLrs = msm_finish_g1(ln->mL);
-    const HG2 eB2s = msm_finish_g2(ln->mB);
-    if (out.want_parts) {
-        // the five plain MSM values of the reference (parity hooks): strip the folded zero-knowledge terms again
-        const HG1 rd = g1_mul(pk->delta_g1, r).neg(), sd = g1_mul(pk->delta_g1, s).neg();
-        uint64_t rs[4]; (HFr::from_canonical(r) * HFr::from_canonical(s)).to_canonical(rs);
-        out.At = eAr.add(rd).to_affine(); out.Bt_h = eB1s.add(sd).to_affine(); out.Ht = eH.to_affine();
-        out.Lt = eLrs.add(g1_mul(pk->delta_g1, rs)).to_affine();
-        out.Bt_g = eB2s.add(HG2::from_affine(pk->delta_g2).mul(s).neg()).to_affine();
-    }
-    const HG1 gA = HG1::from_affine(pk->alpha_g1).add(eAr);
-    const HG1 g1B = HG1::from_affine(pk->beta_g1).add(eB1s);
-    const HG2 g2B = HG2::from_affine(pk->beta_g2).add(eB2s);
-    const HG1 gC = eH.add(eLrs).add(gA.mul(s)).add(g1B.mul(r));
-    out.A = gA.to_affine(); out.B = g2B.to_affine(); out.C = gC.to_affine();
+    const HG1 eH = msm_finish_g1(ln->mH);
+    if (out.want_parts) out.Ht = eH.to_affine();
+    out.C = eH.add(c_part).to_affine();
+    out.host_tail_ms = (float)(1e3 * (now_s() - t_sync));
     return 0;
 }
 

@@ -125,6 +125,7 @@ struct ProofPoints {
     bool want_parts = false;                            // also compute the five plain MSM values (costs four host scalar multiplications)
     float gpu_ms = 0, qap_ms = 0, msm_h_ms = 0, acc_h_ms = 0;   // CUDA-event timings of the last run (acc_h: H accumulate kernel)
     float a_done_ms = 0, b_done_ms = 0, l_done_ms = 0;          // when the A, B, L query MSMs (side streams) finished, from the start
+    float host_tail_ms = 0;                             // host work left after the GPU finished (the rest overlaps the H-query MSM)
     int launches = 0;
 };
 // Two halves of one proof on a lane the caller holds.  submit: H2D copy of the assignment + every kernel, asynchronous.

@@ -84,7 +84,8 @@ const char *zkb200_last_error(void);
 /* Replaces r1cs_gg_ppzksnark_prover (r1cs_gg_ppzksnark.tcc:390-506) for a caller-supplied full assignment
  * (primary || auxiliary, num_variables x 32 B) and explicit r, s.  assignment == NULL re-proves the assignment already
  * resident on the GPU.  proof_hex: 513 bytes.  parts (optional, 384 B): the five MSM results At | Bt.g | Bt.h | Ht | Lt.
- * timings_ms (optional, 8 floats): GPU total, QAP witness map, H MSM, host finish, H-MSM bucket-accumulate kernel, and the times at
+ * timings_ms (optional, 8 floats): GPU total, QAP witness map, H MSM, host work left after the GPU finished (most of the proof assembly
+ * overlaps the H MSM), H-MSM bucket-accumulate kernel, and the times at
  * which the A, B and L query MSMs (side streams) were done, counted from the start (CUDA events).
  * Returns 0 = proof, 1 = constraint system not satisfied (proof_hex = default proof), <0 = error. */
 int zkb200_prove(void *pk, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32], char *proof_hex, uint8_t *parts,

@@ -34,6 +34,8 @@ lib.zkb200_bench_msm.argtypes = [C.c_int, C.c_size_t, C.c_int, C.c_int]
 lib.zkb200_last_breakdown_ms.argtypes = [C.POINTER(C.c_double)]
 lib.zkb200_flush_l2.restype = None
 lib.zkb200_device_sync.restype = None
+lib.zkb200_device_timer.restype = C.c_float
+lib.zkb200_device_timer.argtypes = [C.c_int]
 lib.zkb200_bench_msm_slice.restype = C.c_float
 lib.zkb200_bench_msm_slice.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_char_p]
 lib.zkb200_bench_imad_peak.restype = C.c_float

@@ -400,6 +400,19 @@ void zkb200_flush_l2(void) {
     ZK_CUDA(cudaDeviceSynchronize());
 }
 void zkb200_device_sync(void) { if (!ensure_device()) ZK_CUDA(cudaDeviceSynchronize()); }
+// Device-clock stopwatch around a region that runs on many streams: both calls synchronise the whole device first and then record a CUDA
+// event, so the elapsed time is GPU time between two quiescent points.  stop = 0 starts; stop = 1 returns the milliseconds since the start.
+float zkb200_device_timer(int stop) {
+    if (ensure_device()) return -1;
+    static cudaEvent_t ev[64][2];
+    if (!ev[g_device][0]) { ZK_CUDA(cudaEventCreate(&ev[g_device][0])); ZK_CUDA(cudaEventCreate(&ev[g_device][1])); }
+    ZK_CUDA(cudaDeviceSynchronize());
+    ZK_CUDA(cudaEventRecord(ev[g_device][stop ? 1 : 0], 0));
+    ZK_CUDA(cudaEventSynchronize(ev[g_device][stop ? 1 : 0]));
+    if (!stop) return 0;
+    float ms = 0; ZK_CUDA(cudaEventElapsedTime(&ms, ev[g_device][0], ev[g_device][1]));
+    return ms;
+}
 
 float zkb200_bench_imad_peak(int mode) {
     if (ensure_device()) return -1;

@@ -177,6 +177,9 @@ int zkb200_g1_sum(size_t n, const uint8_t *points, uint8_t out[64]);
 /* bench hygiene: overwrite a 256 MB scratch buffer (2x L2) and synchronise; plain cudaDeviceSynchronize */
 void zkb200_flush_l2(void);
 void zkb200_device_sync(void);
+/* device-clock stopwatch for a region spread over many streams: synchronises the device, then records a CUDA event.
+ * stop = 0 starts, stop = 1 returns the milliseconds elapsed on the GPU since the start */
+float zkb200_device_timer(int stop);
 /* integer-multiply peaks of the GPU in 1e12 ops/s (the MSM roofline denominators): mode 0 = 32x32->32 multiply-add (IMAD),
  * mode 1 = 32x32->64 multiply-add in carry chains (IMAD.WIDE.U32.X, the instruction the field multiplication is made of),
  * mode 2 = whole 254-bit Montgomery multiplications */

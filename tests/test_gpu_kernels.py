@@ -171,3 +171,22 @@ def test_msm_point_range_split_adds_up(zk):
     fb = C.create_string_buffer(64)
     zk.lib.zkb200_bench_msm_slice(1, 0, n, -16, 1, fb)
     assert fb.raw == full.raw
+
+
+@pytest.mark.parametrize("n", [3000, 70000])
+def test_msm_skewed_buckets_against_reference(zk, ref, n):
+    """Bucket sizes as lopsided as a BlockMaze witness: most scalars share a handful of values, so a few buckets hold nearly all entries
+    (the equal-range accumulation cuts them into many pieces and the CTA-wide fold sums them), the rest are empty or hold one entry."""
+    rng = random.Random(n + 1)
+    b1, b2 = ref.g1_bases_bytes(n, 99), ref.g2_bases_bytes(n, 98)
+    big = (1 << 253) + 5
+    sc = [rng.choices([2, 1, big, 0xFFFFFFFF, 0, None], [50, 20, 10, 10, 5, 5])[0] for _ in range(n)]
+    sc = [rng.randrange(O.R_MOD) if x is None else x for x in sc]
+    s = fb(sc)
+    for c in (0, 8, 16):
+        assert zk.msm_g1(b1, s, c) == ref.msm_g1_bytes(b1, s, 1)[0], c
+    assert zk.msm_g2(b2, s) == ref.msm_g2_bytes(b2, s, 1)[0]
+    # every scalar the same: ONE bucket per window holds all n entries
+    s = fb([0x1234567] * n)
+    assert zk.msm_g1(b1, s) == ref.msm_g1_bytes(b1, s, 1)[0]
+    assert zk.g1_sum([zk.msm_g1(b1[:64 * 1000], s[:32 * 1000]), zk.msm_g1(b1[64 * 1000:], s[32 * 1000:])]) == zk.msm_g1(b1, s)

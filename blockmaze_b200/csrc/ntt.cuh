@@ -4,9 +4,9 @@
 //                                                                           basic_radix2_domain_aux.tcc:45-79,172-180)
 //   step_radix2_domain   idem for m = 2^k + 2^r (mint/redeem: 196608)      (.../domains/step_radix2_domain.tcc:21-248)
 //
-// Design (B200): a size-2^logn transform is 1-3 shared-memory passes.  Each pass brings a 2048-element tile (64 KB, SoA
-// by limb so butterflies are bank-conflict free) into shared memory, runs up to 10 butterfly stages there and writes
-// it back, i.e. one HBM/L2 round trip per <= 10 stages.  The first pass gathers its input in bit-reversed order (so
+// Design (B200): a size-2^logn transform is 1-3 shared-memory passes.  Each pass brings a 512..2048-element tile (<= 64 KB, SoA
+// by limb so butterflies are bank-conflict free) into shared memory, runs up to 10 butterfly stages there -- two stages at a
+// time as radix-4 steps in registers -- and writes it back, i.e. one HBM/L2 round trip per <= 10 stages.  The first pass gathers its input in bit-reversed order (so
 // the CLRS decimation-in-time schedule of the reference is kept and the output is in natural order) and can multiply
 // by g^i on the way in (coset shift); the last pass can multiply by a per-index power table on the way out (g^-i / n).
 // Twiddles omega^j, j < n/2, come from a table built once per domain.
@@ -50,7 +50,14 @@ __device__ __forceinline__ void st_fr(Fr *p, const Fr &r) {
 #ifndef ZK_NTT_INLINE_MUL
 #define ZK_NTT_INLINE_MUL 1      // butterfly multiplication inlined (one per loop body; measured 2-3 % faster than the call)
 #endif
-constexpr int NTT_MAX_THREADS = 512;
+__device__ __forceinline__ Fr ntt_mul(const Fr &a, const Fr &b) {
+#if ZK_NTT_INLINE_MUL
+    return Fr::mul_impl(a, b);
+#else
+    return a * b;
+#endif
+}
+constexpr int NTT_MAX_THREADS = 256;
 constexpr int NTT_TILE_LOG = 11;          // at most 2048 elements * 32 B = 64 KB of shared memory per CTA; 4 elements per thread
 
 // One pass = stages s0+1 .. s0+k of the decimation-in-time schedule over `n = 2^logn` elements.
@@ -85,28 +92,56 @@ ntt_pass_kernel(const Fr *__restrict__ src, Fr *__restrict__ dst, const Fr *__re
         for (int w = 0; w < 8; w++) sm[w * N + slot] = x.v[w];
     }
 
-    const int half = N >> 1;
-    for (int q = 1; q <= k; q++) {
+    // Butterfly stages.  Two stages at a time (radix-4 in registers): a thread takes the four elements that differ in index bits q-1 and
+    // q, multiplies by three twiddles (four multiplications, as two radix-2 stages would) and writes them back -- half the shared-memory
+    // traffic and half the barriers of a stage-by-stage schedule, and two independent multiplications in flight.  An odd k starts
+    // with one radix-2 stage.
+    int q = 1;
+    if (k & 1) {
         __syncthreads();
-        const int hq = 1 << (q - 1);
+        const int half = N >> 1;
         for (int u = threadIdx.x; u < half; u += nthreads) {
             const int g = u >> (k - 1), tt = u & ((1 << (k - 1)) - 1);
-            const int tlow = tt & (hq - 1);
-            const int t = ((tt >> (q - 1)) << q) | tlow;
-            const int i0 = (g << k) | t, i1 = i0 + hq;
-            const uint32_t low = (set0 + g) & lowmask;
-            const uint32_t j = ((uint32_t)tlow << s0) | low;
+            const int i0 = (g << k) | (tt << 1), i1 = i0 + 1;
+            const uint32_t j = (set0 + g) & lowmask;                  // tlow = 0 at the first stage
             Fr a, b;
 #pragma unroll
             for (int w = 0; w < 8; w++) { a.v[w] = sm[w * N + i0]; b.v[w] = sm[w * N + i1]; }
-#if ZK_NTT_INLINE_MUL
-            if (j != 0) b = Fr::mul_impl(b, ldg_fr(tw + ((size_t)j << (logn - s0 - q))));
-#else
-            if (j != 0) b = b * ldg_fr(tw + ((size_t)j << (logn - s0 - q)));
-#endif
+            if (j != 0) b = ntt_mul(b, ldg_fr(tw + ((size_t)j << (logn - s0 - 1))));
             Fr s = a + b, d = a - b;
 #pragma unroll
             for (int w = 0; w < 8; w++) { sm[w * N + i0] = s.v[w]; sm[w * N + i1] = d.v[w]; }
+        }
+        q = 2;
+    }
+    const int quarter = N >> 2;
+    for (; q < k; q += 2) {
+        __syncthreads();
+        const int hq = 1 << (q - 1);
+        for (int u = threadIdx.x; u < quarter; u += nthreads) {
+            const int g = u >> (k - 2), tt = u & ((1 << (k - 2)) - 1);
+            const int tlow = tt & (hq - 1);
+            const int i0 = (g << k) | ((tt >> (q - 1)) << (q + 1)) | tlow;
+            const uint32_t low = (set0 + g) & lowmask;
+            const uint32_t j = ((uint32_t)tlow << s0) | low, j2 = ((uint32_t)(tlow + hq) << s0) | low;
+            Fr x0, x1, x2, x3;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                x0.v[w] = sm[w * N + i0]; x1.v[w] = sm[w * N + i0 + hq]; x2.v[w] = sm[w * N + i0 + 2 * hq]; x3.v[w] = sm[w * N + i0 + 3 * hq];
+            }
+            if (j != 0) {                                               // stage q: (x0, x1) and (x2, x3), same twiddle
+                const Fr w1 = ldg_fr(tw + ((size_t)j << (logn - s0 - q)));
+                x1 = ntt_mul(x1, w1); x3 = ntt_mul(x3, w1);
+            }
+            const Fr a0 = x0 + x1, a1 = x0 - x1;
+            Fr a2 = x2 + x3, a3 = x2 - x3;
+            if (j != 0) a2 = ntt_mul(a2, ldg_fr(tw + ((size_t)j << (logn - s0 - q - 1))));      // stage q+1: (a0, a2) and (a1, a3)
+            a3 = ntt_mul(a3, ldg_fr(tw + ((size_t)j2 << (logn - s0 - q - 1))));
+            x0 = a0 + a2; x2 = a0 - a2; x1 = a1 + a3; x3 = a1 - a3;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                sm[w * N + i0] = x0.v[w]; sm[w * N + i0 + hq] = x1.v[w]; sm[w * N + i0 + 2 * hq] = x2.v[w]; sm[w * N + i0 + 3 * hq] = x3.v[w];
+            }
         }
     }
     __syncthreads();

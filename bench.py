@@ -390,7 +390,8 @@ def main():
                                     "what": "modular multiplications the kernel really issues (10 per mixed addition, 16 per point) against a kernel of back-to-back ff.cuh multiplications"},
                          "peaks": {k: round(v, 2) for k, v in pk_.items()},
                          "note": "integer-multiply roofline (SURVEY.md 8d): algorithmic 23936 wide multiply-adds per point / CUDA-event kernel time; "
-                                 "peak = carry-chained mad.lo.cc/madc.hi.cc (IMAD.WIDE.U32.X) microbenchmark in this run"},
+                                 "peak = carry-chained mad.lo.cc/madc.hi.cc (IMAD.WIDE.U32.X) microbenchmark in this run.  The algorithmic figure counts the reference's "
+                                 "mixed addition (7M+4S = 11 multiplications); the kernel's XYZZ addition needs 10, so this ratio tops out at 1.10 -- 'issued' is the strict one"},
         }
         line.update(extras)
         if world == 1 and not args.no_cpu_baseline and args.workload == "send":

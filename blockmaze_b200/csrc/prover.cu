@@ -333,7 +333,8 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool e
     ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, msm_accumulate_kernel<Fq>, 128, 0));
     ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, msm_accumulate_kernel<Fq2>, 128, 0));
     if (const char *e = getenv("ZKB200_ACC_CTAS")) { const int v = atoi(e); if (v > 0 && v < occ1) occ1 = v; if (v > 0 && v < occ2) occ2 = v; }
-    acc_threads_g1 = (uint32_t)(sms * (occ1 > 0 ? occ1 : 1) * 128);
+    int waves = 1; if (const char *e = getenv("ZKB200_ACC_WAVES")) { waves = atoi(e); if (waves < 1) waves = 1; }
+    acc_threads_g1 = (uint32_t)(sms * (occ1 > 0 ? occ1 : 1) * 128 * waves);
     acc_threads_g2 = (uint32_t)(sms * (occ2 > 0 ? occ2 : 1) * 128);
     ZK_CUDA(cudaEventCreate(&ev_acc0)); ZK_CUDA(cudaEventCreate(&ev_acc1));
     const size_t nout = (size_t)(regions + 1) * bpw;

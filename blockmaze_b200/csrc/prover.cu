@@ -1,8 +1,9 @@
 // GPU pipeline of the Groth16 prover for BlockMaze's circuits (replaces r1cs_gg_ppzksnark_prover,
 // libsnark/zk_proof_systems/ppzksnark/r1cs_gg_ppzksnark/r1cs_gg_ppzksnark.tcc:390-506, and everything below it:
 // r1cs_to_qap_witness_map r1cs_to_qap.tcc:205-334, libfqfft domains, libff multi_exp).  One DevicePk per (circuit, GPU):
-// fixed-base tables, constraint matrices, twiddles and all work buffers stay resident in HBM; a proof is one H2D copy of the
-// (compact) assignment, ~60 kernel launches on four streams, and a D2H copy of a few hundred partial sums.
+// fixed-base tables, constraint matrices and twiddles stay resident in HBM, and so do a few "lanes" of work buffers so that several
+// proofs are in flight; a proof is one H2D copy of the (compact) assignment, ~42 kernel launches on five streams, and a D2H copy of
+// a hundred partial sums.
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>

@@ -57,6 +57,35 @@ __global__ void k_widex(uint32_t *out, int iters) {
     for (int k = 0; k < 18; k++) r ^= v[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
+// FP64 FMA issue rate (data point for a 52-bit-limb floating-point multiplication, DESIGN.md "what comes next")
+__global__ void k_dfma(uint32_t *out, int iters) {
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - blockIdx.x * 1e-9;
+    double x[8];
+    for (int k = 0; k < 8; k++) x[k] = a * (k + 1);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = __fma_rz(x[k], b, a);
+    }
+    double r = 0;
+    for (int k = 0; k < 8; k++) r += x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)__double2ll_rz(r);
+}
+// 64-bit integer add chains (IADD3 + IADD3.X pairs on the ALU pipe)
+__global__ void k_add64(uint32_t *out, int iters) {
+    unsigned long long x[8], b = blockIdx.x * 40503ull + threadIdx.x + 3;
+    for (int k = 0; k < 8; k++) x[k] = b * (k + 1);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) asm volatile("add.u64 %0, %0, %1;" : "+l"(x[k]) : "l"(x[(k + 1) & 7]));
+    }
+    unsigned long long r = 0;
+    for (int k = 0; k < 8; k++) r ^= x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)(r ^ (r >> 32));
+}
 template <int ILP> __global__ void k_modmul(uint32_t *out, int iters) {
     Fq x[ILP], y;
     for (int k = 0; k < 8; k++) { y.v[k] = Fq::r2().v[k] ^ (threadIdx.x & 0xff); }
@@ -109,9 +138,10 @@ int main() {
     const int occ[] = {4, 8, 16, 24, 32, 48, 64};
     for (int w : occ) {
         printf("{\"warps_per_sm\": %d, \"imad_lo_T\": %.3f, \"imad_wide_T\": %.3f, \"imad_widex_T\": %.3f, "
-               "\"modmul_inl_G\": %.2f, \"modmul_inl_ilp2_G\": %.2f, \"modmul_call_G\": %.2f}\n", w,
+               "\"modmul_inl_G\": %.2f, \"modmul_inl_ilp2_G\": %.2f, \"modmul_call_G\": %.2f, \"dfma_T\": %.3f, \"add64_T\": %.3f}\n", w,
                run(k_lo, w, 2048, 64, sms) / 1e12, run(k_wide, w, 2048, 64, sms) / 1e12, run(k_widex, w, 2048, 32, sms) / 1e12,
-               run(k_modmul<1>, w, 2048, 1, sms) / 1e9, run(k_modmul<2>, w, 1024, 2, sms) / 1e9, run(k_modmul_call, w, 2048, 1, sms) / 1e9);
+               run(k_modmul<1>, w, 2048, 1, sms) / 1e9, run(k_modmul<2>, w, 1024, 2, sms) / 1e9, run(k_modmul_call, w, 2048, 1, sms) / 1e9,
+               run(k_dfma, w, 2048, 64, sms) / 1e12, run(k_add64, w, 2048, 64, sms) / 1e12);
         fflush(stdout);
     }
     return 0;

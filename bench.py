@@ -352,7 +352,9 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         ach = 64.0 * (1 << 24) / (ms_ntt * 1e-3) / 1e9
         extras["roofline_ntt"] = {"bound": "hbm", "kernel": "ntt_pass_kernel x3 (2^24-point forward NTT)", "achieved": round(ach, 1), "peak": hbm_peak,
-                                  "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": None, "ms": round(ms_ntt, 4),
+                                  "unit": "GB/s", "frac": round(ach / hbm_peak, 4),
+                                  "traffic": {"dram_bytes_per_transform": 4010000000, "source": "profiles/r01_notes.md (B) (ncu --set full of the three passes: 2.54 GB read + 1.47 GB written)"},
+                                  "ms": round(ms_ntt, 4),
                                   "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
         mm_peak = 1e3 * float(api.lib.zkb200_bench_imad_peak(2))
         mm_rate = 12.0 * (1 << 24) / (ms_ntt * 1e-3) / 1e9          # (n/2) * log2(n) butterflies, one modular multiplication each

@@ -176,6 +176,37 @@ def pk_prove_on_free_lane(pk, a, r, s):
     return out["proof_hex"]
 
 
+def test_single_lane_key_and_unsatisfied_proof_in_flight(zk):
+    """ZKB200_LANES=1 (smallest memory footprint) proves the same bytes; an unsatisfied assignment submitted beside a good one on a
+    two-lane key reports rc = 1 / the default proof for that lane only."""
+    g, w = gold("mint")
+    old = os.environ.get("ZKB200_LANES")
+    try:
+        os.environ["ZKB200_LANES"] = "1"
+        pk1 = zk.ProvingKey(os.path.join(key_dir(), "mintpk.txt"))
+        assert pk1.lanes == 1
+        assert pk1.prove(w, int(g["r"], 16), int(g["s"], 16))["proof_hex"] == g["proof_hex"]
+        pk1.close()
+        os.environ["ZKB200_LANES"] = "2"
+        pk2 = zk.ProvingKey(os.path.join(key_dir(), "mintpk.txt"))
+        assert pk2.lanes == 2
+        bad = bytearray(w)
+        bad[32 * 777] ^= 1
+        a, b = pk2.lane_acquire(), pk2.lane_acquire()
+        pk2.submit(a, bytes(bad), 5, 7)
+        pk2.submit(b, w, int(g["r"], 16), int(g["s"], 16))
+        rb, ra = pk2.collect(b), pk2.collect(a)
+        assert rb["rc"] == 0 and rb["proof_hex"] == g["proof_hex"]
+        assert ra["rc"] == 1 and ra["proof_hex"][:10] == "0000000000"
+        pk2.lane_release(a); pk2.lane_release(b)
+        pk2.close()
+    finally:
+        if old is None:
+            os.environ.pop("ZKB200_LANES", None)
+        else:
+            os.environ["ZKB200_LANES"] = old
+
+
 def test_cgo_concurrent_callers(zk):
     """gen*proof from several threads at once (goroutines in geth): calls overlap on the lanes, every proof verifies."""
     from concurrent.futures import ThreadPoolExecutor

@@ -255,14 +255,14 @@ def main():
         barrier()
         api.lib.zkb200_device_timer(0)        # CUDA events on the device, bracketed by device synchronisations (and the barriers)
         t0 = time.perf_counter()
-        launches = 0
+        launches, acc_inflight = 0, []
         for i in range(args.steps):
             ln = lanes[i % depth]
             if i >= depth:
-                launches += pk.collect(ln)["launches"]
+                res = pk.collect(ln); launches += res["launches"]; acc_inflight.append(res["timings_ms"][4])
             pk.submit(ln, None, r, s)
         for i in range(args.steps, args.steps + min(depth, args.steps)):
-            launches += pk.collect(lanes[i % depth])["launches"]
+            res = pk.collect(lanes[i % depth]); launches += res["launches"]; acc_inflight.append(res["timings_ms"][4])
         dev_ms = float(api.lib.zkb200_device_timer(1))
         t1 = time.perf_counter()
         barrier()
@@ -321,7 +321,7 @@ def main():
         pool.shutdown()
         windows.append((t0, t1))
         units, dt = reduce_counts_and_time(len(txs), max(dev_ms * 1e-3, t1 - t0), dist)
-        units_e, dt_e, launches, acc_ms, qap_ms, msm_ms, gpu_ms, brk = units, dt, 0, [0.0], [0.0], [0.0], [0.0], []
+        units_e, dt_e, launches, acc_ms, qap_ms, msm_ms, gpu_ms, brk, acc_inflight = units, dt, 0, [0.0], [0.0], [0.0], [0.0], [], []
         args.steps = 1
         nvars = 0
         workload = ("mixed batch of 1024 synthetic mint/send/deposit/redeem transactions (256 each) sharded round-robin over the GPUs, through gen*proof() "
@@ -388,12 +388,17 @@ def main():
             "gpu_launches": launches,
             "gpu_ms_per_proof": {"what": "one proof at a time, CUDA events", "total": round(statistics.mean(gpu_ms), 3), "qap_witness_map": round(statistics.mean(qap_ms), 3),
                                  "msm_H": round(statistics.mean(msm_ms), 3), "msm_H_accumulate_kernel_alone": round(acc_avg, 3)},
-            "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel<Fq> (H query, %d points)" % n_h, "achieved": round(ach, 3), "peak": round(imad_peak, 2),
+            "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel<Fq> (H query, %d points), timed alone after an L2 flush" % n_h, "achieved": round(ach, 3), "peak": round(imad_peak, 2),
                          "unit": "TIMAD/s", "frac": round(ach / imad_peak, 4) if imad_peak else None,
                          "traffic": {"dram_bytes_per_launch": 501680000, "source": "profiles/r01_notes.md (B) (ncu --set full: dram__bytes_read.sum 487.22 MB + dram__bytes_write.sum 14.46 MB of this launch)"},
                          "issued": {"modmul_G_per_s": round(modmul_rate, 2), "modmul_peak_G_per_s": round(pk_["modmul_G"], 2),
                                     "frac": round(modmul_rate / pk_["modmul_G"], 4) if pk_["modmul_G"] else None,
                                     "what": "modular multiplications the kernel really issues (10 per mixed addition, 16 per point) against a kernel of back-to-back ff.cuh multiplications"},
+                         "timed_region": {"kernel_ms_avg": round(statistics.mean(acc_inflight), 3) if args.workload == "send" and acc_inflight else None,
+                                          "frac": round(IMAD_PER_G1_POINT * n_h / (statistics.mean(acc_inflight) * 1e-3) / 1e12 / imad_peak, 4)
+                                          if args.workload == "send" and acc_inflight and imad_peak else None,
+                                          "what": "the same kernel timed by CUDA events on its stream inside the timed region of `value`, where it shares the SMs "
+                                                  "with the kernels of the other proofs in flight (so this is a lower bound of its own efficiency)"},
                          "peaks": {k: round(v, 2) for k, v in pk_.items()},
                          "note": "integer-multiply roofline (SURVEY.md 8d): algorithmic 23936 wide multiply-adds per point / CUDA-event kernel time; "
                                  "peak = carry-chained mad.lo.cc/madc.hi.cc (IMAD.WIDE.U32.X) microbenchmark in this run.  The algorithmic figure counts the reference's "

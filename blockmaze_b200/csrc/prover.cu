@@ -334,13 +334,16 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool e
     ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, msm_accumulate_kernel<Fq>, 128, 0));
     ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, msm_accumulate_kernel<Fq2>, 128, 0));
     if (const char *e = getenv("ZKB200_ACC_CTAS")) { const int v = atoi(e); if (v > 0 && v < occ1) occ1 = v; if (v > 0 && v < occ2) occ2 = v; }
-    int waves = 1; if (const char *e = getenv("ZKB200_ACC_WAVES")) { waves = atoi(e); if (waves < 1) waves = 1; }
-    acc_threads_g1 = (uint32_t)(sms * (occ1 > 0 ? occ1 : 1) * 128 * waves);
+    // A proof that has the GPU to itself cuts the entry list into `waves_alone` waves of shorter ranges: dynamic CTA placement then evens
+    // out SM-level variance and the accumulate kernel is 5-10 % faster, at the price of more pieces to fold.  With other proofs in flight
+    // the extra fold work costs more than the tail it removes (those proofs fill the tail anyway), so one wave is used.  G1 only.
+    waves_alone = 3; if (const char *e = getenv("ZKB200_ACC_WAVES")) { waves_alone = atoi(e); if (waves_alone < 1) waves_alone = 1; if (waves_alone > 4) waves_alone = 4; }
+    acc_threads_g1 = (uint32_t)(sms * (occ1 > 0 ? occ1 : 1) * 128);
     acc_threads_g2 = (uint32_t)(sms * (occ2 > 0 ? occ2 : 1) * 128);
     ZK_CUDA(cudaEventCreate(&ev_acc0)); ZK_CUDA(cudaEventCreate(&ev_acc1));
     const size_t nout = (size_t)(regions + 1) * bpw;
     if (g1) {
-        ZK_CUDA(cudaMalloc(&buckets_g1, (size_t)(acc_threads_g1 + total + 1) * sizeof(G1XYZZ)));
+        ZK_CUDA(cudaMalloc(&buckets_g1, ((size_t)acc_threads_g1 * waves_alone + total + 1) * sizeof(G1XYZZ)));
         ZK_CUDA(cudaMalloc(&out_g1, nout * sizeof(G1XYZZ)));
         ZK_CUDA(cudaMallocHost(&h_out_g1, nout * sizeof(G1XYZZ)));
     }
@@ -379,7 +382,7 @@ void *msm_expand_bases(const void *bases, uint32_t n, int c, bool g2) {
 template <class F>
 static void msm_points(cudaStream_t st, MsmPlan &p, const MsmShape &sh, const Affine<F> *bases, XYZZ<F> *partial, XYZZ<F> *out, void *h_out, bool timed) {
     const uint32_t *off = (const uint32_t *)p.offsets;
-    const uint32_t T = sizeof(F) == 32 ? p.acc_threads_g1 : p.acc_threads_g2;
+    const uint32_t T = sizeof(F) == 32 ? p.acc_threads_g1 * (p.alone ? (uint32_t)p.waves_alone : 1u) : p.acc_threads_g2;
     uint32_t *heavy = (uint32_t *)(sizeof(F) == 32 ? p.heavy : p.heavy_g2);
     ZK_CUDA(cudaMemsetAsync(heavy, 0, 4, st));
     if (timed) ZK_CUDA(cudaEventRecord(p.ev_acc0, st));
@@ -751,6 +754,8 @@ void prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint6
     side_queries();                           // enqueued while the GPU is busy with the QAP map: they run beside it and are mostly done when H starts
     if (g_isolate_h) wait_side();
     ZK_CUDA(cudaEventRecord(ln->ev_h0, st));
+    ln->mH.alone = true;                       // no other proof of this key in flight (a benign race: only the schedule depends on it)
+    for (int i = 0; i < pk->nlanes; i++) if (pk->lanes[i] != ln && pk->lanes[i]->pending) ln->mH.alone = false;
     msm_run(st, ln->mH, ScalarRef{ln->tmp, nullptr, 0, 1}, pk->H_skip, pk->H, nullptr);
     ZK_CUDA(cudaEventRecord(ln->ev_h1, st));
     wait_side();

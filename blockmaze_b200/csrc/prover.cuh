@@ -51,6 +51,7 @@ struct MsmPlan {
     void *heavy = nullptr, *heavy_g2 = nullptr;          // queues of oversized buckets for the CTA-wide fold
     cudaEvent_t ev_sorted = nullptr;                     // digit sort done (the G2 half may start on its own stream)
     uint32_t acc_threads_g1 = 0, acc_threads_g2 = 0;     // threads of one resident wave of the accumulate kernel (multiple of 128)
+    int waves_alone = 1; bool alone = false;             // G1: waves to use when this MSM has the GPU to itself (set per run)
     void *buckets_g1 = nullptr, *buckets_g2 = nullptr;   // bucket pieces, slot = thread + bucket  [acc_threads + total + 1]
     void *out_g1 = nullptr, *out_g2 = nullptr;           // device partial sums  [(windows+1) * bpw]
     void *h_out_g1 = nullptr, *h_out_g2 = nullptr;       // pinned host copies

@@ -198,92 +198,63 @@ struct Compression {
     Compression(Tape &t, const Refs &prev_output, const Refs &new_block, const Refs &output) : prev(prev_output), block(new_block), out(output) {
         base = t.alloc(VARS);
     }
+    // 32 consecutive bit variables (least significant bit first) of one word
+    static void set_bits(Tape &t, uint32_t at, uint64_t x, int n = 32) { uint64_t *o = t.v + at; for (int k = 0; k < n; k++) o[k] = (x >> k) & 1; }
+    static uint32_t rotr(uint32_t x, int r) { return (x >> r) | (x << (32 - r)); }
     void witness(Tape &t) const {
+        // Word-level evaluation: every bit variable of the gadget is a bit of one of the 32-bit words below, so the words are computed
+        // natively and their bits stored in runs of 32 (the reference evaluates bit by bit through the protoboard).
         uint64_t W[64];                       // packed_W values
-        int32_t wbit[64][32];                 // refs of W_bits[i][k], k = 0 is the least significant bit
         for (int i = 0; i < 16; i++) {
             uint64_t x = 0;
-            for (int k = 0; k < 32; k++) { wbit[i][k] = block[32 * i + 31 - k]; x |= (t.get(wbit[i][k]) & 1) << k; }
+            for (int k = 0; k < 32; k++) x |= (t.get(block[32 * i + 31 - k]) & 1) << k;
             W[i] = x; t.set(base + i, x);
         }
         for (int i = 16; i < 64; i++) {
             const uint32_t mb = base + 64 + (uint32_t)(i - 16) * 152;
-            // small sigma0 on W[i-15] (7, 18, >>3), small sigma1 on W[i-2] (17, 19, >>10): result bits then XOR3 tmps
-            uint64_t sig[2];
-            const int rot1[2] = {7, 17}, rot2[2] = {18, 19}, sh[2] = {3, 10};
-            const int src[2] = {i - 15, i - 2};
-            uint32_t cur = mb + 2;
-            for (int s = 0; s < 2; s++) {
-                const int32_t *wb = wbit[src[s]];
-                uint64_t val = 0;
-                const uint32_t rb = cur, tb = cur + 32;
-                for (int j = 0; j < 32; j++) {
-                    const uint64_t A = t.get(wb[(j + rot1[s]) % 32]) & 1, B = t.get(wb[(j + rot2[s]) % 32]) & 1;
-                    uint64_t o = A ^ B;
-                    if (j + sh[s] < 32) { t.set(tb + j, o); o ^= t.get(wb[j + sh[s]]) & 1; }
-                    t.set(rb + j, o);
-                    val |= o << j;
-                }
-                sig[s] = val;
-                cur += 32 + (32 - sh[s]);
-            }
-            t.set(mb, sig[0]); t.set(mb + 1, sig[1]);
-            const uint64_t unred = sig[0] + sig[1] + W[i - 16] + W[i - 7];
+            // small sigma0 on W[i-15] (7, 18, >>3), small sigma1 on W[i-2] (17, 19, >>10): 32 result bits, then the XOR3 tmps of the
+            // positions that have a shifted-in third operand
+            const uint32_t x0 = (uint32_t)W[i - 15], x1 = (uint32_t)W[i - 2];
+            const uint32_t ab0 = rotr(x0, 7) ^ rotr(x0, 18), ab1 = rotr(x1, 17) ^ rotr(x1, 19);
+            const uint64_t sig0 = ab0 ^ (x0 >> 3), sig1 = ab1 ^ (x1 >> 10);
+            set_bits(t, mb + 2, sig0); set_bits(t, mb + 2 + 32, ab0, 32 - 3);
+            const uint32_t c1 = mb + 2 + 32 + (32 - 3);
+            set_bits(t, c1, sig1); set_bits(t, c1 + 32, ab1, 32 - 10);
+            t.set(mb, sig0); t.set(mb + 1, sig1);
+            const uint64_t unred = sig0 + sig1 + W[i - 16] + W[i - 7];
             t.set(mb + 117, unred);
-            for (int k = 0; k < 32; k++) { wbit[i][k] = (int32_t)(mb + 118 + k); t.set(mb + 118 + k, (unred >> k) & 1); }
-            t.set(mb + 150, (unred >> 32) & 1); t.set(mb + 151, (unred >> 33) & 1);
+            set_bits(t, mb + 118, unred, 34);       // 32 result bits, then the two overflow bits at mb + 150, mb + 151
             W[i] = unred & 0xffffffffull;
             t.set(base + i, W[i]);
         }
-        // working variables as arrays of bit refs (LSB first)
-        int32_t regs[8][32];
-        for (int r = 0; r < 8; r++) for (int k = 0; k < 32; k++) regs[r][k] = prev[32 * r + 31 - k];
-        auto word = [&](const int32_t *b) { uint64_t x = 0; for (int k = 0; k < 32; k++) x |= (t.get(b[k]) & 1) << k; return x; };
+        // working variables
+        uint32_t r8[8];
+        for (int r = 0; r < 8; r++) { uint32_t x = 0; for (int k = 0; k < 32; k++) x |= (uint32_t)(t.get(prev[32 * r + 31 - k]) & 1) << k; r8[r] = x; }
+        uint32_t a = r8[0], b = r8[1], c = r8[2], d = r8[3], e = r8[4], f = r8[5], g = r8[6], h = r8[7];
         const uint32_t rbase = base + 64 + 48 * 152;
         uint64_t packed_d[64], packed_h[64], packed_new_a[64], packed_new_e[64];
         for (int i = 0; i < 64; i++) {
             const uint32_t rb = rbase + (uint32_t)i * 272;
-            const int32_t *a = regs[0], *b = regs[1], *c = regs[2], *d = regs[3], *e = regs[4], *f = regs[5], *g = regs[6], *h = regs[7];
             // big sigma0 on a (2,13,22) and big sigma1 on e (6,11,25): 32 result bits then 32 XOR3 tmps each
-            uint64_t S[2];
-            const int r1[2] = {2, 6}, r2[2] = {13, 11}, r3[2] = {22, 25};
-            const int32_t *srcw[2] = {a, e};
-            for (int s = 0; s < 2; s++) {
-                const uint32_t resb = rb + 66 + (uint32_t)s * 64, tmpb = resb + 32;
-                uint64_t val = 0;
-                for (int j = 0; j < 32; j++) {
-                    const uint64_t A = t.get(srcw[s][(j + r1[s]) % 32]) & 1, B = t.get(srcw[s][(j + r2[s]) % 32]) & 1, C = t.get(srcw[s][(j + r3[s]) % 32]) & 1;
-                    t.set(tmpb + j, A ^ B);
-                    const uint64_t o = A ^ B ^ C;
-                    t.set(resb + j, o);
-                    val |= o << j;
-                }
-                S[s] = val;
-            }
-            t.set(rb + 64, S[0]); t.set(rb + 65, S[1]);
-            uint64_t ch = 0, mj = 0;
-            for (int j = 0; j < 32; j++) {
-                const uint64_t x = t.get(e[j]) & 1, y = t.get(f[j]) & 1, z = t.get(g[j]) & 1;
-                const uint64_t o = x ? y : z;
-                t.set(rb + 195 + j, o); ch |= o << j;
-                const uint64_t m = ((t.get(a[j]) & 1) + (t.get(b[j]) & 1) + (t.get(c[j]) & 1)) >> 1;
-                t.set(rb + 228 + j, m); mj |= m << j;
-            }
+            const uint32_t t0 = rotr(a, 2) ^ rotr(a, 13), t1 = rotr(e, 6) ^ rotr(e, 11);
+            const uint64_t S0 = t0 ^ rotr(a, 22), S1 = t1 ^ rotr(e, 25);
+            set_bits(t, rb + 66, S0); set_bits(t, rb + 66 + 32, t0);
+            set_bits(t, rb + 130, S1); set_bits(t, rb + 130 + 32, t1);
+            t.set(rb + 64, S0); t.set(rb + 65, S1);
+            const uint64_t ch = (e & f) | (~e & g), mj = (a & b) | (a & c) | (b & c);
+            set_bits(t, rb + 195, ch); set_bits(t, rb + 228, mj);
             t.set(rb + 194, ch); t.set(rb + 227, mj);
-            packed_d[i] = word(d); packed_h[i] = word(h);
+            packed_d[i] = d; packed_h[i] = h;
             t.set(rb + 260, packed_d[i]); t.set(rb + 261, packed_h[i]);
-            const uint64_t ua = packed_h[i] + S[1] + ch + K256[i] + W[i] + S[0] + mj;
-            const uint64_t ue = packed_d[i] + packed_h[i] + S[1] + ch + K256[i] + W[i];
+            const uint64_t ua = packed_h[i] + S1 + ch + K256[i] + W[i] + S0 + mj;
+            const uint64_t ue = packed_d[i] + packed_h[i] + S1 + ch + K256[i] + W[i];
             t.set(rb + 262, ua); t.set(rb + 263, ue);
-            for (int k = 0; k < 32; k++) { t.set(rb + k, (ua >> k) & 1); t.set(rb + 32 + k, (ue >> k) & 1); }
+            set_bits(t, rb, ua); set_bits(t, rb + 32, ue);
             for (int k = 0; k < 3; k++) { t.set(rb + 266 + k, (ua >> (32 + k)) & 1); t.set(rb + 269 + k, (ue >> (32 + k)) & 1); }
             packed_new_a[i] = ua & 0xffffffffull; packed_new_e[i] = ue & 0xffffffffull;
             t.set(rb + 264, packed_new_a[i]); t.set(rb + 265, packed_new_e[i]);
             // rotate registers: h=g, g=f, f=e, e=new_e, d=c, c=b, b=a, a=new_a
-            for (int k = 0; k < 32; k++) {
-                regs[7][k] = regs[6][k]; regs[6][k] = regs[5][k]; regs[5][k] = regs[4][k]; regs[4][k] = (int32_t)(rb + 32 + k);
-                regs[3][k] = regs[2][k]; regs[2][k] = regs[1][k]; regs[1][k] = regs[0][k]; regs[0][k] = (int32_t)(rb + k);
-            }
+            h = g; g = f; f = e; e = (uint32_t)packed_new_e[i]; d = c; c = b; b = a; a = (uint32_t)packed_new_a[i];
         }
         const uint32_t fb = rbase + 64 * 272;
         for (int i = 0; i < 4; i++) {

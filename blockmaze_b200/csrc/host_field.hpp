@@ -41,9 +41,16 @@ template <class T> struct HFp {
         u128 b = 0;
         for (int i = 0; i < 4; i++) { u128 d = (u128)x[i] - T::MOD[i] - (uint64_t)b; x[i] = (uint64_t)d; b = (d >> 64) & 1; }
     }
+    // r = x - MOD if x >= MOD (branch-free select)
+    static void cond_sub(uint64_t x[4]) {
+        uint64_t d[4]; u128 b = 0;
+        for (int i = 0; i < 4; i++) { const u128 t = (u128)x[i] - T::MOD[i] - (uint64_t)b; d[i] = (uint64_t)t; b = (t >> 64) & 1; }
+        const uint64_t keep = (uint64_t)0 - (uint64_t)b;               // all ones if x < MOD
+        for (int i = 0; i < 4; i++) x[i] = (x[i] & keep) | (d[i] & ~keep);
+    }
     HFp operator+(const HFp &o) const {
         HFp r; u128 c = 0;
-        for (int i = 0; i < 4; i++) { c += (u128)v[i] + o.v[i]; r.v[i] = (uint64_t)c; c >>= 64; }
+        for (int i = 0; i < 4; i++) { c += (u128)v[i] + o.v[i]; r.v[i] = (uint64_t)c; c >>= 64; }      // no carry out: both < 2^254
         if (geq_mod(r.v)) sub_mod(r.v);
         return r;
     }
@@ -55,19 +62,24 @@ template <class T> struct HFp {
     }
     HFp neg() const { return is_zero() ? *this : zero() - *this; }
     HFp dbl() const { return *this + *this; }
-    HFp operator*(const HFp &o) const {             // CIOS
-        uint64_t t[6] = {0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < 4; i++) {
-            u128 c = 0;
-            for (int j = 0; j < 4; j++) { c += (u128)v[j] * o.v[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
-            c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
-            uint64_t m = t[0] * T::INV;
-            c = (u128)m * T::MOD[0] + t[0]; c >>= 64;
-            for (int j = 1; j < 4; j++) { c += (u128)m * T::MOD[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
-            c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+    // Montgomery product, CIOS without the extra carry word (valid because the top limb of both moduli is < 2^62), fully unrolled
+    HFp operator*(const HFp &o) const {
+        const uint64_t *a = v, *b = o.v;
+        uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+#define ZKH_ROW(bi)                                                                                                    \
+        {                                                                                                              \
+            u128 x = (u128)a[0] * (bi) + t0; uint64_t A = (uint64_t)(x >> 64);                                         \
+            const uint64_t m = (uint64_t)x * T::INV;                                                                   \
+            u128 y = (u128)m * T::MOD[0] + (uint64_t)x; uint64_t C = (uint64_t)(y >> 64);                              \
+            x = (u128)a[1] * (bi) + t1 + A; A = (uint64_t)(x >> 64); y = (u128)m * T::MOD[1] + (uint64_t)x + C; C = (uint64_t)(y >> 64); t0 = (uint64_t)y; \
+            x = (u128)a[2] * (bi) + t2 + A; A = (uint64_t)(x >> 64); y = (u128)m * T::MOD[2] + (uint64_t)x + C; C = (uint64_t)(y >> 64); t1 = (uint64_t)y; \
+            x = (u128)a[3] * (bi) + t3 + A; A = (uint64_t)(x >> 64); y = (u128)m * T::MOD[3] + (uint64_t)x + C; C = (uint64_t)(y >> 64); t2 = (uint64_t)y; \
+            t3 = C + A;                                                                                                \
         }
-        HFp r; memcpy(r.v, t, 32);
-        if (t[4] || geq_mod(r.v)) sub_mod(r.v);
+        ZKH_ROW(b[0]) ZKH_ROW(b[1]) ZKH_ROW(b[2]) ZKH_ROW(b[3])
+#undef ZKH_ROW
+        HFp r; r.v[0] = t0; r.v[1] = t1; r.v[2] = t2; r.v[3] = t3;
+        cond_sub(r.v);
         return r;
     }
     HFp sqr() const { return *this * *this; }

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -58,7 +59,41 @@ static Fq12 mul(const Fq12 &a, const Fq12 &b) {
     const Fq6 v0 = mul(a.c0, b.c0), v1 = mul(a.c1, b.c1);
     return Fq12{v0 + mul_by_v(v1), mul(a.c0 + a.c1, b.c0 + b.c1) - v0 - v1};
 }
-static Fq12 sqr(const Fq12 &a) { return mul(a, a); }
+// complex squaring: (a0 + a1 w)^2 with w^2 = v  ->  2 Fq6 multiplications
+static Fq12 sqr(const Fq12 &a) {
+    const Fq6 ab = mul(a.c0, a.c1);
+    return Fq12{mul(a.c0 + a.c1, a.c0 + mul_by_v(a.c1)) - ab - mul_by_v(ab), ab + ab};
+}
+// Squaring in the cyclotomic subgroup (every element after the easy part of the final exponentiation): Granger-Scott over
+// Fq4 = Fq2[y]/(y^2 - xi), y = w^3.  alpha = A + B w + C w^2 with A = (c0.c0, c1.c1), B = (c1.c0, c0.c2), C = (c0.c1, c1.c2);
+// alpha^2 = (3 A^2 - 2 conj A) + (3 y C^2 + 2 conj B) w + (3 B^2 - 2 conj C) w^2.  Three Fq4 squarings = 9 Fq2 multiplications.
+static void fq4_sqr(const HFq2 &a, const HFq2 &b, HFq2 &even, HFq2 &odd) {
+    const HFq2 ab = a * b;
+    even = (a + b) * (a + mul_xi(b)) - ab - mul_xi(ab);
+    odd = ab + ab;
+}
+static HFq2 three_minus_two(const HFq2 &t, const HFq2 &z) { const HFq2 d = t - z; return d + d + t; }     // 3t - 2z
+static HFq2 three_plus_two(const HFq2 &t, const HFq2 &z) { const HFq2 d = t + z; return d + d + t; }      // 3t + 2z
+static Fq12 cyclotomic_sqr(const Fq12 &a) {
+    HFq2 a0, a1, b0, b1, c0, c1;
+    fq4_sqr(a.c0.c0, a.c1.c1, a0, a1);          // A^2
+    fq4_sqr(a.c1.c0, a.c0.c2, b0, b1);          // B^2
+    fq4_sqr(a.c0.c1, a.c1.c2, c0, c1);          // C^2
+    Fq12 r;
+    r.c0.c0 = three_minus_two(a0, a.c0.c0); r.c1.c1 = three_plus_two(a1, a.c1.c1);
+    r.c1.c0 = three_plus_two(mul_xi(c1), a.c1.c0); r.c0.c2 = three_minus_two(c0, a.c0.c2);
+    r.c0.c1 = three_minus_two(b0, a.c0.c1); r.c1.c2 = three_plus_two(b1, a.c1.c2);
+    return r;
+}
+// f * (x0 + x2 v^2 + x4 v w): the sparse line element of the Miller loop (libff's mul_by_024), 15 Fq2 multiplications
+static Fq6 mul_by_02(const Fq6 &a, const HFq2 &x0, const HFq2 &x2) {
+    return Fq6{a.c0 * x0 + mul_xi(a.c1 * x2), a.c1 * x0 + mul_xi(a.c2 * x2), a.c2 * x0 + a.c0 * x2};
+}
+static Fq6 mul_by_1(const Fq6 &a, const HFq2 &x1) { return Fq6{mul_xi(a.c2 * x1), a.c0 * x1, a.c1 * x1}; }
+static Fq12 mul_sparse(const Fq12 &f, const HFq2 &x0, const HFq2 &x2, const HFq2 &x4) {
+    const Fq6 v0 = mul_by_02(f.c0, x0, x2), v1 = mul_by_1(f.c1, x4);
+    return Fq12{v0 + mul_by_v(v1), mul(f.c0 + f.c1, Fq6{x0, x4, x2}) - v0 - v1};
+}
 static Fq12 inverse(const Fq12 &a) {
     const Fq6 d = inverse(mul(a.c0, a.c0) - mul_by_v(mul(a.c1, a.c1)));
     return Fq12{mul(a.c0, d), mul(a.c1, d).neg()};
@@ -90,7 +125,7 @@ static Fq12 frobenius(const Fq12 &a) {
 static Fq12 pow_z(const Fq12 &a) {           // a^z, z = 4965661367192848881 (alt_bn128_init.cpp:327)
     const uint64_t z = 4965661367192848881ull;
     Fq12 r = Fq12::one();
-    for (int i = 63; i >= 0; i--) { r = sqr(r); if ((z >> i) & 1) r = mul(r, a); }
+    for (int i = 63; i >= 0; i--) { r = cyclotomic_sqr(r); if ((z >> i) & 1) r = mul(r, a); }       // a is in the cyclotomic subgroup
     return r;
 }
 static Fq12 final_exponentiation(const Fq12 &elt) {
@@ -98,7 +133,8 @@ static Fq12 final_exponentiation(const Fq12 &elt) {
     const Fq12 C = mul(elt.conj(), inverse(elt));
     const Fq12 f = mul(frobenius(frobenius(C)), C);
     // last chunk (alt_bn128_pairing.cpp:137-228); exp_by_neg_z = conj(pow_z) on the cyclotomic subgroup
-    const Fq12 A = pow_z(f).conj(), B = sqr(A), Cc = sqr(B), D = mul(Cc, B), E = pow_z(D).conj(), Fv = sqr(E), G = pow_z(Fv).conj();
+    const Fq12 A = pow_z(f).conj(), B = cyclotomic_sqr(A), Cc = cyclotomic_sqr(B), D = mul(Cc, B), E = pow_z(D).conj(), Fv = cyclotomic_sqr(E),
+               G = pow_z(Fv).conj();
     const Fq12 H = D.conj(), I = G.conj(), J = mul(I, E), K = mul(J, H), L = mul(K, B), M = mul(K, E), N = mul(M, f);
     const Fq12 O = frobenius(L), P = mul(O, N), Q = frobenius(frobenius(K)), R = mul(Q, P), S = f.conj(), T = mul(S, L);
     const Fq12 U = frobenius(frobenius(frobenius(T)));
@@ -127,32 +163,52 @@ static void addition_step(const HFq2 &x2, const HFq2 &y2, G2Proj &cur, EllCoeffs
 }
 static Fq12 line_mul(const Fq12 &f, const EllCoeffs &c, const HFq &px, const HFq &py) {
     // mul_by_024(ell_0, PY*ell_VW, PX*ell_VV): the sparse factor is (c0 = (ell_0, 0, ell_VV'), c1 = (0, ell_VW', 0))  (fp12_2over3over2.tcc:244-248)
-    const Fq12 a{Fq6{c.ell_0, HFq2::zero(), scale(c.ell_VV, px)}, Fq6{HFq2::zero(), scale(c.ell_VW, py), HFq2::zero()}};
-    return mul(f, a);
+    return mul_sparse(f, c.ell_0, scale(c.ell_VV, px), scale(c.ell_VW, py));
 }
-// product of Miller loops over (P_i, Q_i), affine inputs, none at infinity
-static Fq12 multi_miller(const std::vector<HG1Affine> &Ps, const std::vector<HG2Affine> &Qs) {
-    const unsigned __int128 loop = ((unsigned __int128)1 << 64) | 0x9d797039be763ba8ull;   // 29793968203157093288 = 6z+2 (alt_bn128_init.cpp:324)
+// Line coefficients of the whole Miller loop for one G2 point (libff's alt_bn128_ate_precompute_G2): they depend on Q only, so the two
+// G2 points of a verification key (gamma, delta) are prepared once per key and only the proof's B is prepared per verification.
+static const unsigned __int128 ATE_LOOP = ((unsigned __int128)1 << 64) | 0x9d797039be763ba8ull;   // 29793968203157093288 = 6z+2 (alt_bn128_init.cpp:324)
+struct G2Prepared { std::vector<EllCoeffs> coeffs; };
+static G2Prepared prepare_g2(const HG2Affine &Q) {
     const Frob &F = frob();
-    const size_t n = Ps.size();
-    std::vector<G2Proj> R(n);
-    for (size_t k = 0; k < n; k++) R[k] = G2Proj{Qs[k].x, Qs[k].y, HFq2::one()};
-    Fq12 f = Fq12::one();
+    G2Prepared out;
+    out.coeffs.reserve(104);
+    G2Proj R{Q.x, Q.y, HFq2::one()};
     EllCoeffs c;
     for (int i = 63; i >= 0; i--) {            // bit 64 is the MSB and is skipped
+        doubling_step(R, c); out.coeffs.push_back(c);
+        if ((ATE_LOOP >> i) & 1) { addition_step(Q.x, Q.y, R, c); out.coeffs.push_back(c); }
+    }
+    // Q1 = pi(Q), Q2 = -pi^2(Q)  (alt_bn128_G2::mul_by_q: x^q * xi^((q-1)/3), y^q * xi^((q-1)/2); alt_bn128_g2.cpp)
+    const HFq2 q1x = conj2(Q.x) * F.g2, q1y = conj2(Q.y) * F.g3;
+    const HFq2 q2x = conj2(q1x) * F.g2, q2y = (conj2(q1y) * F.g3).neg();
+    addition_step(q1x, q1y, R, c); out.coeffs.push_back(c);
+    addition_step(q2x, q2y, R, c); out.coeffs.push_back(c);
+    return out;
+}
+// product of Miller loops over (P_i, prepared Q_i), affine P, none at infinity: one Fq12 squaring per bit for all pairs
+static Fq12 multi_miller(const std::vector<HG1Affine> &Ps, const std::vector<const G2Prepared *> &Qs) {
+    const size_t n = Ps.size();
+    Fq12 f = Fq12::one();
+    size_t idx = 0;
+    for (int i = 63; i >= 0; i--) {
         f = sqr(f);
-        for (size_t k = 0; k < n; k++) { doubling_step(R[k], c); f = line_mul(f, c, Ps[k].x, Ps[k].y); }
-        if ((loop >> i) & 1)
-            for (size_t k = 0; k < n; k++) { addition_step(Qs[k].x, Qs[k].y, R[k], c); f = line_mul(f, c, Ps[k].x, Ps[k].y); }
+        for (size_t k = 0; k < n; k++) f = line_mul(f, Qs[k]->coeffs[idx], Ps[k].x, Ps[k].y);
+        idx++;
+        if ((ATE_LOOP >> i) & 1) {
+            for (size_t k = 0; k < n; k++) f = line_mul(f, Qs[k]->coeffs[idx], Ps[k].x, Ps[k].y);
+            idx++;
+        }
     }
-    for (size_t k = 0; k < n; k++) {
-        // Q1 = pi(Q), Q2 = -pi^2(Q)  (alt_bn128_G2::mul_by_q: x^q * xi^((q-1)/3), y^q * xi^((q-1)/2); alt_bn128_g2.cpp)
-        const HFq2 q1x = conj2(Qs[k].x) * F.g2, q1y = conj2(Qs[k].y) * F.g3;
-        const HFq2 q2x = conj2(q1x) * F.g2, q2y = (conj2(q1y) * F.g3).neg();
-        addition_step(q1x, q1y, R[k], c); f = line_mul(f, c, Ps[k].x, Ps[k].y);
-        addition_step(q2x, q2y, R[k], c); f = line_mul(f, c, Ps[k].x, Ps[k].y);
-    }
+    for (int e = 0; e < 2; e++, idx++)
+        for (size_t k = 0; k < n; k++) f = line_mul(f, Qs[k]->coeffs[idx], Ps[k].x, Ps[k].y);
     return f;
+}
+static Fq12 multi_miller(const std::vector<HG1Affine> &Ps, const std::vector<HG2Affine> &Qs) {
+    std::vector<G2Prepared> prep; prep.reserve(Qs.size());
+    std::vector<const G2Prepared *> ptr;
+    for (const HG2Affine &q : Qs) { prep.push_back(prepare_g2(q)); ptr.push_back(&prep.back()); }
+    return multi_miller(Ps, ptr);
 }
 
 // ---- verification key ---------------------------------------------------------------------------------------------------
@@ -179,10 +235,25 @@ static bool fq2_sqrt(const HFq2 &a, HFq2 &out) {
 }
 static bool lsb(const HFq &x) { uint64_t c[4]; x.to_canonical(c); return c[0] & 1; }
 
+// Fixed-base table of one gamma_ABC point: tab[k][d-1] = d * 16^k * P (k < 64, d = 1..15), so input * P is 64 additions, no doublings
+struct FixedBase { std::vector<HG1> tab; };
+static FixedBase fixed_base(const HG1Affine &P) {
+    FixedBase f; f.tab.resize(64 * 15);
+    HG1 base = HG1::from_affine(P);
+    for (int k = 0; k < 64; k++) {
+        HG1 cur = base;
+        for (int d = 1; d <= 15; d++) { f.tab[k * 15 + d - 1] = cur; cur = cur.add(base); }
+        base = cur;                                         // 16 * base
+    }
+    return f;
+}
 struct VerificationKey {
     Fq12 alpha_beta;
     HG2Affine gamma_g2, delta_g2;
     std::vector<HG1Affine> gamma_abc;        // [0] = first, then one per public input
+    // derived once per key (libsnark's "processed" verification key goes half of this way)
+    G2Prepared gamma_prep, delta_prep;
+    std::vector<FixedBase> abc_tab;          // for gamma_abc[1..]
     bool ok = false;
 };
 struct VkReader {
@@ -242,11 +313,15 @@ static VerificationKey parse_vk(const std::string &data) {
     if (k2 != k) r.fail = true;
     for (uint64_t i = 0; i < k && !r.fail; i++) { vk.gamma_abc.push_back(r.g1()); r.expect('\n'); }
     vk.ok = !r.fail;
+    if (vk.ok) {
+        vk.gamma_prep = prepare_g2(vk.gamma_g2); vk.delta_prep = prepare_g2(vk.delta_g2);
+        for (size_t i = 1; i < vk.gamma_abc.size(); i++) vk.abc_tab.push_back(fixed_base(vk.gamma_abc[i]));
+    }
     return vk;
 }
 
 static std::mutex g_vk_mu;
-static VerificationKey g_vk[4];
+static std::shared_ptr<const VerificationKey> g_vk[4];
 static std::string g_vk_dir[4];
 static const char *NAMES[4] = {"mint", "send", "deposit", "redeem"};
 static std::string key_dir_now() { return zkw::key_dir(); }
@@ -279,16 +354,20 @@ static void push_blob(std::vector<bool> &b, const uint8_t *blob, size_t nbytes) 
 static void push_u64(std::vector<bool> &b, uint64_t v) { uint8_t le[8]; for (int i = 0; i < 8; i++) le[i] = (uint8_t)(v >> (8 * i)); push_blob(b, le, 8); }
 
 static bool verify(int circuit, const char *proof, const std::vector<bool> &input_bits) {
-    std::lock_guard<std::mutex> lk(g_vk_mu);
-    const std::string dir = key_dir_now();
-    if (!g_vk[circuit].ok || g_vk_dir[circuit] != dir) {
-        std::ifstream fh(dir + "/" + NAMES[circuit] + "vk.txt", std::ios::binary);
-        std::string data((std::istreambuf_iterator<char>(fh)), std::istreambuf_iterator<char>());
-        g_vk[circuit] = parse_vk(data);
-        g_vk_dir[circuit] = dir;
-        if (!g_vk[circuit].ok) { fprintf(stderr, "zkb200: cannot read verification key %s/%svk.txt\n", dir.c_str(), NAMES[circuit]); return false; }
+    std::shared_ptr<const VerificationKey> held;                       // concurrent verifications share the key and do not hold the lock
+    {
+        std::lock_guard<std::mutex> lk(g_vk_mu);
+        const std::string dir = key_dir_now();
+        if (!g_vk[circuit] || !g_vk[circuit]->ok || g_vk_dir[circuit] != dir) {
+            std::ifstream fh(dir + "/" + NAMES[circuit] + "vk.txt", std::ios::binary);
+            std::string data((std::istreambuf_iterator<char>(fh)), std::istreambuf_iterator<char>());
+            g_vk[circuit] = std::make_shared<const VerificationKey>(parse_vk(data));
+            g_vk_dir[circuit] = dir;
+            if (!g_vk[circuit]->ok) { fprintf(stderr, "zkb200: cannot read verification key %s/%svk.txt\n", dir.c_str(), NAMES[circuit]); return false; }
+        }
+        held = g_vk[circuit];
     }
-    const VerificationKey &vk = g_vk[circuit];
+    const VerificationKey &vk = *held;
     if (!proof || strnlen(proof, 512) < 512) return false;
     HFq c[8];
     for (int i = 0; i < 8; i++) if (!hex_fq(proof + 64 * i, c[i])) return false;
@@ -301,17 +380,22 @@ static bool verify(int circuit, const char *proof, const std::vector<bool> &inpu
     const std::vector<HFr> inputs = pack_bits(input_bits);
     if (inputs.size() + 1 != vk.gamma_abc.size()) return false;
     HG1 acc = HG1::from_affine(vk.gamma_abc[0]);
-    for (size_t i = 0; i < inputs.size(); i++) {
+    for (size_t i = 0; i < inputs.size(); i++) {                        // accumulate(): sum of input_i * gamma_ABC[i + 1], fixed-base windows
         uint64_t k[4]; inputs[i].to_canonical(k);
-        acc = acc.add(HG1::from_affine(vk.gamma_abc[i + 1]).mul(k));
+        const FixedBase &fb = vk.abc_tab[i];
+        for (int w = 0; w < 64; w++) {
+            const unsigned d = (unsigned)((k[w >> 4] >> ((w & 15) * 4)) & 15);
+            if (d) acc = acc.add(fb.tab[w * 15 + d - 1]);
+        }
     }
     const HG1Affine acc_a = acc.to_affine();
-    // e(A, B) == alpha_beta * e(acc, gamma) * e(C, delta)   <=>   FE( ML(A,B) * conj(ML(acc,gamma) * ML(C,delta)) ) == alpha_beta
-    std::vector<HG1Affine> Ps; std::vector<HG2Affine> Qs;
-    if (!acc_a.is_inf()) { Ps.push_back(acc_a); Qs.push_back(vk.gamma_g2); }
-    Ps.push_back(Cp); Qs.push_back(vk.delta_g2);
-    const Fq12 l = multi_miller({A}, {B}), r = multi_miller(Ps, Qs);
-    return final_exponentiation(mul(l, r.conj())) == vk.alpha_beta;
+    // e(A, B) == alpha_beta * e(acc, gamma) * e(C, delta)   <=>   FE( ML(A,B) * ML(-acc,gamma) * ML(-C,delta) ) == alpha_beta:
+    // one Miller loop over the three pairs (one Fq12 squaring per bit for all of them), one final exponentiation
+    const G2Prepared b_prep = prepare_g2(B);
+    std::vector<HG1Affine> Ps{A}; std::vector<const G2Prepared *> Qs{&b_prep};
+    if (!acc_a.is_inf()) { Ps.push_back(HG1Affine{acc_a.x, acc_a.y.neg()}); Qs.push_back(&vk.gamma_prep); }
+    Ps.push_back(HG1Affine{Cp.x, Cp.y.neg()}); Qs.push_back(&vk.delta_prep);
+    return final_exponentiation(multi_miller(Ps, Qs)) == vk.alpha_beta;
 }
 } // namespace
 

@@ -193,3 +193,21 @@ def test_equal_range_accumulation_index_math():
             pieces = [slots.pop(t + b) for t in range(t0, t1 + 1)]
             assert all(pb == b for pb, _ in pieces) and sum(c for _, c in pieces) == counts[b]
         assert not slots
+
+
+def test_verifier_concurrent_calls(api, ref):
+    """verify*proof from several threads at once (the key is shared without a lock): every reference proof verifies, a proof whose C was
+    replaced by its A (a valid point) fails."""
+    from concurrent.futures import ThreadPoolExecutor
+    if not os.path.exists(os.path.join(ref.KEY_DIR, "mintvk.txt")):
+        pytest.skip("reference keys not present")
+    api.set_key_dir(ref.KEY_DIR)
+    jobs = []
+    for c in ("mint", "send", "deposit", "redeem"):
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", c + ".json")))
+        va = api.verify_args(c, g["args"])
+        bad = g["proof_hex"][:384] + g["proof_hex"][:128]
+        jobs += [(c, g["proof_hex"], va, True), (c, bad, va, False)] * 3
+    with ThreadPoolExecutor(6) as pool:
+        got = list(pool.map(lambda j: api.verify_proof(j[0], j[1], j[2]), jobs))
+    assert got == [j[3] for j in jobs]

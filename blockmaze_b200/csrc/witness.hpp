@@ -4,7 +4,7 @@
 //
 // The assignment layout is an artefact of gadget construction order in the reference (protoboard::allocate_var_index,
 // libsnark/gadgetlib1/protoboard.tcc:37-49); each generator below documents the order it reproduces.  Parity is checked
-// element-for-element against the reference gadgets (tests/test_witness.py via oracle/_ref).
+// element-for-element against the reference gadgets (tests/test_host.py via oracle/_ref).
 #pragma once
 #include <cstdint>
 #include <cstring>

@@ -4,4 +4,4 @@ Everything computes on the GPU through the C-ABI declared in include/zkb200.h; t
 this package on a machine without the built library raises immediately.
 """
 from .api import *  # noqa: F401,F403
-from .api import lib, init, smoke, ProvingKey, ZkError  # noqa: F401
+from .api import lib, init, ProvingKey, ZkError  # noqa: F401

@@ -43,6 +43,28 @@ lib.zkb200_bench_imad_peak.argtypes = [C.c_int]
 
 lib.zkb200_set_key_dir.argtypes = [C.c_char_p]
 lib.zkb200_set_random_words.argtypes = [C.c_void_p, C.c_size_t]
+lib.zkb200_set_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
+lib.zkb200_active_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
+lib.zkb200_pk_load_on.restype = C.c_void_p
+lib.zkb200_pk_load_on.argtypes = [C.c_char_p, C.c_int]
+lib.zkb200_pk_device.argtypes = [C.c_void_p]
+lib.zkb200_default_proof.restype = C.c_char_p
+lib.zkb200_sched_create.restype = C.c_void_p
+lib.zkb200_sched_create.argtypes = [C.c_int]
+lib.zkb200_sched_pick.argtypes = [C.c_void_p]
+lib.zkb200_sched_done.argtypes = [C.c_void_p, C.c_int]
+lib.zkb200_sched_done.restype = None
+lib.zkb200_sched_inflight.argtypes = [C.c_void_p, C.c_int]
+lib.zkb200_sched_free.argtypes = [C.c_void_p]
+lib.zkb200_sched_free.restype = None
+
+
+class Tx(C.Structure):
+    """zkb200_tx: one transaction of a zkb200_prove_batch call."""
+    _fields_ = [("circuit", C.c_int), ("n", C.c_int), ("u", C.c_uint64 * 3), ("s", C.c_char_p * 14)]
+
+
+lib.zkb200_prove_batch.argtypes = [C.c_size_t, C.POINTER(Tx), C.c_char_p, C.c_int]
 
 # gen<Circuit>proof argument types (SRC/<c>/<c>cgo.hpp) and verify<Circuit>proof argument types
 GEN_SIGS = {
@@ -73,6 +95,9 @@ lib.zkb200_witness_deposit.restype = C.c_long
 lib.zkb200_witness_deposit.argtypes = GEN_SIGS["deposit"] + [C.c_void_p, C.c_size_t]
 
 lib.zkb200_g1_sum.argtypes = [C.c_size_t, C.c_char_p, C.c_char_p]
+lib.zkb200_g2_sum.argtypes = [C.c_size_t, C.c_char_p, C.c_char_p]
+lib.zkb200_synth_scalars.argtypes = [C.c_size_t, C.c_size_t, C.c_char_p]
+lib.zkb200_synth_bases.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_char_p]
 lib.zkb200_set_isolate_h.argtypes = [C.c_int]
 lib.zkb200_set_isolate_h.restype = None
 lib.zkb200_pk_lanes.argtypes = [C.c_void_p]
@@ -131,6 +156,29 @@ def g1_sum(points):
     return out.raw
 
 
+def g2_sum(points):
+    out = C.create_string_buffer(128)
+    lib.zkb200_g2_sum(len(points), b"".join(points), out)
+    return out.raw
+
+
+def synth_scalars(first, n):
+    """Scalars first .. first+n of the sweep's synthetic input: libff SHA512_rng<Fr>(i), 32 B canonical each."""
+    out = C.create_string_buffer(32 * max(1, n))
+    if lib.zkb200_synth_scalars(first, n, out) != 0:
+        raise ZkError(last_error())
+    return out.raw[:32 * n]
+
+
+def synth_bases(group, first, n):
+    """Bases first .. first+n of the sweep's synthetic input: SHA512_rng<Fr>(2^32 + i) * generator; group 1 = G1 (64 B), 2 = G2 (128 B)."""
+    size = 64 * group
+    out = C.create_string_buffer(size * max(1, n))
+    if lib.zkb200_synth_bases(group, first, n, out) != 0:
+        raise ZkError(last_error())
+    return out.raw[:size * n]
+
+
 def msm_g2(bases, scalars, window_bits=0):
     out = C.create_string_buffer(128)
     if lib.zkb200_msm_g2(len(scalars) // 32, bytes(bases), bytes(scalars), window_bits, out) != 0:
@@ -156,9 +204,54 @@ def set_key_dir(path):
 
 
 def set_random_words(words):
-    """Pin (r, s): a std::random_device-style 32-bit word stream (empty list = back to the OS entropy source)."""
+    """Test hook: pin (r, s) with a std::random_device-style 32-bit word stream (empty list = back to the OS entropy source).
+    Needs ZKB200_TEST_RNG=1 in the environment."""
     arr = (C.c_uint32 * max(1, len(words)))(*words)
-    lib.zkb200_set_random_words(C.cast(arr, C.c_void_p), len(words))
+    if lib.zkb200_set_random_words(C.cast(arr, C.c_void_p), len(words)) != 0:
+        raise ZkError("zkb200_set_random_words refused: ZKB200_TEST_RNG=1 is not set")
+
+
+def set_devices(devices=()):
+    """Active devices of the cgo surface (gen_proof / prove_batch); empty = every visible device.  Returns how many."""
+    arr = (C.c_int * max(1, len(devices)))(*devices)
+    n = lib.zkb200_set_devices(arr, len(devices))
+    if n < 0:
+        raise ZkError("zkb200_set_devices: bad device list")
+    return n
+
+
+def active_devices():
+    arr = (C.c_int * 64)()
+    return list(arr[:lib.zkb200_active_devices(arr, 64)])
+
+
+def _tx(circuit, args):
+    """gen<Circuit>proof argument list -> zkb200_tx (uint64 and string arguments in order of appearance)."""
+    t = Tx()
+    t.circuit = CIRCUITS.index(circuit)
+    ints = [a for a in args if isinstance(a, int)]
+    strs = [a for a in args if not isinstance(a, int)]
+    if circuit == "deposit":                      # the int `n` (number of leaves) sits among the strings
+        sig = GEN_SIGS["deposit"]
+        ints = [a for a, ty in zip(args, sig) if ty is C.c_uint64]
+        t.n = [a for a, ty in zip(args, sig) if ty is C.c_int][0]
+        strs = [a for a, ty in zip(args, sig) if ty is C.c_char_p]
+    for i, v in enumerate(ints):
+        t.u[i] = v
+    for i, v in enumerate(strs):
+        t.s[i] = v.encode() if isinstance(v, str) else v
+    return t
+
+
+def prove_batch(jobs, threads=0):
+    """jobs: list of (circuit, gen<Circuit>proof argument list).  Proves them on every active device (zkb200_prove_batch).
+    Returns (proof strings, number of default proofs)."""
+    arr = (Tx * max(1, len(jobs)))(*[_tx(c, a) for c, a in jobs])
+    out = C.create_string_buffer(513 * max(1, len(jobs)))
+    bad = lib.zkb200_prove_batch(len(jobs), arr, out, threads)
+    if bad < 0:
+        raise ZkError("zkb200_prove_batch: bad arguments")
+    return [out.raw[513 * i:513 * i + 512].decode() for i in range(len(jobs))], bad
 
 
 def helper(name, *args):
@@ -223,8 +316,8 @@ def keygen(cs_source_pk, out_pk, out_vk, words=()):
 class ProvingKey:
     """A proving key resident on the GPU (zkb200_pk_load)."""
 
-    def __init__(self, path):
-        self.handle = lib.zkb200_pk_load(os.fsencode(path))
+    def __init__(self, path, device=None):
+        self.handle = lib.zkb200_pk_load(os.fsencode(path)) if device is None else lib.zkb200_pk_load_on(os.fsencode(path), device)
         if not self.handle:
             raise ZkError(last_error())
         info = (C.c_uint64 * 8)()
@@ -288,31 +381,3 @@ class ProvingKey:
             lib.zkb200_pk_free(self.handle)
             self.handle = None
 
-
-def smoke():
-    """One small invocation of the hot path on cuda:0, checked against the oracle (test infrastructure)."""
-    import random
-    import sys
-    sys.path.insert(0, os.path.dirname(_HERE))
-    from oracle import bn254_oracle as O
-    init(0)
-    rng = random.Random(1)
-    for ms in (1 << 10, 768):
-        dom = O.get_evaluation_domain(ms)
-        v = [rng.randrange(O.R_MOD) for _ in range(dom.m)]
-        raw = b"".join(x.to_bytes(32, "little") for x in v)
-        got = domain_op(ms, "cosetFFT", raw)
-        exp = b"".join(x.to_bytes(32, "little") for x in dom.cosetFFT(v, O.FR_GENERATOR))
-        assert got == exp, "NTT mismatch against the oracle"
-    n = 64
-    pts, P = [], O.G1_ONE
-    for _ in range(n):
-        P = O.G1.add(P, O.G1.dbl(P))
-        pts.append(O.G1.to_affine(P))
-    sc = [rng.randrange(O.R_MOD) for _ in range(n)]
-    sc[3], sc[5] = 0, 1
-    bases = b"".join(x.to_bytes(32, "little") + y.to_bytes(32, "little") for x, y in pts)
-    got = msm_g1(bases, b"".join(x.to_bytes(32, "little") for x in sc))
-    exp = O.G1.to_affine(O.G1.multi_exp_with_mixed_addition([O.G1.from_affine(p) for p in pts], sc))
-    assert got == exp[0].to_bytes(32, "little") + exp[1].to_bytes(32, "little"), "MSM mismatch against the oracle"
-    print("blockmaze_b200 smoke ok")

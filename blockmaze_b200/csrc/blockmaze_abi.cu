@@ -3,55 +3,119 @@
 // SRC/{mint,send,deposit,redeem}/*cgo.cpp; the proving itself runs on the GPU against proving keys that are parsed once per
 // process and stay resident (the reference re-reads and re-parses the key file inside every gen*proof call,
 // mintcgo.cpp:299-302).
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/zkb200.h"
 #include "prover.cuh"
+#include "sched.hpp"
 #include "witness.hpp"
 
 using namespace zkw;
 
-static std::mutex g_abi_mu;
+// Everything the cgo layer keeps between calls.  One geth process drives EVERY GPU of the box: a
+// circuit's proving key is parsed once and made resident on each active device, and every gen*proof call goes to the device with the
+// fewest proofs in flight (zkb::DeviceSched), then to a free lane of that device's copy of the key.  The reference's only parallelism
+// knob is the OpenMP chunk count of its multi_exp (r1cs_gg_ppzksnark.tcc:429-433); zktx.go:383-404 stays unchanged.
+struct KeySet {                                  // one circuit, one resident copy per active device
+    std::vector<int> devices;
+    std::vector<void *> pk;
+    ~KeySet() { for (void *p : pk) if (p) zkb200_pk_free(p); }
+};
+static std::mutex g_abi_mu;                      // key directory, device list, random stream
+static std::mutex g_key_mu[4];                   // loading one circuit's keys does not block the callers of another
 static std::string g_key_dir;
+static std::vector<int> g_devices;               // active devices of the cgo layer (empty = not decided yet)
+static std::shared_ptr<zkb::DeviceSched> g_sched;
+static std::shared_ptr<KeySet> g_keys[4];
 static std::vector<uint32_t> g_words;
 static size_t g_word_pos = 0;
-static void *g_pk[4] = {nullptr, nullptr, nullptr, nullptr};
 static thread_local double g_last_ms[4] = {0, 0, 0, 0};      // witness generation, prove call, of which GPU, host finish (last gen*proof of this thread)
+static thread_local int g_last_device = -1;
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const char *CIRCUIT_NAMES[4] = {"mint", "send", "deposit", "redeem"};
 
 std::string zkw::key_dir() {
+    std::lock_guard<std::mutex> lk(g_abi_mu);
     if (!g_key_dir.empty()) return g_key_dir;
     const char *e = getenv("ZKB200_KEY_DIR");
     return e ? std::string(e) : std::string("/usr/local/prfKey");        // hard-coded in the reference (mintcgo.cpp:302)
 }
 
-void zkb200_set_key_dir(const char *dir) {
-    std::lock_guard<std::mutex> lk(g_abi_mu);
-    g_key_dir = dir ? dir : "";
-    for (int c = 0; c < 4; c++) if (g_pk[c]) { zkb200_pk_free(g_pk[c]); g_pk[c] = nullptr; }
+static void drop_keys() {                        // resident keys are reference-counted: a proof in flight keeps its KeySet alive
+    for (int c = 0; c < 4; c++) { std::lock_guard<std::mutex> lk(g_key_mu[c]); g_keys[c].reset(); }
 }
-void zkb200_set_random_words(const uint32_t *words, size_t n_words) {
+void zkb200_set_key_dir(const char *dir) {
+    { std::lock_guard<std::mutex> lk(g_abi_mu); g_key_dir = dir ? dir : ""; }
+    drop_keys();
+}
+// The devices gen*proof spreads over: zkb200_set_devices() > $ZKB200_DEVICES ("all" or "0,2,3") > the device of an explicit zkb200_init()
+// (one process per GPU, as bench.py under torchrun) > $ZKB200_DEVICE > every visible device.
+static std::vector<int> decide_devices() {
+    std::vector<int> out;
+    const int count = zkb200_device_count();
+    if (const char *e = getenv("ZKB200_DEVICES")) {
+        if (strcmp(e, "all") != 0) {
+            for (const char *p = e; *p;) { char *q; const long d = strtol(p, &q, 10); if (q == p) break; if (d >= 0 && d < count) out.push_back((int)d); p = (*q == ',') ? q + 1 : q; }
+        }
+        if (out.empty()) for (int d = 0; d < count; d++) out.push_back(d);
+        return out;
+    }
+    const int chosen = zkb200_current_device();
+    if (chosen >= 0) return {chosen};
+    if (const char *e = getenv("ZKB200_DEVICE")) { const int d = atoi(e); if (d >= 0 && d < count) return {d}; }
+    for (int d = 0; d < count; d++) out.push_back(d);
+    return out;
+}
+int zkb200_set_devices(const int *devices, int n) {
+    const int count = zkb200_device_count();
+    std::vector<int> v;
+    for (int i = 0; i < n; i++) { if (devices[i] < 0 || devices[i] >= count) return -1; v.push_back(devices[i]); }
+    if (n == 0) for (int d = 0; d < count; d++) v.push_back(d);
+    if (v.empty()) return -1;
+    { std::lock_guard<std::mutex> lk(g_abi_mu); g_devices = v; g_sched = std::make_shared<zkb::DeviceSched>((int)v.size()); }
+    drop_keys();
+    return (int)v.size();
+}
+int zkb200_active_devices(int *out, int cap) {
+    std::lock_guard<std::mutex> lk(g_abi_mu);
+    if (g_devices.empty()) { g_devices = decide_devices(); g_sched = std::make_shared<zkb::DeviceSched>((int)g_devices.size()); }
+    for (int i = 0; i < (int)g_devices.size() && i < cap; i++) out[i] = g_devices[i];
+    return (int)g_devices.size();
+}
+
+// Test hook: pins the prover randomness.  It only exists when the process was started with ZKB200_TEST_RNG=1 -- a pinned (r, s) reused
+// across proofs leaks witness relations, so production processes cannot switch it on by accident -- and it never wraps: once the words
+// are used up the prover is back on std::random_device.
+int zkb200_set_random_words(const uint32_t *words, size_t n_words) {
+    const char *e = getenv("ZKB200_TEST_RNG");
+    if (n_words && !(e && atoi(e) == 1)) {
+        fprintf(stderr, "zkb200: zkb200_set_random_words refused (set ZKB200_TEST_RNG=1 in test processes only)\n");
+        return -1;
+    }
     std::lock_guard<std::mutex> lk(g_abi_mu);
     g_words.assign(words, words + n_words);
     g_word_pos = 0;
+    return 0;
 }
 
 // Fr::random_element (fp.tcc:695-721, bigint.tcc:167-179): 8 x 32-bit words -> mont_repr, clear bits >= 254, retry while >= r.
-// The field element is the one whose MONTGOMERY representative is that integer; returns its canonical value.
+// The field element is the one whose MONTGOMERY representative is that integer; returns its canonical value.  Caller holds g_abi_mu.
 static void next_random_fr(uint64_t out[4]) {
     static std::random_device rd;
     for (;;) {
         uint32_t w[8];
         for (int i = 0; i < 8; i++) {
-            if (!g_words.empty()) { w[i] = g_words[g_word_pos % g_words.size()]; g_word_pos++; }
-            else w[i] = rd();
+            if (g_word_pos < g_words.size()) w[i] = g_words[g_word_pos++];
+            else { if (!g_words.empty()) { g_words.clear(); g_word_pos = 0; } w[i] = rd(); }
         }
         uint64_t m[4];
         for (int i = 0; i < 4; i++) m[i] = (uint64_t)w[2 * i] | ((uint64_t)w[2 * i + 1] << 32);
@@ -60,17 +124,24 @@ static void next_random_fr(uint64_t out[4]) {
     }
 }
 
-static void *circuit_pk(int circuit) {
-    if (!g_pk[circuit]) {
-        const std::string path = key_dir() + "/" + CIRCUIT_NAMES[circuit] + "pk.txt";
-        g_pk[circuit] = zkb200_pk_load(path.c_str());
-        if (!g_pk[circuit]) {
-            // the reference's behaviour on a missing key file is undefined (assert compiled out, mintcgo.cpp:69); fail loudly instead
-            fprintf(stderr, "zkb200: cannot load %s: %s\n", path.c_str(), zkb200_last_error());
-            abort();
-        }
+// the circuit's keys on every active device; parsed once, uploaded by one thread per device
+static std::shared_ptr<KeySet> circuit_keys(int circuit, std::shared_ptr<zkb::DeviceSched> &sched) {
+    int devs[64];
+    const int nd = zkb200_active_devices(devs, 64);
+    { std::lock_guard<std::mutex> lk(g_abi_mu); sched = g_sched; }
+    std::lock_guard<std::mutex> lk(g_key_mu[circuit]);
+    if (g_keys[circuit] && (int)g_keys[circuit]->devices.size() == nd && std::equal(devs, devs + nd, g_keys[circuit]->devices.begin())) return g_keys[circuit];
+    const std::string path = key_dir() + "/" + CIRCUIT_NAMES[circuit] + "pk.txt";
+    auto ks = std::make_shared<KeySet>();
+    ks->devices.assign(devs, devs + nd);
+    ks->pk.assign(nd, nullptr);
+    if (zkb200_pk_load_many(path.c_str(), devs, nd, ks->pk.data()) != 0) {
+        // the reference's behaviour on a missing key file is undefined (assert compiled out, mintcgo.cpp:69); fail loudly instead
+        fprintf(stderr, "zkb200: cannot load %s: %s\n", path.c_str(), zkb200_last_error());
+        abort();
     }
-    return g_pk[circuit];
+    g_keys[circuit] = ks;
+    return ks;
 }
 
 static char *dup_hex(const std::string &s, size_t cap) {       // `new char[cap]`, NUL-terminated, like the reference helpers
@@ -79,11 +150,15 @@ static char *dup_hex(const std::string &s, size_t cap) {       // `new char[cap]
     memcpy(p, s.data(), s.size() < cap - 1 ? s.size() : cap - 1);
     return p;
 }
-// gen*proof core: take a free lane of the resident key, generate the witness straight into that lane's pinned staging buffer (no
-// intermediate copy), prove on it.  Only the key lookup and the random draws are serialised: concurrent callers overlap.
+// gen*proof core: pick the least-loaded device, take a free lane of its copy of the key, generate the witness straight into that lane's
+// pinned staging buffer (no intermediate copy), prove on it.  Only the key lookup and the random draws are serialised: concurrent callers
+// overlap, on one GPU and across GPUs.
 template <class Fn> static char *prove_timed(int circuit, Fn make) {
-    void *pk;
-    { std::lock_guard<std::mutex> lk(g_abi_mu); pk = circuit_pk(circuit); }
+    std::shared_ptr<zkb::DeviceSched> sched;
+    const std::shared_ptr<KeySet> ks = circuit_keys(circuit, sched);          // held for the whole call: zkb200_set_key_dir cannot free it under us
+    const int slot = sched->pick();
+    void *pk = ks->pk[slot];
+    g_last_device = ks->devices[slot];
     const int lane = zkb200_lane_acquire(pk);
     uint64_t *ext = zkb200_lane_staging(pk, lane);             // pinned: the generator writes the compact assignment in place
     const double t0 = now_ms();
@@ -98,9 +173,12 @@ template <class Fn> static char *prove_timed(int circuit, Fn make) {
     const int rc = zkb200_prove_compact(pk, a.lo(), a.wide.data(), a.wide.size(), (const uint8_t *)r, (const uint8_t *)s, p, tm);
     g_last_ms[1] = now_ms() - t1; g_last_ms[2] = tm[0]; g_last_ms[3] = tm[3];
     zkb200_lane_release(pk, lane);
+    sched->done(slot);
+    if (rc < 0) { fprintf(stderr, "zkb200: prover rejected the %s witness (%d)\n", CIRCUIT_NAMES[circuit], rc); abort(); }   // generator bug, never a wrong proof
     if (rc == 1) printf("can not generate %s proof\n", CIRCUIT_NAMES[circuit]);      // mintcgo.cpp:209
     return p;
 }
+int zkb200_last_device(void) { return g_last_device; }
 
 // ---- helpers ---------------------------------------------------------------------------------------------------------------
 char *genCMT(uint64_t value, char *sn_string, char *r_string) {
@@ -198,11 +276,7 @@ char *genDepositproof(uint64_t value, uint64_t value_old, char *sn_old_string, c
         // the reference throws from IncrementalMerkleTree::path() here (uncaught C++ exception under cgo); report failure instead
         printf("can not generate deposit proof\n");
         char *p = new char[1153]; memset(p, 0, 1153);
-        uint64_t zero[4] = {0, 0, 0, 0};
-        void *pk;
-        { std::lock_guard<std::mutex> lk(g_abi_mu); pk = circuit_pk(ZKB200_DEPOSIT); }
-        std::vector<uint64_t> bad((size_t)DEPOSIT_VARS + 1, 0); bad[0] = 1;      // all-zero assignment: unsatisfied -> default proof
-        zkb200_prove_compact(pk, bad.data(), nullptr, 0, (const uint8_t *)zero, (const uint8_t *)zero, p, nullptr);
+        memcpy(p, zkb200_default_proof(), 512);                 // r1cs_gg_ppzksnark_proof default constructor: the three generators
         return p;
     }
     std::vector<uint8_t> eff(leaves.begin(), leaves.begin() + (first + 1) * 32);
@@ -263,3 +337,51 @@ long zkb200_witness_deposit(uint64_t value, uint64_t value_old, const char *sn_o
 }
 
 // ---- verification: see verifier.cpp -------------------------------------------------------------------------------------------
+
+// ---- batch entry point: many transactions, every GPU ----------------------------------------------------------------------------
+// A pool of caller threads (default: active devices x lanes of a key) drains the list through the same gen*proof functions a single
+// geth goroutine calls; the device scheduler spreads them, the lanes overlap them on each GPU.
+int zkb200_prove_batch(size_t n, const zkb200_tx *txs, char *proofs, int threads) {
+    if (n && (!txs || !proofs)) return -1;
+    for (size_t i = 0; i < n; i++) if (txs[i].circuit < 0 || txs[i].circuit > 3) return -1;
+    if (threads <= 0) {
+        int devs[64];
+        const int nd = zkb200_active_devices(devs, 64);
+        int lanes = 3;
+        if (const char *e = getenv("ZKB200_LANES")) lanes = atoi(e) > 0 ? atoi(e) : 3;
+        threads = nd * lanes;
+    }
+    if ((size_t)threads > n) threads = (int)n;
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    auto work = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n) return;
+            const zkb200_tx &t = txs[i];
+            char **s = (char **)t.s;
+            char *p = nullptr;
+            switch (t.circuit) {
+            case ZKB200_MINT: p = genMintproof(t.u[0], t.u[1], s[0], s[1], s[2], s[3], s[4], s[5], t.u[2], s[6]); break;
+            case ZKB200_REDEEM: p = genRedeemproof(t.u[0], t.u[1], s[0], s[1], s[2], s[3], s[4], s[5], t.u[2], s[6]); break;
+            case ZKB200_SEND: p = genSendproof(t.u[0], s[0], s[1], s[2], s[3], s[4], t.u[1], s[5], t.u[2], s[6], s[7], s[8], s[9], s[10]); break;
+            default: p = genDepositproof(t.u[0], t.u[1], s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], t.u[2], s[8], s[9], s[10], s[11], t.n, s[12], s[13]); break;
+            }
+            memcpy(proofs + 513 * i, p, 512); proofs[513 * i + 512] = 0;
+            if (memcmp(p, "0000000000", 10) == 0) failed++;
+            delete[] p;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(work);
+    work();
+    for (auto &th : pool) th.join();
+    return failed.load();
+}
+
+// ---- device scheduler hooks (CPU unit tests of the dispatch policy) ---------------------------------------------------------------
+void *zkb200_sched_create(int n_devices) { return new zkb::DeviceSched(n_devices); }
+int zkb200_sched_pick(void *h) { return ((zkb::DeviceSched *)h)->pick(); }
+void zkb200_sched_done(void *h, int slot) { ((zkb::DeviceSched *)h)->done(slot); }
+int zkb200_sched_inflight(void *h, int slot) { return ((zkb::DeviceSched *)h)->inflight(slot); }
+void zkb200_sched_free(void *h) { delete (zkb::DeviceSched *)h; }

@@ -4,6 +4,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/zkb200.h"
 #include "prover.cuh"
@@ -14,13 +15,27 @@ using namespace zk;
 using namespace zkp;
 
 static std::string g_err;
+static std::mutex g_err_mu;
+static void set_err(const std::string &e) { std::lock_guard<std::mutex> lk(g_err_mu); g_err = e; }
+// Device of the layer-2 calls that take no key handle (kernel entry points, benches).  Everything that takes a key handle runs on the
+// device that key is resident on, and the cgo layer spreads over all active devices (blockmaze_abi.cu) -- nothing here pins a process to one GPU.
 static int g_device = -1;
+static bool g_explicit = false;              // zkb200_init() was called by the user (not by ensure_device)
 static std::mutex g_mu;
 
+static int init_device(int device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { set_err("no CUDA device: the B200 prover has no CPU fallback"); return -1; }
+    if (device < 0 || device >= count) { set_err("bad device index"); return -1; }
+    g_device = device;
+    device_init(device);
+    ntt_init_attrs();            // this translation unit's own instances of the NTT kernels (function attributes are per device)
+    return 0;
+}
 static int ensure_device() {
     if (g_device >= 0) { cudaSetDevice(g_device); return 0; }
     const char *e = getenv("ZKB200_DEVICE");
-    return zkb200_init(e ? atoi(e) : 0);
+    return init_device(e ? atoi(e) : 0);
 }
 
 template <class F> __global__ void to_mont_generic_kernel(F *a, size_t n) {
@@ -43,23 +58,86 @@ template <class F> __global__ void field_op_kernel(const F *a, const F *b, F *ou
     out[i] = z;
 }
 
-__global__ void fill_scalars_kernel(uint32_t *out, size_t n, uint64_t seed, size_t first = 0) {      // splitmix64 stream, reduced below 2^253
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    for (int w = 0; w < 4; w++) {
-        uint64_t z = seed + ((first + i) * 4 + w + 1) * 0x9E3779B97F4A7C15ull;
-        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
-        out[i * 8 + 2 * w] = (uint32_t)z; out[i * 8 + 2 * w + 1] = (uint32_t)(z >> 32);
-    }
-    out[i * 8 + 7] &= 0x1fffffffu;
+// ---- synthetic inputs of the kernel sweep (BASELINE.json configs[4]) -------------------------------------------------
+// Scalars are libff's SHA512_rng<Fr>(idx) (libff/common/rng.tcc:26-72): SHA-512 of (idx:u64 LE || iter:u64 LE), the first 32 digest bytes
+// read as a little-endian integer, bits >= 254 cleared, next iter while the value is not below r.  Bases are P_i = h_i * G with
+// h_i = SHA512_rng(2^32 + i): distinct points with no structure a bucket method could profit from (the reference's own profile repeats one
+// point, multiexp_profile.cpp:20-31).  Both are functions of the GLOBAL index, so a slice of the problem can be made on any GPU, and the
+// host side of the sweep feeds exactly these bytes to libff / libfqfft.
+__device__ __constant__ uint64_t SHA512_K[80] = {
+    0x428a2f98d728ae22ull, 0x7137449123ef65cdull, 0xb5c0fbcfec4d3b2full, 0xe9b5dba58189dbbcull, 0x3956c25bf348b538ull, 0x59f111f1b605d019ull, 0x923f82a4af194f9bull, 0xab1c5ed5da6d8118ull,
+    0xd807aa98a3030242ull, 0x12835b0145706fbeull, 0x243185be4ee4b28cull, 0x550c7dc3d5ffb4e2ull, 0x72be5d74f27b896full, 0x80deb1fe3b1696b1ull, 0x9bdc06a725c71235ull, 0xc19bf174cf692694ull,
+    0xe49b69c19ef14ad2ull, 0xefbe4786384f25e3ull, 0x0fc19dc68b8cd5b5ull, 0x240ca1cc77ac9c65ull, 0x2de92c6f592b0275ull, 0x4a7484aa6ea6e483ull, 0x5cb0a9dcbd41fbd4ull, 0x76f988da831153b5ull,
+    0x983e5152ee66dfabull, 0xa831c66d2db43210ull, 0xb00327c898fb213full, 0xbf597fc7beef0ee4ull, 0xc6e00bf33da88fc2ull, 0xd5a79147930aa725ull, 0x06ca6351e003826full, 0x142929670a0e6e70ull,
+    0x27b70a8546d22ffcull, 0x2e1b21385c26c926ull, 0x4d2c6dfc5ac42aedull, 0x53380d139d95b3dfull, 0x650a73548baf63deull, 0x766a0abb3c77b2a8ull, 0x81c2c92e47edaee6ull, 0x92722c851482353bull,
+    0xa2bfe8a14cf10364ull, 0xa81a664bbc423001ull, 0xc24b8b70d0f89791ull, 0xc76c51a30654be30ull, 0xd192e819d6ef5218ull, 0xd69906245565a910ull, 0xf40e35855771202aull, 0x106aa07032bbd1b8ull,
+    0x19a4c116b8d2d0c8ull, 0x1e376c085141ab53ull, 0x2748774cdf8eeb99ull, 0x34b0bcb5e19b48a8ull, 0x391c0cb3c5c95a63ull, 0x4ed8aa4ae3418acbull, 0x5b9cca4f7763e373ull, 0x682e6ff3d6b2b8a3ull,
+    0x748f82ee5defb2fcull, 0x78a5636f43172f60ull, 0x84c87814a1f0ab72ull, 0x8cc702081a6439ecull, 0x90befffa23631e28ull, 0xa4506cebde82bde9ull, 0xbef9a3f7b2c67915ull, 0xc67178f2e372532bull,
+    0xca273eceea26619cull, 0xd186b8c721c0c207ull, 0xeada7dd6cde0eb1eull, 0xf57d4f7fee6ed178ull, 0x06f067aa72176fbaull, 0x0a637dc5a2c898a6ull, 0x113f9804bef90daeull, 0x1b710b35131c471bull,
+    0x28db77f523047d84ull, 0x32caab7b40c72493ull, 0x3c9ebe0a15c9bebcull, 0x431d67c49c100d4cull, 0x4cc5d4becb3e42b6ull, 0x597f299cfc657e2aull, 0x5fcb6fab3ad6faecull, 0x6c44198c4a475817ull};
+__device__ __forceinline__ uint64_t rotr64(uint64_t x, int n) { return (x >> n) | (x << (64 - n)); }
+__device__ __forceinline__ uint64_t bswap64(uint64_t x) {
+    return ((uint64_t)__byte_perm((uint32_t)x, 0, 0x0123) << 32) | __byte_perm((uint32_t)(x >> 32), 0, 0x0123);
 }
-template <class F> __global__ void gen_bases_kernel(Affine<F> gen, Affine<F> *out, size_t n, size_t first = 0) {   // P_i = ((i+1) * 0x9E3779B97F4A7C15 mod 2^64 | 1) * G
+// first 32 bytes of SHA-512(a LE || b LE) as four little-endian 64-bit limbs
+__device__ void sha512_two_words(uint64_t a, uint64_t b, uint64_t out[4]) {
+    uint64_t w[16];
+    w[0] = bswap64(a); w[1] = bswap64(b); w[2] = 0x8000000000000000ull;
+    for (int i = 3; i < 15; i++) w[i] = 0;
+    w[15] = 128;                                             // message length in bits
+    uint64_t h[8] = {0x6a09e667f3bcc908ull, 0xbb67ae8584caa73bull, 0x3c6ef372fe94f82bull, 0xa54ff53a5f1d36f1ull,
+                     0x510e527fade682d1ull, 0x9b05688c2b3e6c1full, 0x1f83d9abfb41bd6bull, 0x5be0cd19137e2179ull};
+    uint64_t s[8];
+    for (int i = 0; i < 8; i++) s[i] = h[i];
+    for (int t = 0; t < 80; t++) {
+        if (t >= 16) {
+            const uint64_t w15 = w[(t - 15) & 15], w2 = w[(t - 2) & 15];
+            const uint64_t s0 = rotr64(w15, 1) ^ rotr64(w15, 8) ^ (w15 >> 7), s1 = rotr64(w2, 19) ^ rotr64(w2, 61) ^ (w2 >> 6);
+            w[t & 15] = w[t & 15] + s0 + w[(t - 7) & 15] + s1;
+        }
+        const uint64_t S1 = rotr64(s[4], 14) ^ rotr64(s[4], 18) ^ rotr64(s[4], 41), ch = (s[4] & s[5]) ^ (~s[4] & s[6]);
+        const uint64_t t1 = s[7] + S1 + ch + SHA512_K[t] + w[t & 15];
+        const uint64_t S0 = rotr64(s[0], 28) ^ rotr64(s[0], 34) ^ rotr64(s[0], 39), maj = (s[0] & s[1]) ^ (s[0] & s[2]) ^ (s[1] & s[2]);
+        const uint64_t t2 = S0 + maj;
+        s[7] = s[6]; s[6] = s[5]; s[5] = s[4]; s[4] = s[3] + t1; s[3] = s[2]; s[2] = s[1]; s[1] = s[0]; s[0] = t1 + t2;
+    }
+    for (int i = 0; i < 4; i++) out[i] = bswap64(h[i] + s[i]);   // digest bytes are big-endian words; the bigint reads the bytes little-endian
+}
+__device__ void sha512_rng_fr(uint64_t idx, uint32_t out[8]) {
+    for (uint64_t iter = 0;; iter++) {
+        uint64_t v[4];
+        sha512_two_words(idx, iter, v);
+        v[3] &= 0x3fffffffffffffffull;                       // bits >= 254 cleared (the modulus has 254 bits)
+        Fr x; for (int i = 0; i < 4; i++) { x.v[2 * i] = (uint32_t)v[i]; x.v[2 * i + 1] = (uint32_t)(v[i] >> 32); }
+        Fr y = x; y.reduce_once();
+        if (y == x) { for (int i = 0; i < 8; i++) out[i] = x.v[i]; return; }      // below r: accepted
+    }
+}
+__global__ void fill_scalars_kernel(uint32_t *out, size_t n, size_t first = 0) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint64_t k = (first + i + 1) * 0x9E3779B97F4A7C15ull | 1ull;
-    uint32_t kk[8] = {(uint32_t)k, (uint32_t)(k >> 32), 0, 0, 0, 0, 0, 0};
-    XYZZ<F> g = XYZZ<F>::from_affine(gen), r = XYZZ<F>::inf();
-    for (int b = 63; b >= 0; b--) { r = r.dbl(); if ((kk[b >> 5] >> (b & 31)) & 1) r.add(g); }
+    sha512_rng_fr(first + i, out + i * 8);
+}
+// table[k*15 + d-1] = d * 16^k * G (affine), k < 64, d = 1..15: one thread per k
+template <class F> __global__ void gen_table_kernel(Affine<F> gen, Affine<F> *table) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 64) return;
+    XYZZ<F> base = XYZZ<F>::from_affine(gen);
+    for (int j = 0; j < 4 * k; j++) base = base.dbl();
+    const Affine<F> b = base.to_affine();
+    XYZZ<F> cur = XYZZ<F>::from_affine(b);
+    for (int d = 1; d <= 15; d++) { table[k * 15 + d - 1] = cur.to_affine(); cur.add_affine(b); }
+}
+template <class F> __global__ void gen_bases_kernel(const Affine<F> *__restrict__ table, Affine<F> *out, size_t n, size_t first = 0) {   // P_i = SHA512_rng(2^32 + i) * G
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t h[8];
+    sha512_rng_fr((1ull << 32) + first + i, h);
+    XYZZ<F> r = XYZZ<F>::inf();
+    for (int k = 0; k < 64; k++) {
+        const uint32_t d = (h[k >> 3] >> ((k & 7) * 4)) & 15;
+        if (d) r.add_affine(table[k * 15 + d - 1]);
+    }
     out[i] = r.to_affine();
 }
 
@@ -113,22 +191,44 @@ __global__ void imad_peak_kernel(uint32_t *out, int iters, int mode) {
 // every exported function below is declared extern "C" in include/zkb200.h, which fixes its linkage
 
 int zkb200_init(int device) {
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { g_err = "no CUDA device: the B200 prover has no CPU fallback"; return -1; }
-    if (device < 0 || device >= count) { g_err = "bad device index"; return -1; }
-    g_device = device;
-    device_init(device);
-    ntt_init_attrs();            // this translation unit's own instances of the NTT kernels
-    return 0;
+    const int rc = init_device(device);
+    if (rc == 0) g_explicit = true;
+    return rc;
 }
-const char *zkb200_last_error(void) { return g_err.c_str(); }
+int zkb200_ensure_device(void) { return ensure_device() ? -1 : g_device; }
+int zkb200_device_count(void) { int count = 0; return cudaGetDeviceCount(&count) == cudaSuccess ? count : 0; }
+int zkb200_current_device(void) { return g_explicit ? g_device : -1; }
+const char *zkb200_last_error(void) { std::lock_guard<std::mutex> lk(g_err_mu); static thread_local std::string copy; copy = g_err; return copy.c_str(); }
 
+void *zkb200_pk_load_on(const char *path, int device) {
+    if (device < 0 || device >= zkb200_device_count()) { set_err("bad device index"); return nullptr; }
+    std::string err;
+    DevicePk *pk = pk_load(path, device, err);
+    if (!pk) set_err(err);
+    return pk;
+}
 void *zkb200_pk_load(const char *path) {
     if (ensure_device()) return nullptr;
-    std::string err;
-    DevicePk *pk = pk_load(path, g_device, err);
-    if (!pk) g_err = err;
-    return pk;
+    return zkb200_pk_load_on(path, g_device);
+}
+// one parse of the key file, one resident copy per device, uploaded by one host thread per device
+int zkb200_pk_load_many(const char *path, const int *devices, int n, void **out) {
+    if (n <= 0 || !devices || !out) return -1;
+    const int count = zkb200_device_count();
+    for (int i = 0; i < n; i++) { out[i] = nullptr; if (devices[i] < 0 || devices[i] >= count) { set_err("bad device index"); return -1; } }
+    std::string err; double parse_s = 0;
+    zkpk::ParsedPk *P = pk_parse_file(path, err, &parse_s);
+    if (!P) { set_err(err); return -1; }
+    std::vector<std::string> errs(n);
+    std::vector<std::thread> th;
+    for (int i = 1; i < n; i++) th.emplace_back([&, i]() { out[i] = pk_from_parsed(*P, devices[i], errs[i], parse_s); });
+    out[0] = pk_from_parsed(*P, devices[0], errs[0], parse_s);
+    for (auto &t : th) t.join();
+    pk_parsed_free(P);
+    int rc = 0;
+    for (int i = 0; i < n; i++) if (!out[i]) { set_err(errs[i]); rc = -1; }
+    if (rc) for (int i = 0; i < n; i++) if (out[i]) { pk_free((DevicePk *)out[i]); out[i] = nullptr; }
+    return rc;
 }
 void zkb200_pk_free(void *pk) { pk_free((DevicePk *)pk); }
 int zkb200_pk_info(void *h, uint64_t info[8], double seconds[3]) {
@@ -147,6 +247,8 @@ static void put_g2(uint8_t *o, const zkh::HG2Affine &a) {
     put_fq(o, a.x.c0); put_fq(o + 32, a.x.c1); put_fq(o + 64, a.y.c0); put_fq(o + 96, a.y.c1);
 }
 
+int zkb200_pk_device(void *h) { return h ? ((DevicePk *)h)->device : -1; }
+
 static const char *DEFAULT_PROOF =   // (G1::one, G2::one, G1::one): r1cs_gg_ppzksnark_proof default ctor (r1cs_gg_ppzksnark.hpp:309-315)
     "0000000000000000000000000000000000000000000000000000000000000001"
     "0000000000000000000000000000000000000000000000000000000000000002"
@@ -156,6 +258,8 @@ static const char *DEFAULT_PROOF =   // (G1::one, G2::one, G1::one): r1cs_gg_ppz
     "12c85ea5db8c6deb4aab71808dcb408fe3d1e7690c43d37b4ce6cc0166fa7daa"
     "0000000000000000000000000000000000000000000000000000000000000001"
     "0000000000000000000000000000000000000000000000000000000000000002";
+
+const char *zkb200_default_proof(void) { return DEFAULT_PROOF; }
 
 // proof bytes, parity hooks and timings of a collected proof
 static int finish_outputs(ProofPoints &pp, double host_ms, char *proof_hex_out, uint8_t *parts, float *timings_ms) {
@@ -174,9 +278,9 @@ static int prove_any(void *h, const uint8_t *assignment, const uint64_t *lo, con
     ProofPoints pp;
     pp.want_parts = parts != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
-    if (lo) prove_compact(pk, lo, wide, nwide, rr, ss, pp); else prove(pk, assignment, rr, ss, pp);
-    const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    (void)total_ms;
+    const int rc = lo ? prove_compact(pk, lo, wide, nwide, rr, ss, pp) : prove(pk, assignment, rr, ss, pp);
+    (void)t0;
+    if (rc < 0) { set_err("prove: malformed input (" + std::to_string(rc) + ")"); return rc; }
     return finish_outputs(pp, pp.host_tail_ms, proof_hex_out, parts, timings_ms);
 }
 int zkb200_prove(void *h, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32], char *proof_hex_out, uint8_t *parts, float *timings_ms) {
@@ -199,15 +303,13 @@ int zkb200_prove_submit(void *h, int lane, const uint8_t *assignment, const uint
     Lane *ln = held_lane(h, lane);
     if (!ln || ln->pending) return -1;
     uint64_t rr[4], ss[4]; memcpy(rr, r, 32); memcpy(ss, s, 32);
-    prove_submit((DevicePk *)h, ln, assignment, nullptr, nullptr, 0, rr, ss);
-    return 0;
+    return prove_submit((DevicePk *)h, ln, assignment, nullptr, nullptr, 0, rr, ss);
 }
 int zkb200_prove_submit_compact(void *h, int lane, const uint64_t *lo, const void *wide, size_t nwide, const uint8_t r[32], const uint8_t s[32]) {
     Lane *ln = held_lane(h, lane);
     if (!ln || ln->pending || !lo) return -1;
     uint64_t rr[4], ss[4]; memcpy(rr, r, 32); memcpy(ss, s, 32);
-    prove_submit((DevicePk *)h, ln, nullptr, lo, (const WideIn *)wide, (uint32_t)nwide, rr, ss);
-    return 0;
+    return prove_submit((DevicePk *)h, ln, nullptr, lo, (const WideIn *)wide, (uint32_t)nwide, rr, ss);
 }
 int zkb200_prove_collect(void *h, int lane, char *proof_hex_out, uint8_t *parts, float *timings_ms) {
     Lane *ln = held_lane(h, lane);
@@ -242,10 +344,10 @@ long zkb200_domain_op(size_t min_size, int op, uint8_t *data, size_t n, int *kin
     if (ensure_device()) return -1;
     std::lock_guard<std::mutex> lk(g_mu);
     Domain *d = get_domain(min_size);
-    if (!d) { g_err = "no evaluation domain for that size"; return -1; }
+    if (!d) { set_err("no evaluation domain for that size"); return -1; }
     if (kind) *kind = d->step ? 1 : 0;
     if (!data) return d->m;
-    if (n != d->m || op < 0 || op > 4) { g_err = "domain_op: wrong vector length or op"; return -1; }
+    if (n != d->m || op < 0 || op > 4) { set_err("domain_op: wrong vector length or op"); return -1; }
     Fr *buf, *tmp;
     ZK_CUDA(cudaMalloc(&buf, n * 32)); ZK_CUDA(cudaMalloc(&tmp, n * 32));
     ZK_CUDA(cudaMemcpy(buf, data, n * 32, cudaMemcpyHostToDevice));
@@ -319,7 +421,7 @@ float zkb200_bench_ntt(int logn, int batch, int iters) {
     const size_t n = 1ull << logn;
     Fr *src, *dst;
     ZK_CUDA(cudaMalloc(&src, n * 32 * batch)); ZK_CUDA(cudaMalloc(&dst, n * 32 * batch));
-    fill_scalars_kernel<<<(unsigned)((n * batch + 255) / 256), 256>>>((uint32_t *)src, n * batch, 7);
+    fill_scalars_kernel<<<(unsigned)((n * batch + 255) / 256), 256>>>((uint32_t *)src, n * batch, 0);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const PowMul none{nullptr, nullptr, 0};
     for (int b = 0; b < batch; b++) ntt_launch(0, src + b * n, dst + b * n, (const Fr *)d->tw_big_f, logn, none, none);   // warm-up
@@ -334,20 +436,20 @@ float zkb200_bench_ntt(int logn, int batch, int iters) {
     return ms / (float)(iters * batch);
 }
 
-// slice [first, first+n) of the synthetic MSM problem (bases P_i, scalars s_i are functions of the GLOBAL index i), so that a single
-// large MSM can be split by point range over several GPUs: every rank calls this with its slice and the partial points are added.
-float zkb200_bench_msm_slice(int group, size_t first, size_t n, int window_bits, int iters, uint8_t *out_point) {
-    if (ensure_device()) return -1;
-    const int c = window_bits > 0 ? window_bits : (window_bits < 0 ? -window_bits : default_window(n));
-    uint32_t *sc; ZK_CUDA(cudaMalloc(&sc, (n + 1) * 32));
-    if (n) fill_scalars_kernel<<<(unsigned)((n + 255) / 256), 256>>>(sc, n, 11, first);
-    void *bases;
+template <class F> __global__ void from_mont_generic_kernel(F *a, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = a[i].from_mont();
+}
+// device array of n (+1 spare) synthetic bases P_{first+i}, Montgomery form; group 1 = G1, 2 = G2
+static void *synth_bases_device(int group, size_t first, size_t n) {
+    void *bases, *table;
     if (group == 1) {
-        ZK_CUDA(cudaMalloc(&bases, (n + 1) * sizeof(G1Affine)));
+        ZK_CUDA(cudaMalloc(&bases, (n + 1) * sizeof(G1Affine))); ZK_CUDA(cudaMalloc(&table, 64 * 15 * sizeof(G1Affine)));
         G1Affine g; g.x = Fq::one(); g.y = Fq::one() + Fq::one();
-        if (n) gen_bases_kernel<Fq><<<(unsigned)((n + 127) / 128), 128>>>(g, (G1Affine *)bases, n, first);
+        gen_table_kernel<Fq><<<1, 64>>>(g, (G1Affine *)table);
+        if (n) gen_bases_kernel<Fq><<<(unsigned)((n + 127) / 128), 128>>>((const G1Affine *)table, (G1Affine *)bases, n, first);
     } else {
-        ZK_CUDA(cudaMalloc(&bases, (n + 1) * sizeof(G2Affine)));
+        ZK_CUDA(cudaMalloc(&bases, (n + 1) * sizeof(G2Affine))); ZK_CUDA(cudaMalloc(&table, 64 * 15 * sizeof(G2Affine)));
         // G2 generator (alt_bn128_init.cpp:265-269), Montgomery form computed on the host
         const char *gs[4] = {"10857046999023057135944570762232829481370756359578518086990519993285655852781",
                              "11559732032986387107991004021392285783925812861821192530917403151452391805634",
@@ -355,8 +457,43 @@ float zkb200_bench_msm_slice(int group, size_t first, size_t n, int window_bits,
                              "4082367875863433681332203403145435568316851327593401208105741076214120093531"};
         zkh::HFq v[4]; for (int i = 0; i < 4; i++) zkh::HFq::from_dec(gs[i], strlen(gs[i]), v[i]);
         G2Affine g; memcpy(&g, v, 128);
-        if (n) gen_bases_kernel<Fq2><<<(unsigned)((n + 127) / 128), 128>>>(g, (G2Affine *)bases, n, first);
+        gen_table_kernel<Fq2><<<1, 64>>>(g, (G2Affine *)table);
+        if (n) gen_bases_kernel<Fq2><<<(unsigned)((n + 127) / 128), 128>>>((const G2Affine *)table, (G2Affine *)bases, n, first);
     }
+    ZK_CUDA(cudaGetLastError());
+    ZK_CUDA(cudaDeviceSynchronize());
+    cudaFree(table);
+    return bases;
+}
+// the synthetic inputs themselves, for the host legs of the sweep and the parity tests: canonical little-endian bytes
+int zkb200_synth_scalars(size_t first, size_t n, uint8_t *out) {
+    if (ensure_device()) return -1;
+    uint32_t *sc; ZK_CUDA(cudaMalloc(&sc, (n + 1) * 32));
+    if (n) fill_scalars_kernel<<<(unsigned)((n + 255) / 256), 256>>>(sc, n, first);
+    ZK_CUDA(cudaGetLastError());
+    ZK_CUDA(cudaMemcpy(out, sc, n * 32, cudaMemcpyDeviceToHost));
+    cudaFree(sc);
+    return 0;
+}
+int zkb200_synth_bases(int group, size_t first, size_t n, uint8_t *out) {
+    if (ensure_device() || (group != 1 && group != 2)) return -1;
+    void *bases = synth_bases_device(group, first, n);
+    const size_t nf = n * (group == 1 ? 2 : 4);
+    if (nf) from_mont_generic_kernel<Fq><<<(unsigned)((nf + 255) / 256), 256>>>((Fq *)bases, nf);
+    ZK_CUDA(cudaGetLastError());
+    ZK_CUDA(cudaMemcpy(out, bases, nf * 32, cudaMemcpyDeviceToHost));
+    cudaFree(bases);
+    return 0;
+}
+
+// slice [first, first+n) of the synthetic MSM problem (bases P_i, scalars s_i are functions of the GLOBAL index i), so that a single
+// large MSM can be split by point range over several GPUs: every rank calls this with its slice and the partial points are added.
+float zkb200_bench_msm_slice(int group, size_t first, size_t n, int window_bits, int iters, uint8_t *out_point) {
+    if (ensure_device()) return -1;
+    const int c = window_bits > 0 ? window_bits : (window_bits < 0 ? -window_bits : default_window(n));
+    uint32_t *sc; ZK_CUDA(cudaMalloc(&sc, (n + 1) * 32));
+    if (n) fill_scalars_kernel<<<(unsigned)((n + 255) / 256), 256>>>(sc, n, first);
+    void *bases = synth_bases_device(group, first, n);
     ZK_CUDA(cudaDeviceSynchronize());
     const bool expanded = window_bits < 0;          // negative window_bits: fixed-base (expanded) layout with |window_bits| bits
     MsmPlan plan; plan.init((uint32_t)n, c, 0, group == 1, group == 2, expanded);
@@ -387,31 +524,56 @@ int zkb200_g1_sum(size_t n, const uint8_t *points, uint8_t out[64]) {
     put_g1(out, acc.to_affine());
     return 0;
 }
+int zkb200_g2_sum(size_t n, const uint8_t *points, uint8_t out[128]) {
+    zkh::HG2 acc = zkh::HG2::inf();
+    for (size_t i = 0; i < n; i++) {
+        uint64_t c[16]; memcpy(c, points + 128 * i, 128);
+        uint64_t any = 0; for (int k = 0; k < 16; k++) any |= c[k];
+        if (!any) continue;
+        zkh::HG2Affine a{zkh::HFq2{zkh::HFq::from_canonical(c), zkh::HFq::from_canonical(c + 4)}, zkh::HFq2{zkh::HFq::from_canonical(c + 8), zkh::HFq::from_canonical(c + 12)}};
+        acc = acc.add(zkh::HG2::from_affine(a));
+    }
+    put_g2(out, acc.to_affine());
+    return 0;
+}
 float zkb200_bench_msm(int group, size_t n, int window_bits, int iters) { return zkb200_bench_msm_slice(group, 0, n, window_bits, iters, nullptr); }
 
-// write a buffer twice the size of L2 so the next step starts with a cold L2 (bench hygiene)
+// write a buffer twice the size of L2 on every device in use so the next step starts with a cold L2 (bench hygiene)
 void zkb200_flush_l2(void) {
     if (ensure_device()) return;
     static void *buf[64];
-    const size_t bytes = 256u << 20;
-    if (!buf[g_device]) ZK_CUDA(cudaMalloc(&buf[g_device], bytes));
     static int flip = 0;
-    ZK_CUDA(cudaMemset(buf[g_device], ++flip, bytes));
-    ZK_CUDA(cudaDeviceSynchronize());
+    const size_t bytes = 256u << 20;
+    ++flip;
+    for (int d : devices_in_use()) {
+        ZK_CUDA(cudaSetDevice(d));
+        if (!buf[d]) ZK_CUDA(cudaMalloc(&buf[d], bytes));
+        ZK_CUDA(cudaMemsetAsync(buf[d], flip, bytes, 0));
+    }
+    zkb200_device_sync();
 }
-void zkb200_device_sync(void) { if (!ensure_device()) ZK_CUDA(cudaDeviceSynchronize()); }
-// Device-clock stopwatch around a region that runs on many streams: both calls synchronise the whole device first and then record a CUDA
-// event, so the elapsed time is GPU time between two quiescent points.  stop = 0 starts; stop = 1 returns the milliseconds since the start.
+void zkb200_device_sync(void) {
+    if (ensure_device()) return;
+    for (int d : devices_in_use()) { ZK_CUDA(cudaSetDevice(d)); ZK_CUDA(cudaDeviceSynchronize()); }
+    cudaSetDevice(g_device);
+}
+// Device-clock stopwatch around a region that runs on many streams (and, in a single process driving several GPUs, on many devices): both
+// calls synchronise every device in use first and then record a CUDA event on each, so the elapsed time is GPU time between two quiescent
+// points.  stop = 0 starts; stop = 1 returns the milliseconds since the start (the longest over the devices).
 float zkb200_device_timer(int stop) {
     if (ensure_device()) return -1;
     static cudaEvent_t ev[64][2];
-    if (!ev[g_device][0]) { ZK_CUDA(cudaEventCreate(&ev[g_device][0])); ZK_CUDA(cudaEventCreate(&ev[g_device][1])); }
-    ZK_CUDA(cudaDeviceSynchronize());
-    ZK_CUDA(cudaEventRecord(ev[g_device][stop ? 1 : 0], 0));
-    ZK_CUDA(cudaEventSynchronize(ev[g_device][stop ? 1 : 0]));
-    if (!stop) return 0;
-    float ms = 0; ZK_CUDA(cudaEventElapsedTime(&ms, ev[g_device][0], ev[g_device][1]));
-    return ms;
+    float worst = 0;
+    zkb200_device_sync();
+    for (int d : devices_in_use()) {
+        ZK_CUDA(cudaSetDevice(d));
+        if (!ev[d][0]) { ZK_CUDA(cudaEventCreate(&ev[d][0])); ZK_CUDA(cudaEventCreate(&ev[d][1])); }
+        ZK_CUDA(cudaEventRecord(ev[d][stop ? 1 : 0], 0));
+        ZK_CUDA(cudaEventSynchronize(ev[d][stop ? 1 : 0]));
+        if (stop) { float ms = 0; if (cudaEventElapsedTime(&ms, ev[d][0], ev[d][1]) == cudaSuccess && ms > worst) worst = ms; else cudaGetLastError(); }
+    }
+    cudaSetDevice(g_device);
+    return worst;
 }
 
 float zkb200_bench_imad_peak(int mode) {

@@ -178,7 +178,7 @@ int zkb200_keygen(const char *cs_source_pk_path, const uint32_t *words, size_t n
       cs_off += dec_u64(P.L.size()).size() + 1 + P.L.size() * 34;
       (void)c; }
     const std::string cs_text((const char *)data.data() + cs_off, data.size() - cs_off);
-    if (zkb200_init(getenv("ZKB200_DEVICE") ? atoi(getenv("ZKB200_DEVICE")) : 0)) return -3;
+    if (zkb200_ensure_device() < 0) return -3;
 
     const uint64_t ni = P.num_inputs, n = P.num_inputs + P.num_aux, nc = P.num_constraints;
     WordStream ws{n_words ? words : nullptr, n_words};

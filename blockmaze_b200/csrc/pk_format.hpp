@@ -109,7 +109,7 @@ inline bool parse_pk(const uint8_t *data, size_t len, ParsedPk &pk) {
     uint64_t k = c.dec();
     ZK_REQ(k <= (1ull << 28));
     pk.B_idx.resize(k);
-    for (uint64_t i = 0; i < k; i++) { pk.B_idx[i] = (uint32_t)c.dec(); ZK_REQ(true); }
+    for (uint64_t i = 0; i < k; i++) { const uint64_t idx = c.dec(); ZK_REQ(idx < pk.B_domain && pk.B_domain <= (1ull << 28)); pk.B_idx[i] = (uint32_t)idx; }
     uint64_t k2 = c.dec();
     ZK_REQ(k2 == k);
     pk.B_g1.resize(k); pk.B_g2.resize(k);

@@ -23,7 +23,8 @@ using zkh::HFr; using zkh::HFq; using zkh::HFq2; using zkh::HG1; using zkh::HG2;
 static thread_local int g_launches = 0;     // kernels launched by this thread since the last prove_submit() began
 static int g_last_launches = 0;
 static bool g_isolate_h = false;            // measurement mode, see set_isolate_h()
-#define ZK_LAUNCH(kernel, grid, block, smem, stream, ...) do { kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); g_launches++; } while (0)
+// a launch-configuration failure (shared memory over the limit, bad grid) is not sticky: check it at the launch or the kernel silently does not run
+#define ZK_LAUNCH(kernel, grid, block, smem, stream, ...) do { kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); ZK_CUDA(cudaGetLastError()); g_launches++; } while (0)
 
 void cuda_check(cudaError_t e, const char *what) {
     if (e != cudaSuccess) {
@@ -39,9 +40,18 @@ static double now_s() { return std::chrono::duration<double>(std::chrono::steady
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 static bool g_attrs_done[64];
+static std::mutex g_attrs_mu;
 void device_init(int device) {
     ZK_CUDA(cudaSetDevice(device));
-    if (device < 64 && !g_attrs_done[device]) { ntt_init_attrs(); g_attrs_done[device] = true; }
+    if (device < 64 && !g_attrs_done[device]) {
+        std::lock_guard<std::mutex> lk(g_attrs_mu);
+        if (!g_attrs_done[device]) { ntt_init_attrs(); g_attrs_done[device] = true; }
+    }
+}
+std::vector<int> devices_in_use() {
+    std::vector<int> v;
+    for (int d = 0; d < 64; d++) if (g_attrs_done[d]) v.push_back(d);
+    return v;
 }
 
 // =====================================================================================================================
@@ -141,6 +151,7 @@ static void ntt(cudaStream_t st, const void *src, void *dst, const void *tw, int
     }
     NttPass ps[4]; g_launches += ntt_plan_passes(logn, ps);
     ntt_launch(st, (const Fr *)src, (Fr *)dst, (const Fr *)tw, logn, pre, post, batch, stride);
+    ZK_CUDA(cudaGetLastError());
 }
 
 // inverse transform src -> dst (dst != src), coefficient i additionally multiplied by `post` (e.g. g^i for the coset shift
@@ -526,21 +537,37 @@ Lane *lane_of_staging(DevicePk *pk, const void *p) {
     return nullptr;
 }
 
-DevicePk *pk_load(const char *path, int device, std::string &err) {
+zkpk::ParsedPk *pk_parse_file(const char *path, std::string &err, double *seconds) {
     const double t0 = now_s();
     std::ifstream fh(path, std::ios::binary | std::ios::ate);
     if (!fh.is_open()) { err = std::string("cannot open proving key ") + path; return nullptr; }
     const size_t len = (size_t)fh.tellg();
     std::vector<uint8_t> data(len);
     fh.seekg(0); fh.read((char *)data.data(), (std::streamsize)len);
-    zkpk::ParsedPk P;
-    if (!zkpk::parse_pk(data.data(), len, P)) { err = P.error; return nullptr; }
-    data.clear(); data.shrink_to_fit();
-    const double t1 = now_s();
+    zkpk::ParsedPk *P = new zkpk::ParsedPk();
+    if (!zkpk::parse_pk(data.data(), len, *P)) { err = P->error; delete P; return nullptr; }
+    // a B_query entry must be a whole (G2, G1) pair or absent: one skip flag serves both halves (kc_multiexp.tcc:21-89 never emits anything else)
+    for (size_t i = 0; i < P->B_g1.size(); i++)
+        if (((P->B_g1[i].flags ^ P->B_g2[i].flags) >> 1) & 1) { err = "proving key B_query entry " + std::to_string(i) + " has only one half at infinity"; delete P; return nullptr; }
+    if (seconds) *seconds = now_s() - t0;
+    return P;
+}
+void pk_parsed_free(zkpk::ParsedPk *P) { delete P; }
 
+DevicePk *pk_load(const char *path, int device, std::string &err) {
+    double parse_s = 0;
+    zkpk::ParsedPk *P = pk_parse_file(path, err, &parse_s);
+    if (!P) return nullptr;
+    DevicePk *pk = pk_from_parsed(*P, device, err, parse_s);
+    delete P;
+    return pk;
+}
+
+DevicePk *pk_from_parsed(const zkpk::ParsedPk &P, int device, std::string &err, double parse_seconds) {
+    const double t0 = now_s() - parse_seconds;
     device_init(device);
     DevicePk *pk = new DevicePk();
-    pk->device = device; pk->parse_seconds = t1 - t0;
+    pk->device = device; pk->parse_seconds = parse_seconds;
     pk->num_inputs = P.num_inputs; pk->num_vars = P.num_inputs + P.num_aux; pk->num_constraints = P.num_constraints;
     if (P.A.size() != pk->num_vars + 1 || P.L.size() != pk->num_vars - pk->num_inputs || P.B_domain != pk->num_vars + 1) {
         err = "proving key query sizes do not match its constraint system"; delete pk; return nullptr;
@@ -666,8 +693,7 @@ static void upload_compact(DevicePk *pk, Lane *ln, const uint64_t *lo, const Wid
     uint64_t *pin = (uint64_t *)ln->h_w_pinned;
     if (lo != pin) memcpy(pin, lo, (size_t)(n + 1) * 8);
     WideIn *pw = (WideIn *)ln->h_wide_pinned;
-    if (nwide > MAX_WIDE - 3) nwide = MAX_WIDE - 3;                  // (circuits here have <= 10)
-    if (nwide) memcpy(pw, wide, nwide * sizeof(WideIn));
+    if (nwide) memcpy(pw, wide, nwide * sizeof(WideIn));             // nwide <= MAX_WIDE - 3 and every idx in [1, n]: checked by prove_submit
     for (int k = 0; k < 3; k++) { pw[nwide + k].idx = n + 1 + k; pw[nwide + k].pad = 0; memcpy(pw[nwide + k].v, zk_scalars + 4 * k, 32); }
     nwide += 3;
     ZK_CUDA(cudaMemcpyAsync(ln->w_lo, pin, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -717,8 +743,14 @@ int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int
 
 static HG1 g1_mul(const HG1Affine &p, const uint64_t k[4]) { return HG1::from_affine(p).mul(k); }
 
-void prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4],
-                  const uint64_t s[4]) {
+int prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4],
+                 const uint64_t s[4]) {
+    // malformed input is an error, never a proof of something else
+    if (HFr::geq_mod(r) || HFr::geq_mod(s)) return -4;
+    if (lo) {
+        if (nwide > MAX_WIDE - 3 || (nwide && !wide)) return -2;
+        for (uint32_t k = 0; k < nwide; k++) if (wide[k].idx == 0 || wide[k].idx > pk->num_vars) return -3;
+    }
     device_init(pk->device);
     g_launches = 0;
     cudaStream_t st = ln->s_main;
@@ -762,6 +794,7 @@ void prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint6
     ZK_CUDA(cudaEventRecord(ln->ev_t1, st));
     ln->launches = g_launches;
     ln->pending = true;
+    return 0;
 }
 
 int prove_collect(DevicePk *pk, Lane *ln, ProofPoints &out) {
@@ -814,16 +847,16 @@ int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const ui
     Lane *ln = nullptr;
     if (!assignment) { while (!(ln = lane_try(pk, 0))) std::this_thread::yield(); }
     else ln = lane_acquire(pk);
-    prove_submit(pk, ln, assignment, nullptr, nullptr, 0, r, s);
-    const int rc = prove_collect(pk, ln, out);
+    int rc = prove_submit(pk, ln, assignment, nullptr, nullptr, 0, r, s);
+    if (rc == 0) rc = prove_collect(pk, ln, out);
     lane_release(pk, ln);
     return rc;
 }
 int prove_compact(DevicePk *pk, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4], const uint64_t s[4], ProofPoints &out) {
     Lane *own = lane_of_staging(pk, lo);               // the caller generated the witness in a lane it already holds
     Lane *ln = own ? own : lane_acquire(pk);
-    prove_submit(pk, ln, nullptr, lo, wide, nwide, r, s);
-    const int rc = prove_collect(pk, ln, out);
+    int rc = prove_submit(pk, ln, nullptr, lo, wide, nwide, r, s);
+    if (rc == 0) rc = prove_collect(pk, ln, out);
     if (!own) lane_release(pk, ln);
     return rc;
 }

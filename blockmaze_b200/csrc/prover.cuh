@@ -7,6 +7,8 @@
 #include <vector>
 #include "host_field.hpp"
 
+namespace zkpk { struct ParsedPk; }
+
 namespace zkp {
 
 void cuda_check(cudaError_t e, const char *what);     // aborts loudly: there is no CPU fallback
@@ -113,6 +115,10 @@ struct DevicePk {
 };
 
 DevicePk *pk_load(const char *path, int device, std::string &err);     // lanes: env ZKB200_LANES (default 3)
+// the two halves of pk_load, so that one parse of the key file can be made resident on several GPUs
+zkpk::ParsedPk *pk_parse_file(const char *path, std::string &err, double *seconds);
+void pk_parsed_free(zkpk::ParsedPk *P);
+DevicePk *pk_from_parsed(const zkpk::ParsedPk &P, int device, std::string &err, double parse_seconds);
 void pk_free(DevicePk *pk);
 Lane *lane_acquire(DevicePk *pk);                       // blocks until a lane is free
 Lane *lane_try(DevicePk *pk, int index);                // lane `index` if it is free, else nullptr
@@ -136,8 +142,9 @@ struct ProofPoints {
 //   neither   : reuse the assignment already resident on the lane (bench "value" leg).
 // collect: waits for the lane's streams, sums the partial points and assembles the proof on the host.
 struct WideIn { uint32_t idx; uint32_t pad; uint64_t v[4]; };
-void prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4],
-                  const uint64_t s[4]);
+// returns 0, or < 0 without touching the lane: -2 too many wide values, -3 wide index out of range, -4 r or s not below the group order
+int prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4],
+                 const uint64_t s[4]);
 int prove_collect(DevicePk *pk, Lane *ln, ProofPoints &out);
 // synchronous conveniences: acquire a lane (or use the one that owns `lo`), submit, collect, release
 int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const uint64_t s[4], ProofPoints &out);
@@ -147,6 +154,7 @@ uint64_t *compact_staging(Lane *ln);                    // pinned, (num_vars + 1
 int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied);
 
 void device_init(int device);
+std::vector<int> devices_in_use();                  // every device device_init() has been called for
 std::string proof_hex(const ProofPoints &p);           // mintcgo.cpp:112-187 layout
 // measurement mode: the H-query MSM of the next proofs starts only after the A, B, L queries are done, so that the CUDA-event time of
 // its kernels is that of the kernels alone (roofline); costs latency, never used otherwise

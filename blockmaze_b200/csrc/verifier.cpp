@@ -334,8 +334,10 @@ static bool hex_fq(const char *s, HFq &out) {      // 64 lowercase hex chars, bi
         if (ch >= '0' && ch <= '9') d = ch - '0'; else if (ch >= 'a' && ch <= 'f') d = ch - 'a' + 10; else return false;
         v[3 - i / 16] |= (uint64_t)d << (4 * (15 - i % 16));
     }
-    if (HFq::geq_mod(v)) return false;
-    out = HFq::from_canonical(v);
+    // The reference builds Fq from the raw 256-bit integer (libsnarkBigintFromBytes -> Fp_model(bigint), fp.tcc:190-194: mul_reduce by
+    // R^2), i.e. it REDUCES mod q: an encoding such as x + q is accepted by reference nodes, so it must be accepted here as well or a
+    // mixed network forks.  R^2 is the left operand so that the row accumulator stays below 2q for any 256-bit v.
+    out = HFq::raw(FqTag::R2) * HFq::raw(v);
     return true;
 }
 // pack_bit_vector_into_field_element_vector (field_utils.tcc:79-103): chunks of 253 bits, bit j of a chunk -> 2^j

@@ -63,23 +63,61 @@ bool verifyRedeemproof(char *data, char *cmtA_old_string, char *sn_old_string, c
 /* circuits, in the order used by every *_circuit argument */
 enum { ZKB200_MINT = 0, ZKB200_SEND = 1, ZKB200_DEPOSIT = 2, ZKB200_REDEEM = 3 };
 
-/* Select the CUDA device this process proves on (default 0, or env ZKB200_DEVICE).  Returns 0, or -1 if no GPU. */
+/* Devices.  Nothing pins a process to one GPU: a key handle runs on the device it is resident on, and the cgo surface of layer (1)
+ * spreads its calls over the ACTIVE devices -- zkb200_set_devices() > env ZKB200_DEVICES ("all" or "0,2,3") > the device of an explicit
+ * zkb200_init() (one process per GPU, as bench.py under torchrun) > env ZKB200_DEVICE > every visible device.  An unchanged geth process
+ * therefore proves on all GPUs of the box (reference: one OpenMP knob, r1cs_gg_ppzksnark.tcc:429-433; zktx.go:383-404 stays as it is).
+ *   zkb200_init           device of the layer-(2) calls that take no key handle (kernel entry points, benches).  0, or -1 if no GPU.
+ *   zkb200_set_devices    active devices of layer (1); n = 0 selects every visible device.  Returns how many, or -1.  Resident keys are dropped.
+ *   zkb200_active_devices copies the active device list, returns its length
+ *   zkb200_last_device    device that proved this thread's last gen*proof */
 int zkb200_init(int device);
+int zkb200_ensure_device(void);
+int zkb200_device_count(void);
+int zkb200_current_device(void);
+int zkb200_set_devices(const int *devices, int n);
+int zkb200_active_devices(int *out, int cap);
+int zkb200_last_device(void);
 /* Directory holding <circuit>pk.txt / <circuit>vk.txt.  Default: env ZKB200_KEY_DIR, else /usr/local/prfKey
  * (hard-coded in the reference: mintcgo.cpp:302,336). */
 void zkb200_set_key_dir(const char *dir);
-/* Pin the prover randomness: the next proofs draw (r, s) from this std::random_device-style 32-bit word stream exactly as
- * libff's Fr::random_element does (fp.tcc:695-721, bigint.tcc:167-179).  n_words = 0 returns to /dev/urandom. */
-void zkb200_set_random_words(const uint32_t *words, size_t n_words);
+/* TEST HOOK -- pin the prover randomness: the next proofs draw (r, s) from this std::random_device-style 32-bit word stream exactly as
+ * libff's Fr::random_element does (fp.tcc:695-721, bigint.tcc:167-179).  Refused (-1) unless the process runs with ZKB200_TEST_RNG=1;
+ * the stream is never reused: when it is exhausted, or with n_words = 0, the prover is back on std::random_device. */
+int zkb200_set_random_words(const uint32_t *words, size_t n_words);
 
 /* Replaces r1cs_gg_ppzksnark_proving_key operator>> (r1cs_gg_ppzksnark.tcc:68-88): parse the file, decompress the points
  * on the GPU, keep everything resident.  Returns a handle or NULL (zkb200_last_error() says why). */
-void *zkb200_pk_load(const char *path);
+void *zkb200_pk_load(const char *path);                       /* on the zkb200_init device */
+void *zkb200_pk_load_on(const char *path, int device);
+/* one parse of the file, one resident copy per listed device (uploaded concurrently); out[i] belongs to devices[i].  0 or -1. */
+int zkb200_pk_load_many(const char *path, const int *devices, int n, void **out);
+int zkb200_pk_device(void *pk);
 void zkb200_pk_free(void *pk);
 /* info[0..7] = num_variables, num_inputs, num_constraints, domain m, domain kind (0 basic_radix2, 1 step_radix2),
  * nnz(A)+nnz(B)+nnz(C), distinct coefficients, B_query entries.  seconds[0..2] = total load, parse, GPU decompression + fixed-base table expansion. */
 int zkb200_pk_info(void *pk, uint64_t info[8], double seconds[3]);
 const char *zkb200_last_error(void);
+
+/* The proof the reference returns for an unsatisfiable witness (r1cs_gg_ppzksnark_proof default constructor, r1cs_gg_ppzksnark.hpp:309-315):
+ * 512 hex characters of (G1::one, G2::one, G1::one). */
+const char *zkb200_default_proof(void);
+
+/* Batch entry point over layer (1): n transactions, proved on every active device with all lanes busy (a pool of `threads` caller threads,
+ * 0 = active devices x lanes, drains the list through gen*proof).  A transaction carries the arguments of its gen<Circuit>proof call:
+ *   u[] = the uint64 arguments in order of appearance, s[] = the string arguments in order of appearance, n = genDepositproof's `n`.
+ *   mint / redeem: u = value, value_old, value_s;        s = sn_old, r_old, sn, r, cmtA_old, cmtA, sk
+ *   send         : u = value_A, value_s, value_A_new;    s = r_s, sn, r, cmt_s, cmtA, pk_recv, sn_A_new, r_A_new, cmt_A_new, sk, pk_sender
+ *   deposit      : u = value, value_old, value_s;        s = sn_old, r_old, sn, r, sns, rs, cmtB_old, cmtB, pk, sn_A_old, cmtS, cmtarray, RT, sk
+ * proofs: n x 513 bytes (512 hex + NUL each).  Returns the number of default proofs (unsatisfiable transactions), or -1 on bad arguments. */
+typedef struct zkb200_tx { int circuit; int n; uint64_t u[3]; const char *s[14]; } zkb200_tx;
+int zkb200_prove_batch(size_t n, const zkb200_tx *txs, char *proofs, int threads);
+/* the device-dispatch policy on its own (host only; CPU unit tests): least proofs in flight, ties round-robin */
+void *zkb200_sched_create(int n_devices);
+int zkb200_sched_pick(void *sched);
+void zkb200_sched_done(void *sched, int slot);
+int zkb200_sched_inflight(void *sched, int slot);
+void zkb200_sched_free(void *sched);
 
 /* Replaces r1cs_gg_ppzksnark_prover (r1cs_gg_ppzksnark.tcc:390-506) for a caller-supplied full assignment
  * (primary || auxiliary, num_variables x 32 B) and explicit r, s.  assignment == NULL re-proves the assignment already
@@ -87,7 +125,8 @@ const char *zkb200_last_error(void);
  * timings_ms (optional, 8 floats): GPU total, QAP witness map, H MSM, host work left after the GPU finished (most of the proof assembly
  * overlaps the H MSM), H-MSM bucket-accumulate kernel, and the times at
  * which the A, B and L query MSMs (side streams) were done, counted from the start (CUDA events).
- * Returns 0 = proof, 1 = constraint system not satisfied (proof_hex = default proof), <0 = error. */
+ * Returns 0 = proof, 1 = constraint system not satisfied (proof_hex = default proof), <0 = error (-2 more than 61 wide values,
+ * -3 a wide value's index outside [1, num_variables], -4 r or s not below the group order): malformed input never yields a proof. */
 int zkb200_prove(void *pk, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32], char *proof_hex, uint8_t *parts,
                  float *timings_ms);
 /* Same prover fed with the COMPACT assignment the native witness generators produce: lo[0..num_variables] = low 64 bits of every
@@ -162,19 +201,24 @@ int zkb200_field_op(int field, int op, size_t n, const uint8_t *a, const uint8_t
 
 /* Device-resident benchmarks (inputs generated / kept in HBM, timed with CUDA events on the launching stream).
  * zkb200_bench_ntt: `iters` forward size-2^logn transforms over a buffer of `batch` independent vectors; returns ms per transform.
- * zkb200_bench_msm: dense 254-bit MSM over n synthetic bases (group: 1 = G1, 2 = G2); returns ms per MSM.  window_bits > 0:
+ * zkb200_bench_msm: dense 254-bit MSM over n synthetic bases and scalars (zkb200_synth_*; group: 1 = G1, 2 = G2); returns ms per MSM.  window_bits > 0:
  * windowed layout (bases as given, Horner on the host); window_bits < 0: fixed-base layout with |window_bits| bits (the table
  * 2^(c*k)*P is built once outside the timed region, as for a resident proving key); 0: default windowed. */
 float zkb200_bench_ntt(int logn, int batch, int iters);
 float zkb200_bench_msm(int group, size_t n, int window_bits, int iters);
 /* The same synthetic problem restricted to points [first, first+n): bases and scalars are functions of the GLOBAL index, so a single
  * large MSM splits by point range over several GPUs (one partial point per GPU, added on the host).  out_point
- * (64 B G1 / 128 B G2, may be NULL) receives the partial sum.  Also returns the points/scalars to the host for cross-checks when small. */
+ * (64 B G1 / 128 B G2, may be NULL) receives the partial sum. */
 float zkb200_bench_msm_slice(int group, size_t first, size_t n, int window_bits, int iters, uint8_t *out_point);
-/* Host-side sum of n affine G1 points (64 B each as in zkb200_msm_g1; all-zero = infinity): the "one partial point per GPU summed on the
- * host" step of an MSM split by point range. */
+/* Host-side sum of n affine G1 (64 B each as in zkb200_msm_g1) / G2 (128 B) points, all-zero = infinity: the "one partial point per GPU
+ * summed on the host" step of an MSM split by point range. */
 int zkb200_g1_sum(size_t n, const uint8_t *points, uint8_t out[64]);
-/* bench hygiene: overwrite a 256 MB scratch buffer (2x L2) and synchronise; plain cudaDeviceSynchronize */
+int zkb200_g2_sum(size_t n, const uint8_t *points, uint8_t out[128]);
+/* The synthetic inputs of the sweep as canonical bytes, so that the host legs (libff multi_exp, libfqfft FFT) see IDENTICAL inputs:
+ * scalar i = libff SHA512_rng<Fr>(i) (libff/common/rng.tcc:26-72); base i = SHA512_rng<Fr>(2^32 + i) * generator (group 1 = G1, 2 = G2). */
+int zkb200_synth_scalars(size_t first, size_t n, uint8_t *out);
+int zkb200_synth_bases(int group, size_t first, size_t n, uint8_t *out);
+/* bench hygiene, over every device in use: overwrite a 256 MB scratch buffer (2x L2) and synchronise; plain cudaDeviceSynchronize */
 void zkb200_flush_l2(void);
 void zkb200_device_sync(void);
 /* device-clock stopwatch for a region spread over many streams: synchronises the device, then records a CUDA event.

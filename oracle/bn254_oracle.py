@@ -766,3 +766,17 @@ def sha256_compress(left, right):
         h, g, f, e, d, c, b, a = g, f, e, (d + t1) & M, c, b, a, (t1 + t2) & M
     out = [(x + y) & M for x, y in zip(Hs, (a, b, c, d, e, f, g, h))]
     return b"".join(x.to_bytes(4, "big") for x in out)
+
+
+def sha512_rng(idx):
+    """libff::SHA512_rng<Fr> (libff/common/rng.tcc:26-72): SHA-512 of (idx:u64 LE || iter:u64 LE), the first 32 digest bytes read as a
+    little-endian integer, the bits above the modulus' top bit (>= 254) cleared, next iter while the value is not below r.  The scalar
+    stream of the synthetic kernel sweep; bases there are sha512_rng(2^32 + i) * generator."""
+    import hashlib
+    import struct
+    it = 0
+    while True:
+        v = int.from_bytes(hashlib.sha512(struct.pack("<QQ", idx, it)).digest()[:32], "little") & ((1 << 254) - 1)
+        if v < R_MOD:
+            return v
+        it += 1

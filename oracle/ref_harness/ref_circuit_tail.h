@@ -47,4 +47,30 @@ static int finish_prove(const libsnark::r1cs_gg_ppzksnark_proof<ppT> &proof, cha
     if (!S.outdir.empty()) write_file(S.outdir + "/proof.hex", h.data(), 512);
     return 0;
 }
+// ---- verification with an explicit key path -------------------------------------------------------------------------------------
+// The reference's verify<Circuit>proof (SRC/<c>/<c>cgo.cpp) reads /usr/local/prfKey/<c>vk.txt, a path compiled in.  ref_<c>_verify below
+// runs the same steps on a key file given by the caller: the reference's own loader (deserializevkFromFile), the proof decoding of
+// verify<Circuit>proof (mintcgo.cpp:340-404: hex pairs -> bytes by convertFromAscii, big-endian bytes -> bigint by libsnarkBigintFromBytes,
+// bigint assigned to the coordinate, i.e. Fp_model(bigint) which REDUCES mod q; Z stays one), then the reference's verify_<c>_proof
+// template, which packs the public inputs (gadget::witness_map) and calls r1cs_gg_ppzksnark_verifier_strong_IC (r1cs_gg_ppzksnark.tcc:613-623).
+static libsnark::r1cs_gg_ppzksnark_verification_key<ppT> g_vk;
+static std::string g_vk_path;
+static const libsnark::r1cs_gg_ppzksnark_verification_key<ppT> &load_vk(const char *path) {
+    ppT::init_public_params();
+    if (g_vk_path != path) { g_vk = deserializevkFromFile(path); g_vk_path = path; }
+    return g_vk;
+}
+static libff::bigint<libff::alt_bn128_r_limbs> coord_from_hex(const char *hex64) {
+    uint8_t raw[64];
+    for (int i = 0, j = 0; i < 64; i += 2, j++) raw[j] = uint8_t(convertFromAscii(uint8_t(hex64[i])) * 16 + convertFromAscii(uint8_t(hex64[i + 1])));
+    return libsnarkBigintFromBytes(raw);
+}
+static libsnark::r1cs_gg_ppzksnark_proof<ppT> proof_from_hex(const char *data) {
+    libsnark::r1cs_gg_ppzksnark_proof<ppT> proof;          // default: the three generators, so every Z is one
+    proof.g_A.X = coord_from_hex(data); proof.g_A.Y = coord_from_hex(data + 64);
+    proof.g_B.X.c1 = coord_from_hex(data + 128); proof.g_B.X.c0 = coord_from_hex(data + 192);
+    proof.g_B.Y.c1 = coord_from_hex(data + 256); proof.g_B.Y.c0 = coord_from_hex(data + 320);
+    proof.g_C.X = coord_from_hex(data + 384); proof.g_C.Y = coord_from_hex(data + 448);
+    return proof;
+}
 } // namespace refhook

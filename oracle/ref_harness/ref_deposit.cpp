@@ -50,4 +50,11 @@ int ref_deposit_prove(uint64_t value, uint64_t value_old, const char *sn_old, co
     auto proof = run(value, value_old, sn_old, r_old, sn, r, sns, rs, cmtB_old, cmtB, value_s, pk, sn_A_old, cmtS, cmtarray, n, sk);
     return finish_prove(proof, proof_hex, pts, timings);
 }
+int ref_deposit_verify(const char *vk_path, const char *proof_hex, const char *RT, const char *pk, const char *cmtb_old, const char *snold, const char *cmtb,
+                       const char *sns) {
+    uint256 rt = uint256S(RT), cmtB_old = uint256S(cmtb_old), sn_old = uint256S(snold), cmtB = uint256S(cmtb), sn_s = uint256S(sns);
+    uint160 pk_recv = uint160S(pk);
+    const auto &vk = load_vk(vk_path);            // first: it also runs init_public_params(), which the proof's default constructor needs
+    return verify_deposit_proof<ppT>(vk, proof_from_hex(proof_hex), rt, pk_recv, cmtB_old, sn_old, cmtB, sn_s) ? 1 : 0;
+}
 }

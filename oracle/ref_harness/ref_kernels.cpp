@@ -10,6 +10,7 @@
 #include <boost/optional.hpp>
 #include "libff/algebra/curves/alt_bn128/alt_bn128_pp.hpp"
 #include "libff/algebra/scalar_multiplication/multiexp.hpp"
+#include "libff/common/rng.hpp"
 #include "libfqfft/evaluation_domain/get_evaluation_domain.hpp"
 #include "libsnark/knowledge_commitment/kc_multiexp.hpp"
 #include "libsnark/reductions/r1cs_to_qap/r1cs_to_qap.hpp"
@@ -53,7 +54,10 @@ long ref_domain_size(size_t min_size, int *kind) {
 
 // op: 0 FFT, 1 iFFT, 2 cosetFFT(g=multiplicative_generator), 3 icosetFFT, 4 divide_by_Z_on_coset.
 // data: m elements of 32 bytes (canonical LE), transformed in place.  Returns m or -1.
-long ref_domain_op(size_t min_size, int op, uint8_t *data, size_t n) {
+long ref_domain_op_timed(size_t min_size, int op, uint8_t *data, size_t n, double *seconds);
+long ref_domain_op(size_t min_size, int op, uint8_t *data, size_t n) { return ref_domain_op_timed(min_size, op, data, n, nullptr); }
+// same, *seconds (optional) = wall time of the transform alone (conversion of the bytes excluded)
+long ref_domain_op_timed(size_t min_size, int op, uint8_t *data, size_t n, double *seconds) {
     ensure_init();
     try {
         auto d = libfqfft::get_evaluation_domain<FrT>(min_size);
@@ -61,6 +65,7 @@ long ref_domain_op(size_t min_size, int op, uint8_t *data, size_t n) {
         std::vector<FrT> a(n);
         for (size_t i = 0; i < n; i++) a[i] = get_fp<FrT>(data + 32 * i);
         const FrT g = FrT::multiplicative_generator;
+        struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); const double t0 = ts.tv_sec + 1e-9 * ts.tv_nsec;
         switch (op) {
         case 0: d->FFT(a); break;
         case 1: d->iFFT(a); break;
@@ -69,6 +74,8 @@ long ref_domain_op(size_t min_size, int op, uint8_t *data, size_t n) {
         case 4: d->divide_by_Z_on_coset(a); break;
         default: return -1;
         }
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        if (seconds) *seconds = ts.tv_sec + 1e-9 * ts.tv_nsec - t0;
         for (size_t i = 0; i < n; i++) put_fp(data + 32 * i, a[i]);
         return (long)d->m;
     } catch (...) { return -1; }
@@ -168,6 +175,13 @@ int ref_kc_msm(size_t domain_size, size_t k, const uint64_t *indices, const uint
     clock_gettime(CLOCK_MONOTONIC, &ts);
     if (seconds) *seconds = ts.tv_sec + 1e-9 * ts.tv_nsec - t0;
     put_g2(out_g2, r.g); put_g1(out_g1, r.h);
+    return 0;
+}
+
+// libff's deterministic field sampler (libff/common/rng.tcc:26-72), the scalar stream of the kernel sweep
+int ref_sha512_rng(uint64_t first, size_t n, uint8_t *out) {
+    ensure_init();
+    for (size_t i = 0; i < n; i++) put_fp(out + 32 * i, libff::SHA512_rng<FrT>(first + i));
     return 0;
 }
 

@@ -30,4 +30,9 @@ int ref_mint_prove(uint64_t value, uint64_t value_old, const char *sn_old, const
     auto proof = run(value, value_old, sn_old, r_old, sn, r, cmtA_old, cmtA, value_s, sk);
     return finish_prove(proof, proof_hex, pts, timings);
 }
+int ref_mint_verify(const char *vk_path, const char *proof_hex, const char *cmtA_old_s, const char *sn_old_s, const char *cmtA_s, uint64_t value_s) {
+    uint256 sn_old = uint256S(sn_old_s), cmtA_old = uint256S(cmtA_old_s), cmtA = uint256S(cmtA_s);
+    const auto &vk = load_vk(vk_path);            // first: it also runs init_public_params(), which the proof's default constructor needs
+    return verify_mint_proof<ppT>(vk, proof_from_hex(proof_hex), cmtA_old, sn_old, cmtA, value_s) ? 1 : 0;
+}
 }

@@ -35,4 +35,9 @@ int ref_send_prove(uint64_t value_A, const char *r_s, const char *sn, const char
     auto proof = run(value_A, r_s, sn, r, cmt_s, cmtA, value_s, pk_recv, value_A_new, sn_A_new, r_A_new, cmt_A_new, sk, pk_sender);
     return finish_prove(proof, proof_hex, pts, timings);
 }
+int ref_send_verify(const char *vk_path, const char *proof_hex, const char *cmtA_old_s, const char *sn_old_s, const char *cmtS_s, const char *cmtA_new_s) {
+    uint256 cmtA_old = uint256S(cmtA_old_s), sn_old = uint256S(sn_old_s), cmtS = uint256S(cmtS_s), cmtA_new = uint256S(cmtA_new_s);
+    const auto &vk = load_vk(vk_path);            // first: it also runs init_public_params(), which the proof's default constructor needs
+    return verify_send_proof<ppT>(vk, proof_from_hex(proof_hex), cmtA_old, sn_old, cmtS, cmtA_new) ? 1 : 0;
+}
 }

@@ -78,6 +78,22 @@ def domain_op_bytes(min_size, op, data, mt=False):
     return buf.raw
 
 
+def domain_op_timed(min_size, op, data, mt=False):
+    """(transformed bytes, seconds of the transform alone)."""
+    L = lib("kernels_mt" if mt else "kernels")
+    L.ref_domain_op_timed.restype = C.c_long
+    buf = C.create_string_buffer(bytes(data), len(data))
+    sec = C.c_double(0)
+    m = L.ref_domain_op_timed(C.c_size_t(min_size), OPS[op], buf, C.c_size_t(len(data) // 32), C.byref(sec))
+    if m < 0:
+        raise ValueError("ref_domain_op failed")
+    return buf.raw, sec.value
+
+
+def threads(mt=True):
+    return int(lib("kernels_mt" if mt else "kernels").ref_threads())
+
+
 def domain_op(min_size, op, vals, mt=False):
     return fr_list(domain_op_bytes(min_size, op, fr_bytes(vals), mt))
 
@@ -120,6 +136,13 @@ def g2_bases_bytes(n, step=7):
     out = C.create_string_buffer(128 * n)
     L.ref_g2_bases(C.c_size_t(n), int(step).to_bytes(32, "little"), out)
     return out.raw
+
+
+def sha512_rng(first, n):
+    """libff::SHA512_rng<Fr>(first + i), i < n, as canonical ints."""
+    out = C.create_string_buffer(32 * n)
+    lib("kernels").ref_sha512_rng(C.c_uint64(first), C.c_size_t(n), out)
+    return fr_list(out.raw)
 
 
 def g1_mul(a, k):
@@ -222,3 +245,63 @@ def prove(circuit, args, words, outdir=None, mt=False):
     rc = f(*_enc(args), C.cast(W, C.c_void_p), len(words), outdir.encode() if outdir else None,
            C.cast(hexbuf, C.c_void_p), C.cast(pts, C.c_void_p), C.cast(tim, C.c_void_p))
     return dict(rc=rc, proof_hex=hexbuf.value.decode(), pts=pts.raw, timings=list(tim))
+
+
+VERIFY_SIGS = {"mint": [C.c_char_p] * 5 + [C.c_uint64], "redeem": [C.c_char_p] * 5 + [C.c_uint64], "send": [C.c_char_p] * 6, "deposit": [C.c_char_p] * 8}
+
+
+def _verify_here(circuit, proof_hex, verify_args, vk_path):
+    L = lib(circuit)
+    f = getattr(L, "ref_%s_verify" % circuit)
+    f.restype = C.c_int
+    f.argtypes = VERIFY_SIGS[circuit]
+    return bool(f(vk_path.encode(), proof_hex.encode(), *_enc(verify_args)))
+
+
+# The reference's key parsers read decimal text with std::istream, and oracle/_ref/libff.so carries its own instantiations of the
+# libstdc++ locale facets (GNU-unique symbols): they only work when libff.so enters the process BEFORE any other copy of libstdc++
+# (libzkb200.so, numpy, torch all bring one).  Anything that parses a key file -- verification, the live prover -- therefore runs in
+# a fresh interpreter that loads nothing but the reference.
+_CHILD = ("import sys, json\nsys.path.insert(0, %r)\nfrom oracle import refapi as R\n"
+          "print('RESULT ' + json.dumps(R._child(json.loads(sys.stdin.read()))))\n")
+
+
+def _child(req):
+    if req["op"] == "verify":
+        return [_verify_here(c, p, a, vk) for c, p, a, vk in req["jobs"]]
+    if req["op"] == "prove":
+        load_pk(req["circuit"], req["pk_path"], mt=req["mt"])
+        return [prove(req["circuit"], a, w, mt=req["mt"])["proof_hex"] for a, w in req["jobs"]]
+    raise ValueError(req["op"])
+
+
+def _isolated(req, timeout=1800):
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    env.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+    out = subprocess.run([sys.executable, "-c", _CHILD % os.path.dirname(HERE)], input=json.dumps(req), capture_output=True, text=True,
+                         timeout=timeout, env=env)
+    for line in out.stdout.splitlines():
+        if line.startswith("RESULT "):
+            return json.loads(line[7:])
+    raise RuntimeError("reference child process failed: " + out.stderr[-2000:])
+
+
+def verify_many(jobs):
+    """jobs: (circuit, proof_hex, verify_args, vk_path or None).  The reference verifier (verify_<c>_proof ->
+    r1cs_gg_ppzksnark_verifier_strong_IC) on explicit verification-key files, in a clean child process.  Returns a list of bools."""
+    return _isolated({"op": "verify", "jobs": [(c, p, list(a), vk or os.path.join(KEY_DIR, c + "vk.txt")) for c, p, a, vk in jobs]})
+
+
+def verify(circuit, proof_hex, verify_args, vk_path=None):
+    """verify_args: the arguments of verify<Circuit>proof after the proof string."""
+    return verify_many([(circuit, proof_hex, verify_args, vk_path)])[0]
+
+
+def prove_isolated(circuit, jobs, pk_path=None, mt=True):
+    """jobs: (gen<Circuit>proof args, pinned words).  Loads the pk with the reference's own parser and proves, in a clean child process.
+    Returns the proof strings."""
+    return _isolated({"op": "prove", "circuit": circuit, "pk_path": pk_path or os.path.join(KEY_DIR, circuit + "pk.txt"), "mt": mt,
+                      "jobs": [(list(a), list(w)) for a, w in jobs]})

@@ -3,6 +3,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("ZKB200_TEST_RNG", "1")      # the pinned-randomness hook of the library only exists in test processes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))

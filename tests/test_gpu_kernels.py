@@ -190,3 +190,92 @@ def test_msm_skewed_buckets_against_reference(zk, ref, n):
     s = fb([0x1234567] * n)
     assert zk.msm_g1(b1, s) == ref.msm_g1_bytes(b1, s, 1)[0]
     assert zk.g1_sum([zk.msm_g1(b1[:64 * 1000], s[:32 * 1000]), zk.msm_g1(b1[64 * 1000:], s[32 * 1000:])]) == zk.msm_g1(b1, s)
+
+
+def test_synthetic_sweep_inputs_are_the_documented_streams(zk):
+    """zkb200_synth_scalars / zkb200_synth_bases: scalar i == libff SHA512_rng<Fr>(i) (oracle restatement, pinned against libff in
+    tests/test_oracle_pinned.py); base i == SHA512_rng(2^32 + i) * generator for G1 and G2.  Slices are functions of the global index."""
+    n = 3000
+    want = [O.sha512_rng(i) for i in range(n)]
+    assert fl(zk.synth_scalars(0, n)) == want
+    assert fl(zk.synth_scalars(1000, 50)) == want[1000:1050]
+    assert fl(zk.synth_scalars((1 << 33) + 5, 4)) == [O.sha512_rng((1 << 33) + 5 + i) for i in range(4)]
+    b1 = zk.synth_bases(1, 0, 40)
+    for i in (0, 1, 39):
+        p = O.G1.to_affine(O.G1.mul(O.sha512_rng((1 << 32) + i), O.G1_ONE))
+        assert b1[64 * i:64 * i + 64] == g1b(p)
+    assert zk.synth_bases(1, 17, 5) == b1[64 * 17:64 * 22]
+    b2 = zk.synth_bases(2, 0, 6)
+    assert zk.synth_bases(2, 3, 2) == b2[128 * 3:128 * 5]
+
+
+def test_synthetic_g2_bases_against_reference(zk, ref):
+    b2 = zk.synth_bases(2, 5, 3)
+    gen = ref.g2_from(_ref_g2_gen(ref))
+    for i in range(3):
+        assert ref.g2_bytes(ref.g2_mul(gen, O.sha512_rng((1 << 32) + 5 + i))) == b2[128 * i:128 * i + 128]
+
+
+def _ref_g2_gen(ref):
+    import ctypes as C
+    out = C.create_string_buffer(128)
+    ref.lib("kernels").ref_g2_gen(out)
+    return out.raw
+
+
+@pytest.mark.slow
+def test_sweep_sizes_against_reference_on_identical_inputs(zk, ref):
+    """the host legs of the sweep see the inputs the GPU sees, and the results are compared -- G1 MSM at 2^20 and G2 MSM
+    at 2^18 against libff multi_exp (all host threads), NTT at 2^20 element-wise against libfqfft, on the SHA512_rng streams."""
+    import ctypes as C
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    n = 1 << 20
+    sc = zk.synth_scalars(0, n)
+    b1 = zk.synth_bases(1, 0, n)
+    got = C.create_string_buffer(64)
+    zk.lib.zkb200_bench_msm_slice(1, 0, n, 0, 1, got)                  # the bench's own device-resident path
+    want = ref.msm_g1_bytes(b1, sc, 0, chunks=0, mt=True)[0]
+    assert got.raw == want
+    assert zk.msm_g1(b1, sc) == want                                     # and the host-buffer entry point
+    fx = C.create_string_buffer(64)
+    zk.lib.zkb200_bench_msm_slice(1, 0, n, -16, 1, fx)                 # fixed-base layout (what the prover's H query uses)
+    assert fx.raw == want
+    m = 1 << 18
+    b2 = zk.synth_bases(2, 0, m)
+    got2 = C.create_string_buffer(128)
+    zk.lib.zkb200_bench_msm_slice(2, 0, m, 0, 1, got2)
+    assert got2.raw == ref.msm_g2_bytes(b2, sc[:32 * m], 0, chunks=0, mt=True)[0]
+    assert zk.domain_op(n, "FFT", sc) == ref.domain_op_bytes(n, "FFT", sc, mt=True)
+    # a split by point range adds up to the same points (G1 on 8 slices, G2 on 3)
+    parts = []
+    for k in range(8):
+        o = C.create_string_buffer(64)
+        zk.lib.zkb200_bench_msm_slice(1, k * (n // 8), n // 8, 0, 1, o)
+        parts.append(o.raw)
+    assert zk.g1_sum(parts) == want
+    parts, cuts = [], [0, 100000, 100001, m]
+    for a, b in zip(cuts, cuts[1:]):
+        o = C.create_string_buffer(128)
+        zk.lib.zkb200_bench_msm_slice(2, a, b - a, 0, 1, o)
+        parts.append(o.raw)
+    assert zk.g2_sum(parts) == got2.raw
+
+
+@pytest.mark.slow
+def test_ntt_round_trip_at_2_24(zk):
+    """The largest sweep size (512 MB per vector, three passes): iFFT(FFT(a)) == a and icosetFFT(cosetFFT(a)) == a on the SHA512_rng stream,
+    plus a few evaluations checked against Horner on the host."""
+    n = 1 << 24
+    raw = zk.synth_scalars(0, n)
+    ev = zk.domain_op(n, "FFT", raw)
+    assert zk.domain_op(n, "iFFT", ev) == raw
+    del ev
+    assert zk.domain_op(n, "icosetFFT", zk.domain_op(n, "cosetFFT", raw)) == raw
+    k = 48
+    sparse = raw[:32 * k] + bytes(32 * (n - k))
+    evs = zk.domain_op(n, "FFT", sparse)
+    a = fl(raw[:32 * k])
+    w = O.get_root_of_unity(n)
+    for i in (0, 1, 54321, n // 2 + 7, n - 1):
+        x = pow(w, i, O.R_MOD)
+        assert int.from_bytes(evs[32 * i:32 * i + 32], "little") == sum(c * pow(x, j, O.R_MOD) for j, c in enumerate(a)) % O.R_MOD

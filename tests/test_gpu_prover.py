@@ -219,21 +219,120 @@ def test_cgo_concurrent_callers(zk):
         assert zk.verify_proof(c, p, zk.verify_args(c, args))
 
 
-def test_reference_verifier_accepts_gpu_proof(zk, ref):
-    """The UNMODIFIED reference verifier (libzk_mint.so verifyMintproof) accepts a GPU proof.  It reads the hard-coded
-    /usr/local/prfKey, so this only runs where that directory exists (the build container)."""
+@pytest.mark.parametrize("circuit", CIRCUITS)
+def test_reference_verifier_accepts_gpu_proof(zk, ref, circuit):
+    """north_star: a GPU proof 'must pass the reference verifier'.  The UNMODIFIED reference verifier (verify_<c>_proof ->
+    r1cs_gg_ppzksnark_verifier_strong_IC, oracle/ref_harness ref_<c>_verify on the vk file that travels with the repo) accepts proofs of
+    synthetic transactions made through the cgo surface with fresh randomness, and rejects them for another transaction's inputs."""
+    zk.set_key_dir(key_dir())
+    vk = os.path.join(key_dir(), circuit + "vk.txt")
+    a1, a2 = F.synthetic(circuit, 11), F.synthetic(circuit, 12)
+    p1, p2 = zk.gen_proof(circuit, a1), zk.gen_proof(circuit, a2)
+    v1, v2 = zk.verify_args(circuit, a1), zk.verify_args(circuit, a2)
+    dflt = zk.lib.zkb200_default_proof().decode()
+    assert ref.verify_many([(circuit, p1, v1, vk), (circuit, p2, v2, vk), (circuit, p1, v2, vk), (circuit, dflt, v1, vk)]) == [True, True, False, False]
+
+
+@pytest.mark.parametrize("circuit", CIRCUITS)
+def test_synthetic_transactions_byte_identical_to_reference(zk, ref, circuit):
+    """Three synthetic transactions per circuit (deposit: 256-leaf Merkle tree, BASELINE.json configs[2]) proved through the cgo surface
+    with the random_device word stream pinned == the proof of the reference prover for the same arguments and words
+    (tests/golden/synthetic.json, written by tests/golden/make_synthetic_golden.py from oracle/_ref), all 512 characters."""
+    rows = json.load(open(os.path.join(GOLD, "synthetic.json")))[circuit]
+    assert len(rows) >= 3
+    zk.set_key_dir(key_dir())
+    for row in rows:
+        assert row["args"] == F.synthetic(circuit, row["seed"])          # the fixture generator has not drifted from the golden file
+        zk.set_random_words(row["words"])
+        try:
+            proof = zk.gen_proof(circuit, row["args"])
+        finally:
+            zk.set_random_words([])
+        assert proof == row["proof_hex"], (circuit, row["seed"])
+        assert zk.verify_args(circuit, row["args"]) == row["verify_args"]
+        assert zk.verify_proof(circuit, proof, row["verify_args"])
+
+
+@pytest.mark.slow
+def test_live_reference_prover_on_this_box_matches_gpu(zk, ref):
+    """No golden file in between: the reference prover (libref_mint_mt.so, pk parsed by the reference's own loader, ~40 s) runs on this
+    box's CPU for a transaction that is not in any fixture and must return the GPU prover's 512 characters."""
+    import random
+    if not ref.available("mint_mt"):
+        pytest.fail("oracle/_ref/libref_mint_mt.so must travel to the GPU box")
+    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+    seed = random.SystemRandom().randrange(10 ** 6, 10 ** 9)
+    args = F.synthetic("mint", seed)
+    words = O.fixed_rng_words(seed, 64)
+    theirs = ref.prove_isolated("mint", [(args, words)], os.path.join(key_dir(), "mintpk.txt"))[0]
+    zk.set_key_dir(key_dir())
+    zk.set_random_words(words)
+    try:
+        ours = zk.gen_proof("mint", args)
+    finally:
+        zk.set_random_words([])
+    assert ours == theirs and ours[:10] != "0000000000", seed
+
+
+def test_malformed_prover_input_is_an_error_not_a_proof(zk, pks):
+    """zkb200_prove_compact: too many wide values, a wide index outside the assignment, r or s not below the group order -> rc < 0 and no
+    proof bytes (round 1 truncated the wide list silently and would have proved a different assignment)."""
     import ctypes as C
-    so = os.path.join(ref.REF_DIR, "libzk_mint.so")
-    if not (os.path.exists(so) and os.path.exists("/usr/local/prfKey/mintvk.txt")):
-        pytest.skip("reference libzk_mint.so / /usr/local/prfKey not available on this box")
-    zk.set_key_dir("/usr/local/prfKey")
-    args = F.synthetic("mint", 11)
-    proof = zk.gen_proof("mint", args)
-    L = C.CDLL(so)
-    L.verifyMintproof.restype = C.c_bool
-    L.verifyMintproof.argtypes = [C.c_char_p] * 4 + [C.c_uint64]
-    va = zk.verify_args("mint", args)
-    assert L.verifyMintproof(proof.encode(), *[x.encode() if isinstance(x, str) else x for x in va])
+    from blockmaze_b200 import api
+    pk = pks("mint")
+    n = pk.num_variables
+    lo = (C.c_uint64 * (n + 1))()
+    lo[0] = 1
+
+    class Wide(C.Structure):
+        _fields_ = [("idx", C.c_uint32), ("pad", C.c_uint32), ("v", C.c_uint64 * 4)]
+    out = C.create_string_buffer(513)
+    one = (1).to_bytes(32, "little")
+    f = api.lib.zkb200_prove_compact
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p]
+    w = (Wide * 62)()
+    for i in range(62):
+        w[i].idx = i + 1
+    assert f(pk.handle, lo, w, 62, one, one, out, None) == -2 and out.raw[:1] == b"\0"
+    w[0].idx = 0
+    assert f(pk.handle, lo, w, 1, one, one, out, None) == -3
+    w[0].idx = n + 1
+    assert f(pk.handle, lo, w, 1, one, one, out, None) == -3
+    w[0].idx = n
+    assert f(pk.handle, lo, w, 1, O.R_MOD.to_bytes(32, "little"), one, out, None) == -4
+    assert f(pk.handle, lo, w, 1, one, ((1 << 256) - 1).to_bytes(32, "little"), out, None) == -4
+    assert out.raw[:1] == b"\0"
+    assert f(pk.handle, lo, w, 1, one, one, out, None) == 1 and out.raw[:10] == b"0000000000"      # well-formed but unsatisfied: default proof
+
+
+def test_prove_batch_spreads_over_every_device(zk, ref):
+    """zkb200_prove_batch / the device scheduler behind gen*proof: one process, every visible GPU (1 here on a single-GPU box, 8 on the
+    scaling box).  Every proof verifies (reference verifier), an unsatisfiable transaction comes back as the default proof, and with
+    more than one device each of them proved something."""
+    from blockmaze_b200 import api
+    zk.set_key_dir(key_dir())
+    nd = api.set_devices([])                                    # every visible device
+    try:
+        assert nd == api.lib.zkb200_device_count() and api.active_devices() == list(range(nd))
+        names = ["mint", "send", "deposit", "redeem"]
+        jobs = [(names[i % 4], F.synthetic(names[i % 4], 300 + i)) for i in range(8 * max(1, nd))]
+        bad = list(F.synthetic("mint", 999)); bad[8] += 1
+        jobs.append(("mint", bad))
+        proofs, n_default = api.prove_batch(jobs)
+        assert n_default == 1 and proofs[-1][:10] == "0000000000"
+        assert all(ref.verify_many([(c, p, zk.verify_args(c, a), os.path.join(key_dir(), c + "vk.txt")) for (c, a), p in zip(jobs[:-1], proofs[:-1])]))
+        # gen*proof from plain caller threads lands on every device
+        from concurrent.futures import ThreadPoolExecutor
+        seen = set()
+
+        def one(i):
+            zk.gen_proof("mint", F.synthetic("mint", 500 + i))
+            seen.add(api.lib.zkb200_last_device())
+        with ThreadPoolExecutor(3 * nd) as pool:
+            list(pool.map(one, range(12 * nd)))
+        assert seen == set(range(nd))
+    finally:
+        api.set_devices([0])
 
 
 @pytest.mark.parametrize("circuit", CIRCUITS)

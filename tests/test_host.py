@@ -211,3 +211,107 @@ def test_verifier_concurrent_calls(api, ref):
     with ThreadPoolExecutor(6) as pool:
         got = list(pool.map(lambda j: api.verify_proof(j[0], j[1], j[2]), jobs))
     assert got == [j[3] for j in jobs]
+
+
+@pytest.mark.parametrize("circuit", CIRCUITS)
+def test_verifier_agrees_with_reference_verifier_incl_noncanonical_encodings(api, ref, circuit):
+    """Same verdict as the reference verifier (verify_<c>_proof -> r1cs_gg_ppzksnark_verifier_strong_IC, run on an explicit vk path by
+    oracle/ref_harness) on: the golden proof; tampered proofs; and NON-CANONICAL coordinate encodings x + k*q < 2^256.  The reference
+    builds Fq from the raw 256-bit integer (Fp_model(bigint), fp.tcc:190-194), which reduces mod q, so it ACCEPTS those -- a drop-in
+    verifier must too, or a mixed network forks on such a transaction."""
+    if not ref.available(circuit) or not os.path.exists(os.path.join(ref.KEY_DIR, circuit + "vk.txt")):
+        pytest.skip("reference circuit harness / keys not present")
+    api.set_key_dir(ref.KEY_DIR)
+    g = json.load(open(os.path.join(GOLD, circuit + ".json")))
+    va = api.verify_args(circuit, g["args"])
+    h = g["proof_hex"]
+    q = O.Q_MOD
+
+    def bump(proof, coord, k):
+        v = int(proof[64 * coord:64 * coord + 64], 16) + k * q
+        assert v < 1 << 256
+        return proof[:64 * coord] + "%064x" % v + proof[64 * coord + 64:]
+
+    cases = [h, bump(h, 0, 1), bump(h, 1, 1), bump(h, 2, 1), bump(h, 5, 2), bump(h, 6, 3), bump(bump(h, 7, 4), 0, 4),
+             h[:384] + h[:128],                                       # C := A
+             bump(h[:384] + h[:128], 6, 1),
+             h[:200] + ("1" if h[200] != "1" else "2") + h[201:],     # off the curve
+             "f" * 64 + h[64:]]                                       # 2^256 - 1 as A.x
+    bad = list(va)
+    bad[0] = bad[0][:-1] + ("1" if bad[0][-1] != "1" else "2")
+    verdicts = ref.verify_many([(circuit, p, va, None) for p in cases] + [(circuit, h, bad, None)])
+    assert verdicts[:7] == [True] * 7 and not any(verdicts[7:])       # pins the reference's behaviour
+    assert [api.verify_proof(circuit, p, va) for p in cases] + [api.verify_proof(circuit, h, bad)] == verdicts
+
+
+def test_device_scheduler_policy(api):
+    """zkb::DeviceSched (csrc/sched.hpp), the policy gen*proof uses to spread proofs over the GPUs of one box: least proofs in flight,
+    ties round-robin.  Host-only, so it is checked here without a GPU."""
+    import random
+    lib = api.lib
+    s = lib.zkb200_sched_create(4)
+    try:
+        first = [lib.zkb200_sched_pick(s) for _ in range(8)]
+        assert first == [0, 1, 2, 3, 0, 1, 2, 3]                      # an idle box fills in rotation
+        assert [lib.zkb200_sched_inflight(s, d) for d in range(4)] == [2, 2, 2, 2]
+        lib.zkb200_sched_done(s, 2); lib.zkb200_sched_done(s, 2)
+        assert lib.zkb200_sched_pick(s) == 2 and lib.zkb200_sched_pick(s) == 2      # the drained device takes the next two
+        held = [0, 1, 2, 3, 0, 1, 2, 3]
+        rng = random.Random(5)
+        for _ in range(2000):                                          # random arrivals and completions: load never differs by more than one ...
+            if held and rng.random() < 0.5:
+                d = held.pop(rng.randrange(len(held)))
+                lib.zkb200_sched_done(s, d)
+            else:
+                load = [lib.zkb200_sched_inflight(s, d) for d in range(4)]
+                d = lib.zkb200_sched_pick(s)
+                assert load[d] == min(load)                            # ... because a pick always goes to a least-loaded device
+                held.append(d)
+        for d in held:
+            lib.zkb200_sched_done(s, d)
+        assert [lib.zkb200_sched_inflight(s, d) for d in range(4)] == [0, 0, 0, 0]
+        lib.zkb200_sched_done(s, 1)                                    # spurious completion is ignored
+        assert lib.zkb200_sched_inflight(s, 1) == 0 and lib.zkb200_sched_inflight(s, 9) == -1
+    finally:
+        lib.zkb200_sched_free(s)
+    # concurrent callers (goroutines in geth): totals add up and stay balanced
+    from concurrent.futures import ThreadPoolExecutor
+    s = lib.zkb200_sched_create(8)
+    counts = [0] * 8
+
+    def job(_):
+        d = lib.zkb200_sched_pick(s)
+        counts[d] += 1
+        lib.zkb200_sched_done(s, d)
+    with ThreadPoolExecutor(16) as pool:
+        list(pool.map(job, range(4000)))
+    assert sum(counts) == 4000 and all(lib.zkb200_sched_inflight(s, d) == 0 for d in range(8))
+    lib.zkb200_sched_free(s)
+
+
+def test_prove_batch_rejects_bad_arguments_without_touching_a_gpu(api):
+    assert api.lib.zkb200_prove_batch(0, None, None, 0) == 0
+    t = (api.Tx * 1)()
+    t[0].circuit = 7
+    out = C.create_string_buffer(513)
+    assert api.lib.zkb200_prove_batch(1, t, out, 1) == -1
+    assert api.lib.zkb200_prove_batch(1, None, out, 1) == -1
+    tx = api._tx("deposit", F.deposit_fixture())
+    assert tx.circuit == 2 and tx.n == 16 and list(tx.u) == [264, 255, 9] and tx.s[11].startswith(b"0x") and len(tx.s[11]) == 16 * 66
+    tx = api._tx("send", F.send_fixture())
+    assert tx.circuit == 1 and list(tx.u) == [22, 8, 14] and tx.s[10] is not None and tx.s[11] is None
+
+
+def test_random_words_hook_needs_test_env(api):
+    """zkb200_set_random_words pins (r, s): a production process (no ZKB200_TEST_RNG=1) cannot switch it on."""
+    import subprocess, sys
+    code = ("import os, sys; os.environ.pop('ZKB200_TEST_RNG', None); sys.path.insert(0, %r)\n"
+            "import ctypes as C; from blockmaze_b200 import api\n"
+            "w = (C.c_uint32 * 16)(*range(16))\n"
+            "print('RC', api.lib.zkb200_set_random_words(C.cast(w, C.c_void_p), 16), api.lib.zkb200_set_random_words(None, 0))\n" % ROOT)
+    env = {k: v for k, v in os.environ.items() if k != "ZKB200_TEST_RNG"}
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert "RC -1 0" in out.stdout, out.stdout + out.stderr
+    w = (C.c_uint32 * 16)(*range(16))
+    assert api.lib.zkb200_set_random_words(C.cast(w, C.c_void_p), 16) == 0          # this process has the variable (tests/conftest.py)
+    assert api.lib.zkb200_set_random_words(None, 0) == 0

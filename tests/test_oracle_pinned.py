@@ -169,3 +169,10 @@ def test_pk_header_and_prover_pieces_against_golden(ref):
     rng = random.Random(3)
     rows = rng.sample(pk.cs.rows, 3000)
     assert all(O.lc_eval(a, full) * O.lc_eval(b, full) % O.R_MOD == O.lc_eval(c, full) for a, b, c in rows)
+
+
+def test_sha512_rng_restatement_equals_libff(ref):
+    """The scalar stream of the synthetic kernel sweep: oracle.sha512_rng == libff::SHA512_rng<Fr> (rng.tcc:26-72), incl. indices whose first
+    digests are rejected (a quarter of all draws) and the 2^32 + i range the bases use."""
+    for first in (0, 12345, 1 << 32, (1 << 40) + 3):
+        assert ref.sha512_rng(first, 300) == [O.sha512_rng(first + i) for i in range(300)]

@@ -59,6 +59,25 @@ def imad_peaks(api):
             "modmul_G": 1e3 * float(api.lib.zkb200_bench_imad_peak(2))}
 
 
+def host_threads():
+    """Every host core for the reference's OpenMP build, whatever the launcher exported (torch.distributed.run sets OMP_NUM_THREADS=1,
+    which voided the round-1 ratios at N >= 2).  Must run before libgomp is loaded."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
+
+
+def omp_threads(want):
+    """Force and read back the OpenMP thread count of the already loaded runtime."""
+    import ctypes
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(int(want))
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return int(os.environ.get("OMP_NUM_THREADS", "1"))
+
+
 def shard_batch(seeds, rank, world):
     """Independent transactions are dealt to the ranks with no inter-GPU traffic.  The transaction type is
     seed % 4 and deposit proofs cost ~2x a mint, so the deal rotates by seed // 4 to give every rank the same type mix."""
@@ -107,11 +126,19 @@ class ClockSampler:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
+        out = self.stats(windows)
         self.proc.terminate()
+        return out
+
+    def stats(self, windows):
+        """Clocks and throttle reasons of the samples that fall into the given (t0, t1) windows; the sampler keeps running."""
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for t, line in self.lines:
-            if not any(a <= t <= b for a, b in windows):
+        for t, line in list(self.lines):
+            if not any(a - 0.05 <= t <= b + 0.05 for a, b in windows):
                 continue
             f = [x.strip() for x in line.split(",")]
             try:
@@ -137,9 +164,10 @@ def reference_arm(args, rank, world):
     if not Rf.available(circuit + "_mt"):
         emit(({"impl": "reference", "unavailable": "oracle/_ref/libref_send_mt.so not built (needs /root/reference at build time)"}))
         return
-    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+    cores = host_threads()              # torchrun exports OMP_NUM_THREADS=1: the reference arm always takes every host core
     t0 = time.perf_counter()
     Rf.load_pk(circuit, os.path.join(key_dir(), circuit + "pk.txt"), mt=True)
+    cores = omp_threads(cores)
     t_load = time.perf_counter() - t0
     words = O.fixed_rng_words(42, 64)
     txs = [F.synthetic(circuit, s) for s in range(max(1, args.warmup) + args.steps)]
@@ -156,7 +184,7 @@ def reference_arm(args, rank, world):
         assert res["rc"] == 0
         phases = [a + b for a, b in zip(phases, res["timings"])]
     dt = time.perf_counter() - t0
-    cores = int(os.environ["OMP_NUM_THREADS"])
+    assert cores > 1 or (os.cpu_count() or 1) == 1, "reference arm ran single-threaded on a multi-core host"
     v = timed / dt
     line.update(value=v, ms_per_step=1e3 * dt / timed,
                 config={"workload": WORKLOADS["send"], "detail": "reference path per step: gadget construction + witness + is_satisfied + r1cs_gg_ppzksnark_prover, pk resident",
@@ -168,6 +196,164 @@ def reference_arm(args, rank, world):
     emit((line))
 
 
+FMA_PIPE_INSTR_PER_SEND_PROOF = None      # filled from profiles/r02_fma_pipe.json when present (ncu sm__inst_executed_pipe_fma.sum of one send proof)
+
+
+def load_fma_count():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_fma_pipe.json")))
+    except (OSError, ValueError):
+        return None
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        return {}
+
+
+def verify_sample(api, circuit, txs, proofs, count=8):
+    """The bench checks what it timed: `count` of the proofs (spread over the run) go through verify<Circuit>proof."""
+    idx = sorted(set(int(i * (len(proofs) - 1) / max(1, count - 1)) for i in range(min(count, len(proofs)))))
+    for i in idx:
+        assert proofs[i][:10] != "0000000000", "prover returned the default proof for a valid transaction"
+        assert api.verify_proof(circuit, proofs[i], api.verify_args(circuit, txs[i])), "a timed proof does not verify"
+    return len(idx)
+
+
+def run_mixed(api, F, rank, world, dist, barrier, depth, sampler, single_process_gpus=0):
+    """BASELINE.json configs[3]: 1024 synthetic transactions, type = seed mod 4 (256 of each circuit), through gen*proof.
+    One process per GPU (torchrun): the batch is dealt to the ranks by shard_batch, no data-path collective (strong scaling).
+    --single-process: this one process proves the whole batch on `single_process_gpus` devices through zkb200_prove_batch."""
+    names = ["mint", "send", "deposit", "redeem"]
+    mine = list(range(1024)) if single_process_gpus else shard_batch(list(range(1024)), rank, world)
+    jobs = [(names[sd % 4], F.synthetic(names[sd % 4], sd)) for sd in mine]
+    nthreads = depth * max(1, single_process_gpus)
+    warm = [(c, F.synthetic(c, 5000 + rank + 10 * k)) for k in range(max(2, nthreads // 2)) for c in names]
+    api.prove_batch(warm, nthreads)                      # loads the four keys on every active device, warms every lane
+    barrier()
+    api.lib.zkb200_device_timer(0)
+    t0 = time.perf_counter()
+    proofs, bad = api.prove_batch(jobs, nthreads)
+    dev_ms = float(api.lib.zkb200_device_timer(1))
+    t1 = time.perf_counter()
+    barrier()
+    assert bad == 0, "%d of the batch came back as default proofs" % bad
+    checked = 0
+    for c in names:                                      # two of each circuit through verify*proof
+        sel = [i for i, (cc, _) in enumerate(jobs) if cc == c]
+        checked += verify_sample(api, c, [jobs[i][1] for i in sel], [proofs[i] for i in sel], 2)
+    units, dt = reduce_counts_and_time(len(jobs), max(dev_ms * 1e-3, t1 - t0), None if single_process_gpus else dist)
+    return {"metric": "proofs_per_sec", "value": units / dt, "unit": "proofs/s", "n_gpus": single_process_gpus or world, "scaling": "strong",
+            "seconds": dt, "transactions": units, "verified_sample": checked, "callers_per_gpu": depth,
+            "mode": "one process, library device scheduler (zkb200_prove_batch)" if single_process_gpus else "one process per GPU, batch dealt round-robin by type",
+            "workload": WORKLOADS["mixed1024"], "clocks": sampler.stats([(t0, t1)]),
+            "timing": "max(CUDA events after device synchronisations, wall clock) around the batch, host work included; max over ranks"}
+
+
+def run_msm_split(api, dist, rank, world, barrier, logn, iters, sampler):
+    """BASELINE.json configs[4], second half: ONE MSM of 2^logn points split by point range over the GPUs, G1 then G2; every GPU returns one
+    partial point and rank 0 adds them on the host (zkb200_g1_sum / zkb200_g2_sum; no collective on the data path -- the 64/128-byte points
+    travel through the rendezvous gather).  Inputs: SHA512_rng scalars, bases SHA512_rng(2^32+i)*G (zkb200_synth_*), functions of the
+    global index.  The sum is checked against profiles/msm_split_golden.json (the single-GPU result, itself cross-checked against libff at
+    2^20 by tests/test_gpu_kernels.py::test_sweep_sizes_against_reference_on_identical_inputs)."""
+    import ctypes as C
+    n = 1 << logn
+    per = n // world
+    first, count = rank * per, (per if rank < world - 1 else n - per * (world - 1))
+    out = {}
+    for group, name, size in ((1, "g1", 64), (2, "g2", 128)):
+        buf = C.create_string_buffer(size)
+        barrier()
+        t0 = time.perf_counter()
+        ms = float(api.lib.zkb200_bench_msm_slice(group, first, count, 0, max(1, iters), buf))       # one untimed run inside, then `iters` timed ones
+        t1 = time.perf_counter()
+        barrier()
+        units, tmax = reduce_counts_and_time(count, ms * 1e-3, dist)
+        pts = [buf.raw]
+        if dist is not None:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, buf.raw)
+            pts = gathered
+        if rank == 0:
+            total = (api.g1_sum if group == 1 else api.g2_sum)(pts)
+            x = "%064x" % int.from_bytes(total[:32], "little")
+            gold = None
+            try:
+                gold = json.load(open(os.path.join(ROOT, "profiles", "msm_split_golden.json"))).get("%s_2^%d_x" % (name, logn))
+            except (OSError, ValueError):
+                pass
+            if gold is not None:
+                assert x == gold, "MSM split result differs from the recorded single-GPU result"
+            out[name] = {"value": units / tmax, "unit": "points/s", "ms_per_msm": round(1e3 * tmax, 3), "points": units, "result_x": x,
+                         "result_matches_golden": None if gold is None else True,
+                         "frac_of_imad_peak": None, "clocks": sampler.stats([(t0, t1)])}
+    if rank == 0:
+        out.update({"metric": "msm_points_per_sec", "n_gpus": world, "scaling": "strong", "log2_points": logn,
+                    "workload": "single MSM of 2^%d points split by point range, one partial point per GPU summed on the host; G1 and G2" % logn})
+    return out
+
+
+def kernel_sweep(api):
+    """BASELINE.json configs[4]: BN254 G1/G2 MSM and Fr NTT at 2^16..2^24 on one GPU next to libff multi_exp / libfqfft FFT on the host
+    cores.  The host legs get IDENTICAL inputs (zkb200_synth_scalars / zkb200_synth_bases: libff's SHA512_rng stream) and every host result
+    is compared with the GPU's; they stop at 2^20 (G2: 2^18), where they already take seconds."""
+    import ctypes as C
+    hbm = measured_peaks().get("hbm_gbs", 6650.0)
+    imad = float(api.lib.zkb200_bench_imad_peak(1))
+    cpu, cores = None, 0
+    try:
+        from oracle import refapi as Rf
+        if Rf.available("kernels_mt"):
+            cores = host_threads()
+            cpu = Rf
+            Rf.lib("kernels_mt")
+            cores = omp_threads(cores)
+    except Exception:
+        cpu = None
+    rows = []
+    for lg in (16, 18, 20, 22, 24):
+        n = 1 << lg
+        row = {"log2_n": lg}
+        ms = float(api.lib.zkb200_bench_ntt(lg, 1, 5))
+        row["ntt_ms"] = round(ms, 4)
+        row["ntt_GBps"] = round(64.0 * n / (ms * 1e-3) / 1e9, 1)
+        row["ntt_frac_of_hbm"] = round(row["ntt_GBps"] / hbm, 4)
+        g1 = C.create_string_buffer(64)
+        ms = float(api.lib.zkb200_bench_msm_slice(1, 0, n, 0, 2, g1))
+        row["msm_g1_ms"] = round(ms, 3)
+        row["msm_g1_frac_of_imad"] = round(IMAD_PER_G1_POINT * n / (ms * 1e-3) / 1e12 / imad, 4)
+        fx = C.create_string_buffer(64)
+        ms = float(api.lib.zkb200_bench_msm_slice(1, 0, n, -16, 2, fx))
+        assert fx.raw == g1.raw, "fixed-base and windowed MSM disagree"
+        row["msm_g1_fixed_base_ms"] = round(ms, 3)
+        row["msm_g1_fixed_base_frac_of_imad"] = round(IMAD_PER_G1_POINT * n / (ms * 1e-3) / 1e12 / imad, 4)
+        g2 = C.create_string_buffer(128)
+        ms = float(api.lib.zkb200_bench_msm_slice(2, 0, n, 0, 1 if lg >= 22 else 2, g2))
+        row["msm_g2_ms"] = round(ms, 3)
+        row["msm_g2_frac_of_imad"] = round(3 * IMAD_PER_G1_POINT * n / (ms * 1e-3) / 1e12 / imad, 4)
+        if cpu is not None and lg <= 20:
+            sc = api.synth_scalars(0, n)
+            want, sec = cpu.msm_g1_bytes(api.synth_bases(1, 0, n), sc, 0, chunks=0, mt=True)
+            assert want == g1.raw, "G1 MSM differs from libff multi_exp at 2^%d" % lg
+            row["cpu_msm_g1_s"] = round(sec, 3)
+            ev, sec = cpu.domain_op_timed(n, "FFT", sc, mt=True)
+            assert ev == api.domain_op(n, "FFT", sc), "NTT differs from libfqfft at 2^%d" % lg
+            row["cpu_fft_s"] = round(sec, 4)
+            if lg <= 18:
+                want, sec = cpu.msm_g2_bytes(api.synth_bases(2, 0, n), sc, 0, chunks=0, mt=True)
+                assert want == g2.raw, "G2 MSM differs from libff multi_exp at 2^%d" % lg
+                row["cpu_msm_g2_s"] = round(sec, 3)
+            row["host_results_equal_gpu"] = True
+        rows.append(row)
+    return {"metric": "kernel_sweep", "unit": "ms", "n_gpus": 1,
+            "data": "synthetic: scalars libff SHA512_rng<Fr>(i), bases SHA512_rng<Fr>(2^32+i)*G, NTT input = the scalar stream; identical bytes on GPU and host",
+            "peaks": {"hbm_GBps": hbm, "imad_wide_T_per_s": round(imad, 2), "cpu_threads": cores},
+            "algorithmic": {"ntt_bytes_per_element": 64, "imad_per_g1_point": IMAD_PER_G1_POINT, "imad_per_g2_point": 3 * IMAD_PER_G1_POINT},
+            "rows": rows}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -177,7 +363,10 @@ def main():
     ap.add_argument("--workload", default="send", choices=["send", "mixed1024", "sweep", "msm_split"])
     ap.add_argument("--logn", type=int, default=24, help="msm_split: log2 of the total number of points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip per-circuit latency table and NTT roofline")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-circuit latency table, the NTT roofline and the extra BASELINE.json configs "
+                    "(mixed1024, msm_split24, kernel sweep) that the default run appends to its JSON line")
+    ap.add_argument("--single-process", action="store_true", help="mixed1024: ONE process drives all --gpus devices through the library's own "
+                    "device scheduler (what an unchanged geth process gets); do not launch under torchrun")
     args = ap.parse_args()
     capture_stdout()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -206,129 +395,123 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    def finish(line):
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank == 0 and line is not None:
+            emit(line)
+
+    sampler = ClockSampler(local)
     if args.workload == "sweep":
-        if rank == 0:
-            emit((kernel_sweep(api)))
+        finish(kernel_sweep(api) if rank == 0 else None)
         return
     if args.workload == "msm_split":
-        msm_split(args, api, dist, rank, world, barrier)
+        res = run_msm_split(api, dist, rank, world, barrier, args.logn, max(1, args.steps // 50), sampler)
+        if rank == 0:
+            res.update({"value": res["g1"]["value"], "unit": "points/s", "ms_per_step": res["g1"]["ms_per_msm"], "higher_is_better": True, "data": "synthetic",
+                        "dtype": "u32", "config": {"workload": res["workload"]}})
+        finish(res if rank == 0 else None)
+        return
+    if args.workload == "mixed1024":
+        single = args.gpus if args.single_process else 0
+        if single:
+            assert world == 1, "--single-process is not launched under torchrun"
+            assert api.set_devices(list(range(single))) == single
+        res = run_mixed(api, F, rank, world, dist, barrier, 3, sampler, single)
+        if rank == 0:
+            res.update({"steps": 1, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"], "higher_is_better": True, "vs_baseline": None, "dtype": "u32",
+                        "data": "synthetic", "config": {"workload": WORKLOADS["mixed1024"], "detail": res["mode"]},
+                        "e2e": {"value": res["value"], "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": None})
+        finish(res if rank == 0 else None)
         return
 
-    circuits = ["send"] if args.workload == "send" else ["mint", "send", "deposit", "redeem"]
-    pks = {c: zk.ProvingKey(os.path.join(kd, c + "pk.txt")) for c in circuits}
-    pk = pks["send"]
+    # ---- default workload: send ---------------------------------------------------------------------------------------------------------
+    pk = zk.ProvingKey(os.path.join(kd, "sendpk.txt"))
     rng = random.Random(1000 + rank)
     r, s = rng.randrange(1, FR_MODULUS), rng.randrange(1, FR_MODULUS)      # pinned per rank
-    sampler = ClockSampler(local)
     windows = []
-
     from concurrent.futures import ThreadPoolExecutor
     depth = pk.lanes                       # proofs in flight per GPU (zkb200.h "lanes")
 
-    if args.workload == "send":
-        tx0 = F.synthetic("send", rank)
-        w0 = api.witness("send", tx0)
-        # ---- sequential pass (one proof at a time, L2 flushed before each): per-kernel CUDA-event times for the rooflines ----------
-        res = pk.prove(w0, r, s)
-        assert res["rc"] == 0
-        acc_ms, qap_ms, msm_ms, gpu_ms = [], [], [], []
-        for i in range(args.warmup + min(args.steps, 30)):
-            api.lib.zkb200_flush_l2()
-            res = pk.prove(None, r, s)
-            if i >= args.warmup:
-                gpu_ms.append(res["timings_ms"][0]); qap_ms.append(res["timings_ms"][1]); msm_ms.append(res["timings_ms"][2])
-        api.lib.zkb200_set_isolate_h(1)      # roofline: the H-query accumulate kernel timed with nothing beside it
-        for i in range(args.warmup + min(args.steps, 30)):
-            api.lib.zkb200_flush_l2()
-            res = pk.prove(None, r, s)
-            if i >= args.warmup:
-                acc_ms.append(res["timings_ms"][4])
-        api.lib.zkb200_set_isolate_h(0)
-        # ---- leg 1: `value` -- assignment resident in HBM, `depth` proofs in flight ------------------------------------------------
-        lanes = [pk.lane_acquire() for _ in range(depth)]
-        for ln in lanes:                     # make the assignment resident on every lane
-            pk.submit(ln, w0, r, s)
-        for ln in lanes:
-            assert pk.collect(ln)["rc"] == 0
-        for i in range(args.warmup):
-            pk.submit(lanes[i % depth], None, r, s); pk.collect(lanes[i % depth])
-        barrier()
-        api.lib.zkb200_device_timer(0)        # CUDA events on the device, bracketed by device synchronisations (and the barriers)
-        t0 = time.perf_counter()
-        launches, acc_inflight = 0, []
-        for i in range(args.steps):
-            ln = lanes[i % depth]
-            if i >= depth:
-                res = pk.collect(ln); launches += res["launches"]; acc_inflight.append(res["timings_ms"][4])
-            pk.submit(ln, None, r, s)
-        for i in range(args.steps, args.steps + min(depth, args.steps)):
-            res = pk.collect(lanes[i % depth]); launches += res["launches"]; acc_inflight.append(res["timings_ms"][4])
-        dev_ms = float(api.lib.zkb200_device_timer(1))
-        t1 = time.perf_counter()
-        barrier()
-        for ln in lanes:
-            pk.lane_release(ln)
-        windows.append((t0, t1))
-        wall_value = t1 - t0
-        units, dt = reduce_counts_and_time(args.steps, dev_ms * 1e-3, dist)
-        # ---- leg 2: `e2e` -- the cgo call a BlockMaze node makes, host string arguments in, proof string out; `depth` caller threads
-        #      (goroutines in geth), each call synchronous --------------------------------------------------------------------------
-        txs = [F.synthetic("send", rank + world * (i + 1)) for i in range(args.warmup + args.steps)]
-        lat, brk = [], []
-        for i in range(args.warmup + min(args.steps, 30)):          # single caller: latency and its breakdown
-            ta = time.perf_counter()
-            proof = api.gen_proof("send", txs[i])
-            if i >= args.warmup:
-                lat.append(time.perf_counter() - ta)
-                brk.append(api.last_breakdown_ms())
-        pool = ThreadPoolExecutor(depth)
-        list(pool.map(lambda tx: api.gen_proof("send", tx), txs[:args.warmup]))
-        barrier()
-        api.lib.zkb200_device_timer(0)
-        t2 = time.perf_counter()
-        proofs = list(pool.map(lambda tx: api.gen_proof("send", tx), txs[args.warmup:]))
-        dev_ms_e = float(api.lib.zkb200_device_timer(1))
-        t3 = time.perf_counter()
-        barrier()
-        pool.shutdown()
-        windows.append((t2, t3))
-        assert all(not p_.startswith("0000000000") for p_ in proofs + [proof]), "prover returned the default proof for a valid transaction"
-        units_e, dt_e = reduce_counts_and_time(args.steps, max(dev_ms_e * 1e-3, t3 - t2), dist)      # host work counts: the slower clock
-        nvars = pk.num_variables
-        workload = ("send circuit (%d constraints, %d variables, QAP domain 2^18): one Groth16 proof per step per GPU, %d proofs in flight; value = resident "
-                    "assignment through submit/collect, e2e = genSendproof() cgo calls from %d caller threads" % (CONSTRAINTS["send"], nvars, depth, depth))
-        d2h = 4 + sum(128 * (p + 1) * b for p, b in ((24, 4), (24, 4), (24, 4))) + 256 * 25 * 4 + 128 * 19 * 16
-    else:
-        # mixed batch of 1024 synthetic transactions, type = seed mod 4, sharded round-robin over the ranks (strong scaling)
-        names = ["mint", "send", "deposit", "redeem"]
-        mine = shard_batch(list(range(1024)), rank, world)
-        txs = [(names[sd % 4], F.synthetic(names[sd % 4], sd)) for sd in mine]
-        for c in names:
-            api.gen_proof(c, F.synthetic(c, 5000 + rank))
-        lat = []
+    tx0 = F.synthetic("send", rank)
+    w0 = api.witness("send", tx0)
+    # ---- sequential pass (one proof at a time, L2 flushed before each): per-kernel CUDA-event times for the rooflines ----------
+    res = pk.prove(w0, r, s)
+    assert res["rc"] == 0
+    proof0 = res["proof_hex"]
+    assert api.verify_proof("send", proof0, api.verify_args("send", tx0)), "the proof of the resident assignment does not verify"
+    acc_ms, qap_ms, msm_ms, gpu_ms = [], [], [], []
+    for i in range(args.warmup + min(args.steps, 30)):
+        api.lib.zkb200_flush_l2()
+        res = pk.prove(None, r, s)
+        if i >= args.warmup:
+            gpu_ms.append(res["timings_ms"][0]); qap_ms.append(res["timings_ms"][1]); msm_ms.append(res["timings_ms"][2])
+    api.lib.zkb200_set_isolate_h(1)      # roofline: the H-query accumulate kernel timed with nothing beside it
+    for i in range(args.warmup + min(args.steps, 30)):
+        api.lib.zkb200_flush_l2()
+        res = pk.prove(None, r, s)
+        if i >= args.warmup:
+            acc_ms.append(res["timings_ms"][4])
+    api.lib.zkb200_set_isolate_h(0)
+    # ---- leg 1: `value` -- assignment resident in HBM, `depth` proofs in flight ------------------------------------------------
+    lanes = [pk.lane_acquire() for _ in range(depth)]
+    for ln in lanes:                     # make the assignment resident on every lane
+        pk.submit(ln, w0, r, s)
+    for ln in lanes:
+        assert pk.collect(ln)["rc"] == 0
+    for i in range(args.warmup):
+        pk.submit(lanes[i % depth], None, r, s); pk.collect(lanes[i % depth])
+    barrier()
+    api.lib.zkb200_device_timer(0)        # CUDA events on the device, bracketed by device synchronisations (and the barriers)
+    t0 = time.perf_counter()
+    launches, acc_inflight, value_proofs = 0, [], set()
+    for i in range(args.steps):
+        ln = lanes[i % depth]
+        if i >= depth:
+            res = pk.collect(ln); launches += res["launches"]; acc_inflight.append(res["timings_ms"][4]); value_proofs.add(res["proof_hex"])
+        pk.submit(ln, None, r, s)
+    for i in range(args.steps, args.steps + min(depth, args.steps)):
+        res = pk.collect(lanes[i % depth]); launches += res["launches"]; acc_inflight.append(res["timings_ms"][4]); value_proofs.add(res["proof_hex"])
+    dev_ms = float(api.lib.zkb200_device_timer(1))
+    t1 = time.perf_counter()
+    barrier()
+    for ln in lanes:
+        pk.lane_release(ln)
+    assert value_proofs == {proof0}, "proofs of the timed `value` region differ from the verified proof of the same assignment, r and s"
+    windows.append((t0, t1))
+    wall_value = t1 - t0
+    units, dt = reduce_counts_and_time(args.steps, dev_ms * 1e-3, dist)
+    # ---- leg 2: `e2e` -- the cgo call a BlockMaze node makes, host string arguments in, proof string out; `depth` caller threads
+    #      (goroutines in geth), each call synchronous --------------------------------------------------------------------------
+    txs = [F.synthetic("send", rank + world * (i + 1)) for i in range(args.warmup + args.steps)]
+    lat, brk = [], []
+    for i in range(args.warmup + min(args.steps, 30)):          # single caller: latency and its breakdown
+        ta = time.perf_counter()
+        api.gen_proof("send", txs[i])
+        if i >= args.warmup:
+            lat.append(time.perf_counter() - ta)
+            brk.append(api.last_breakdown_ms())
+    pool = ThreadPoolExecutor(depth)
+    list(pool.map(lambda tx: api.gen_proof("send", tx), txs[:args.warmup]))
+    barrier()
+    api.lib.zkb200_device_timer(0)
+    t2 = time.perf_counter()
+    proofs = list(pool.map(lambda tx: api.gen_proof("send", tx), txs[args.warmup:]))
+    dev_ms_e = float(api.lib.zkb200_device_timer(1))
+    t3 = time.perf_counter()
+    barrier()
+    pool.shutdown()
+    windows.append((t2, t3))
+    assert all(not p_.startswith("0000000000") for p_ in proofs), "prover returned the default proof for a valid transaction"
+    verified = verify_sample(api, "send", txs[args.warmup:], proofs, 8)
+    units_e, dt_e = reduce_counts_and_time(args.steps, max(dev_ms_e * 1e-3, t3 - t2), dist)      # host work counts: the slower clock
+    nvars = pk.num_variables
+    workload = ("send circuit (%d constraints, %d variables, QAP domain 2^18): one Groth16 proof per step per GPU, %d proofs in flight; value = resident "
+                "assignment through submit/collect, e2e = genSendproof() cgo calls from %d caller threads" % (CONSTRAINTS["send"], nvars, depth, depth))
+    d2h = 4 + sum(128 * (p + 1) * b for p, b in ((24, 4), (24, 4), (24, 4))) + 256 * 25 * 4 + 128 * 19 * 16
+    clocks = sampler.stats(windows)
 
-        def one(ctx):
-            ta = time.perf_counter(); api.gen_proof(ctx[0], ctx[1]); return time.perf_counter() - ta
-        pool = ThreadPoolExecutor(depth)
-        list(pool.map(one, [(c, F.synthetic(c, 6000 + rank)) for c in names] * 2))
-        barrier()
-        api.lib.zkb200_device_timer(0)
-        t0 = time.perf_counter()
-        lat = list(pool.map(one, txs))
-        dev_ms = float(api.lib.zkb200_device_timer(1))
-        t1 = time.perf_counter()
-        barrier()
-        pool.shutdown()
-        windows.append((t0, t1))
-        units, dt = reduce_counts_and_time(len(txs), max(dev_ms * 1e-3, t1 - t0), dist)
-        units_e, dt_e, launches, acc_ms, qap_ms, msm_ms, gpu_ms, brk, acc_inflight = units, dt, 0, [0.0], [0.0], [0.0], [0.0], [], []
-        args.steps = 1
-        nvars = 0
-        workload = ("mixed batch of 1024 synthetic mint/send/deposit/redeem transactions (256 each) sharded round-robin over the GPUs, through gen*proof() "
-                    "from %d caller threads per GPU" % depth)
-        d2h = 0
-
-    clocks = sampler.stop(windows)
     extras = {}
     if rank == 0 and not args.no_extras:
         # p50 end-to-end latency per circuit through the cgo surface (BASELINE.json metric, configs[0..3])
@@ -337,23 +520,20 @@ def main():
             if not os.path.exists(os.path.join(kd, c + "pk.txt")):
                 continue
             ts = []
-            for i in range(7):
+            for i in range(9):
                 tx = F.synthetic(c, 9000 + i)
                 ta = time.perf_counter(); api.gen_proof(c, tx); ts.append(1e3 * (time.perf_counter() - ta))
             per[c] = round(statistics.median(ts[2:]), 3)
         extras["p50_latency_ms_per_circuit_e2e"] = per
         # NTT roofline at a size that does not fit L2 (2^24 x 32 B = 512 MB): algorithmic bytes 64*n per transform
         ms_ntt = api.lib.zkb200_bench_ntt(24, 1, 5)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
+        peaks = measured_peaks()
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         ach = 64.0 * (1 << 24) / (ms_ntt * 1e-3) / 1e9
-        extras["roofline_ntt"] = {"bound": "hbm", "kernel": "ntt_pass_kernel x3 (2^24-point forward NTT)", "achieved": round(ach, 1), "peak": hbm_peak,
+        prof = load_fma_count() or {}
+        extras["roofline_ntt"] = {"bound": "hbm", "kernel": "ntt passes of one 2^24-point forward NTT", "achieved": round(ach, 1), "peak": hbm_peak,
                                   "unit": "GB/s", "frac": round(ach / hbm_peak, 4),
-                                  "traffic": {"dram_bytes_per_transform": 4010000000, "source": "profiles/r01_notes.md (B) (ncu --set full of the three passes: 2.54 GB read + 1.47 GB written)"},
+                                  "traffic": prof.get("ntt24_dram_bytes", {"dram_bytes_per_transform": 4010000000, "source": "profiles/r01_notes.md (B)"}),
                                   "ms": round(ms_ntt, 4),
                                   "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
         mm_peak = 1e3 * float(api.lib.zkb200_bench_imad_peak(2))
@@ -371,133 +551,79 @@ def main():
         n_h = DOMAIN["send"] - 1
         ach = IMAD_PER_G1_POINT * n_h / (acc_avg * 1e-3) / 1e12 if acc_avg > 0 else 0.0
         modmul_rate = MODMUL_PER_G1_ADD * 16 * n_h / (acc_avg * 1e-3) / 1e9 if acc_avg > 0 else 0.0
+        msm_h_avg = statistics.mean(msm_ms)
+        prof = load_fma_count() or {}
+        fma_instr = prof.get("fma_pipe_warp_instr_per_send_proof")
+        sm_mhz = clocks.get("sm_mhz") or measured_peaks().get("sm_max_mhz", 1965.0)
+        step_ms = 1e3 * dt / args.steps
+        nominal = 148 * 128 * sm_mhz * 1e6 / 4 / 1e12      # 148 SMs x 128 lanes, one wide multiply-add per lane every 4 clocks
         line = {
             "metric": "proofs_per_sec", "value": units / dt, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload == "send" else "strong",
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "detail": workload, "l2": "no flush in the timed loops: every proof streams ~0.6 GB of fixed-base tables (all 16 windows of the H, A, B, L queries), "
+            "config": {"workload": WORKLOADS["send"], "detail": workload, "l2": "no flush in the timed loops: every proof streams ~0.6 GB of fixed-base tables (all 16 windows of the H, A, B, L queries), "
                              "5x the 126 MB L2; the sequential pass behind gpu_ms_per_proof and the rooflines flushes L2 (256 MB memset) before every proof",
                        "proofs_in_flight": depth,
                        "timing": "value: CUDA events after device synchronisations around the K steps (wall clock of the same region: %.3f ms/step); "
-                                 "e2e: max(that, wall clock), host work included; max over ranks" % (1e3 * wall_value / max(1, args.steps)) if args.workload == "send" else "max(CUDA events after device synchronisations, wall clock) around the batch, host work included; max over ranks",
-                       "randomness": "r, s pinned per rank"},
+                                 "e2e: max(that, wall clock), host work included; max over ranks" % (1e3 * wall_value / max(1, args.steps)),
+                       "randomness": "value leg: r, s pinned per rank; e2e leg: fresh r, s per proof (std::random_device)",
+                       "checked": "value leg: every proof of the timed region equals the proof of the same (assignment, r, s) made beforehand, which verifySendproof accepts; "
+                                  "e2e leg: %d of the timed proofs, spread over the region, pass verifySendproof" % verified},
             "clocks": clocks,
-            "e2e": {"value": units_e / dt_e, "unit": "proofs/s", "h2d_bytes_per_step": (nvars + 1) * 8 + 40 * 8 if nvars else 0, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": units_e / dt_e, "unit": "proofs/s", "h2d_bytes_per_step": (nvars + 1) * 8 + 40 * 8, "d2h_bytes_per_step": d2h,
                     "p50_latency_ms": round(1e3 * statistics.median(lat), 3),
-                    "breakdown_ms": {k: round(statistics.median(b[k] for b in brk), 3) for k in brk[0]} if args.workload == "send" else None},
+                    "breakdown_ms": {k: round(statistics.median(b[k] for b in brk), 3) for k in brk[0]}},
             "gpu_launches": launches,
             "gpu_ms_per_proof": {"what": "one proof at a time, CUDA events", "total": round(statistics.mean(gpu_ms), 3), "qap_witness_map": round(statistics.mean(qap_ms), 3),
-                                 "msm_H": round(statistics.mean(msm_ms), 3), "msm_H_accumulate_kernel_alone": round(acc_avg, 3)},
+                                 "msm_H": round(msm_h_avg, 3), "msm_H_accumulate_kernel_alone": round(acc_avg, 3)},
             "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel<Fq> (H query, %d points), timed alone after an L2 flush" % n_h, "achieved": round(ach, 3), "peak": round(imad_peak, 2),
                          "unit": "TIMAD/s", "frac": round(ach / imad_peak, 4) if imad_peak else None,
-                         "traffic": {"dram_bytes_per_launch": 501680000, "source": "profiles/r01_notes.md (B) (ncu --set full: dram__bytes_read.sum 487.22 MB + dram__bytes_write.sum 14.46 MB of this launch)"},
+                         "traffic": prof.get("acc_h_dram_bytes", {"dram_bytes_per_launch": 501680000, "source": "profiles/r01_notes.md (B)"}),
+                         "nominal_peak": {"value": round(nominal, 2), "what": "148 SMs x 128 lanes x %.0f MHz / 4 clocks per wide multiply-add" % sm_mhz,
+                                          "frac": round(ach / nominal, 4) if nominal else None},
                          "issued": {"modmul_G_per_s": round(modmul_rate, 2), "modmul_peak_G_per_s": round(pk_["modmul_G"], 2),
                                     "frac": round(modmul_rate / pk_["modmul_G"], 4) if pk_["modmul_G"] else None,
                                     "what": "modular multiplications the kernel really issues (10 per mixed addition, 16 per point) against a kernel of back-to-back ff.cuh multiplications"},
-                         "timed_region": {"kernel_ms_avg": round(statistics.mean(acc_inflight), 3) if args.workload == "send" and acc_inflight else None,
+                         "timed_region": {"kernel_ms_avg": round(statistics.mean(acc_inflight), 3) if acc_inflight else None,
                                           "frac": round(IMAD_PER_G1_POINT * n_h / (statistics.mean(acc_inflight) * 1e-3) / 1e12 / imad_peak, 4)
-                                          if args.workload == "send" and acc_inflight and imad_peak else None,
+                                          if acc_inflight and imad_peak else None,
                                           "what": "the same kernel timed by CUDA events on its stream inside the timed region of `value`, where it shares the SMs "
                                                   "with the kernels of the other proofs in flight (so this is a lower bound of its own efficiency)"},
+                         "whole_msm_frac": {"value": round(IMAD_PER_G1_POINT * n_h / (msm_h_avg * 1e-3) / 1e12 / imad_peak, 4) if imad_peak and msm_h_avg else None,
+                                            "what": "the same algorithmic count over the WHOLE H-query MSM of a proof running alone (digit sort + accumulate + fold + bucket reduction, %.3f ms)" % msm_h_avg},
+                         "step_multiply_pipe_util": {"value": round(fma_instr * 32 / (imad_peak * 1e12) / (step_ms * 1e-3), 4) if fma_instr and imad_peak else None,
+                                                     "fma_pipe_warp_instr_per_proof": fma_instr,
+                                                     "what": "FMA-pipe warp instructions of one send proof (ncu, profiles/r02_fma_pipe.json) x 32 lanes / measured wide-IMAD peak / ms_per_step: "
+                                                             "how busy the multiply pipe is over a pipelined step if every one of them were a wide multiply-add"},
                          "peaks": {k: round(v, 2) for k, v in pk_.items()},
                          "note": "integer-multiply roofline (SURVEY.md 8d): algorithmic 23936 wide multiply-adds per point / CUDA-event kernel time; "
                                  "peak = carry-chained mad.lo.cc/madc.hi.cc (IMAD.WIDE.U32.X) microbenchmark in this run.  The algorithmic figure counts the reference's "
                                  "mixed addition (7M+4S = 11 multiplications); the kernel's XYZZ addition needs 10, so this ratio tops out at 1.10 -- 'issued' is the strict one"},
         }
         line.update(extras)
-        if world == 1 and not args.no_cpu_baseline and args.workload == "send":
+        if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank == 0:
-        emit((line))
-
-
-def kernel_sweep(api):
-    """BASELINE.json configs[4]: BN254 G1/G2 MSM and Fr NTT at 2^16..2^24 on one GPU, next to libff multi_exp / libfqfft FFT on the host
-    cores (CPU legs up to 2^20: beyond that they take minutes)."""
-    import ctypes as C
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    hbm = peaks.get("hbm_gbs", 6650.0)
-    imad = float(api.lib.zkb200_bench_imad_peak(1))
-    cpu = None
-    try:
-        from oracle import refapi as Rf
-        if Rf.available("kernels_mt"):
-            os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
-            cpu = Rf.lib("kernels_mt")
-            cpu.ref_fft_seconds.restype = C.c_double
-            cpu.ref_msm_g1_seconds.restype = C.c_double
-    except Exception:
-        cpu = None
-    rows = []
-    for lg in (16, 18, 20, 22, 24):
-        n = 1 << lg
-        row = {"log2_n": lg}
-        ms = float(api.lib.zkb200_bench_ntt(lg, 1, 5))
-        row["ntt_ms"] = round(ms, 4)
-        row["ntt_GBps"] = round(64.0 * n / (ms * 1e-3) / 1e9, 1)
-        row["ntt_frac_of_hbm"] = round(row["ntt_GBps"] / hbm, 4)
-        ms = float(api.lib.zkb200_bench_msm(1, n, 0, 2))
-        row["msm_g1_ms"] = round(ms, 3)
-        row["msm_g1_TIMADps"] = round(IMAD_PER_G1_POINT * n / (ms * 1e-3) / 1e12, 3)
-        row["msm_g1_frac_of_imad"] = round(row["msm_g1_TIMADps"] / imad, 4)
-        ms = float(api.lib.zkb200_bench_msm(1, n, -16, 2))
-        row["msm_g1_fixed_base_ms"] = round(ms, 3)
-        row["msm_g1_fixed_base_frac_of_imad"] = round(IMAD_PER_G1_POINT * n / (ms * 1e-3) / 1e12 / imad, 4)
-        if lg <= 22:
-            ms = float(api.lib.zkb200_bench_msm(2, n, 0, 2))
-            row["msm_g2_ms"] = round(ms, 3)
-            row["msm_g2_frac_of_imad"] = round(3 * IMAD_PER_G1_POINT * n / (ms * 1e-3) / 1e12 / imad, 4)
-        if cpu is not None and lg <= 20:
-            row["cpu_fft_s"] = round(cpu.ref_fft_seconds(C.c_size_t(n), 1), 4)
-            row["cpu_msm_g1_s"] = round(cpu.ref_msm_g1_seconds(C.c_size_t(n), C.c_size_t(0)), 3)
-        rows.append(row)
-    return {"metric": "kernel_sweep", "unit": "ms", "n_gpus": 1, "data": "synthetic (splitmix64 scalars < 2^253, bases k_i*G)",
-            "peaks": {"hbm_GBps": hbm, "imad_T_per_s": round(imad, 2), "cpu_threads": int(os.environ.get("OMP_NUM_THREADS", "0") or 0)},
-            "algorithmic": {"ntt_bytes_per_element": 64, "imad_per_g1_point": IMAD_PER_G1_POINT, "imad_per_g2_point": 3 * IMAD_PER_G1_POINT},
-            "rows": rows}
-
-
-def msm_split(args, api, dist, rank, world, barrier):
-    """BASELINE.json configs[4], second half: ONE large G1 MSM split by point range over the GPUs; every GPU returns one partial point
-    and rank 0 adds them on the host (no collective on the data path; the 64-byte points travel through the rendezvous gather)."""
-    n = 1 << args.logn
-    per = n // world
-    first, count = rank * per, (per if rank < world - 1 else n - per * (world - 1))
-    import ctypes as C
-    out = C.create_string_buffer(64)
-    api.lib.zkb200_bench_msm_slice(1, first, count, 0, 1, out)          # warm-up, also builds the slice
-    barrier()
-    t0 = time.perf_counter()
-    ms = float(api.lib.zkb200_bench_msm_slice(1, first, count, 0, max(1, args.steps // 4), out))
-    barrier()
-    units, tmax = reduce_counts_and_time(count, ms * 1e-3, dist)
-    pts = [out.raw]
-    if dist is not None:
-        gathered = [None] * world
-        dist.all_gather_object(gathered, out.raw)
-        pts = gathered
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank == 0:
-        total = api.g1_sum(pts)                 # one partial point per GPU, summed on the host (zkb200_g1_sum)
-        emit(({"metric": "msm_points_per_sec", "value": units / tmax, "unit": "points/s", "n_gpus": world, "ms_per_step": 1e3 * tmax,
-                          "higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "u32",
-                          "config": {"workload": "single G1 MSM of 2^%d points split by point range, one partial point per GPU summed on the host" % args.logn},
-                          "result_x": "%064x" % int.from_bytes(total[:32], "little")}))
+    pk.close()
+    # ---- the other BASELINE.json configs, appended to the same line so that the driver's runs (N = 1, 2, 4, 8) carry them ------------------
+    if not args.no_extras:
+        mixed = run_mixed(api, F, rank, world, dist, barrier, depth, sampler)
+        split = run_msm_split(api, dist, rank, world, barrier, 24, 3, sampler)
+        if rank == 0:
+            line["mixed1024"] = mixed
+            imad_peak = line["roofline"]["peak"]
+            for name, per_point in (("g1", IMAD_PER_G1_POINT), ("g2", 3 * IMAD_PER_G1_POINT)):
+                split[name]["frac_of_imad_peak"] = round(per_point * split[name]["value"] / 1e12 / (imad_peak * world), 4) if imad_peak else None
+            line["msm_split24"] = split
+            if world == 1:
+                line["kernel_sweep"] = kernel_sweep(api)
+    finish(line)
 
 
 def cpu_baseline():
     """Reference libsnark prover (MULTICORE) on this box's host cores: one send proof, pk load excluded."""
     code = ("import sys,os,json,time; sys.path.insert(0,%r); sys.path.insert(0,%r)\n"
             "from oracle import refapi as Rf, bn254_oracle as O; import fixtures as F\n"
-            "os.environ.setdefault('OMP_NUM_THREADS', str(os.cpu_count() or 1))\n"
+            "os.environ['OMP_NUM_THREADS'] = str(len(os.sched_getaffinity(0)))\n"
             "Rf.load_pk('send', os.path.join(%r,'sendpk.txt'), mt=True)\n"
             "w=O.fixed_rng_words(42,64); Rf.prove('send',F.synthetic('send',0),w,mt=True)\n"
             "t=time.perf_counter(); n=3\n"

@@ -66,6 +66,14 @@ class Tx(C.Structure):
 
 lib.zkb200_prove_batch.argtypes = [C.c_size_t, C.POINTER(Tx), C.c_char_p, C.c_int]
 
+
+class VTx(C.Structure):
+    """zkb200_vtx: one proof of a zkb200_verify_batch call."""
+    _fields_ = [("circuit", C.c_int), ("value_s", C.c_uint64), ("proof", C.c_char_p), ("s", C.c_char_p * 6)]
+
+
+lib.zkb200_verify_batch.argtypes = [C.c_size_t, C.POINTER(VTx), C.c_char_p, C.c_int]
+
 # gen<Circuit>proof argument types (SRC/<c>/<c>cgo.hpp) and verify<Circuit>proof argument types
 GEN_SIGS = {
     "mint": [C.c_uint64, C.c_uint64] + [C.c_char_p] * 6 + [C.c_uint64, C.c_char_p],
@@ -274,6 +282,24 @@ def last_breakdown_ms():
 
 def verify_proof(circuit, proof_hex, args):
     return bool(getattr(lib, "verify%sproof" % circuit.capitalize())(proof_hex.encode(), *_enc(args)))
+
+
+def verify_batch(items, threads=0):
+    """items: (circuit, proof_hex, verify<Circuit>proof arguments after the proof).  One random-linear-combination check for the whole
+    batch (zkb200_verify_batch); returns the list of per-proof verdicts."""
+    arr = (VTx * max(1, len(items)))()
+    for t, (c, proof, args) in zip(arr, items):
+        t.circuit = CIRCUITS.index(c)
+        t.proof = proof.encode()
+        strs = [a for a in args if not isinstance(a, int)]
+        for i, v in enumerate(strs):
+            t.s[i] = v.encode()
+        ints = [a for a in args if isinstance(a, int)]
+        t.value_s = ints[0] if ints else 0
+    ok = C.create_string_buffer(max(1, len(items)))
+    if lib.zkb200_verify_batch(len(items), arr, ok, threads) < 0:
+        raise ZkError("zkb200_verify_batch: bad arguments or unreadable verification key")
+    return [bool(b) for b in ok.raw[:len(items)]]
 
 
 def verify_args(circuit, gen_args):

@@ -12,7 +12,9 @@
 #include <fstream>
 #include <memory>
 #include <mutex>
+#include <random>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/zkb200.h"
 #include "host_field.hpp"
@@ -355,50 +357,224 @@ static void push_blob(std::vector<bool> &b, const uint8_t *blob, size_t nbytes) 
 }
 static void push_u64(std::vector<bool> &b, uint64_t v) { uint8_t le[8]; for (int i = 0; i < 8; i++) le[i] = (uint8_t)(v >> (8 * i)); push_blob(b, le, 8); }
 
-static bool verify(int circuit, const char *proof, const std::vector<bool> &input_bits) {
-    std::shared_ptr<const VerificationKey> held;                       // concurrent verifications share the key and do not hold the lock
-    {
-        std::lock_guard<std::mutex> lk(g_vk_mu);
-        const std::string dir = key_dir_now();
-        if (!g_vk[circuit] || !g_vk[circuit]->ok || g_vk_dir[circuit] != dir) {
-            std::ifstream fh(dir + "/" + NAMES[circuit] + "vk.txt", std::ios::binary);
-            std::string data((std::istreambuf_iterator<char>(fh)), std::istreambuf_iterator<char>());
-            g_vk[circuit] = std::make_shared<const VerificationKey>(parse_vk(data));
-            g_vk_dir[circuit] = dir;
-            if (!g_vk[circuit]->ok) { fprintf(stderr, "zkb200: cannot read verification key %s/%svk.txt\n", dir.c_str(), NAMES[circuit]); return false; }
-        }
-        held = g_vk[circuit];
+static std::shared_ptr<const VerificationKey> vk_for(int circuit) {        // concurrent verifications share the key and do not hold the lock
+    std::lock_guard<std::mutex> lk(g_vk_mu);
+    const std::string dir = key_dir_now();
+    if (!g_vk[circuit] || !g_vk[circuit]->ok || g_vk_dir[circuit] != dir) {
+        std::ifstream fh(dir + "/" + NAMES[circuit] + "vk.txt", std::ios::binary);
+        std::string data((std::istreambuf_iterator<char>(fh)), std::istreambuf_iterator<char>());
+        g_vk[circuit] = std::make_shared<const VerificationKey>(parse_vk(data));
+        g_vk_dir[circuit] = dir;
+        if (!g_vk[circuit]->ok) { fprintf(stderr, "zkb200: cannot read verification key %s/%svk.txt\n", dir.c_str(), NAMES[circuit]); return nullptr; }
     }
-    const VerificationKey &vk = *held;
+    return g_vk[circuit];
+}
+struct ParsedProof { HG1Affine A, C; HG2Affine B; };
+// proof string -> points; false when the string is malformed or a point is off its curve (proof.is_well_formed(), r1cs_gg_ppzksnark.tcc:537-541)
+static bool parse_proof(const char *proof, ParsedProof &out) {
     if (!proof || strnlen(proof, 512) < 512) return false;
     HFq c[8];
     for (int i = 0; i < 8; i++) if (!hex_fq(proof + 64 * i, c[i])) return false;
-    const HG1Affine A{c[0], c[1]}, Cp{c[6], c[7]};
-    const HG2Affine B{HFq2{c[3], c[2]}, HFq2{c[5], c[4]}};            // string order is c1 then c0 (mintcgo.cpp:150-169)
-    // proof.is_well_formed(): every point on its curve
+    out.A = HG1Affine{c[0], c[1]}; out.C = HG1Affine{c[6], c[7]};
+    out.B = HG2Affine{HFq2{c[3], c[2]}, HFq2{c[5], c[4]}};            // string order is c1 then c0 (mintcgo.cpp:150-169)
     const HFq three = HFq::from_u64(3);
-    if (!(A.y.sqr() == A.x.sqr() * A.x + three) || !(Cp.y.sqr() == Cp.x.sqr() * Cp.x + three)) return false;
-    if (!(B.y.sqr() == B.x.sqr() * B.x + twist_b())) return false;
-    const std::vector<HFr> inputs = pack_bits(input_bits);
-    if (inputs.size() + 1 != vk.gamma_abc.size()) return false;
-    HG1 acc = HG1::from_affine(vk.gamma_abc[0]);
-    for (size_t i = 0; i < inputs.size(); i++) {                        // accumulate(): sum of input_i * gamma_ABC[i + 1], fixed-base windows
-        uint64_t k[4]; inputs[i].to_canonical(k);
+    if (!(out.A.y.sqr() == out.A.x.sqr() * out.A.x + three) || !(out.C.y.sqr() == out.C.x.sqr() * out.C.x + three)) return false;
+    return out.B.y.sqr() == out.B.x.sqr() * out.B.x + twist_b();
+}
+// sum of k[i] * gamma_ABC[i + 1] over the fixed-base tables of the key (accumulate(), r1cs_gg_ppzksnark.tcc:549-553)
+static HG1 abc_combination(const VerificationKey &vk, const std::vector<HFr> &k_mont, HG1 acc) {
+    for (size_t i = 0; i < k_mont.size(); i++) {
+        uint64_t k[4]; k_mont[i].to_canonical(k);
         const FixedBase &fb = vk.abc_tab[i];
         for (int w = 0; w < 64; w++) {
             const unsigned d = (unsigned)((k[w >> 4] >> ((w & 15) * 4)) & 15);
             if (d) acc = acc.add(fb.tab[w * 15 + d - 1]);
         }
     }
-    const HG1Affine acc_a = acc.to_affine();
+    return acc;
+}
+static bool check_one(const VerificationKey &vk, const ParsedProof &pp, const std::vector<HFr> &inputs) {
+    if (inputs.size() + 1 != vk.gamma_abc.size()) return false;
+    const HG1Affine acc_a = abc_combination(vk, inputs, HG1::from_affine(vk.gamma_abc[0])).to_affine();
     // e(A, B) == alpha_beta * e(acc, gamma) * e(C, delta)   <=>   FE( ML(A,B) * ML(-acc,gamma) * ML(-C,delta) ) == alpha_beta:
     // one Miller loop over the three pairs (one Fq12 squaring per bit for all of them), one final exponentiation
-    const G2Prepared b_prep = prepare_g2(B);
-    std::vector<HG1Affine> Ps{A}; std::vector<const G2Prepared *> Qs{&b_prep};
+    const G2Prepared b_prep = prepare_g2(pp.B);
+    std::vector<HG1Affine> Ps{pp.A}; std::vector<const G2Prepared *> Qs{&b_prep};
     if (!acc_a.is_inf()) { Ps.push_back(HG1Affine{acc_a.x, acc_a.y.neg()}); Qs.push_back(&vk.gamma_prep); }
-    Ps.push_back(HG1Affine{Cp.x, Cp.y.neg()}); Qs.push_back(&vk.delta_prep);
+    Ps.push_back(HG1Affine{pp.C.x, pp.C.y.neg()}); Qs.push_back(&vk.delta_prep);
     return final_exponentiation(multi_miller(Ps, Qs)) == vk.alpha_beta;
 }
+static bool verify(int circuit, const char *proof, const std::vector<bool> &input_bits) {
+    const std::shared_ptr<const VerificationKey> held = vk_for(circuit);
+    if (!held) return false;
+    ParsedProof pp;
+    if (!parse_proof(proof, pp)) return false;
+    return check_one(*held, pp, pack_bits(input_bits));
+}
+
+// public-input bits of one verify<Circuit>proof call: the blobs in argument order (value_s last for mint / redeem), exactly as the
+// four entry points below pack them
+static std::vector<bool> input_bits_of(int circuit, const char *const *s, uint64_t value_s) {
+    std::vector<bool> bits;
+    uint8_t blob[32];
+    if (circuit == ZKB200_DEPOSIT) {            // RT, pk (20 bytes), cmtB_old, sn_old, cmtB, sn_s
+        for (int i = 0; i < 6; i++) { const size_t nb = i == 1 ? 20 : 32; zkw::parse_hex_blob(s[i], blob, nb); push_blob(bits, blob, nb); }
+        return bits;
+    }
+    const int n = circuit == ZKB200_SEND ? 4 : 3;
+    for (int i = 0; i < n; i++) { zkw::parse_hex_blob(s[i], blob, 32); push_blob(bits, blob, 32); }
+    if (circuit != ZKB200_SEND) push_u64(bits, value_s);
+    return bits;
+}
+
+// ---- batch verification ------------------------------------------------------------------------------------------------------------
+// Every BlockMaze node verifies each zk transaction twice, in the pool and at block import (core/tx_pool.go:619-641,
+// core/state_processor.go:113-158), one r1cs_gg_ppzksnark_verifier_strong_IC call each (r1cs_gg_ppzksnark.tcc:524-623): three Miller loops and
+// a final exponentiation per proof.  A block's worth of proofs is checked here with ONE final exponentiation: with random 128-bit z_i,
+//     prod_i e(z_i A_i, B_i) * prod_c [ e(-sum_i z_i acc_i, gamma_c) * e(-sum_i z_i C_i, delta_c) ]  ==  prod_c alpha_beta_c ^ (sum_i z_i)
+// (c runs over the circuits present; sum_i z_i acc_i is one fixed-base combination per circuit because the z_i fold into the input
+// scalars).  Per proof that leaves one Miller loop and two 128-bit G1 multiplications.  The verdicts are those of the per-proof check:
+// malformed proofs are rejected up front as there, a B outside the order-r subgroup (where the pairing is not bilinear and the
+// combination proves nothing) is sent to the per-proof check, and if the combined equation fails every proof is checked on its own, so
+// the only difference is a 2^-128 chance of accepting a batch that holds an invalid proof.
+// Membership of Q in E'(Fq2) in the order-r subgroup.  By definition [r]Q = O; on a BN curve the twisted Frobenius psi acts on G2 as
+// multiplication by q = t - 1 = 6z^2 (mod r), and psi(Q) = [6z^2]Q holds ONLY on G2 (El Housni, Guillevic, Piellard, "Co-factor clearing and
+// subgroup membership testing on pairing-friendly curves", 2022, section 4.3), so a 127-bit multiplication replaces the 254-bit one.
+// psi = alt_bn128_G2::mul_by_q (alt_bn128_g2.cpp: x^q * xi^((q-1)/3), y^q * xi^((q-1)/2)), the map prepare_g2() uses for Q1.
+static const uint64_t FR_ORDER[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+static const uint64_t SIX_Z_SQUARED[4] = {0xf83e9682e87cfd46ull, 0x6f4d8248eeb859fbull, 0, 0};       // 6 * 4965661367192848881^2
+static bool g2_in_subgroup_by_order(const HG2Affine &Q) { return HG2::from_affine(Q).mul(FR_ORDER).is_inf(); }
+static bool g2_in_subgroup(const HG2Affine &Q) {
+    const Frob &F = frob();
+    const HG2Affine psi{conj2(Q.x) * F.g2, conj2(Q.y) * F.g3};
+    const HG2Affine m = HG2::from_affine(Q).mul(SIX_Z_SQUARED).to_affine();
+    return !m.is_inf() && m.x == psi.x && m.y == psi.y;
+}
+static Fq12 pow_cyclotomic(const Fq12 &a, const uint64_t e[4]) {          // a in the cyclotomic subgroup (a pairing value)
+    Fq12 r = Fq12::one();
+    bool started = false;
+    for (int i = 255; i >= 0; i--) {
+        if (started) r = cyclotomic_sqr(r);
+        if ((e[i >> 6] >> (i & 63)) & 1) { r = started ? mul(r, a) : a; started = true; }
+    }
+    return r;
+}
+struct BatchItem { int circuit; ParsedProof pp; std::vector<HFr> inputs; uint64_t z[2]; };
+struct BatchPartial {                       // what one worker thread contributes
+    Fq12 f = Fq12::one();
+    HG1 sumC[4] = {HG1::inf(), HG1::inf(), HG1::inf(), HG1::inf()};
+};
+static void batch_worker(const std::vector<BatchItem *> &items, size_t lo, size_t hi, BatchPartial &out) {
+    // Miller loops of a few proofs at a time share their Fq12 squarings
+    const size_t GROUP = 8;
+    for (size_t g = lo; g < hi; g += GROUP) {
+        const size_t ge = g + GROUP < hi ? g + GROUP : hi;
+        std::vector<G2Prepared> prep; prep.reserve(ge - g);
+        std::vector<HG1Affine> Ps; std::vector<const G2Prepared *> Qs;
+        for (size_t i = g; i < ge; i++) {
+            const BatchItem &it = *items[i];
+            const uint64_t z[4] = {it.z[0], it.z[1], 0, 0};
+            Ps.push_back(HG1::from_affine(it.pp.A).mul(z).to_affine());
+            prep.push_back(prepare_g2(it.pp.B));
+            out.sumC[it.circuit] = out.sumC[it.circuit].add(HG1::from_affine(it.pp.C).mul(z));
+        }
+        for (const G2Prepared &p : prep) Qs.push_back(&p);
+        std::vector<HG1Affine> P2; std::vector<const G2Prepared *> Q2;
+        for (size_t k = 0; k < Ps.size(); k++) if (!Ps[k].is_inf()) { P2.push_back(Ps[k]); Q2.push_back(Qs[k]); }
+        if (!P2.empty()) out.f = mul(out.f, multi_miller(P2, Q2));
+    }
+}
+} // namespace
+
+// test hook: both membership tests on one point (128 B canonical, on the twist curve); bit 0 = endomorphism test, bit 1 = [r]Q = O
+int zkb200_g2_subgroup_check(const uint8_t point[128]) {
+    uint64_t c[16]; memcpy(c, point, 128);
+    const HG2Affine Q{HFq2{HFq::from_canonical(c), HFq::from_canonical(c + 4)}, HFq2{HFq::from_canonical(c + 8), HFq::from_canonical(c + 12)}};
+    return (g2_in_subgroup(Q) ? 1 : 0) | (g2_in_subgroup_by_order(Q) ? 2 : 0);
+}
+
+int zkb200_verify_batch(size_t n, const zkb200_vtx *items, uint8_t *ok, int threads) {
+    if (n && (!items || !ok)) return -1;
+    for (size_t i = 0; i < n; i++) { ok[i] = 0; if (items[i].circuit < 0 || items[i].circuit > 3) return -1; }
+    std::shared_ptr<const VerificationKey> vks[4];
+    std::vector<BatchItem> parsed(n);
+    std::vector<BatchItem *> batch;                 // well-formed, B in the subgroup, input count right
+    std::vector<size_t> batch_idx, single_idx;
+    std::random_device rd;
+    for (size_t i = 0; i < n; i++) {
+        const int c = items[i].circuit;
+        if (!vks[c]) vks[c] = vk_for(c);
+        if (!vks[c]) return -1;
+        BatchItem &it = parsed[i];
+        it.circuit = c;
+        if (!parse_proof(items[i].proof, it.pp)) continue;                          // verdict 0, as the per-proof check
+        it.inputs = pack_bits(input_bits_of(c, items[i].s, items[i].value_s));
+        if (it.inputs.size() + 1 != vks[c]->gamma_abc.size()) continue;
+        if (!g2_in_subgroup(it.pp.B)) { single_idx.push_back(i); continue; }
+        do { it.z[0] = ((uint64_t)rd() << 32) | rd(); it.z[1] = ((uint64_t)rd() << 32) | rd(); } while (!(it.z[0] | it.z[1]));
+        batch.push_back(&it); batch_idx.push_back(i);
+    }
+    bool batch_ok = true;
+    if (batch.size() == 1) { single_idx.push_back(batch_idx[0]); batch.clear(); batch_idx.clear(); }
+    if (!batch.empty()) {
+        if (threads <= 0) { threads = (int)std::thread::hardware_concurrency(); if (threads > 32) threads = 32; if (threads < 1) threads = 1; }
+        if ((size_t)threads > (batch.size() + 3) / 4) threads = (int)((batch.size() + 3) / 4);
+        std::vector<BatchPartial> part(threads);
+        std::vector<std::thread> pool;
+        const size_t per = (batch.size() + threads - 1) / threads;
+        for (int t = 1; t < threads; t++) {
+            const size_t lo = t * per, hi = lo + per < batch.size() ? lo + per : batch.size();
+            if (lo < hi) pool.emplace_back(batch_worker, std::cref(batch), lo, hi, std::ref(part[t]));
+        }
+        batch_worker(batch, 0, per < batch.size() ? per : batch.size(), part[0]);
+        for (auto &th : pool) th.join();
+        Fq12 f = Fq12::one();
+        HG1 sumC[4] = {HG1::inf(), HG1::inf(), HG1::inf(), HG1::inf()};
+        for (const BatchPartial &p : part) { f = mul(f, p.f); for (int c = 0; c < 4; c++) sumC[c] = sumC[c].add(p.sumC[c]); }
+        // per circuit: the combined scalars of gamma_ABC (Fr arithmetic), then the two pairs against the prepared gamma and delta
+        Fq12 rhs = Fq12::one();
+        std::vector<HG1Affine> Ps; std::vector<const G2Prepared *> Qs;
+        for (int c = 0; c < 4; c++) {
+            bool any = false;
+            for (const BatchItem *it : batch) if (it->circuit == c) { any = true; break; }
+            if (!any) continue;
+            const VerificationKey &vk = *vks[c];
+            HFr zsum = HFr::zero();
+            std::vector<HFr> comb(vk.gamma_abc.size() - 1, HFr::zero());
+            for (const BatchItem *it : batch) if (it->circuit == c) {
+                const uint64_t z4[4] = {it->z[0], it->z[1], 0, 0};
+                const HFr z = HFr::from_canonical(z4);
+                zsum = zsum + z;
+                for (size_t j = 0; j < comb.size(); j++) comb[j] = comb[j] + z * it->inputs[j];
+            }
+            uint64_t zs[4]; zsum.to_canonical(zs);
+            const HG1Affine acc = abc_combination(vk, comb, HG1::from_affine(vk.gamma_abc[0]).mul(zs)).to_affine();
+            if (!acc.is_inf()) { Ps.push_back(HG1Affine{acc.x, acc.y.neg()}); Qs.push_back(&vk.gamma_prep); }
+            const HG1Affine sc = sumC[c].to_affine();
+            if (!sc.is_inf()) { Ps.push_back(HG1Affine{sc.x, sc.y.neg()}); Qs.push_back(&vk.delta_prep); }
+            rhs = mul(rhs, pow_cyclotomic(vk.alpha_beta, zs));
+        }
+        if (!Ps.empty()) f = mul(f, multi_miller(Ps, Qs));
+        batch_ok = final_exponentiation(f) == rhs;
+    }
+    if (batch_ok) for (size_t i : batch_idx) ok[i] = 1;
+    else single_idx.insert(single_idx.end(), batch_idx.begin(), batch_idx.end());      // at least one is bad: find out which
+    // per-proof checks (the reference's verdict by construction), spread over the same number of threads
+    if (!single_idx.empty()) {
+        if (threads <= 0) threads = 1;
+        const int nt = (size_t)threads < single_idx.size() ? threads : (int)single_idx.size();
+        std::vector<std::thread> pool;
+        auto work = [&](int t) { for (size_t k = t; k < single_idx.size(); k += nt) { const size_t i = single_idx[k]; ok[i] = check_one(*vks[parsed[i].circuit], parsed[i].pp, parsed[i].inputs) ? 1 : 0; } };
+        for (int t = 1; t < nt; t++) pool.emplace_back(work, t);
+        work(0);
+        for (auto &th : pool) th.join();
+    }
+    int good = 0;
+    for (size_t i = 0; i < n; i++) good += ok[i];
+    return good;
+}
+
+namespace {
 } // namespace
 
 // e(P, Q) as libff's alt_bn128_reduced_pairing computes it; out = the 12 Fq coefficients in the order operator<< prints them

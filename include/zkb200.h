@@ -112,6 +112,17 @@ const char *zkb200_default_proof(void);
  * proofs: n x 513 bytes (512 hex + NUL each).  Returns the number of default proofs (unsatisfiable transactions), or -1 on bad arguments. */
 typedef struct zkb200_tx { int circuit; int n; uint64_t u[3]; const char *s[14]; } zkb200_tx;
 int zkb200_prove_batch(size_t n, const zkb200_tx *txs, char *proofs, int threads);
+/* Batch verification (callers core/tx_pool.go:619-641, core/state_processor.go:113-158 verify every zk transaction of a
+ * block one by one with r1cs_gg_ppzksnark_verifier_strong_IC, r1cs_gg_ppzksnark.tcc:524-623).  One item = the arguments of one
+ * verify<Circuit>proof call: s[] = its string arguments after the proof, in order; value_s for mint / redeem.  Circuits may be mixed.
+ * A random linear combination checks all proofs with one final exponentiation; ok[i] receives the verdict of item i, identical to
+ * verify<Circuit>proof's (if the combined check fails, or a proof's B lies outside the order-r subgroup, the proofs concerned are checked
+ * one by one).  threads: host threads to use, 0 = all.  Returns the number of valid proofs, or -1 on bad arguments / unreadable key. */
+typedef struct zkb200_vtx { int circuit; uint64_t value_s; const char *proof; const char *s[6]; } zkb200_vtx;
+int zkb200_verify_batch(size_t n, const zkb200_vtx *items, uint8_t *ok, int threads);
+/* test hook: the two G2 membership tests of the batch verifier on one point of the twist curve (x.c0 x.c1 y.c0 y.c1, canonical):
+ * bit 0 = psi(Q) == [6z^2]Q (the fast test it uses), bit 1 = [r]Q == O (the definition) */
+int zkb200_g2_subgroup_check(const uint8_t point[128]);
 /* the device-dispatch policy on its own (host only; CPU unit tests): least proofs in flight, ties round-robin */
 void *zkb200_sched_create(int n_devices);
 int zkb200_sched_pick(void *sched);

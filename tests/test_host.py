@@ -315,3 +315,97 @@ def test_random_words_hook_needs_test_env(api):
     w = (C.c_uint32 * 16)(*range(16))
     assert api.lib.zkb200_set_random_words(C.cast(w, C.c_void_p), 16) == 0          # this process has the variable (tests/conftest.py)
     assert api.lib.zkb200_set_random_words(None, 0) == 0
+
+
+def _batch_items():
+    """Reference proofs of all four circuits: the reference fixtures plus the synthetic goldens (16 proofs, mixed circuits)."""
+    items = []
+    syn = json.load(open(os.path.join(GOLD, "synthetic.json")))
+    for c in CIRCUITS:
+        g = json.load(open(os.path.join(GOLD, c + ".json")))
+        items.append((c, g["proof_hex"], g["args"]))
+        items += [(c, row["proof_hex"], row["args"]) for row in syn[c]]
+    return items
+
+
+def test_batch_verifier_matches_per_proof_and_reference_verdicts(api, ref):
+    """zkb200_verify_batch (random linear combination, one final exponentiation per batch) gives the verdicts of
+    verify<Circuit>proof and of the reference verifier: an all-valid mixed batch, batches with one / several bad proofs of every kind
+    (wrong inputs, a valid point swapped in, off-curve, malformed hex, non-canonical but valid encodings), single-item and empty batches."""
+    if not os.path.exists(os.path.join(ref.KEY_DIR, "mintvk.txt")) or not ref.available("mint"):
+        pytest.skip("reference keys / harness not present")
+    api.set_key_dir(ref.KEY_DIR)
+    good = [(c, p, api.verify_args(c, a)) for c, p, a in _batch_items()]
+    assert api.verify_batch(good) == [True] * len(good)
+    assert api.verify_batch(good, threads=1) == [True] * len(good)
+    assert api.verify_batch([]) == [] and api.verify_batch(good[:1]) == [True]
+    q = O.Q_MOD
+    mixed = list(good)
+    c, p, va = mixed[2]
+    mixed[2] = (c, p[:384] + p[:128], va)                                                       # C := A (valid point, wrong proof)
+    c, p, va = mixed[5]
+    mixed[5] = (c, p, [va[0][:-1] + ("1" if va[0][-1] != "1" else "2")] + list(va[1:]))       # wrong public input
+    c, p, va = mixed[7]
+    mixed[7] = (c, "%064x" % (int(p[:64], 16) + q) + p[64:], va)                                # A.x + q: valid for the reference, so valid here
+    c, p, va = mixed[9]
+    mixed[9] = (c, p[:200] + ("1" if p[200] != "1" else "2") + p[201:], va)                    # B off the curve
+    c, p, va = mixed[11]
+    mixed[11] = (c, "zz" + p[2:], va)                                                           # not hex
+    c, p, va = mixed[12]
+    mixed[12] = (mixed[13][0], p, mixed[13][2]) if mixed[13][0] == c else (c, mixed[13][1], va)   # another transaction's proof
+    want = [api.verify_proof(c, p, va) for c, p, va in mixed]
+    assert want.count(False) == 5 and want[7] is True
+    assert api.verify_batch(mixed) == want
+    assert ref.verify_many([(c, p, va, None) for c, p, va in mixed]) == want
+    # a B that is on the twist curve but outside the order-r subgroup goes to the per-proof path and gets its verdict
+    c, p, va = good[0]
+    x = 1
+    while True:                                           # a point of E'(Fq2) from a small x; its order divides #E' = r * (2q - r), almost surely not r
+        x += 1
+        try:
+            y = O.fq2_sqrt(O.Fq2(x, 0) * O.Fq2(x, 0) * O.Fq2(x, 0) + O.TWIST_B)
+            break
+        except ValueError:
+            continue
+    assert O.G2.mul(O.R_MOD, O.G2.from_affine((O.Fq2(x, 0), y))) != O.G2.zero()          # really outside the subgroup
+    hx = lambda v: "%064x" % v
+    off = p[:128] + hx(0) + hx(x) + hx(y.c1) + hx(y.c0) + p[384:]
+    assert api.verify_batch(good[:3] + [(c, off, va)] + good[3:6]) == [True] * 3 + [api.verify_proof(c, off, va)] + [True] * 3
+
+
+def test_batch_verifier_is_faster_than_one_by_one(api, ref):
+    import time
+    if not os.path.exists(os.path.join(ref.KEY_DIR, "mintvk.txt")):
+        pytest.skip("reference keys not present")
+    api.set_key_dir(ref.KEY_DIR)
+    good = [(c, p, api.verify_args(c, a)) for c, p, a in _batch_items()] * 4            # 64 proofs
+    t0 = time.perf_counter(); assert all(api.verify_proof(c, p, va) for c, p, va in good); t1 = time.perf_counter()
+    assert all(api.verify_batch(good, threads=1)); t2 = time.perf_counter()
+    print("one by one %.1f ms/proof, batch (1 thread) %.1f ms/proof" % (1e3 * (t1 - t0) / len(good), 1e3 * (t2 - t1) / len(good)))
+    assert (t2 - t1) < 0.8 * (t1 - t0)
+
+
+def test_g2_subgroup_fast_test_equals_definition(api):
+    """The batch verifier's membership test psi(Q) == [6z^2]Q against the definition [r]Q == O: multiples of the generator are in, points
+    of the twist curve built from arbitrary x (cofactor 2q - r, so almost never in G2) are out, and the two tests never disagree."""
+    import random
+    rng = random.Random(9)
+    enc = lambda P: b"".join(int(v).to_bytes(32, "little") for v in (P[0].c0, P[0].c1, P[1].c0, P[1].c1))
+    gen = (O.Fq2(*O.G2_GEN[0]), O.Fq2(*O.G2_GEN[1]))
+    for k in (1, 2, 12345, rng.randrange(O.R_MOD), O.R_MOD - 1):
+        P = O.G2.to_affine(O.G2.mul(k, O.G2.from_affine(gen)))
+        assert api.lib.zkb200_g2_subgroup_check(enc(P)) == 3
+    outside = 0
+    while outside < 12:
+        x = O.Fq2(rng.randrange(O.Q_MOD), rng.randrange(O.Q_MOD))
+        try:
+            y = O.fq2_sqrt(x * x * x + O.TWIST_B)
+        except ValueError:
+            continue
+        got = api.lib.zkb200_g2_subgroup_check(enc((x, y)))
+        assert got in (0, 3)
+        outside += got == 0
+        # clearing the cofactor lands in G2 again
+        if outside == 1:
+            h = 2 * O.Q_MOD - O.R_MOD
+            assert api.lib.zkb200_g2_subgroup_check(enc(O.G2.to_affine(O.G2.mul(h, O.G2.from_affine((x, y)))))) == 3

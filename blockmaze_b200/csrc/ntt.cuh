@@ -57,6 +57,9 @@ __device__ __forceinline__ Fr ntt_mul(const Fr &a, const Fr &b) {
     return a * b;
 #endif
 }
+#ifndef ZK_NTT_MINBLOCKS
+#define ZK_NTT_MINBLOCKS 2       // CTAs of NTT_MAX_THREADS per SM the register allocation must allow (2 -> 128 registers, 3 -> 80, 4 -> 64)
+#endif
 constexpr int NTT_MAX_THREADS = 256;
 constexpr int NTT_TILE_LOG = 11;          // at most 2048 elements * 32 B = 64 KB of shared memory per CTA; 4 elements per thread
 
@@ -64,7 +67,7 @@ constexpr int NTT_TILE_LOG = 11;          // at most 2048 elements * 32 B = 64 K
 //   set  = the 2^k elements that differ only in index bits [s0, s0+k)
 //   tile = G = 2^logG sets with consecutive low bits, so global accesses are G*32-byte contiguous runs
 template <bool FIRST>
-static __global__ void __launch_bounds__(NTT_MAX_THREADS, 2)
+static __global__ void __launch_bounds__(NTT_MAX_THREADS, ZK_NTT_MINBLOCKS)
 ntt_pass_kernel(const Fr *__restrict__ src, Fr *__restrict__ dst, const Fr *__restrict__ tw,
                 int logn, int s0, int k, int logG, PowMul pre, PowMul post, int last, size_t batch_stride) {
     extern __shared__ uint32_t sm[];

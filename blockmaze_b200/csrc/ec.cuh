@@ -79,7 +79,7 @@ template <class F> struct XYZZ {
         ZZZ = ZZZ * PPP;
     }
     // the same mixed addition with every field multiplication inlined (G1 accumulate kernel variant, see msm.cuh)
-    template <class M> ZK_HD void add_affine_with(const Affine<F> &a, M mul) {
+    template <class M, class S> ZK_HD void add_affine_with(const Affine<F> &a, M mul, S sqr) {
         if (a.is_inf()) return;
         if (is_inf()) { X = a.x; Y = a.y; ZZ = F::one(); ZZZ = F::one(); return; }
         F U2 = mul(a.x, ZZ), S2 = mul(a.y, ZZZ);
@@ -88,8 +88,8 @@ template <class F> struct XYZZ {
             if (R.is_zero()) *this = dbl_affine(a); else *this = inf();
             return;
         }
-        F PP = mul(Pp, Pp), PPP = mul(Pp, PP), Q = mul(X, PP);
-        F X3 = mul(R, R) - PPP - Q.dbl();
+        F PP = sqr(Pp), PPP = mul(Pp, PP), Q = mul(X, PP);
+        F X3 = sqr(R) - PPP - Q.dbl();
         Y = mul(R, Q - X3) - mul(Y, PPP);
         X = X3;
         ZZ = mul(ZZ, PP);

@@ -285,7 +285,102 @@ template <class P> struct Fp {
         r.reduce_once();
         return r;
     }
-    ZK_HD Fp sqr() const { return *this * *this; }
+    // Montgomery square a*a*R^-1 mod p with 36 + 64 wide multiply-adds instead of 64 + 64 (a_i*a_j = a_j*a_i is computed once).
+    //   1. off-diagonal products a_i*a_j (i < j) go row by row into an even- and an odd-column accumulator like the rows of mul_impl; a chain
+    //      that ends deposits its carry in the next column, which no earlier row has touched (row i reaches column i+8 at most);
+    //   2. t = 2*(E + O) + sum a_i^2 * 2^(64 i): the diagonal products sit on disjoint column pairs, so they are ONE 16-limb carry chain;
+    //   3. Montgomery reduction of the 16 limbs: the m_i*p half-rows of mul_impl on accumulators that start from t[0..8) and take in t[i+8]
+    //      at the END of row i -- the columns where a row deposits a carry (i+8 of either accumulator) are then still small, as in mul_impl.
+    ZK_HD Fp sqr() const {
+#if defined(__CUDA_ARCH__) && !defined(ZK_INLINE_MUL)
+        return sqr_call(*this);
+#else
+        return sqr_impl(*this);
+#endif
+    }
+#if defined(__CUDACC__)
+    static __device__ __noinline__ Fp sqr_call(const Fp a) { return sqr_impl(a); }
+#endif
+    ZK_HD static Fp sqr_impl(const Fp &a) {
+        uint32_t off[2][16];                       // off[0]: products whose low limb sits at an even column, off[1]: odd
+#pragma unroll
+        for (int k = 0; k < 16; k++) { off[0][k] = 0; off[1][k] = 0; }
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+#pragma unroll
+            for (int par = 1; par <= 2; par++) {   // chain of the products a_i*a_j with j = i+par, i+par+2, ...
+                if (i + par > 7) continue;
+                uint32_t *X = off[(2 * i + par) & 1];
+                Carry c;
+                int last = 0;
+#pragma unroll
+                for (int j = i + par; j < 8; j += 2) {
+                    if (j == i + par) c.mad_lo_cc(X[i + j], a.v[i], a.v[j], X[i + j]); else c.madc_lo_cc(X[i + j], a.v[i], a.v[j], X[i + j]);
+                    c.madc_hi_cc(X[i + j + 1], a.v[i], a.v[j], X[i + j + 1]);
+                    last = i + j + 1;
+                }
+                if (last + 1 < 16) c.addc(X[last + 1], X[last + 1], 0);
+            }
+        }
+        uint32_t t[16];
+        {   // t = (E + O), then doubled
+            Carry c;
+            c.add_cc(t[0], off[0][0], off[1][0]);
+#pragma unroll
+            for (int k = 1; k < 15; k++) c.addc_cc(t[k], off[0][k], off[1][k]);
+            c.addc(t[15], off[0][15], off[1][15]);
+            Carry d;
+            d.add_cc(t[0], t[0], t[0]);
+#pragma unroll
+            for (int k = 1; k < 15; k++) d.addc_cc(t[k], t[k], t[k]);
+            d.addc(t[15], t[15], t[15]);
+            Carry e;                               // + the diagonal
+            e.mad_lo_cc(t[0], a.v[0], a.v[0], t[0]);
+            e.madc_hi_cc(t[1], a.v[0], a.v[0], t[1]);
+#pragma unroll
+            for (int i = 1; i < 8; i++) {
+                e.madc_lo_cc(t[2 * i], a.v[i], a.v[i], t[2 * i]);
+                if (i < 7) e.madc_hi_cc(t[2 * i + 1], a.v[i], a.v[i], t[2 * i + 1]); else e.madc_hi(t[2 * i + 1], a.v[i], a.v[i], t[2 * i + 1]);
+            }
+        }
+        uint32_t acc[2][18];
+#pragma unroll
+        for (int k = 0; k < 18; k++) { acc[0][k] = k < 8 ? t[k] : 0; acc[1][k] = 0; }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t *H = acc[i & 1], *Cc = acc[(i & 1) ^ 1];
+            Carry e;
+            if (i > 0) e.add_cc(H[i], H[i], Cc[i]);            // the whole column i, its carry rides into the chain below
+            const uint32_t m = mul_lo(H[i], P::INV);
+            if (i > 0) e.madc_lo_cc(Cc[i + 1], P::mod(1), m, Cc[i + 1]); else e.mad_lo_cc(Cc[i + 1], P::mod(1), m, Cc[i + 1]);
+            e.madc_hi_cc(Cc[i + 2], P::mod(1), m, Cc[i + 2]);
+#pragma unroll
+            for (int j = 3; j < 8; j += 2) {
+                e.madc_lo_cc(Cc[i + j], P::mod(j), m, Cc[i + j]);
+                if (j < 7) e.madc_hi_cc(Cc[i + j + 1], P::mod(j), m, Cc[i + j + 1]);
+                else e.madc_hi(Cc[i + j + 1], P::mod(j), m, Cc[i + j + 1]);
+            }
+            Carry f;
+            f.mad_lo_cc(H[i], P::mod(0), m, H[i]);
+            f.madc_hi_cc(H[i + 1], P::mod(0), m, H[i + 1]);
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) {
+                f.madc_lo_cc(H[i + j], P::mod(j), m, H[i + j]);
+                f.madc_hi_cc(H[i + j + 1], P::mod(j), m, H[i + j + 1]);
+            }
+            f.addc(Cc[i + 8], Cc[i + 8], 0);
+            Carry g;                                           // now take in limb i+8 of the square (column i+9 is untouched so far)
+            g.add_cc(acc[0][i + 8], acc[0][i + 8], t[i + 8]);
+            g.addc(acc[0][i + 9], acc[0][i + 9], 0);
+        }
+        Fp r; Carry c;
+        c.add_cc(r.v[0], acc[0][8], acc[1][8]);
+#pragma unroll
+        for (int k = 1; k < 7; k++) c.addc_cc(r.v[k], acc[0][8 + k], acc[1][8 + k]);
+        c.addc(r.v[7], acc[0][15], acc[1][15]);
+        r.reduce_once();
+        return r;
+    }
 
     // canonical <-> Montgomery
     ZK_HD Fp to_mont() const { return *this * r2(); }

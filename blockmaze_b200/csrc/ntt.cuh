@@ -60,6 +60,19 @@ __device__ __forceinline__ Fr ntt_mul(const Fr &a, const Fr &b) {
 #ifndef ZK_NTT_MINBLOCKS
 #define ZK_NTT_MINBLOCKS 2       // CTAs of NTT_MAX_THREADS per SM the register allocation must allow (2 -> 128 registers, 3 -> 80, 4 -> 64)
 #endif
+// Twiddles are stored PER STAGE, compactly: stage L (butterflies of span 2^L, L = 1..logn) owns the 2^(L-1) powers w_L^j of the primitive
+// 2^L-th root at offset 2^(L-1) - 1, so a stage walks its own contiguous run instead of striding through one table of n/2 powers (where
+// every stage but the last used 1/2, 1/4, ... of each line it fetched: round 1 measured 1.46 GB of DRAM reads for the 0.5 GB of the last
+// pass of a 2^24 transform).  n - 1 elements per direction instead of n/2.
+__device__ __forceinline__ const Fr *ntt_tw(const Fr *levels, int stage, uint32_t j) { return levels + ((1u << (stage - 1)) - 1u) + j; }
+// levels[2^(L-1) - 1 + j] = flat[j << (logn - L)], flat[j] = w^j (j < n/2)
+static __global__ void ntt_tw_levels_kernel(const Fr *__restrict__ flat, int logn, Fr *__restrict__ levels) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;          // position in the level table, 0 .. n-2
+    if (e >= (1u << logn) - 1u) return;
+    const int L = 32 - __clz(e + 1);                                    // stage: 2^(L-1) <= e + 1 < 2^L
+    const uint32_t j = e + 1 - (1u << (L - 1));
+    levels[e] = flat[(size_t)j << (logn - L)];
+}
 constexpr int NTT_MAX_THREADS = 256;
 constexpr int NTT_TILE_LOG = 11;          // at most 2048 elements * 32 B = 64 KB of shared memory per CTA; 4 elements per thread
 
@@ -114,7 +127,7 @@ ntt_pass_kernel(const Fr *__restrict__ src, Fr *__restrict__ dst, const Fr *__re
             Fr a, b;
 #pragma unroll
             for (int w = 0; w < 8; w++) { a.v[w] = sm[w * N + i0]; b.v[w] = sm[w * N + i1]; }
-            if (j != 0) b = ntt_mul(b, ldg_fr(tw + ((size_t)j << (logn - s0 - 1))));
+            if (j != 0) b = ntt_mul(b, ldg_fr(ntt_tw(tw, s0 + 1, j)));
             Fr s = a + b, d = a - b;
 #pragma unroll
             for (int w = 0; w < 8; w++) { sm[w * N + i0] = s.v[w]; sm[w * N + i1] = d.v[w]; }
@@ -137,13 +150,13 @@ ntt_pass_kernel(const Fr *__restrict__ src, Fr *__restrict__ dst, const Fr *__re
                 x0.v[w] = sm[w * N + i0]; x1.v[w] = sm[w * N + i0 + hq]; x2.v[w] = sm[w * N + i0 + 2 * hq]; x3.v[w] = sm[w * N + i0 + 3 * hq];
             }
             if (j != 0) {                                               // stage q: (x0, x1) and (x2, x3), same twiddle
-                const Fr w1 = ldg_fr(tw + ((size_t)j << (logn - s0 - q)));
+                const Fr w1 = ldg_fr(ntt_tw(tw, s0 + q, j));
                 x1 = ntt_mul(x1, w1); x3 = ntt_mul(x3, w1);
             }
             const Fr a0 = x0 + x1, a1 = x0 - x1;
             Fr a2 = x2 + x3, a3 = x2 - x3;
-            if (j != 0) a2 = ntt_mul(a2, ldg_fr(tw + ((size_t)j << (logn - s0 - q - 1))));      // stage q+1: (a0, a2) and (a1, a3)
-            a3 = ntt_mul(a3, ldg_fr(tw + ((size_t)j2 << (logn - s0 - q - 1))));
+            if (j != 0) a2 = ntt_mul(a2, ldg_fr(ntt_tw(tw, s0 + q + 1, j)));      // stage q+1: (a0, a2) and (a1, a3)
+            a3 = ntt_mul(a3, ldg_fr(ntt_tw(tw, s0 + q + 1, j2)));
             x0 = a0 + a2; x2 = a0 - a2; x1 = a1 + a3; x3 = a1 - a3;
 #pragma unroll
             for (int w = 0; w < 8; w++) {
@@ -188,7 +201,7 @@ static inline int ntt_plan_passes(int logn, NttPass out[4]) {
     return np;
 }
 
-// dst != src.  tw = omega^j (j < n/2) for a forward transform, omega^-j for an inverse one (Montgomery form).
+// dst != src.  tw = per-stage twiddle table (ntt_tw) of omega for a forward transform, of omega^-1 for an inverse one (Montgomery form).
 // `batch` transforms, `batch_stride` elements apart in both src and dst, share one launch per pass.
 static inline void ntt_launch(cudaStream_t st, const Fr *src, Fr *dst, const Fr *tw, int logn, PowMul pre, PowMul post, int batch = 1,
                               size_t batch_stride = 0) {

@@ -69,6 +69,18 @@ static void *dev_pow_table(HFr base, HFr scale, uint32_t count, uint64_t stride)
     if (count) { pow_table_kernel<<<cdiv(cdiv(count, 64), 128), 128>>>(out, to_dev(base), to_dev(scale), count, stride); ZK_CUDA(cudaGetLastError()); }
     return out;
 }
+// per-stage twiddle table of a size-2^logn transform (ntt.cuh ntt_tw): built from the flat power table, which is then dropped
+static void *dev_tw_levels(HFr w, int logn) {
+    const uint32_t n = 1u << logn;
+    if (logn == 0) { void *p; ZK_CUDA(cudaMalloc(&p, 32)); return p; }
+    void *flat = dev_pow_table(w, HFr::one(), n / 2, 1);
+    Fr *levels; ZK_CUDA(cudaMalloc(&levels, (size_t)n * 32));
+    ntt_tw_levels_kernel<<<cdiv(n, 256), 256>>>((const Fr *)flat, logn, levels);
+    ZK_CUDA(cudaGetLastError());
+    ZK_CUDA(cudaDeviceSynchronize());
+    ZK_CUDA(cudaFree(flat));
+    return levels;
+}
 static void *dev_const(const HFr *v, size_t n) {
     void *p; ZK_CUDA(cudaMalloc(&p, n * 32)); ZK_CUDA(cudaMemcpy(p, v, n * 32, cudaMemcpyHostToDevice)); return p;
 }
@@ -96,8 +108,8 @@ Domain *Domain::build(uint64_t min_size) {
         d->log_big = ilog2_ceil(d->big); d->log_small = ilog2_ceil(d->small); d->compr = d->big / d->small;
     }
     const HFr wb = root_of_unity(d->log_big);
-    d->tw_big_f = dev_pow_table(wb, one, d->big / 2, 1);
-    d->tw_big_i = dev_pow_table(wb.inverse(), one, d->big / 2, 1);
+    d->tw_big_f = dev_tw_levels(wb, d->log_big);
+    d->tw_big_i = dev_tw_levels(wb.inverse(), d->log_big);
     const HFr big_inv = HFr::from_u64(d->big).inverse(), m_inv = HFr::from_u64(d->m).inverse();
     d->c_big_inv = dev_const(&big_inv, 1);
     d->c_m_inv = dev_const(&m_inv, 1);
@@ -115,8 +127,8 @@ Domain *Domain::build(uint64_t min_size) {
         d->zt = dev_const(&z, 1); d->z1 = z;
     } else {
         const HFr ws = root_of_unity(d->log_small), om = root_of_unity(d->log_big + 1);
-        d->tw_small_f = dev_pow_table(ws, one, d->small / 2, 1);
-        d->tw_small_i = dev_pow_table(ws.inverse(), one, d->small / 2, 1);
+        d->tw_small_f = dev_tw_levels(ws, d->log_small);
+        d->tw_small_i = dev_tw_levels(ws.inverse(), d->log_small);
         d->tw_step_f = dev_pow_table(om, one, d->big, 1);
         d->tw_step_i = dev_pow_table(om.inverse(), one, d->big, 1);
         const HFr small_inv = HFr::from_u64(d->small).inverse();

@@ -20,7 +20,7 @@ struct Domain {
     int log_big = 0, log_small = 0;
     bool step = false;
     uint32_t compr = 1;
-    // twiddles (device, Montgomery): w_n^j j < n/2 for the two power-of-two sub-transforms, forward and inverse
+    // twiddles (device, Montgomery): per-stage tables (ntt.cuh ntt_tw) of the two power-of-two sub-transforms, forward and inverse
     void *tw_big_f = nullptr, *tw_big_i = nullptr, *tw_small_f = nullptr, *tw_small_i = nullptr;
     // step only: omega^j / omega^-j, j < big, omega = primitive (2*big)-th root
     void *tw_step_f = nullptr, *tw_step_i = nullptr;

@@ -496,7 +496,9 @@ float zkb200_bench_msm_slice(int group, size_t first, size_t n, int window_bits,
     void *bases = synth_bases_device(group, first, n);
     ZK_CUDA(cudaDeviceSynchronize());
     const bool expanded = window_bits < 0;          // negative window_bits: fixed-base (expanded) layout with |window_bits| bits
-    MsmPlan plan; plan.init((uint32_t)n, c, 0, group == 1, group == 2, expanded);
+    int aff = 0;                                     // affine halving rounds in front of the accumulation: off unless asked for, as in the prover
+    if (const char *e = getenv("ZKB200_AFFINE_ROUNDS")) aff = atoi(e);
+    MsmPlan plan; plan.init((uint32_t)n, c, 0, group == 1, group == 2, expanded, expanded ? aff : 0);
     if (expanded) { void *e = msm_expand_bases(bases, (uint32_t)n, c, group == 2); ZK_CUDA(cudaDeviceSynchronize()); cudaFree(bases); bases = e; }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     msm_run(0, plan, ScalarRef{sc, nullptr, 0, 0}, nullptr, group == 1 ? bases : nullptr, group == 2 ? bases : nullptr);

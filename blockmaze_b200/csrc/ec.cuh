@@ -137,7 +137,7 @@ template <class F> struct XYZZ {
         if (is_inf()) return Affine<F>::inf();
         // x = X/ZZ, y = Y/ZZZ ; 1/ZZ = ZZ^2 ... use 1/ZZZ and ZZ: 1/ZZ = ZZZ^2 / ZZ^4 is no cheaper; invert both via one inversion
         F zz_zzz = ZZ * ZZZ;
-        F inv = zz_zzz.inverse();
+        F inv = zz_zzz.inverse();                     // (Fp: safegcd on the device, see ff.cuh inverse())
         Affine<F> a;
         a.x = X * (inv * ZZZ);
         a.y = Y * (inv * ZZ);

@@ -130,6 +130,10 @@ struct FrParams {   // scalar field r
         return i == 0 ? 0xae216da7u : i == 1 ? 0x1bb8e645u : i == 2 ? 0xe35c59e3u : i == 3 ? 0x53fe3ab1u :
                i == 4 ? 0x53bb8085u : i == 5 ? 0x8c49833du : i == 6 ? 0x7f4e44a5u : 0x0216d0b1u;
     }
+    ZK_HD static constexpr uint32_t r3(int i) {      // R^3 mod r (turns the plain inverse of a Montgomery representative back into Montgomery form)
+        return i == 0 ? 0xb4bf0040u : i == 1 ? 0x5e94d8e1u : i == 2 ? 0x1cfbb6b8u : i == 3 ? 0x2a489cbeu :
+               i == 4 ? 0xa19fcfedu : i == 5 ? 0x893cc664u : i == 6 ? 0x7fcc657cu : 0x0cf8594bu;
+    }
 };
 struct FqParams {   // base field q
     static constexpr uint32_t INV = 0xe4866389u;   // -q^-1 mod 2^32
@@ -144,6 +148,10 @@ struct FqParams {   // base field q
     ZK_HD static constexpr uint32_t r2(int i) {      // R^2 mod q
         return i == 0 ? 0x538afa89u : i == 1 ? 0xf32cfc5bu : i == 2 ? 0xd44501fbu : i == 3 ? 0xb5e71911u :
                i == 4 ? 0x0a417ff6u : i == 5 ? 0x47ab1effu : i == 6 ? 0xcab8351fu : 0x06d89f71u;
+    }
+    ZK_HD static constexpr uint32_t r3(int i) {      // R^3 mod q
+        return i == 0 ? 0xda1530dfu : i == 1 ? 0xb1cd6dafu : i == 2 ? 0xa7283db6u : i == 3 ? 0x62f210e6u :
+               i == 4 ? 0x0ada0afbu : i == 5 ? 0xef7f0b0cu : i == 6 ? 0x2d592544u : 0x20fd6e90u;
     }
 };
 
@@ -399,8 +407,109 @@ template <class P> struct Fp {
         uint32_t ee[8] = {(uint32_t)e, (uint32_t)(e >> 32), 0, 0, 0, 0, 0, 0};
         return pow(ee);
     }
-    // Fermat inverse a^(p-2); returns 0 for 0
+    // Inverse by the Bernstein-Yang "safegcd" division steps (the half-delta variant with 30-bit signed limbs, as in libsecp256k1's
+    // modinv32): 20 batches of 30 branch-free division steps on the low words of (f, g) = (p, x), each batch followed by one update of
+    // the full-width (f, g) and of the Bezout pair (d, e) by the batch's 2x2 transition matrix.  About 16 k instructions, nearly all of
+    // them 32-bit ALU work: 1/25 of the multiply-pipe time of the Fermat inverse below (254 squarings + ~127 multiplications), which is
+    // what makes a per-thread batched inversion affordable inside the multiply-bound MSM kernels (msm.cuh, affine rounds).
+    // Input and output are Montgomery representatives; 0 -> 0.  The reference inverts with GMP's mpn_gcdext (fp.tcc:650-679); any correct
+    // inverse is the same field element.
+    ZK_HD Fp inverse_gcd() const {
+        const int32_t M30 = (int32_t)0x3fffffff;
+        // p and x in nine signed 30-bit limbs
+        int32_t f[9], g[9], m[9], d[9], e[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            const int bit = 30 * i, w = bit >> 5, off = bit & 31;
+            uint32_t pm = P::mod(w < 8 ? w : 7) >> off, xv = v[w < 8 ? w : 7] >> off;
+            if (w >= 8) { pm = 0; xv = 0; }
+            if (off > 2 && w + 1 < 8) { pm |= P::mod(w + 1) << (32 - off); xv |= v[w + 1] << (32 - off); }
+            m[i] = (int32_t)(pm & (uint32_t)M30); f[i] = m[i]; g[i] = (int32_t)(xv & (uint32_t)M30);
+            d[i] = 0; e[i] = 0;
+        }
+        e[0] = 1;
+        const uint32_t minv30 = (0u - P::INV) & (uint32_t)M30;          // p^-1 mod 2^30
+        int32_t zeta = -1;                                               // -(delta + 1/2), delta = 1/2
+        for (int batch = 0; batch < 20; batch++) {
+            // 30 division steps on the low limbs; the matrix (u v; q r) accumulates with a factor 2^30
+            uint32_t u = 1, vv = 0, q = 0, r = 1;
+            uint32_t ff = (uint32_t)f[0], gg = (uint32_t)g[0];
+            for (int i = 0; i < 30; i++) {
+                uint32_t c1 = (uint32_t)(zeta >> 31), c2 = 0u - (gg & 1u);
+                const uint32_t x = (ff ^ c1) - c1, y = (u ^ c1) - c1, z = (vv ^ c1) - c1;
+                gg += x & c2; q += y & c2; r += z & c2;
+                c1 &= c2;
+                zeta = (int32_t)(((uint32_t)zeta ^ c1) - 1u);
+                ff += gg & c1; u += q & c1; vv += r & c1;
+                gg >>= 1; u <<= 1; vv <<= 1;
+            }
+            const int32_t tu = (int32_t)u, tv = (int32_t)vv, tq = (int32_t)q, tr = (int32_t)r;
+            {   // (d, e) <- (u d + v e, q d + r e) / 2^30 mod p, both kept in (-2p, p)
+                const int32_t sd = d[8] >> 31, se = e[8] >> 31;
+                int32_t md = (tu & sd) + (tv & se), me = (tq & sd) + (tr & se);
+                int64_t cd = (int64_t)tu * d[0] + (int64_t)tv * e[0], ce = (int64_t)tq * d[0] + (int64_t)tr * e[0];
+                md -= (int32_t)((minv30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+                me -= (int32_t)((minv30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+                cd += (int64_t)m[0] * md; ce += (int64_t)m[0] * me;
+                cd >>= 30; ce >>= 30;
+#pragma unroll
+                for (int i = 1; i < 9; i++) {
+                    cd += (int64_t)tu * d[i] + (int64_t)tv * e[i]; ce += (int64_t)tq * d[i] + (int64_t)tr * e[i];
+                    cd += (int64_t)m[i] * md; ce += (int64_t)m[i] * me;
+                    d[i - 1] = (int32_t)cd & M30; cd >>= 30; e[i - 1] = (int32_t)ce & M30; ce >>= 30;
+                }
+                d[8] = (int32_t)cd; e[8] = (int32_t)ce;
+            }
+            {   // (f, g) <- (u f + v g, q f + r g) / 2^30, exact
+                int64_t cf = (int64_t)tu * f[0] + (int64_t)tv * g[0], cg = (int64_t)tq * f[0] + (int64_t)tr * g[0];
+                cf >>= 30; cg >>= 30;
+#pragma unroll
+                for (int i = 1; i < 9; i++) {
+                    cf += (int64_t)tu * f[i] + (int64_t)tv * g[i]; cg += (int64_t)tq * f[i] + (int64_t)tr * g[i];
+                    f[i - 1] = (int32_t)cf & M30; cf >>= 30; g[i - 1] = (int32_t)cg & M30; cg >>= 30;
+                }
+                f[8] = (int32_t)cf; g[8] = (int32_t)cg;
+            }
+        }
+        // now g = 0 and f = +-gcd = +-1 (or +-p for x = 0, in which case d = 0): x^-1 = sign(f) * d, brought into [0, p)
+        {
+            int32_t add = d[8] >> 31;
+#pragma unroll
+            for (int i = 0; i < 9; i++) d[i] += m[i] & add;
+            const int32_t neg = f[8] >> 31;
+#pragma unroll
+            for (int i = 0; i < 9; i++) d[i] = (d[i] ^ neg) - neg;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { d[i + 1] += d[i] >> 30; d[i] &= M30; }
+            add = d[8] >> 31;
+#pragma unroll
+            for (int i = 0; i < 9; i++) d[i] += m[i] & add;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { d[i + 1] += d[i] >> 30; d[i] &= M30; }
+        }
+        Fp o;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const int bit = 32 * w, i = bit / 30, off = bit % 30;
+            uint32_t x = (uint32_t)d[i] >> off;
+            if (i + 1 < 9) x |= (uint32_t)d[i + 1] << (30 - off);
+            if (off > 28 && i + 2 < 9) x |= (uint32_t)d[i + 2] << (60 - off);
+            o.v[w] = x;
+        }
+        Fp r3c; for (int i = 0; i < 8; i++) r3c.v[i] = P::r3(i);
+        return o * r3c;                                                  // (xR)^-1 * R^3 / R = x^-1 R
+    }
+    // 1/a, 0 for 0: safegcd on the device (key load does 15-31 normalisations per base, keygen one per point); the host keeps the Fermat
+    // chain, which its tests pin against Python
     ZK_HD Fp inverse() const {
+#if defined(__CUDA_ARCH__)
+        return inverse_gcd();
+#else
+        return inverse_fermat();
+#endif
+    }
+    // Fermat inverse a^(p-2); returns 0 for 0
+    ZK_HD Fp inverse_fermat() const {
         uint32_t e[8]; Carry c;
         c.sub_cc(e[0], P::mod(0), 2);
         for (int i = 1; i < 8; i++) c.subc_cc(e[i], P::mod(i), 0);

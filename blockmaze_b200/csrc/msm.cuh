@@ -114,13 +114,17 @@ static __global__ void msm_scatter_kernel(ScalarSrc src, const uint8_t *skip, Ms
 }
 
 // exclusive scan of `n` counts by one CTA of 32 warps; every warp owns a contiguous slice and reads it coalesced.  offsets[n] = total
-static __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ offsets, uint32_t n) {
+// pad_log > 0 (affine rounds, below): every non-empty bucket's run is padded to a multiple of 2^pad_log entries, and offsets_shifted (if not
+// null) receives offsets >> pad_log, the bucket boundaries after pad_log halving rounds.
+static __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ offsets, uint32_t n,
+                                                               int pad_log = 0, uint32_t *__restrict__ offsets_shifted = nullptr) {
+    const uint32_t pad = (1u << pad_log) - 1u;
     __shared__ uint32_t warp_off[33];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t per = (((n + 31) / 32) + 31) / 32 * 32;
     const uint32_t lo = min(warp * per, n), hi = min(lo + per, n);
     uint32_t sum = 0;
-    for (uint32_t i = lo + lane; i < hi; i += 32) sum += counts[i];
+    for (uint32_t i = lo + lane; i < hi; i += 32) sum += (counts[i] + pad) & ~pad;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
     if (lane == 0) warp_off[warp] = sum;
@@ -136,14 +140,14 @@ static __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t *_
     uint32_t run = warp_off[warp];
     for (uint32_t base = lo; base < hi; base += 32) {
         const uint32_t i = base + lane;
-        const uint32_t v = i < hi ? counts[i] : 0;
+        const uint32_t v = i < hi ? (counts[i] + pad) & ~pad : 0;
         uint32_t incl = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
-        if (i < hi) offsets[i] = run + incl - v;
+        if (i < hi) { offsets[i] = run + incl - v; if (offsets_shifted) offsets_shifted[i] = (run + incl - v) >> pad_log; }
         run += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (threadIdx.x == 0) offsets[n] = warp_off[32];
+    if (threadIdx.x == 0) { offsets[n] = warp_off[32]; if (offsets_shifted) offsets_shifted[n] = warp_off[32] >> pad_log; }
 }
 
 template <class F> __device__ __forceinline__ Affine<F> ld_affine(const Affine<F> *p) {
@@ -157,6 +161,24 @@ template <class F> __device__ __forceinline__ Affine<F> ld_affine(const Affine<F
     }
     return a;
 }
+__device__ __forceinline__ Fq ldg_fq(const Fq *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    const uint4 a = __ldg(q), b = __ldg(q + 1);
+    Fq r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ Fq ld_fq_plain(const Fq *p) {               // written earlier by this very thread: no read-only path
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    const uint4 a = q[0], b = q[1];
+    Fq r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fq(Fq *p, const Fq &r) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ void st_affine(Affine<Fq> *p, const Affine<Fq> &a) { st_fq(&p->x, a.x); st_fq(&p->y, a.y); }
 template <class F> __device__ __forceinline__ void st_xyzz(XYZZ<F> *p, const XYZZ<F> &v) {
     uint4 *q = reinterpret_cast<uint4 *>(p);
     const uint32_t *d = reinterpret_cast<const uint32_t *>(&v);
@@ -242,7 +264,7 @@ static __global__ void __launch_bounds__(128, ZK_ACC_MINBLOCKS) msm_accumulate_k
                 b = lo; next = __ldg(offsets + b + 1);
             }
         }
-        const uint32_t ent = __ldg(entries + e);
+        const uint32_t ent = entries ? __ldg(entries + e) : e;      // entries == nullptr: `bases` is already the bucket-sorted point list
         Affine<F> p = ld_affine(bases + (ent & 0x7fffffffu));
         if (ent & 0x80000000u) p.y = p.y.neg();
 #if ZK_ACC_INLINE_MUL
@@ -256,6 +278,114 @@ static __global__ void __launch_bounds__(128, ZK_ACC_MINBLOCKS) msm_accumulate_k
     }
     st_xyzz(partial + t + b, acc);
 }
+// ---- batched-affine halving rounds (dense fixed-base MSM: the H query) -------------------------------------------------------------
+// An XYZZ += affine addition is 10 multiplications; affine + affine is 5M + 1S + one inversion, and inversions batch (Montgomery's
+// trick: 3 more multiplications per pair, ONE inversion per batch) -- 6 multiplications per addition if the inversion is cheap and the
+// batch long.  On a SIMT machine an inversion shared by a warp costs what 32 private ones cost, so each THREAD batches its own pairs,
+// and with ~55 pairs per thread only the safegcd inversion (ff.cuh inverse_gcd: ~1/25 of a Fermat inverse on the multiply pipe) pays.
+// Layout: the digit sort pads every bucket's run to a multiple of 2^R entries (R rounds; pads are the null entry 0xffffffff = infinity),
+// so a round simply adds items 2i and 2i+1 of the flat list -- partners are always in the same bucket, no segment logic -- and after R
+// rounds bucket b owns items offsets[b] >> R .. offsets[b+1] >> R of the last list, which the XYZZ accumulate kernel then finishes.
+// Thread t takes pairs t, t + T, t + 2T, ... (coalesced): pass 1 multiplies the denominators up and stores the running products, one
+// inversion, pass 2 walks back.  P + P (equal points) uses the tangent slope, P + (-P) and infinities give their result directly.
+constexpr uint32_t MSM_NULL_ENTRY = 0xffffffffu;
+// One pair of a halving round: where its two points live and their coordinates as far as they have been fetched.
+struct AffPair {
+    uint32_t ea, eb;            // FIRST round: sorted entries (base index | sign << 31, or MSM_NULL_ENTRY); later rounds: item indices
+    Fq ax, bx, ay, by;
+};
+template <bool FIRST> __device__ __forceinline__ void aff_fetch_idx(const uint32_t *__restrict__ entries, uint32_t p, AffPair &q) {
+    if (FIRST) { const uint2 e = __ldg(reinterpret_cast<const uint2 *>(entries) + p); q.ea = e.x; q.eb = e.y; }
+    else { q.ea = 2 * p; q.eb = 2 * p + 1; }
+}
+template <bool FIRST> __device__ __forceinline__ void aff_fetch_x(const Affine<Fq> *__restrict__ pts, AffPair &q) {
+    q.ax = (FIRST && q.ea == MSM_NULL_ENTRY) ? Fq::zero() : ldg_fq(&pts[q.ea & 0x7fffffffu].x);
+    q.bx = (FIRST && q.eb == MSM_NULL_ENTRY) ? Fq::zero() : ldg_fq(&pts[q.eb & 0x7fffffffu].x);
+}
+template <bool FIRST> __device__ __forceinline__ void aff_fetch_y(const Affine<Fq> *__restrict__ pts, AffPair &q) {
+    q.ay = (FIRST && q.ea == MSM_NULL_ENTRY) ? Fq::zero() : ldg_fq(&pts[q.ea & 0x7fffffffu].y);
+    q.by = (FIRST && q.eb == MSM_NULL_ENTRY) ? Fq::zero() : ldg_fq(&pts[q.eb & 0x7fffffffu].y);
+    if (FIRST) { if (q.ea != MSM_NULL_ENTRY && (q.ea & 0x80000000u)) q.ay = q.ay.neg(); if (q.eb != MSM_NULL_ENTRY && (q.eb & 0x80000000u)) q.by = q.by.neg(); }
+}
+// can the pair be classified from the x coordinates alone?  (generic chord: distinct x, neither point at infinity)
+template <bool FIRST> __device__ __forceinline__ bool aff_is_generic(const AffPair &q) {
+    if (FIRST) return q.ea != MSM_NULL_ENTRY && q.eb != MSM_NULL_ENTRY && q.ax != q.bx;
+    return !q.ax.is_zero() && !q.bx.is_zero() && q.ax != q.bx;            // later rounds: infinity is (0, 0), so x != 0 rules it out
+}
+// kind of pair and its denominator; y coordinates must be present.  0 = chord, 1 = tangent (P + P), 2 = result a, 3 = result b, 4 = infinity
+template <bool FIRST> __device__ __forceinline__ int aff_classify(const AffPair &q, Fq &den) {
+    const bool ia = FIRST ? q.ea == MSM_NULL_ENTRY : (q.ax.is_zero() && q.ay.is_zero());
+    const bool ib = FIRST ? q.eb == MSM_NULL_ENTRY : (q.bx.is_zero() && q.by.is_zero());
+    den = Fq::one();
+    if (ia && ib) return 4;
+    if (ib) return 2;
+    if (ia) return 3;
+    if (q.ax != q.bx) { den = q.bx - q.ax; return 0; }
+    if (q.ay == q.by && !q.ay.is_zero()) { den = q.ay.dbl(); return 1; }
+    return 4;                                                              // P + (-P)
+}
+constexpr int AFF_UNROLL = 4;          // pairs whose loads are in flight together (the rounds are gather-latency bound otherwise)
+template <bool FIRST>
+static __global__ void __launch_bounds__(128) msm_affine_round_kernel(const Affine<Fq> *__restrict__ pts, const uint32_t *__restrict__ entries,
+                                                                      const uint32_t *__restrict__ offsets, uint32_t total_buckets, int shift_in,
+                                                                      Affine<Fq> *__restrict__ out, Fq *__restrict__ scratch, uint32_t threads) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_pairs = (__ldg(offsets + total_buckets) >> shift_in) >> 1;
+    if (t >= threads || t >= n_pairs) return;
+    const uint32_t mine = (n_pairs - 1 - t) / threads + 1;                 // pairs t, t + T, ... of this thread
+    // ---- pass 1: running product of the denominators ----
+    Fq c = Fq::one();
+    for (uint32_t k0 = 0; k0 < mine; k0 += AFF_UNROLL) {
+        AffPair q[AFF_UNROLL];
+#pragma unroll
+        for (int u = 0; u < AFF_UNROLL; u++) if (k0 + u < mine) aff_fetch_idx<FIRST>(entries, t + (k0 + u) * threads, q[u]);
+#pragma unroll
+        for (int u = 0; u < AFF_UNROLL; u++) if (k0 + u < mine) aff_fetch_x<FIRST>(pts, q[u]);
+#pragma unroll
+        for (int u = 0; u < AFF_UNROLL; u++) {
+            if (k0 + u >= mine) break;
+            Fq den;
+            if (aff_is_generic<FIRST>(q[u])) den = q[u].bx - q[u].ax;
+            else { aff_fetch_y<FIRST>(pts, q[u]); aff_classify<FIRST>(q[u], den); }
+            c = Fq::mul_impl(c, den);
+            st_fq(scratch + t + (k0 + u) * threads, c);
+        }
+    }
+    Fq inv = c.inverse_gcd();
+    // ---- pass 2: walk back, one slope per pair ----
+    for (uint32_t done = 0; done < mine; done += AFF_UNROLL / 2) {
+        AffPair q[AFF_UNROLL / 2]; Fq prev[AFF_UNROLL / 2];
+#pragma unroll
+        for (int u = 0; u < AFF_UNROLL / 2; u++) if (done + u < mine) aff_fetch_idx<FIRST>(entries, t + (mine - 1 - done - u) * threads, q[u]);
+#pragma unroll
+        for (int u = 0; u < AFF_UNROLL / 2; u++) if (done + u < mine) {
+            const uint32_t k = mine - 1 - done - u;
+            aff_fetch_x<FIRST>(pts, q[u]); aff_fetch_y<FIRST>(pts, q[u]);
+            if (k > 0) prev[u] = ld_fq_plain(scratch + t + (k - 1) * threads);
+        }
+#pragma unroll
+        for (int u = 0; u < AFF_UNROLL / 2; u++) {
+            if (done + u >= mine) break;
+            const uint32_t k = mine - 1 - done - u;
+            Fq den;
+            const int kind = aff_classify<FIRST>(q[u], den);
+            const Fq dinv = k > 0 ? Fq::mul_impl(inv, prev[u]) : inv;                    // inv = 1 / (product up to and including this pair)
+            inv = Fq::mul_impl(inv, den);
+            Affine<Fq> r;
+            if (kind <= 1) {
+                Fq num;
+                if (kind == 0) num = q[u].by - q[u].ay; else { const Fq xx = q[u].ax.sqr(); num = xx.dbl() + xx; }
+                const Fq lam = Fq::mul_impl(num, dinv);
+                r.x = Fq::sqr_impl(lam) - q[u].ax - q[u].bx;
+                r.y = Fq::mul_impl(lam, q[u].ax - r.x) - q[u].ay;
+            } else if (kind == 2) { r.x = q[u].ax; r.y = q[u].ay; }
+            else if (kind == 3) { r.x = q[u].bx; r.y = q[u].by; }
+            else r = Affine<Fq>::inf();
+            st_affine(out + t + k * threads, r);
+        }
+    }
+}
+
 // slots of bucket b: first slot and number of pieces (0 for an empty bucket)
 __device__ __forceinline__ uint32_t msm_bucket_span(const uint32_t *__restrict__ offsets, uint32_t L, uint32_t b, uint32_t &slot0) {
     const uint32_t o0 = __ldg(offsets + b), o1 = __ldg(offsets + b + 1);

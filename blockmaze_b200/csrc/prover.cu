@@ -337,8 +337,10 @@ static void decompress_vec(const std::vector<C> &v, A **out, uint8_t **skip, boo
 
 // =====================================================================================================================
 // MSM
-void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool expanded_) {
+void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool expanded_, int affine_rounds_) {
     n = n_; c = c_; windows = (255 + c - 1) / c; nb = 1u << (c - 1); ones = ones_; expanded = expanded_;
+    affine_rounds = (g1 && !g2 && affine_rounds_ > 0) ? (affine_rounds_ > 4 ? 4 : affine_rounds_) : 0;
+    if (const char *e = getenv("ZKB200_AFFINE_ALWAYS")) affine_always = atoi(e) != 0;
     regions = expanded ? 1u : (uint32_t)windows;
     total = regions * nb + ones;
     seg = 4; if (seg > nb) seg = nb;
@@ -348,6 +350,7 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool e
     ZK_CUDA(cudaMalloc(&offsets, (size_t)(total + 1) * 4));
     ZK_CUDA(cudaMalloc(&cursors, (size_t)(total + 1) * 4));
     entries_cap = (size_t)n * windows + 16;
+    if (affine_rounds) entries_cap += (size_t)total * ((1u << affine_rounds) - 1);        // every non-empty bucket padded to a multiple of 2^rounds
     ZK_CUDA(cudaMalloc(&entries, entries_cap * 4));
     ZK_CUDA(cudaMalloc(&heavy, (size_t)(MSM_HEAVY_MAX + 1) * 4)); ZK_CUDA(cudaMalloc(&heavy_g2, (size_t)(MSM_HEAVY_MAX + 1) * 4));
     ZK_CUDA(cudaEventCreateWithFlags(&ev_sorted, cudaEventDisableTiming));
@@ -364,6 +367,15 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool e
     acc_threads_g1 = (uint32_t)(sms * (occ1 > 0 ? occ1 : 1) * 128);
     acc_threads_g2 = (uint32_t)(sms * (occ2 > 0 ? occ2 : 1) * 128);
     ZK_CUDA(cudaEventCreate(&ev_acc0)); ZK_CUDA(cudaEventCreate(&ev_acc1));
+    if (affine_rounds) {
+        int per_sm = 2;                                              // CTAs of 128 threads per SM for the pair rounds: long batches beat occupancy
+        if (const char *e = getenv("ZKB200_AFF_CTAS")) { const int v = atoi(e); if (v > 0 && v <= 16) per_sm = v; }
+        aff_threads = (uint32_t)(sms * per_sm * 128);
+        ZK_CUDA(cudaMalloc(&offsets_shifted, (size_t)(total + 1) * 4));
+        size_t items = entries_cap;
+        for (int r = 0; r < affine_rounds; r++) { items = items / 2 + 1; ZK_CUDA(cudaMalloc(&aff_pts[r], items * sizeof(G1Affine))); }
+        ZK_CUDA(cudaMalloc(&aff_scratch, (entries_cap / 2 + 1) * 32));
+    }
     const size_t nout = (size_t)(regions + 1) * bpw;
     if (g1) {
         ZK_CUDA(cudaMalloc(&buckets_g1, ((size_t)acc_threads_g1 * waves_alone + total + 1) * sizeof(G1XYZZ)));
@@ -378,7 +390,8 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool e
 }
 float MsmPlan::last_acc_ms() const { float ms = 0; if (ev_acc0) cudaEventElapsedTime(&ms, ev_acc0, ev_acc1); return ms; }
 void MsmPlan::release() {
-    void *ps[] = {counts, offsets, cursors, entries, buckets_g1, buckets_g2, out_g1, out_g2, heavy, heavy_g2};
+    void *ps[] = {counts, offsets, cursors, entries, buckets_g1, buckets_g2, out_g1, out_g2, heavy, heavy_g2, offsets_shifted, aff_pts[0], aff_pts[1], aff_pts[2],
+                  aff_pts[3], aff_scratch};
     if (ev_sorted) cudaEventDestroy(ev_sorted);
     for (void *p : ps) if (p) cudaFree(p);
     if (ev_acc0) cudaEventDestroy(ev_acc0);
@@ -405,11 +418,25 @@ void *msm_expand_bases(const void *bases, uint32_t n, int c, bool g2) {
 template <class F>
 static void msm_points(cudaStream_t st, MsmPlan &p, const MsmShape &sh, const Affine<F> *bases, XYZZ<F> *partial, XYZZ<F> *out, void *h_out, bool timed) {
     const uint32_t *off = (const uint32_t *)p.offsets;
+    const uint32_t *entries = (const uint32_t *)p.entries;
+    if (timed) ZK_CUDA(cudaEventRecord(p.ev_acc0, st));
+    if constexpr (sizeof(F) == 32) {
+        if (p.rounds_now) {
+            // halving rounds: list r holds the pairwise sums of list r-1 (list -1 = the sorted entries pointing into the base table)
+            const Affine<Fq> *in = bases;
+            for (int r = 0; r < p.rounds_now; r++) {
+                Affine<Fq> *o = (Affine<Fq> *)p.aff_pts[r];
+                if (r == 0) ZK_LAUNCH(msm_affine_round_kernel<true>, p.aff_threads / 128, 128, 0, st, in, entries, off, p.total, 0, o, (Fq *)p.aff_scratch, p.aff_threads);
+                else ZK_LAUNCH(msm_affine_round_kernel<false>, p.aff_threads / 128, 128, 0, st, in, (const uint32_t *)nullptr, off, p.total, r, o, (Fq *)p.aff_scratch, p.aff_threads);
+                in = o;
+            }
+            bases = in; entries = nullptr; off = (const uint32_t *)p.offsets_shifted;
+        }
+    }
     const uint32_t T = sizeof(F) == 32 ? p.acc_threads_g1 * (p.alone ? (uint32_t)p.waves_alone : 1u) : p.acc_threads_g2;
     uint32_t *heavy = (uint32_t *)(sizeof(F) == 32 ? p.heavy : p.heavy_g2);
     ZK_CUDA(cudaMemsetAsync(heavy, 0, 4, st));
-    if (timed) ZK_CUDA(cudaEventRecord(p.ev_acc0, st));
-    ZK_LAUNCH(msm_accumulate_kernel<F>, T / 128, 128, 0, st, bases, off, (const uint32_t *)p.entries, p.total, T, partial);
+    ZK_LAUNCH(msm_accumulate_kernel<F>, T / 128, 128, 0, st, bases, off, entries, p.total, T, partial);
     if (timed) ZK_CUDA(cudaEventRecord(p.ev_acc1, st));
     ZK_LAUNCH(msm_fold_small_kernel<F>, cdiv(p.total, 128), 128, 0, st, partial, off, p.total, T, heavy);
     ZK_LAUNCH(msm_fold_heavy_kernel<F>, 64, MSM_HEAVY_THREADS, MSM_HEAVY_THREADS * sizeof(XYZZ<F>), st, partial, off, p.total, T, (const uint32_t *)heavy);
@@ -424,7 +451,12 @@ void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, con
     ZK_CUDA(cudaMemsetAsync(p.counts, 0, (size_t)(p.total + 1) * 4, st));
     ZK_CUDA(cudaMemsetAsync(p.cursors, 0, (size_t)(p.total + 1) * 4, st));
     if (p.n) ZK_LAUNCH(msm_count_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (uint32_t *)p.counts);
-    ZK_LAUNCH(msm_scan_kernel, 1, 1024, 0, st, (const uint32_t *)p.counts, (uint32_t *)p.offsets, p.total);
+    // A proof that has the GPU to itself skips the affine rounds: with nothing else resident they are bound by gather latency, not by the
+    // multiply pipe, and the plain XYZZ accumulation finishes sooner; with other proofs in flight their 40 % fewer multiplications win.
+    p.rounds_now = (p.affine_rounds && (!p.alone || p.affine_always)) ? p.affine_rounds : 0;
+    if (p.rounds_now) ZK_CUDA(cudaMemsetAsync(p.entries, 0xff, p.entries_cap * 4, st));          // pads of the bucket runs = null entries
+    ZK_LAUNCH(msm_scan_kernel, 1, 1024, 0, st, (const uint32_t *)p.counts, (uint32_t *)p.offsets, p.total, p.rounds_now,
+              (uint32_t *)(p.rounds_now ? p.offsets_shifted : nullptr));
     if (p.n) ZK_LAUNCH(msm_scatter_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (const uint32_t *)p.offsets, (uint32_t *)p.cursors, (uint32_t *)p.entries);
     // the G2 half of a knowledge-commitment query shares the digit sort and then runs beside the G1 half on its own stream
     if (bases_g2 && st_g2) { ZK_CUDA(cudaEventRecord(p.ev_sorted, st)); ZK_CUDA(cudaStreamWaitEvent(st_g2, p.ev_sorted, 0)); }
@@ -493,7 +525,12 @@ static Lane *lane_create(const DevicePk *pk, int index) {
     ln->mA.init(pk->nA, MSM_C_SIDE, 4096, true, false, true);
     ln->mB.init(pk->nB, MSM_C_SIDE, 4096, true, true, true);
     ln->mL.init(pk->nL, MSM_C_SIDE, 4096, true, false, true);
-    ln->mH.init(pk->nH, MSM_C, 0, true, false, true);
+    // Batched-affine halving rounds in front of the H-query accumulation (msm.cuh): measured and left OFF -- 2 rounds cut the multiplications
+    // per addition from 10 to 6 on paper, but with ~55 pairs per thread the two passes, the pair classification and the inversion put as
+    // many instructions on the multiply pipe as the XYZZ additions they replace (profiles/r02_notes.md).  ZKB200_AFFINE_ROUNDS=2 enables them.
+    int aff = 0;
+    if (const char *e = getenv("ZKB200_AFFINE_ROUNDS")) aff = atoi(e);
+    ln->mH.init(pk->nH, MSM_C, 0, true, false, true, aff);
     int prio_lo = 0, prio_hi = 0;
     ZK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));          // the QAP map + H MSM chain is the critical path
     if (const char *e = getenv("ZKB200_SIDE_PRIO")) { if (atoi(e) == 1) { const int t = prio_lo; prio_lo = prio_hi; prio_hi = t; } else if (atoi(e) == 2) prio_lo = prio_hi; }

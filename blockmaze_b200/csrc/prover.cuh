@@ -58,8 +58,15 @@ struct MsmPlan {
     void *out_g1 = nullptr, *out_g2 = nullptr;           // device partial sums  [(windows+1) * bpw]
     void *h_out_g1 = nullptr, *h_out_g2 = nullptr;       // pinned host copies
     cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr;    // around the G1 accumulate kernel (roofline measurement)
+    // batched-affine halving rounds in front of the XYZZ accumulation (msm.cuh); G1 only, 0 = off
+    int affine_rounds = 0, rounds_now = 0;               // configured / used by the run in flight (a proof alone on the GPU skips them)
+    bool affine_always = false;
+    uint32_t aff_threads = 0;
+    void *offsets_shifted = nullptr;                     // offsets >> affine_rounds
+    void *aff_pts[4] = {nullptr, nullptr, nullptr, nullptr};   // output list of each round (affine points)
+    void *aff_scratch = nullptr;                         // running denominator products, one Fq per pair of the first round
     float last_acc_ms() const;
-    void init(uint32_t n, int c, uint32_t ones, bool g1, bool g2, bool expanded);
+    void init(uint32_t n, int c, uint32_t ones, bool g1, bool g2, bool expanded, int affine_rounds = 0);
     void release();
 };
 struct ScalarRef { const void *scalars; const uint32_t *map; uint32_t offset; int montgomery; };

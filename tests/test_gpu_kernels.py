@@ -37,8 +37,8 @@ def test_field_layer_montgomery_bit_exact(zk, name, p):
     assert fl(zk.field_op(name, "sub", fb(a), fb(b))) == [(x - y) % p for x, y in zip(a, b)]
     assert fl(zk.field_op(name, "to_mont", fb(a))) == [x * (1 << 256) % p for x in a]
     assert fl(zk.field_op(name, "from_mont", fb(a))) == [x * Ri % p for x in a]
-    inv = fl(zk.field_op(name, "inverse", fb(a[:128])))
-    assert inv == [(pow(x * Ri % p, -1, p) * (1 << 256) % p if x else 0) for x in a[:128]]
+    inv = fl(zk.field_op(name, "inverse", fb(a[:3000])))                    # safegcd division steps on the device (ff.cuh inverse_gcd)
+    assert inv == [(pow(x * Ri % p, -1, p) * (1 << 256) % p if x else 0) for x in a[:3000]]
 
 
 def test_field_layer_against_reference(zk, ref):

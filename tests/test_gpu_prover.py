@@ -364,3 +364,31 @@ def test_keygen_keys_prove_and_verify(zk, tmp_path):
         assert not zk.verify_proof("mint", proof, zk.verify_args("mint", other))
     finally:
         zk.set_key_dir(key_dir())
+
+
+def test_affine_halving_rounds_give_the_same_proof():
+    """The experimental batched-affine front end of the H-query MSM (msm.cuh msm_affine_round_kernel, off by default) is switched on in a
+    child process (ZKB200_AFFINE_ROUNDS=2, forced also for a proof that runs alone): same proof bytes for the send and mint goldens, and the
+    fixed-base MSM of the sweep equals the windowed one."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, os, json, zlib, ctypes as C\n"
+        "sys.path.insert(0, %r)\n"
+        "import blockmaze_b200 as zk\n"
+        "zk.init(0)\n"
+        "for c in ('send', 'mint'):\n"
+        "    g = json.load(open(os.path.join(%r, c + '.json')))\n"
+        "    w = zlib.decompress(open(os.path.join(%r, c + '_assignment.bin.z'), 'rb').read())\n"
+        "    pk = zk.ProvingKey(os.path.join(%r, c + 'pk.txt'))\n"
+        "    assert pk.prove(w, int(g['r'], 16), int(g['s'], 16))['proof_hex'] == g['proof_hex'], c\n"
+        "    assert pk.prove(None, int(g['r'], 16), int(g['s'], 16))['proof_hex'] == g['proof_hex'], c\n"
+        "    pk.close()\n"
+        "a, b = C.create_string_buffer(64), C.create_string_buffer(64)\n"
+        "zk.lib.zkb200_bench_msm_slice(1, 0, 300000, 12, 1, a)\n"
+        "zk.lib.zkb200_bench_msm_slice(1, 0, 300000, -16, 1, b)\n"
+        "assert a.raw == b.raw and any(a.raw)\n"
+        "print('AFFINE OK')\n" % (root, GOLD, GOLD, key_dir()))
+    env = dict(os.environ, ZKB200_AFFINE_ROUNDS="2", ZKB200_AFFINE_ALWAYS="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert "AFFINE OK" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]

@@ -103,6 +103,10 @@ lib.zkb200_witness_deposit.restype = C.c_long
 lib.zkb200_witness_deposit.argtypes = GEN_SIGS["deposit"] + [C.c_void_p, C.c_size_t]
 
 lib.zkb200_g1_sum.argtypes = [C.c_size_t, C.c_char_p, C.c_char_p]
+lib.zkb200_witness_defer.argtypes = [C.c_int]
+lib.zkb200_witness_defer.restype = None
+lib.zkb200_last_assignment.restype = C.c_long
+lib.zkb200_last_assignment.argtypes = [C.c_char_p, C.c_size_t]
 lib.zkb200_g2_sum.argtypes = [C.c_size_t, C.c_char_p, C.c_char_p]
 lib.zkb200_synth_scalars.argtypes = [C.c_size_t, C.c_size_t, C.c_char_p]
 lib.zkb200_synth_bases.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_char_p]
@@ -313,8 +317,27 @@ def verify_args(circuit, gen_args):
     return [rt, a[11], a[8], a[2], a[9], a[6]]                # RT, pk, cmtB_old, sn_old, cmtB, sn_s
 
 
-def witness(circuit, args):
-    """Full variable assignment (bytes, num_variables*32) computed by the native host generators."""
+def witness(circuit, args, defer=False):
+    """Full variable assignment (bytes, num_variables*32) computed by the native host generators.  defer=True: the SHA-256 gadget runs
+    come from the seed expansion that gen_proof performs on the GPU (here: its host copy)."""
+    lib.zkb200_witness_defer(1 if defer else 0)
+    try:
+        return _witness(circuit, args)
+    finally:
+        lib.zkb200_witness_defer(0)
+
+
+def last_assignment(circuit):
+    """The assignment on the GPU behind this thread's last gen_proof call (zkb200_last_assignment)."""
+    n = NUM_VARS[circuit]
+    out = C.create_string_buffer(32 * n)
+    got = lib.zkb200_last_assignment(out, 32 * n)
+    if got != n:
+        raise ZkError("zkb200_last_assignment failed (%d)" % got)
+    return out.raw
+
+
+def _witness(circuit, args):
     n = NUM_VARS[circuit]
     out = C.create_string_buffer(32 * n)
     ptr = C.cast(out, C.c_void_p)

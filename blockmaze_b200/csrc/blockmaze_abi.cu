@@ -39,7 +39,10 @@ static std::shared_ptr<KeySet> g_keys[4];
 static std::vector<uint32_t> g_words;
 static size_t g_word_pos = 0;
 static thread_local double g_last_ms[4] = {0, 0, 0, 0};      // witness generation, prove call, of which GPU, host finish (last gen*proof of this thread)
-static thread_local int g_last_device = -1;
+static thread_local int g_last_device = -1, g_last_lane = -1;
+static thread_local void *g_last_pk = nullptr;
+// SHA-256 gadget runs expanded on the GPU (default) or by the host generator (ZKB200_GPU_WITNESS=0)
+static bool gpu_witness() { static const bool on = [] { const char *e = getenv("ZKB200_GPU_WITNESS"); return !(e && atoi(e) == 0); }(); return on; }
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const char *CIRCUIT_NAMES[4] = {"mint", "send", "deposit", "redeem"};
 
@@ -158,7 +161,7 @@ template <class Fn> static char *prove_timed(int circuit, Fn make) {
     const std::shared_ptr<KeySet> ks = circuit_keys(circuit, sched);          // held for the whole call: zkb200_set_key_dir cannot free it under us
     const int slot = sched->pick();
     void *pk = ks->pk[slot];
-    g_last_device = ks->devices[slot];
+    g_last_device = ks->devices[slot]; g_last_pk = pk;
     const int lane = zkb200_lane_acquire(pk);
     uint64_t *ext = zkb200_lane_staging(pk, lane);             // pinned: the generator writes the compact assignment in place
     const double t0 = now_ms();
@@ -170,7 +173,8 @@ template <class Fn> static char *prove_timed(int circuit, Fn make) {
     memset(p, 0, 1153);
     float tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const double t1 = now_ms();
-    const int rc = zkb200_prove_compact(pk, a.lo(), a.wide.data(), a.wide.size(), (const uint8_t *)r, (const uint8_t *)s, p, tm);
+    const int rc = zkb200_prove_compact(pk, a.lo(), a.wide.data(), a.wide.size(), a.seeds.data(), a.seeds.size(), (const uint8_t *)r, (const uint8_t *)s, p, tm);
+    g_last_lane = lane;
     g_last_ms[1] = now_ms() - t1; g_last_ms[2] = tm[0]; g_last_ms[3] = tm[3];
     zkb200_lane_release(pk, lane);
     sched->done(slot);
@@ -179,6 +183,14 @@ template <class Fn> static char *prove_timed(int circuit, Fn make) {
     return p;
 }
 int zkb200_last_device(void) { return g_last_device; }
+// parity hook: the assignment on the GPU behind this thread's last gen*proof (valid until another proof takes that lane)
+long zkb200_last_assignment(uint8_t *out, size_t cap_bytes) {
+    if (!g_last_pk || g_last_lane < 0) return -1;
+    uint64_t info[8];
+    if (zkb200_pk_info(g_last_pk, info, nullptr)) return -1;
+    if (cap_bytes < info[0] * 32) return -1;
+    return zkb200_lane_read_assignment(g_last_pk, g_last_lane, out) ? -1 : (long)info[0];
+}
 
 // ---- helpers ---------------------------------------------------------------------------------------------------------------
 char *genCMT(uint64_t value, char *sn_string, char *r_string) {
@@ -233,7 +245,7 @@ char *genMintproof(uint64_t value, uint64_t value_old, char *sn_old_string, char
     Note note_old, note; uint8_t cmtA_old[32], cmtA[32], sk[32];
     parse_note(note_old, value_old, sn_old_string, r_old_string); parse_note(note, value, sn_string, r_string);
     parse_hex_blob(cmtA_old_string, cmtA_old, 32); parse_hex_blob(cmtA_string, cmtA, 32); parse_hex_blob(sk_string, sk, 32);
-    return prove_timed(ZKB200_MINT, [&](uint64_t *ext) { return mint_witness(note_old, note, cmtA_old, cmtA, value_s, sk, ext); });
+    return prove_timed(ZKB200_MINT, [&](uint64_t *ext) { return mint_witness(note_old, note, cmtA_old, cmtA, value_s, sk, ext, gpu_witness()); });
 }
 char *genRedeemproof(uint64_t value, uint64_t value_old, char *sn_old_string, char *r_old_string, char *sn_string, char *r_string,
                      char *cmtA_old_string, char *cmtA_string, uint64_t value_s, char *sk_string) {
@@ -241,7 +253,7 @@ char *genRedeemproof(uint64_t value, uint64_t value_old, char *sn_old_string, ch
     parse_note(note_old, value_old, sn_old_string, r_old_string); parse_note(note, value, sn_string, r_string);
     parse_hex_blob(cmtA_old_string, cmtA_old, 32); parse_hex_blob(cmtA_string, cmtA, 32); parse_hex_blob(sk_string, sk, 32);
     printf("Trying to generate redeem proof...\n");            // redeemcgo.cpp:310
-    return prove_timed(ZKB200_REDEEM, [&](uint64_t *ext) { return redeem_witness(note_old, note, cmtA_old, cmtA, value_s, sk, ext); });
+    return prove_timed(ZKB200_REDEEM, [&](uint64_t *ext) { return redeem_witness(note_old, note, cmtA_old, cmtA, value_s, sk, ext, gpu_witness()); });
 }
 char *genSendproof(uint64_t value_A, char *r_s_string, char *sn_string, char *r_string, char *cmt_s_string, char *cmtA_string, uint64_t value_s,
                    char *pk_recv_string, uint64_t value_A_new, char *sn_A_new, char *r_A_new, char *cmt_A_new, char *sk_string,
@@ -253,7 +265,7 @@ char *genSendproof(uint64_t value_A, char *r_s_string, char *sn_string, char *r_
     parse_hex_blob(cmt_s_string, cmtS, 32); parse_hex_blob(cmtA_string, cmtA, 32); parse_hex_blob(cmt_A_new, cmtAnew, 32);
     parse_hex_blob(sk_string, sk, 32); parse_hex_blob(pk_sender_string, pk_sender, 20);
     printf("Trying to generate send proof...\n");              // sendcgo.cpp:352
-    return prove_timed(ZKB200_SEND, [&](uint64_t *ext) { return send_witness(note_old, notes, note_new, cmtA, cmtS, cmtAnew, sk, pk_sender, ext); });
+    return prove_timed(ZKB200_SEND, [&](uint64_t *ext) { return send_witness(note_old, notes, note_new, cmtA, cmtS, cmtAnew, sk, pk_sender, ext, gpu_witness()); });
 }
 char *genDepositproof(uint64_t value, uint64_t value_old, char *sn_old_string, char *r_old_string, char *sn_string, char *r_string,
                       char *sns_string, char *rs_string, char *cmtB_old_string, char *cmtB_string, uint64_t value_s, char *pk_string,
@@ -283,10 +295,15 @@ char *genDepositproof(uint64_t value, uint64_t value_old, char *sn_old_string, c
     eff.insert(eff.end(), leaves.begin() + (last + 1) * 32, leaves.end());
     uint8_t siblings[MERKLE_DEPTH][32], rt[32];
     merkle_path((const uint8_t(*)[32])eff.data(), eff.size() / 32, (size_t)first, siblings, rt);
-    return prove_timed(ZKB200_DEPOSIT, [&](uint64_t *ext) { return deposit_witness(note_s, note_old, note, cmtS, cmtB_old, cmtB, rt, (size_t)first, siblings, sn_s, sk, ext); });
+    return prove_timed(ZKB200_DEPOSIT, [&](uint64_t *ext) { return deposit_witness(note_s, note_old, note, cmtS, cmtB_old, cmtB, rt, (size_t)first, siblings, sn_s, sk, ext, gpu_witness()); });
 }
 
 void zkb200_last_breakdown_ms(double out[4]) { for (int i = 0; i < 4; i++) out[i] = g_last_ms[i]; }
+
+// parity hook for the GPU witness path: when on, the zkb200_witness_* functions below run the generator in its deferred mode (SHA-256 runs
+// left out, seeds recorded) and fill the runs in with the host copy of the expansion the GPU kernel performs (witness_sha.hpp)
+static thread_local bool g_witness_defer = false;
+void zkb200_witness_defer(int on) { g_witness_defer = on != 0; }
 
 // ---- witness-only entry points (parity hooks for the assignment layout; declared extern "C" in zkb200.h) ------------------------
 long zkb200_witness_mint(uint64_t value, uint64_t value_old, const char *sn_old, const char *r_old, const char *sn, const char *r,
@@ -294,7 +311,7 @@ long zkb200_witness_mint(uint64_t value, uint64_t value_old, const char *sn_old,
     Note note_old, note; uint8_t cmtA_old[32], cmtA[32], sk[32];
     parse_note(note_old, value_old, sn_old, r_old); parse_note(note, value, sn, r);
     parse_hex_blob(cmtA_old_s, cmtA_old, 32); parse_hex_blob(cmtA_s, cmtA, 32); parse_hex_blob(sk_s, sk, 32);
-    Assignment a = redeem ? redeem_witness(note_old, note, cmtA_old, cmtA, value_s, sk) : mint_witness(note_old, note, cmtA_old, cmtA, value_s, sk);
+    Assignment a = redeem ? redeem_witness(note_old, note, cmtA_old, cmtA, value_s, sk, nullptr, g_witness_defer) : mint_witness(note_old, note, cmtA_old, cmtA, value_s, sk, nullptr, g_witness_defer);
     if (cap < a.num_vars) return -1;
     a.expand(out);
     return a.num_vars;
@@ -307,7 +324,7 @@ long zkb200_witness_send(uint64_t value_A, const char *r_s, const char *sn, cons
     notes.value = value_s; parse_hex_blob(pk_recv, notes.pk, 20); parse_hex_blob(r_s, notes.r, 32); memcpy(notes.sn_old, note_old.sn, 32);
     parse_hex_blob(cmt_s, cmtS, 32); parse_hex_blob(cmtA_s, cmtA, 32); parse_hex_blob(cmt_A_new, cmtAnew, 32);
     parse_hex_blob(sk_s, sk, 32); parse_hex_blob(pk_sender_s, pk_sender, 20);
-    Assignment a = send_witness(note_old, notes, note_new, cmtA, cmtS, cmtAnew, sk, pk_sender);
+    Assignment a = send_witness(note_old, notes, note_new, cmtA, cmtS, cmtAnew, sk, pk_sender, nullptr, g_witness_defer);
     if (cap < a.num_vars) return -1;
     a.expand(out);
     return a.num_vars;
@@ -330,7 +347,7 @@ long zkb200_witness_deposit(uint64_t value, uint64_t value_old, const char *sn_o
     eff.insert(eff.end(), leaves.begin() + (last + 1) * 32, leaves.end());
     uint8_t siblings[MERKLE_DEPTH][32], rt[32];
     merkle_path((const uint8_t(*)[32])eff.data(), eff.size() / 32, (size_t)first, siblings, rt);
-    Assignment a = deposit_witness(note_s, note_old, note, cmtS, cmtB_old, cmtB, rt, (size_t)first, siblings, sn_s, sk);
+    Assignment a = deposit_witness(note_s, note_old, note, cmtS, cmtB_old, cmtB, rt, (size_t)first, siblings, sn_s, sk, nullptr, g_witness_defer);
     if (cap < a.num_vars) return -1;
     a.expand(out);
     return a.num_vars;

@@ -271,14 +271,14 @@ static int finish_outputs(ProofPoints &pp, double host_ms, char *proof_hex_out, 
     return pp.satisfied ? 0 : 1;
 }
 static int prove_any(void *h, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint8_t r[32], const uint8_t s[32],
-                     char *proof_hex_out, uint8_t *parts, float *timings_ms) {
+                     char *proof_hex_out, uint8_t *parts, float *timings_ms, const void *seeds = nullptr, uint32_t nseeds = 0) {
     DevicePk *pk = (DevicePk *)h;
     if (!pk) return -1;
     uint64_t rr[4], ss[4]; memcpy(rr, r, 32); memcpy(ss, s, 32);
     ProofPoints pp;
     pp.want_parts = parts != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
-    const int rc = lo ? prove_compact(pk, lo, wide, nwide, rr, ss, pp) : prove(pk, assignment, rr, ss, pp);
+    const int rc = lo ? prove_compact(pk, lo, wide, nwide, rr, ss, pp, seeds, nseeds) : prove(pk, assignment, rr, ss, pp);
     (void)t0;
     if (rc < 0) { set_err("prove: malformed input (" + std::to_string(rc) + ")"); return rc; }
     return finish_outputs(pp, pp.host_tail_ms, proof_hex_out, parts, timings_ms);
@@ -286,9 +286,15 @@ static int prove_any(void *h, const uint8_t *assignment, const uint64_t *lo, con
 int zkb200_prove(void *h, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32], char *proof_hex_out, uint8_t *parts, float *timings_ms) {
     return prove_any(h, assignment, nullptr, nullptr, 0, r, s, proof_hex_out, parts, timings_ms);
 }
-int zkb200_prove_compact(void *h, const uint64_t *lo, const void *wide, size_t nwide, const uint8_t r[32], const uint8_t s[32], char *proof_hex_out,
-                         float *timings_ms) {
-    return prove_any(h, nullptr, lo, (const WideIn *)wide, (uint32_t)nwide, r, s, proof_hex_out, nullptr, timings_ms);
+int zkb200_prove_compact(void *h, const uint64_t *lo, const void *wide, size_t nwide, const void *seeds, size_t nseeds, const uint8_t r[32], const uint8_t s[32],
+                         char *proof_hex_out, float *timings_ms) {
+    if (nseeds > 0xffffffffull) return -5;
+    return prove_any(h, nullptr, lo, (const WideIn *)wide, (uint32_t)nwide, r, s, proof_hex_out, nullptr, timings_ms, seeds, (uint32_t)nseeds);
+}
+int zkb200_lane_read_assignment(void *h, int lane, uint8_t *out) {
+    DevicePk *pk = (DevicePk *)h;
+    if (!pk || lane < 0 || lane >= pk->nlanes) return -1;
+    return lane_read_assignment(pk, pk->lanes[lane], out);
 }
 int zkb200_pk_lanes(void *h) { return h ? ((DevicePk *)h)->nlanes : 0; }
 int zkb200_lane_acquire(void *h) { return h ? lane_acquire((DevicePk *)h)->index : -1; }
@@ -305,11 +311,13 @@ int zkb200_prove_submit(void *h, int lane, const uint8_t *assignment, const uint
     uint64_t rr[4], ss[4]; memcpy(rr, r, 32); memcpy(ss, s, 32);
     return prove_submit((DevicePk *)h, ln, assignment, nullptr, nullptr, 0, rr, ss);
 }
-int zkb200_prove_submit_compact(void *h, int lane, const uint64_t *lo, const void *wide, size_t nwide, const uint8_t r[32], const uint8_t s[32]) {
+int zkb200_prove_submit_compact(void *h, int lane, const uint64_t *lo, const void *wide, size_t nwide, const void *seeds, size_t nseeds, const uint8_t r[32],
+                                const uint8_t s[32]) {
     Lane *ln = held_lane(h, lane);
     if (!ln || ln->pending || !lo) return -1;
+    if (nseeds > 0xffffffffull) return -5;
     uint64_t rr[4], ss[4]; memcpy(rr, r, 32); memcpy(ss, s, 32);
-    return prove_submit((DevicePk *)h, ln, nullptr, lo, (const WideIn *)wide, (uint32_t)nwide, rr, ss);
+    return prove_submit((DevicePk *)h, ln, nullptr, lo, (const WideIn *)wide, (uint32_t)nwide, rr, ss, seeds, (uint32_t)nseeds);
 }
 int zkb200_prove_collect(void *h, int lane, char *proof_hex_out, uint8_t *parts, float *timings_ms) {
     Lane *ln = held_lane(h, lane);

@@ -4,6 +4,7 @@
 // fixed-base tables, constraint matrices and twiddles stay resident in HBM, and so do a few "lanes" of work buffers so that several
 // proofs are in flight; a proof is one H2D copy of the (compact) assignment, ~42 kernel launches on five streams, and a D2H copy of
 // a hundred partial sums.
+#include <algorithm>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -15,6 +16,7 @@
 #include "pk_format.hpp"
 #include "ntt.cuh"
 #include "msm.cuh"
+#include "witness_sha.hpp"
 
 namespace zkp {
 using namespace zk;
@@ -493,6 +495,9 @@ static void upload_csr(const zkpk::Csr &h, DeviceCsr &d) {
     ZK_CUDA(cudaMemcpy(d.coef, h.coef.data(), (size_t)d.nnz * 4, cudaMemcpyHostToDevice));
 }
 constexpr uint32_t MAX_WIDE = 64;
+struct SeedDev { uint32_t base; uint32_t w[16]; uint32_t h[8]; };      // one SHA-256 compression gadget to expand on the GPU (see sha256_witness_kernel)
+static_assert(sizeof(SeedDev) == 100, "seed layout is part of the C-ABI (zkw::CompressionSeed)");
+constexpr uint32_t SHA_RUN = zkw::SHA_RUN_VARS, MAX_SEEDS = 32;
 constexpr int MSM_C = 16;                  // window bits of the dense H-query MSM: 16 windows, 32768 buckets
 // Witness queries (A, B, L): 97 % of the scalars are 0 or 1 ("ones" buckets), nearly all others fit 64 bits, so only a few thousand
 // entries reach the windowed buckets.  With 16-bit windows they were scattered over 32768 buckets and the bucket reduction (a chain of
@@ -516,6 +521,8 @@ static Lane *lane_create(const DevicePk *pk, int index) {
     ZK_CUDA(cudaMemcpy(ln->w_can, one_can, 32, cudaMemcpyHostToDevice));
     ZK_CUDA(cudaMallocHost(&ln->h_w_pinned, (nw + 1) * 32));
     ZK_CUDA(cudaMalloc(&ln->w_lo, nw * 8)); ZK_CUDA(cudaMalloc(&ln->w_wide, MAX_WIDE * sizeof(WideIn)));
+    ZK_CUDA(cudaMalloc(&ln->d_seeds, MAX_SEEDS * sizeof(SeedDev) + (MAX_SEEDS + 1) * 16));                  // seeds, then the segment table
+    ZK_CUDA(cudaMallocHost(&ln->h_seeds_pinned, MAX_SEEDS * sizeof(SeedDev) + (MAX_SEEDS + 1) * 16));
     ZK_CUDA(cudaMallocHost(&ln->h_wide_pinned, MAX_WIDE * sizeof(WideIn)));
     ZK_CUDA(cudaMalloc(&ln->bufA, 3 * m * 32));                     // A | B | C contiguous: the three transforms of a stage share one launch
     ln->bufB = (char *)ln->bufA + m * 32; ln->bufC = (char *)ln->bufA + 2 * m * 32;
@@ -545,7 +552,8 @@ static Lane *lane_create(const DevicePk *pk, int index) {
     return ln;
 }
 static void lane_destroy(Lane *ln) {
-    void *ps[] = {ln->w_can, ln->w_mont, ln->bufA, ln->tmp, ln->sat_flag, ln->w_lo, ln->w_wide};
+    void *ps[] = {ln->w_can, ln->w_mont, ln->bufA, ln->tmp, ln->sat_flag, ln->w_lo, ln->w_wide, ln->d_seeds};
+    if (ln->h_seeds_pinned) cudaFreeHost(ln->h_seeds_pinned);
     for (void *p : ps) if (p) cudaFree(p);
     if (ln->h_wide_pinned) cudaFreeHost(ln->h_wide_pinned);
     if (ln->h_w_pinned) cudaFreeHost(ln->h_w_pinned);
@@ -737,6 +745,25 @@ __global__ void patch_wide_kernel(const WideIn *__restrict__ wide, uint32_t nwid
     st_fr(w_can + wide[k].idx, c);
     if (wide[k].idx < mont_limit) st_fr(w_mont + wide[k].idx, c.to_mont());
 }
+// ---- SHA-256 gadget witness on the GPU -------------------------------------------------------------------------
+// 97 % of a BlockMaze assignment are the internal variables of sha256_compression_function_gadget instances: per compression a contiguous
+// run of 24 792 variables, every one of them a 32-bit word of the 64-round trace, a bit of such a word, or an unreduced sum with its
+// overflow bits (layout: witness_sha.hpp).  The host generator (witness.cpp) hands over a 100-byte seed per compression -- the run's first
+// variable, the 16 message words, the incoming chaining value -- and one CTA per compression re-runs the rounds (one thread, microseconds)
+// and then writes the run straight into the canonical and the Montgomery assignment.
+__global__ void __launch_bounds__(256) sha256_witness_kernel(const SeedDev *__restrict__ seeds, Fr *__restrict__ w_can, Fr *__restrict__ w_mont) {
+    __shared__ zkw::ShaTrace T;
+    const SeedDev sd = seeds[blockIdx.x];
+    if (threadIdx.x == 0) zkw::sha_trace_build(sd.w, sd.h, T);
+    __syncthreads();
+    for (uint32_t v = threadIdx.x; v < SHA_RUN; v += blockDim.x) {
+        const uint64_t x = zkw::sha_trace_value(T, v);
+        Fr c = Fr::zero(); c.v[0] = (uint32_t)x; c.v[1] = (uint32_t)(x >> 32);
+        st_fr(w_can + sd.base + v, c);
+        st_fr(w_mont + sd.base + v, x <= 1 ? (x ? Fr::one() : c) : c.to_mont());
+    }
+}
+
 static void upload_compact(DevicePk *pk, Lane *ln, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t *zk_scalars, cudaStream_t st) {
     const uint32_t n = (uint32_t)pk->num_vars;
     uint64_t *pin = (uint64_t *)ln->h_w_pinned;
@@ -748,6 +775,54 @@ static void upload_compact(DevicePk *pk, Lane *ln, const uint64_t *lo, const Wid
     ZK_CUDA(cudaMemcpyAsync(ln->w_lo, pin, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     ZK_CUDA(cudaMemcpyAsync(ln->w_wide, pw, nwide * sizeof(WideIn), cudaMemcpyHostToDevice, st));
     ZK_LAUNCH(expand_assignment_kernel, cdiv(n + 1, 256), 256, 0, st, (const uint64_t *)ln->w_lo, n + 1, (Fr *)ln->w_can, (Fr *)ln->w_mont);
+    ZK_LAUNCH(patch_wide_kernel, 1, 64, 0, st, (const WideIn *)ln->w_wide, nwide, n + 1, (Fr *)ln->w_can, (Fr *)ln->w_mont);
+}
+// With seeds, only the variables OUTSIDE the compression runs travel: they are packed to the front of the pinned staging buffer (a few
+// dozen KB instead of 1.8 MB for send) together with a table of (first variable, count) segments, expanded by one small kernel, and the
+// runs are written by sha256_witness_kernel.
+struct SegDev { uint32_t dst, len, src, pad; };
+constexpr uint32_t MAX_SEGS = MAX_SEEDS + 1;
+__global__ void expand_segments_kernel(const uint64_t *__restrict__ packed, const SegDev *__restrict__ segs, uint32_t nseg, uint32_t total,
+                                       Fr *__restrict__ w_can, Fr *__restrict__ w_mont) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    uint32_t k = 0;
+    while (k + 1 < nseg && i >= segs[k + 1].src) k++;
+    const uint32_t dst = segs[k].dst + (i - segs[k].src);
+    const uint64_t x = packed[i];
+    Fr c = Fr::zero(); c.v[0] = (uint32_t)x; c.v[1] = (uint32_t)(x >> 32);
+    st_fr(w_can + dst, c);
+    st_fr(w_mont + dst, x <= 1 ? (x ? Fr::one() : c) : c.to_mont());
+}
+static void upload_compact_seeded(DevicePk *pk, Lane *ln, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const SeedDev *seeds, uint32_t nseeds,
+                                  const uint64_t *zk_scalars, cudaStream_t st) {
+    const uint32_t n = (uint32_t)pk->num_vars;
+    // runs in increasing order of their first variable (the generators emit them that way; sort anyway: the input is untrusted)
+    SeedDev *hs = (SeedDev *)ln->h_seeds_pinned;
+    memcpy(hs, seeds, (size_t)nseeds * sizeof(SeedDev));
+    std::sort(hs, hs + nseeds, [](const SeedDev &a, const SeedDev &b) { return a.base < b.base; });
+    SegDev *segs = (SegDev *)((char *)ln->h_seeds_pinned + MAX_SEEDS * sizeof(SeedDev));
+    uint64_t *pin = (uint64_t *)ln->h_w_pinned;
+    uint32_t nseg = 0, packed = 0, cur = 0;                      // cur: next variable not yet covered
+    for (uint32_t k = 0; k <= nseeds; k++) {
+        const uint32_t stop = k < nseeds ? hs[k].base : n + 1;
+        if (stop > cur) {
+            segs[nseg++] = SegDev{cur, stop - cur, packed, 0};
+            memmove(pin + packed, lo + cur, (size_t)(stop - cur) * 8);      // in place when lo is this lane's staging buffer (packed <= cur)
+            packed += stop - cur;
+        }
+        if (k < nseeds) cur = hs[k].base + SHA_RUN > cur ? hs[k].base + SHA_RUN : cur;      // overlapping runs: still every variable covered once
+    }
+    WideIn *pw = (WideIn *)ln->h_wide_pinned;
+    if (nwide) memcpy(pw, wide, nwide * sizeof(WideIn));
+    for (int k = 0; k < 3; k++) { pw[nwide + k].idx = n + 1 + k; pw[nwide + k].pad = 0; memcpy(pw[nwide + k].v, zk_scalars + 4 * k, 32); }
+    nwide += 3;
+    ZK_CUDA(cudaMemcpyAsync(ln->w_lo, pin, (size_t)packed * 8, cudaMemcpyHostToDevice, st));
+    ZK_CUDA(cudaMemcpyAsync(ln->d_seeds, hs, MAX_SEEDS * sizeof(SeedDev) + (size_t)nseg * sizeof(SegDev), cudaMemcpyHostToDevice, st));
+    ZK_CUDA(cudaMemcpyAsync(ln->w_wide, pw, nwide * sizeof(WideIn), cudaMemcpyHostToDevice, st));
+    const SegDev *dsegs = (const SegDev *)((const char *)ln->d_seeds + MAX_SEEDS * sizeof(SeedDev));
+    if (packed) ZK_LAUNCH(expand_segments_kernel, cdiv(packed, 256), 256, 0, st, (const uint64_t *)ln->w_lo, dsegs, nseg, packed, (Fr *)ln->w_can, (Fr *)ln->w_mont);
+    ZK_LAUNCH(sha256_witness_kernel, nseeds, 256, 0, st, (const SeedDev *)ln->d_seeds, (Fr *)ln->w_can, (Fr *)ln->w_mont);
     ZK_LAUNCH(patch_wide_kernel, 1, 64, 0, st, (const WideIn *)ln->w_wide, nwide, n + 1, (Fr *)ln->w_can, (Fr *)ln->w_mont);
 }
 
@@ -790,16 +865,29 @@ int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int
     return 0;
 }
 
+// parity hook: the canonical assignment [w_1 .. w_n] a lane holds (what the last proof on it was made for)
+int lane_read_assignment(DevicePk *pk, Lane *ln, uint8_t *out) {
+    device_init(pk->device);
+    ZK_CUDA(cudaStreamSynchronize(ln->s_main));
+    ZK_CUDA(cudaMemcpy(out, (const char *)ln->w_can + 32, (size_t)pk->num_vars * 32, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 static HG1 g1_mul(const HG1Affine &p, const uint64_t k[4]) { return HG1::from_affine(p).mul(k); }
 
 int prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4],
-                 const uint64_t s[4]) {
+                 const uint64_t s[4], const void *seeds, uint32_t nseeds) {
     // malformed input is an error, never a proof of something else
     if (HFr::geq_mod(r) || HFr::geq_mod(s)) return -4;
     if (lo) {
         if (nwide > MAX_WIDE - 3 || (nwide && !wide)) return -2;
         for (uint32_t k = 0; k < nwide; k++) if (wide[k].idx == 0 || wide[k].idx > pk->num_vars) return -3;
-    }
+        if (nseeds > MAX_SEEDS || (nseeds && !seeds)) return -5;
+        for (uint32_t k = 0; k < nseeds; k++) {
+            const uint32_t base = ((const SeedDev *)seeds)[k].base;
+            if (base == 0 || (uint64_t)base + SHA_RUN > pk->num_vars + 1) return -5;
+        }
+    } else if (nseeds) return -5;
     device_init(pk->device);
     g_launches = 0;
     cudaStream_t st = ln->s_main;
@@ -808,7 +896,8 @@ int prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64
     memcpy(zks, r, 32); memcpy(zks + 4, s, 32);
     (HFr::from_canonical(r) * HFr::from_canonical(s)).neg().to_canonical(zks + 8);          // -(r*s) mod r
     ZK_CUDA(cudaEventRecord(ln->ev_t0, st));
-    if (lo) upload_compact(pk, ln, lo, wide, nwide, zks, st);
+    if (lo && nseeds) upload_compact_seeded(pk, ln, lo, wide, nwide, (const SeedDev *)seeds, nseeds, zks, st);
+    else if (lo) upload_compact(pk, ln, lo, wide, nwide, zks, st);
     else upload_assignment(pk, ln, assignment, zks, st);
     ZK_CUDA(cudaEventRecord(ln->ev_w, st));
     // A, B, L queries on side streams: scalars are the canonical padded assignment [1 | w]  (r1cs_gg_ppzksnark.tcc:437-484); the trailing
@@ -901,10 +990,11 @@ int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const ui
     lane_release(pk, ln);
     return rc;
 }
-int prove_compact(DevicePk *pk, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4], const uint64_t s[4], ProofPoints &out) {
+int prove_compact(DevicePk *pk, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4], const uint64_t s[4], ProofPoints &out,
+                  const void *seeds, uint32_t nseeds) {
     Lane *own = lane_of_staging(pk, lo);               // the caller generated the witness in a lane it already holds
     Lane *ln = own ? own : lane_acquire(pk);
-    int rc = prove_submit(pk, ln, nullptr, lo, wide, nwide, r, s);
+    int rc = prove_submit(pk, ln, nullptr, lo, wide, nwide, r, s, seeds, nseeds);
     if (rc == 0) rc = prove_collect(pk, ln, out);
     if (!own) lane_release(pk, ln);
     return rc;

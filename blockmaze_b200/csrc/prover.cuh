@@ -89,6 +89,7 @@ struct Lane {
     void *h_w_pinned = nullptr;
     void *w_lo = nullptr, *w_wide = nullptr;              // device: compact assignment staging
     void *h_wide_pinned = nullptr;
+    void *d_seeds = nullptr, *h_seeds_pinned = nullptr;  // SHA-256 compression seeds of a GPU-expanded witness (prover.cu sha256_witness_kernel)
     void *bufA = nullptr, *bufB = nullptr, *bufC = nullptr, *tmp = nullptr;   // m Fr each
     uint32_t *sat_flag = nullptr; uint32_t *h_sat_flag = nullptr;
     MsmPlan mA, mB, mH, mL;
@@ -150,12 +151,16 @@ struct ProofPoints {
 // collect: waits for the lane's streams, sums the partial points and assembles the proof on the host.
 struct WideIn { uint32_t idx; uint32_t pad; uint64_t v[4]; };
 // returns 0, or < 0 without touching the lane: -2 too many wide values, -3 wide index out of range, -4 r or s not below the group order
+//   seeds     : (compact form only) `nseeds` records {uint32 base; uint32 w[16]; uint32 h[8]} of SHA-256 compression gadgets whose runs of
+//               24 792 variables are not in lo (unset there) but expanded on the GPU; -5 if a run does not fit the assignment
 int prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4],
-                 const uint64_t s[4]);
+                 const uint64_t s[4], const void *seeds = nullptr, uint32_t nseeds = 0);
+int lane_read_assignment(DevicePk *pk, Lane *ln, uint8_t *out);
 int prove_collect(DevicePk *pk, Lane *ln, ProofPoints &out);
 // synchronous conveniences: acquire a lane (or use the one that owns `lo`), submit, collect, release
 int prove(DevicePk *pk, const uint8_t *assignment, const uint64_t r[4], const uint64_t s[4], ProofPoints &out);
-int prove_compact(DevicePk *pk, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4], const uint64_t s[4], ProofPoints &out);
+int prove_compact(DevicePk *pk, const uint64_t *lo, const WideIn *wide, uint32_t nwide, const uint64_t r[4], const uint64_t s[4], ProofPoints &out,
+                  const void *seeds = nullptr, uint32_t nseeds = 0);
 uint64_t *compact_staging(Lane *ln);                    // pinned, (num_vars + 1) uint64
 // QAP witness map only; writes (m+1)*32 bytes canonical to host `out_H`
 int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied);

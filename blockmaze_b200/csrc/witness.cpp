@@ -126,12 +126,16 @@ struct Tape {
     std::vector<WideValue> wide;
     uint64_t *v, *ext;
     uint32_t next = 1, cap;
-    Tape(uint32_t nvars, uint64_t *ext_) : ext(ext_), cap(nvars) {
+    bool defer = false;                     // compressions record a seed instead of writing their 24 792 variables
+    std::vector<CompressionSeed> seeds;
+    Tape(uint32_t nvars, uint64_t *ext_, bool defer_ = false) : ext(ext_), cap(nvars), defer(defer_) {
         const size_t words = (size_t)nvars + 1;
-        if (ext) { v = ext; memset(v, 0, words * 8); } else { own.assign(words, 0); v = own.data(); }
+        if (ext) { v = ext; if (!defer) memset(v, 0, words * 8); } else { own.assign(words, 0); v = own.data(); }
         v[0] = 1;
     }
-    uint32_t alloc(uint32_t n = 1) { uint32_t r = next; next += n; return r; }
+    // deferred mode never touches the compression runs (97 % of the tape), so the tape is cleared piecewise as variables are handed out
+    uint32_t alloc(uint32_t n = 1) { uint32_t r = next; next += n; if (defer && ext) memset(v + r, 0, (size_t)n * 8); return r; }
+    uint32_t alloc_run(uint32_t n) { if (!defer) return alloc(n); uint32_t r = next; next += n; return r; }
     Refs alloc_refs(uint32_t n) { uint32_t b = alloc(n); Refs r(n); for (uint32_t i = 0; i < n; i++) r[i] = (int32_t)(b + i); return r; }
     uint64_t get(int32_t ref) const { return ref < 0 ? 0 : v[ref]; }
     void set(uint32_t idx, uint64_t x) { v[idx] = x; }
@@ -192,11 +196,11 @@ static Refs iv_refs() {      // SHA256_default_IV (sha256_components.tcc:36-51):
 // Variables are allocated by its constructor in one contiguous run of 24792 starting at `base`:
 //   [0,64) packed_W | 48 x 152 message-schedule blocks (i = 16..63) | 64 x 272 round blocks | 8 unreduced_output, 8 reduced_output, 8 overflow bits
 struct Compression {
-    static constexpr uint32_t VARS = 24792;
+    static constexpr uint32_t VARS = COMPRESSION_VARS;
     uint32_t base;
     Refs prev, block, out;       // 256 / 512 / 256 refs in digest bit order
     Compression(Tape &t, const Refs &prev_output, const Refs &new_block, const Refs &output) : prev(prev_output), block(new_block), out(output) {
-        base = t.alloc(VARS);
+        base = t.alloc_run(VARS);
     }
     // 32 consecutive bit variables (least significant bit first) of one word
     static void set_bits(Tape &t, uint32_t at, uint64_t x, int n = 32) { uint64_t *o = t.v + at; for (int k = 0; k < n; k++) o[k] = (x >> k) & 1; }
@@ -208,8 +212,22 @@ struct Compression {
         for (int i = 0; i < 16; i++) {
             uint64_t x = 0;
             for (int k = 0; k < 32; k++) x |= (t.get(block[32 * i + 31 - k]) & 1) << k;
-            W[i] = x; t.set(base + i, x);
+            W[i] = x;
         }
+        if (t.defer) {
+            // the run is filled on the GPU from this seed; only the digest bits (variables outside the run) are needed here
+            CompressionSeed sd; sd.base = base;
+            uint32_t st[8]; uint8_t blk[64];
+            for (int i = 0; i < 16; i++) { sd.w[i] = (uint32_t)W[i]; blk[4 * i] = (uint8_t)(W[i] >> 24); blk[4 * i + 1] = (uint8_t)(W[i] >> 16); blk[4 * i + 2] = (uint8_t)(W[i] >> 8); blk[4 * i + 3] = (uint8_t)W[i]; }
+            for (int r = 0; r < 8; r++) { uint32_t x = 0; for (int k = 0; k < 32; k++) x |= (uint32_t)(t.get(prev[32 * r + 31 - k]) & 1) << k; sd.h[r] = st[r] = x; }
+            sha256_block(st, blk);
+            // output slot o = i + 4s takes d[3-i] + new_a[63-i] (s = 0) or h[3-i] + new_e[63-i] (s = 1), i.e. digest word i + 4s (see the end of
+            // the full evaluation below)
+            for (int o = 0; o < 8; o++) for (int k = 0; k < 32; k++) t.setref(out[32 * o + 31 - k], (st[o] >> k) & 1);
+            t.seeds.push_back(sd);
+            return;
+        }
+        for (int i = 0; i < 16; i++) t.set(base + i, W[i]);
         for (int i = 16; i < 64; i++) {
             const uint32_t mb = base + 64 + (uint32_t)(i - 16) * 152;
             // small sigma0 on W[i-15] (7, 18, >>3), small sigma1 on W[i-2] (17, 19, >>10): 32 result bits, then the XOR3 tmps of the
@@ -311,15 +329,15 @@ struct LessCmp {
 };
 
 static Assignment finish(Tape &t) {
-    Assignment a; a.num_vars = t.cap; a.ext = t.ext; a.wide = std::move(t.wide); if (!t.ext) a.own = std::move(t.own); return a;
+    Assignment a; a.num_vars = t.cap; a.ext = t.ext; a.wide = std::move(t.wide); a.seeds = std::move(t.seeds); if (!t.ext) a.own = std::move(t.own); return a;
 }
 } // namespace
 
 // =====================================================================================================================
 // mint  (SRC/mint/circuit/gadget.tcc:71-162 allocation order; :194-246 witness order)
 static Assignment mint_like(bool redeem, const Note &note_old, const Note &note, const uint8_t cmtA_old_d[32], const uint8_t cmtA_d[32],
-                            uint64_t value_s_v, const uint8_t sk_d[32], uint64_t *ext) {
-    Tape t(redeem ? REDEEM_VARS : MINT_VARS, ext);
+                            uint64_t value_s_v, const uint8_t sk_d[32], uint64_t *ext, bool defer) {
+    Tape t(redeem ? REDEEM_VARS : MINT_VARS, ext, defer);
     const uint32_t packed = t.alloc(4);
     Refs cmtA_old = t.alloc_refs(256), sn_old = t.alloc_refs(256), cmtA = t.alloc_refs(256), value_s = t.alloc_refs(64);
     const Refs unpacked = concat({cmtA_old, sn_old, cmtA, value_s});
@@ -352,18 +370,18 @@ static Assignment mint_like(bool redeem, const Note &note_old, const Note &note,
     delete cmp;
     return finish(t);
 }
-Assignment mint_witness(const Note &note_old, const Note &note, const uint8_t cmtA_old[32], const uint8_t cmtA[32], uint64_t value_s, const uint8_t sk[32], uint64_t *ext) {
-    return mint_like(false, note_old, note, cmtA_old, cmtA, value_s, sk, ext);
+Assignment mint_witness(const Note &note_old, const Note &note, const uint8_t cmtA_old[32], const uint8_t cmtA[32], uint64_t value_s, const uint8_t sk[32], uint64_t *ext, bool defer) {
+    return mint_like(false, note_old, note, cmtA_old, cmtA, value_s, sk, ext, defer);
 }
-Assignment redeem_witness(const Note &note_old, const Note &note, const uint8_t cmtA_old[32], const uint8_t cmtA[32], uint64_t value_s, const uint8_t sk[32], uint64_t *ext) {
-    return mint_like(true, note_old, note, cmtA_old, cmtA, value_s, sk, ext);
+Assignment redeem_witness(const Note &note_old, const Note &note, const uint8_t cmtA_old[32], const uint8_t cmtA[32], uint64_t value_s, const uint8_t sk[32], uint64_t *ext, bool defer) {
+    return mint_like(true, note_old, note, cmtA_old, cmtA, value_s, sk, ext, defer);
 }
 
 // =====================================================================================================================
 // send  (SRC/send/circuit/gadget.tcc constructor / generate_r1cs_witness; note.tcc; less_cmp.tcc; commitment.tcc)
 Assignment send_witness(const Note &note_old, const NoteS &note_s, const Note &note, const uint8_t cmtA_old_d[32], const uint8_t cmtS_d[32],
-                        const uint8_t cmtA_d[32], const uint8_t sk_d[32], const uint8_t pk_sender_d[20], uint64_t *ext) {
-    Tape t(SEND_VARS, ext);
+                        const uint8_t cmtA_d[32], const uint8_t sk_d[32], const uint8_t pk_sender_d[20], uint64_t *ext, bool defer) {
+    Tape t(SEND_VARS, ext, defer);
     const uint32_t packed = t.alloc(5);
     Refs cmtA_old = t.alloc_refs(256), sn_old = t.alloc_refs(256), cmtS = t.alloc_refs(256), cmtA = t.alloc_refs(256);
     const Refs unpacked = concat({cmtA_old, sn_old, cmtS, cmtA});
@@ -407,9 +425,9 @@ Assignment send_witness(const Note &note_old, const NoteS &note_s, const Note &n
 // deposit  (SRC/deposit/circuit/gadget.tcc, merkle.tcc, note.tcc; libsnark merkle_tree_check_read_gadget.tcc:32-125)
 Assignment deposit_witness(const NoteS &note_s, const Note &note_old, const Note &note, const uint8_t cmtS_d[32], const uint8_t cmtB_old_d[32],
                            const uint8_t cmtB_d[32], const uint8_t rt_d[32], size_t leaf_index, const uint8_t siblings[MERKLE_DEPTH][32],
-                           const uint8_t sn_s_d[32], const uint8_t sk_d[32], uint64_t *ext) {
+                           const uint8_t sn_s_d[32], const uint8_t sk_d[32], uint64_t *ext, bool defer) {
     const int D = MERKLE_DEPTH;
-    Tape t(DEPOSIT_VARS, ext);
+    Tape t(DEPOSIT_VARS, ext, defer);
     const uint32_t packed = t.alloc(6);
     Refs root = t.alloc_refs(256), pk_recv = t.alloc_refs(160), cmtB_old = t.alloc_refs(256), sn_old = t.alloc_refs(256), cmtB = t.alloc_refs(256),
          sn_s = t.alloc_refs(256);

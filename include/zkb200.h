@@ -78,6 +78,10 @@ int zkb200_current_device(void);
 int zkb200_set_devices(const int *devices, int n);
 int zkb200_active_devices(int *out, int cap);
 int zkb200_last_device(void);
+/* parity hook: copies the assignment (num_variables x 32 B canonical) that sits on the GPU behind this thread's last gen*proof call -- with
+ * the SHA-256 gadget runs expanded on the device (default; ZKB200_GPU_WITNESS=0 has the host generator write them).  Returns the number of
+ * variables or -1.  Only meaningful while no other caller has reused that lane. */
+long zkb200_last_assignment(uint8_t *out, size_t cap_bytes);
 /* Directory holding <circuit>pk.txt / <circuit>vk.txt.  Default: env ZKB200_KEY_DIR, else /usr/local/prfKey
  * (hard-coded in the reference: mintcgo.cpp:302,336). */
 void zkb200_set_key_dir(const char *dir);
@@ -143,9 +147,13 @@ int zkb200_prove(void *pk, const uint8_t *assignment, const uint8_t r[32], const
 /* Same prover fed with the COMPACT assignment the native witness generators produce: lo[0..num_variables] = low 64 bits of every
  * variable (lo[0] = 1, the constant ONE), wide = nwide records {uint32 idx; uint32 pad; uint64 v[4]} for the few values above 64 bits.
  * 8 instead of 32 bytes per variable cross PCIe.  lo may be zkb200_lane_staging() of a lane the caller holds (pinned: no staging copy;
- * the proof then runs on that lane). */
-int zkb200_prove_compact(void *pk, const uint64_t *lo, const void *wide, size_t nwide, const uint8_t r[32], const uint8_t s[32], char *proof_hex,
-                         float *timings_ms);
+ * the proof then runs on that lane).
+ * seeds (optional): nseeds records {uint32 base; uint32 w[16]; uint32 h[8]}, one per sha256_compression_function_gadget instance whose run of
+ * 24 792 internal variables (starting at variable `base`) the GPU fills in from the 16 message words w and the incoming chaining value h
+ * (witness generation on the GPU, SURVEY.md 8f rank 3: these runs are 97 % of a BlockMaze assignment); lo need not be set there.
+ * Returns -5 if a run does not fit the assignment or nseeds > 32. */
+int zkb200_prove_compact(void *pk, const uint64_t *lo, const void *wide, size_t nwide, const void *seeds, size_t nseeds, const uint8_t r[32],
+                         const uint8_t s[32], char *proof_hex, float *timings_ms);
 
 /* Proofs in flight.  A resident proving key owns zkb200_pk_lanes(pk) "lanes" (env ZKB200_LANES, default 3): private copies of every
  * buffer one proof writes, with their own CUDA streams.  zkb200_prove / zkb200_prove_compact / gen*proof are thread-safe and take a
@@ -154,14 +162,17 @@ int zkb200_prove_compact(void *pk, const uint64_t *lo, const void *wide, size_t 
  *   zkb200_lane_acquire  returns a free lane index (blocks while all are busy); zkb200_lane_release gives it back
  *   zkb200_lane_staging  pinned buffer of num_variables + 1 uint64 for the compact assignment of that lane
  *   zkb200_prove_submit  assignment (num_variables x 32 B, host) or NULL = the assignment the lane already holds
- *   zkb200_prove_submit_compact  lo / wide as in zkb200_prove_compact
+ *   zkb200_prove_submit_compact  lo / wide / seeds as in zkb200_prove_compact
  *   zkb200_prove_collect same outputs and return value as zkb200_prove (timings_ms[3], host finish, counts from the call) */
 int zkb200_pk_lanes(void *pk);
 int zkb200_lane_acquire(void *pk);
 void zkb200_lane_release(void *pk, int lane);
 uint64_t *zkb200_lane_staging(void *pk, int lane);
 int zkb200_prove_submit(void *pk, int lane, const uint8_t *assignment, const uint8_t r[32], const uint8_t s[32]);
-int zkb200_prove_submit_compact(void *pk, int lane, const uint64_t *lo, const void *wide, size_t nwide, const uint8_t r[32], const uint8_t s[32]);
+int zkb200_prove_submit_compact(void *pk, int lane, const uint64_t *lo, const void *wide, size_t nwide, const void *seeds, size_t nseeds,
+                                const uint8_t r[32], const uint8_t s[32]);
+/* parity hook: the canonical assignment (num_variables x 32 B) lane `lane` holds, i.e. what its last proof was made for */
+int zkb200_lane_read_assignment(void *pk, int lane, uint8_t *out);
 int zkb200_prove_collect(void *pk, int lane, char *proof_hex, uint8_t *parts, float *timings_ms);
 /* Replaces r1cs_to_qap_witness_map (r1cs_to_qap.tcc:205-334): out_H receives (m+1) x 32 B coefficients_for_H. */
 int zkb200_qap_witness_map(void *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied);
@@ -177,6 +188,10 @@ void zkb200_set_isolate_h(int on);
  * its gadgetlib1 circuit (<circuit>_gadget::generate_r1cs_witness, SRC/<c>/circuit/gadget.tcc), computed natively on the host.
  * Arguments are exactly those of gen<Circuit>proof (redeem != 0 selects the redeem circuit, which shares mint's signature).
  * Returns the number of variables written, -1 if cap (in elements) is too small, -2 if cmtS is not among the deposit leaves. */
+/* parity hook: on != 0 makes the three functions below (on this thread) run the generator the way gen*proof does by default -- the runs of
+ * the SHA-256 compression gadgets left to a separate expansion from 100-byte seeds (on the GPU in gen*proof; here its host copy,
+ * csrc/witness_sha.hpp) -- so that both paths can be compared variable for variable */
+void zkb200_witness_defer(int on);
 long zkb200_witness_mint(uint64_t value, uint64_t value_old, const char *sn_old, const char *r_old, const char *sn, const char *r,
                          const char *cmtA_old, const char *cmtA, uint64_t value_s, const char *sk, int redeem, uint8_t *out, size_t cap);
 long zkb200_witness_send(uint64_t value_A, const char *r_s, const char *sn, const char *r, const char *cmt_s, const char *cmtA, uint64_t value_s,

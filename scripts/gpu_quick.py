@@ -46,8 +46,14 @@ ms = float(api.lib.zkb200_device_timer(1))
 for ln in lanes:
     pk.lane_release(ln)
 out["pipelined_ms_per_proof"] = round(ms / steps, 4)
-lat = []
+lat, brk = [], []
 for i in range(25):
-    t = time.perf_counter(); api.gen_proof(circuit, F.synthetic(circuit, 100 + i)); lat.append(1e3 * (time.perf_counter() - t))
+    t = time.perf_counter(); api.gen_proof(circuit, F.synthetic(circuit, 100 + i)); lat.append(1e3 * (time.perf_counter() - t)); brk.append(api.last_breakdown_ms())
 out["p50_latency_ms"] = round(statistics.median(lat[5:]), 3)
+out["breakdown_ms"] = {k: round(statistics.median(b[k] for b in brk[5:]), 3) for k in brk[0]}
+from concurrent.futures import ThreadPoolExecutor
+txs = [F.synthetic(circuit, 1000 + i) for i in range(300)]
+with ThreadPoolExecutor(depth) as pool:
+    list(pool.map(lambda tx: api.gen_proof(circuit, tx), txs[:12]))
+    t = time.perf_counter(); list(pool.map(lambda tx: api.gen_proof(circuit, tx), txs)); out["e2e_proofs_per_s"] = round(len(txs) / (time.perf_counter() - t), 1)
 print("QUICK " + json.dumps(out))

@@ -1,10 +1,9 @@
 #!/bin/bash
-# GPU run: parity subset with tight timeouts, then quick timing (LIBS = library variants to time)
-mkdir -p gpurun_out/r02b
-( timeout 500 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_prover.py -m gpu -x -q --timeout 120 -k "${TESTS:-field or domain or ntt or msm or proof_byte or cgo_genproof or synthetic or lanes or qap}" ) > gpurun_out/r02b/pytest.log 2>&1
-echo "pytest rc=$?" >> gpurun_out/r02b/pytest.log
-tail -3 gpurun_out/r02b/pytest.log
-for lib in ${LIBS:-libzkb200.so}; do
-  ZKB200_LIB=$PWD/blockmaze_b200/$lib timeout 200 python scripts/gpu_quick.py send 2>&1 | grep QUICK >> gpurun_out/r02b/quick.jsonl
-done
-tail -n 4 gpurun_out/r02b/quick.jsonl
+mkdir -p gpurun_out/r02f
+( timeout 600 python -m pytest tests/test_gpu_prover.py tests/test_cabi_link.py -m gpu -x -q --timeout 200 -k "not live_reference and not keygen" ) > gpurun_out/r02f/pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r02f/pytest.log
+tail -4 gpurun_out/r02f/pytest.log
+for c in send deposit mint; do for gw in 1 0; do
+  ZKB200_GPU_WITNESS=$gw timeout 200 python scripts/gpu_quick.py $c 2>&1 | grep QUICK | sed "s/^QUICK {/QUICK {\"gpu_witness\": $gw, \"circuit\": \"$c\", /" >> gpurun_out/r02f/quick2.jsonl
+done; done
+cut -c1-60,230-600 gpurun_out/r02f/quick2.jsonl

@@ -289,20 +289,26 @@ def test_malformed_prover_input_is_an_error_not_a_proof(zk, pks):
     out = C.create_string_buffer(513)
     one = (1).to_bytes(32, "little")
     f = api.lib.zkb200_prove_compact
-    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p]
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p]
     w = (Wide * 62)()
     for i in range(62):
         w[i].idx = i + 1
-    assert f(pk.handle, lo, w, 62, one, one, out, None) == -2 and out.raw[:1] == b"\0"
+    assert f(pk.handle, lo, w, 62, None, 0, one, one, out, None) == -2 and out.raw[:1] == b"\0"
     w[0].idx = 0
-    assert f(pk.handle, lo, w, 1, one, one, out, None) == -3
+    assert f(pk.handle, lo, w, 1, None, 0, one, one, out, None) == -3
     w[0].idx = n + 1
-    assert f(pk.handle, lo, w, 1, one, one, out, None) == -3
+    assert f(pk.handle, lo, w, 1, None, 0, one, one, out, None) == -3
     w[0].idx = n
-    assert f(pk.handle, lo, w, 1, O.R_MOD.to_bytes(32, "little"), one, out, None) == -4
-    assert f(pk.handle, lo, w, 1, one, ((1 << 256) - 1).to_bytes(32, "little"), out, None) == -4
+    assert f(pk.handle, lo, w, 1, None, 0, O.R_MOD.to_bytes(32, "little"), one, out, None) == -4
+    assert f(pk.handle, lo, w, 1, None, 0, one, ((1 << 256) - 1).to_bytes(32, "little"), out, None) == -4
     assert out.raw[:1] == b"\0"
-    assert f(pk.handle, lo, w, 1, one, one, out, None) == 1 and out.raw[:10] == b"0000000000"      # well-formed but unsatisfied: default proof
+    seeds = (C.c_uint32 * 25)()                                   # one seed record: base, w[16], h[8]
+    seeds[0] = n - 24792 + 2                                      # its run would end one variable past the assignment
+    assert f(pk.handle, lo, w, 1, seeds, 1, one, one, out, None) == -5
+    seeds[0] = 0
+    assert f(pk.handle, lo, w, 1, seeds, 1, one, one, out, None) == -5
+    assert f(pk.handle, lo, w, 1, seeds, 33, one, one, out, None) == -5
+    assert f(pk.handle, lo, w, 1, None, 0, one, one, out, None) == 1 and out.raw[:10] == b"0000000000"      # well-formed but unsatisfied: default proof
 
 
 def test_prove_batch_spreads_over_every_device(zk, ref):
@@ -392,3 +398,20 @@ def test_affine_halving_rounds_give_the_same_proof():
     env = dict(os.environ, ZKB200_AFFINE_ROUNDS="2", ZKB200_AFFINE_ALWAYS="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert "AFFINE OK" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
+
+
+@pytest.mark.parametrize("circuit", CIRCUITS)
+def test_gpu_expanded_witness_equals_reference_assignment(zk, ref, circuit):
+    """SURVEY.md 8(f) rank 3.  gen<Circuit>proof expands the SHA-256 gadget runs (97 % of the variables) ON THE GPU from 100-byte seeds
+    (prover.cu sha256_witness_kernel); the assignment read back from the device equals the assignment the reference's gadgetlib1 circuit
+    produces (golden sha256 for the reference fixture, the reference harness for a synthetic transaction)."""
+    from blockmaze_b200 import api
+    zk.set_key_dir(key_dir())
+    g, w = gold(circuit)
+    assert zk.gen_proof(circuit, g["args"])[:10] != "0000000000"
+    got = api.last_assignment(circuit)
+    assert hashlib.sha256(got).hexdigest() == g["assignment_sha256"] and got == w
+    args = F.synthetic(circuit, 31)
+    assert zk.gen_proof(circuit, args)[:10] != "0000000000"
+    theirs, sat = ref.witness(circuit, args)
+    assert sat and api.last_assignment(circuit) == theirs

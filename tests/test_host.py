@@ -409,3 +409,16 @@ def test_g2_subgroup_fast_test_equals_definition(api):
         if outside == 1:
             h = 2 * O.Q_MOD - O.R_MOD
             assert api.lib.zkb200_g2_subgroup_check(enc(O.G2.to_affine(O.G2.mul(h, O.G2.from_affine((x, y)))))) == 3
+
+
+@pytest.mark.parametrize("circuit", CIRCUITS)
+def test_deferred_sha256_runs_expand_to_the_same_assignment(api, circuit):
+    """GPU witness path, host half: the generator in deferred mode (SHA-256 compression runs left out, 100-byte seeds recorded) plus the
+    seed expansion of csrc/witness_sha.hpp -- the very code the GPU kernel runs -- reproduces the full assignment variable for variable,
+    for the reference fixture (golden sha256) and for synthetic transactions (deposit: 18 compressions, 256-leaf tree)."""
+    g = json.load(open(os.path.join(GOLD, circuit + ".json")))
+    w = api.witness(circuit, g["args"], defer=True)
+    assert hashlib.sha256(w).hexdigest() == g["assignment_sha256"]
+    for seed in (3, 4):
+        args = F.synthetic(circuit, seed)
+        assert api.witness(circuit, args, defer=True) == api.witness(circuit, args)

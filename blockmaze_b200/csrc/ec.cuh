@@ -79,7 +79,8 @@ template <class F> struct XYZZ {
         ZZZ = ZZZ * PPP;
     }
     // the same mixed addition with every field multiplication inlined (G1 accumulate kernel variant, see msm.cuh)
-    template <class M, class S> ZK_HD void add_affine_with(const Affine<F> &a, M mul, S sqr) {
+    // (field operations passed in: mul, sqr, and mul2(a, b, c, d) = a*b + c*d with one reduction)
+    template <class M, class S, class M2> ZK_HD void add_affine_with(const Affine<F> &a, M mul, S sqr, M2 mul2) {
         if (a.is_inf()) return;
         if (is_inf()) { X = a.x; Y = a.y; ZZ = F::one(); ZZZ = F::one(); return; }
         F U2 = mul(a.x, ZZ), S2 = mul(a.y, ZZZ);
@@ -90,7 +91,7 @@ template <class F> struct XYZZ {
         }
         F PP = sqr(Pp), PPP = mul(Pp, PP), Q = mul(X, PP);
         F X3 = sqr(R) - PPP - Q.dbl();
-        Y = mul(R, Q - X3) - mul(Y, PPP);
+        Y = mul2(R, Q - X3, F::modulus_minus(Y), PPP);              // R (Q - X3) - Y PPP
         X = X3;
         ZZ = mul(ZZ, PP);
         ZZZ = mul(ZZZ, PPP);

@@ -293,6 +293,84 @@ template <class P> struct Fp {
         r.reduce_once();
         return r;
     }
+    // (a*b + c*d) * R^-1 mod p with ONE Montgomery reduction: every row adds a*b_i, c*d_i and m_i*p to the same two accumulators, 3*64 + 8
+    // multiplications instead of 2*(2*64 + 8).  a*b + c*d < 2 p^2 keeps the quotient rows exact (2p < R) and the result below 2p; the column
+    // where a row deposits its carries receives three high limbs below 2^30 each (a_7, c_7, p_7 < 2^30), so it still cannot overflow.
+    // The XYZZ addition uses it for Y3 = R*(Q - X3) + (p - Y1)*PPP.
+    ZK_HD static Fp mul2_impl(const Fp &a, const Fp &b, const Fp &c, const Fp &d) {
+        uint32_t acc[2][18];
+#pragma unroll
+        for (int k = 0; k < 18; k++) { acc[0][k] = 0; acc[1][k] = 0; }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t *H = acc[i & 1], *Cc = acc[(i & 1) ^ 1];
+            const uint32_t bi = b.v[i], di = d.v[i];
+            Carry k1;
+            if (i > 0) k1.add_cc(H[i], H[i], Cc[i]);
+            // a*b_i: odd j into Cc (chain k1 carries the merge above), even j into H
+#pragma unroll
+            for (int j = 1; j < 8; j += 2) {
+                if (i == 0 && j == 1) k1.mad_lo_cc(Cc[i + j], a.v[j], bi, Cc[i + j]); else k1.madc_lo_cc(Cc[i + j], a.v[j], bi, Cc[i + j]);
+                if (j < 7) k1.madc_hi_cc(Cc[i + j + 1], a.v[j], bi, Cc[i + j + 1]);
+                else k1.madc_hi(Cc[i + j + 1], a.v[j], bi, Cc[i + j + 1]);
+            }
+            Carry k2;
+            k2.mad_lo_cc(H[i], a.v[0], bi, H[i]);
+            k2.madc_hi_cc(H[i + 1], a.v[0], bi, H[i + 1]);
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) {
+                k2.madc_lo_cc(H[i + j], a.v[j], bi, H[i + j]);
+                k2.madc_hi_cc(H[i + j + 1], a.v[j], bi, H[i + j + 1]);
+            }
+            k2.addc(Cc[i + 8], Cc[i + 8], 0);
+            // c*d_i
+            Carry k3;
+            k3.mad_lo_cc(Cc[i + 1], c.v[1], di, Cc[i + 1]);
+            k3.madc_hi_cc(Cc[i + 2], c.v[1], di, Cc[i + 2]);
+#pragma unroll
+            for (int j = 3; j < 8; j += 2) {
+                k3.madc_lo_cc(Cc[i + j], c.v[j], di, Cc[i + j]);
+                if (j < 7) k3.madc_hi_cc(Cc[i + j + 1], c.v[j], di, Cc[i + j + 1]);
+                else k3.madc_hi(Cc[i + j + 1], c.v[j], di, Cc[i + j + 1]);
+            }
+            Carry k4;
+            k4.mad_lo_cc(H[i], c.v[0], di, H[i]);
+            k4.madc_hi_cc(H[i + 1], c.v[0], di, H[i + 1]);
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) {
+                k4.madc_lo_cc(H[i + j], c.v[j], di, H[i + j]);
+                k4.madc_hi_cc(H[i + j + 1], c.v[j], di, H[i + j + 1]);
+            }
+            k4.addc(Cc[i + 8], Cc[i + 8], 0);
+            // m_i * p
+            const uint32_t m = mul_lo(H[i], P::INV);
+            Carry e;
+            e.mad_lo_cc(Cc[i + 1], P::mod(1), m, Cc[i + 1]);
+            e.madc_hi_cc(Cc[i + 2], P::mod(1), m, Cc[i + 2]);
+#pragma unroll
+            for (int j = 3; j < 8; j += 2) {
+                e.madc_lo_cc(Cc[i + j], P::mod(j), m, Cc[i + j]);
+                if (j < 7) e.madc_hi_cc(Cc[i + j + 1], P::mod(j), m, Cc[i + j + 1]);
+                else e.madc_hi(Cc[i + j + 1], P::mod(j), m, Cc[i + j + 1]);
+            }
+            Carry f;
+            f.mad_lo_cc(H[i], P::mod(0), m, H[i]);
+            f.madc_hi_cc(H[i + 1], P::mod(0), m, H[i + 1]);
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) {
+                f.madc_lo_cc(H[i + j], P::mod(j), m, H[i + j]);
+                f.madc_hi_cc(H[i + j + 1], P::mod(j), m, H[i + j + 1]);
+            }
+            f.addc(Cc[i + 8], Cc[i + 8], 0);
+        }
+        Fp r; Carry cz;
+        cz.add_cc(r.v[0], acc[0][8], acc[1][8]);
+#pragma unroll
+        for (int k = 1; k < 7; k++) cz.addc_cc(r.v[k], acc[0][8 + k], acc[1][8 + k]);
+        cz.addc(r.v[7], acc[0][15], acc[1][15]);
+        r.reduce_once();
+        return r;
+    }
     // Montgomery square a*a*R^-1 mod p with 36 + 64 wide multiply-adds instead of 64 + 64 (a_i*a_j = a_j*a_i is computed once).
     //   1. off-diagonal products a_i*a_j (i < j) go row by row into an even- and an odd-column accumulator like the rows of mul_impl; a chain
     //      that ends deposits its carry in the next column, which no earlier row has touched (row i reaches column i+8 at most);

@@ -268,7 +268,8 @@ static __global__ void __launch_bounds__(128, ZK_ACC_MINBLOCKS) msm_accumulate_k
         Affine<F> p = ld_affine(bases + (ent & 0x7fffffffu));
         if (ent & 0x80000000u) p.y = p.y.neg();
 #if ZK_ACC_INLINE_MUL
-        if constexpr (sizeof(F) == 32) acc.add_affine_with(p, [](const F &x, const F &y) { return F::mul_impl(x, y); }, [](const F &x) { return F::sqr_impl(x); });
+        if constexpr (sizeof(F) == 32) acc.add_affine_with(p, [](const F &x, const F &y) { return F::mul_impl(x, y); }, [](const F &x) { return F::sqr_impl(x); },
+                                                            [](const F &a, const F &b, const F &c, const F &d) { return F::mul2_impl(a, b, c, d); });
         else acc.add_affine(p);
 #elif ZK_ACC_INLINE_ADD
         if (sizeof(F) == 32) acc.add_affine_inl(p); else acc.add_affine(p);

@@ -82,7 +82,8 @@ constexpr int NTT_TILE_LOG = 11;          // at most 2048 elements * 32 B = 64 K
 template <bool FIRST>
 static __global__ void __launch_bounds__(NTT_MAX_THREADS, ZK_NTT_MINBLOCKS)
 ntt_pass_kernel(const Fr *__restrict__ src, Fr *__restrict__ dst, const Fr *__restrict__ tw,
-                int logn, int s0, int k, int logG, PowMul pre, PowMul post, int last, size_t batch_stride) {
+                int logn, int s0, int k, int logG, PowMul pre, PowMul post, int last, size_t batch_stride,
+                const Fr *__restrict__ sub = nullptr, const Fr *__restrict__ sub_scale = nullptr) {
     extern __shared__ uint32_t sm[];
     src += blockIdx.y * batch_stride; dst += blockIdx.y * batch_stride;      // independent transforms of one launch (A, B, C of the QAP map)
     const int N = 1 << (k + logG);
@@ -176,6 +177,7 @@ ntt_pass_kernel(const Fr *__restrict__ src, Fr *__restrict__ dst, const Fr *__re
 #pragma unroll
         for (int w = 0; w < 8; w++) x.v[w] = sm[w * N + slot];
         if (last && post.on()) x = x * post.at(addr);
+        if (last && sub) x = x - ldg_fr(sub + addr) * ldg_fr(sub_scale);      // out = x * post - sub * scale (the QAP map's h = (d - c) / Z, see prover.cu)
         st_fr(dst + addr, x);
     }
 }
@@ -204,7 +206,7 @@ static inline int ntt_plan_passes(int logn, NttPass out[4]) {
 // dst != src.  tw = per-stage twiddle table (ntt_tw) of omega for a forward transform, of omega^-1 for an inverse one (Montgomery form).
 // `batch` transforms, `batch_stride` elements apart in both src and dst, share one launch per pass.
 static inline void ntt_launch(cudaStream_t st, const Fr *src, Fr *dst, const Fr *tw, int logn, PowMul pre, PowMul post, int batch = 1,
-                              size_t batch_stride = 0) {
+                              size_t batch_stride = 0, const Fr *sub = nullptr, const Fr *sub_scale = nullptr) {
     NttPass ps[4];
     const int np = ntt_plan_passes(logn, ps);
     for (int p = 0; p < np; p++) {
@@ -214,9 +216,9 @@ static inline void ntt_launch(cudaStream_t st, const Fr *src, Fr *dst, const Fr 
         const int last = (p == np - 1);
         int threads = N / 4; if (threads < 32) threads = 32; if (threads > NTT_MAX_THREADS) threads = NTT_MAX_THREADS;
         if (p == 0)
-            ntt_pass_kernel<true><<<blocks, threads, smem, st>>>(src, dst, tw, logn, ps[p].s0, ps[p].k, ps[p].logG, pre, post, last, batch_stride);
+            ntt_pass_kernel<true><<<blocks, threads, smem, st>>>(src, dst, tw, logn, ps[p].s0, ps[p].k, ps[p].logG, pre, post, last, batch_stride, sub, sub_scale);
         else
-            ntt_pass_kernel<false><<<blocks, threads, smem, st>>>(dst, dst, tw, logn, ps[p].s0, ps[p].k, ps[p].logG, pre, post, last, batch_stride);
+            ntt_pass_kernel<false><<<blocks, threads, smem, st>>>(dst, dst, tw, logn, ps[p].s0, ps[p].k, ps[p].logG, pre, post, last, batch_stride, sub, sub_scale);
     }
 }
 static inline void ntt_init_attrs() {
@@ -290,6 +292,11 @@ static __global__ void step_ifft_post_kernel(Fr *a, const Fr *tw_big2 /* w^i */,
 // H[i] = (A[i]*B[i] - C[i]) * Zinv(i)  on the coset (r1cs_to_qap.tcc:274-305 with divide_by_Z_on_coset fused).
 //   i <  big : zt[i % compr]      (basic domain: big = m, compr = 1)
 //   i >= big : z1
+// basic domain, C-free variant (see qap_pipeline): only the product of the coset evaluations is needed
+static __global__ void qap_product_kernel(Fr *A, const Fr *B, uint32_t m) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) st_fr(A + i, ld_fr(A + i) * ld_fr(B + i));
+}
 static __global__ void qap_pointwise_kernel(Fr *A, const Fr *B, const Fr *C, uint32_t m, uint32_t big, uint32_t compr, const Fr *zt, Fr z1) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;

@@ -25,6 +25,7 @@ using zkh::HFr; using zkh::HFq; using zkh::HFq2; using zkh::HG1; using zkh::HG2;
 static thread_local int g_launches = 0;     // kernels launched by this thread since the last prove_submit() began
 static int g_last_launches = 0;
 static bool g_isolate_h = false;            // measurement mode, see set_isolate_h()
+static const bool g_qap_skip_c = [] { const char *e = getenv("ZKB200_QAP_SEVEN"); return !(e && atoi(e) != 0); }();   // ZKB200_QAP_SEVEN=1: the reference's seven transforms
 // a launch-configuration failure (shared memory over the limit, bad grid) is not sticky: check it at the launch or the kernel silently does not run
 #define ZK_LAUNCH(kernel, grid, block, smem, stream, ...) do { kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); ZK_CUDA(cudaGetLastError()); g_launches++; } while (0)
 
@@ -127,6 +128,9 @@ Domain *Domain::build(uint64_t min_size) {
         // basic_radix2_domain::divide_by_Z_on_coset (basic_radix2_domain.tcc:102-110): Z(g) = g^m - 1
         HFr z = (g.pow64(d->m) - one).inverse();
         d->zt = dev_const(&z, 1); d->z1 = z;
+        const HFr z_over_m = z * m_inv;
+        d->gi_hi_zninv = dev_pow_table(ginv, z_over_m, nhi, 1024);      // g^-i * Z^-1 / m, high half of the two-level table
+        d->c_z_over_m = dev_const(&z_over_m, 1);
     } else {
         const HFr ws = root_of_unity(d->log_small), om = root_of_unity(d->log_big + 1);
         d->tw_small_f = dev_tw_levels(ws, d->log_small);
@@ -150,7 +154,7 @@ Domain *Domain::build(uint64_t min_size) {
 }
 void Domain::release() {
     void *ps[] = {tw_big_f, tw_big_i, tw_small_f, tw_small_i, tw_step_f, tw_step_i, g_lo, g_hi, g_hi_ninv, gi_lo, gi_hi, gi_hi_ninv,
-                  c_big_inv, c_small_inv, c_m_inv, zt};
+                  c_big_inv, c_small_inv, c_m_inv, zt, gi_hi_zninv, c_z_over_m};
     for (void *p : ps) if (p) cudaFree(p);
 }
 
@@ -158,13 +162,14 @@ static PowMul pm_none() { return PowMul{nullptr, nullptr, 0}; }
 static PowMul pm_const(const void *c) { return PowMul{(const Fr *)c, nullptr, 0}; }
 static PowMul pm_two(const void *lo, const void *hi) { return PowMul{(const Fr *)lo, (const Fr *)hi, 10}; }
 
-static void ntt(cudaStream_t st, const void *src, void *dst, const void *tw, int logn, PowMul pre, PowMul post, int batch = 1, size_t stride = 0) {
+static void ntt(cudaStream_t st, const void *src, void *dst, const void *tw, int logn, PowMul pre, PowMul post, int batch = 1, size_t stride = 0,
+                const void *sub = nullptr, const void *sub_scale = nullptr) {
     if (logn == 0) {
         for (int b = 0; b < batch; b++) ZK_CUDA(cudaMemcpyAsync((Fr *)dst + b * stride, (const Fr *)src + b * stride, 32, cudaMemcpyDeviceToDevice, st));
         return;
     }
     NttPass ps[4]; g_launches += ntt_plan_passes(logn, ps);
-    ntt_launch(st, (const Fr *)src, (Fr *)dst, (const Fr *)tw, logn, pre, post, batch, stride);
+    ntt_launch(st, (const Fr *)src, (Fr *)dst, (const Fr *)tw, logn, pre, post, batch, stride, (const Fr *)sub, (const Fr *)sub_scale);
     ZK_CUDA(cudaGetLastError());
 }
 
@@ -220,7 +225,10 @@ void domain_op(cudaStream_t st, const Domain &d, int op, void *data, void *tmp) 
 #endif
 constexpr int SPMV_G = ZK_SPMV_G;
 struct SpmvArgs { const uint32_t *rowptr[3], *col[3], *coef[3]; Fr *out[3]; };
-__global__ void __launch_bounds__(128) spmv_kernel(SpmvArgs A, const Fr *__restrict__ dict, const Fr *__restrict__ w, uint32_t rows) {
+// The launch covers all m rows of the evaluation vectors: rows past the constraints are the zero padding of the domain, except that aA
+// continues with (1, w_1 .. w_inputs) (r1cs_to_qap.tcc:227-230) -- no separate memsets or copy kernel.
+__global__ void __launch_bounds__(128) spmv_kernel(SpmvArgs A, const Fr *__restrict__ dict, const Fr *__restrict__ w, uint32_t rows, uint32_t m,
+                                                   uint32_t num_inputs) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t i = tid / SPMV_G, sub = tid % SPMV_G;
     const uint32_t *__restrict__ rowptr = A.rowptr[blockIdx.y], *__restrict__ col = A.col[blockIdx.y], *__restrict__ coef = A.coef[blockIdx.y];
@@ -241,12 +249,8 @@ __global__ void __launch_bounds__(128) spmv_kernel(SpmvArgs A, const Fr *__restr
         for (int q = 0; q < 8; q++) o.v[q] = __shfl_down_sync(0xffffffffu, acc.v[q], d, SPMV_G);
         acc = acc + o;
     }
-    if (i < rows && sub == 0) st_fr(A.out[blockIdx.y] + i, acc);
-}
-// the extra rows  aA[num_constraints + i] = (1, w_1 .. w_inputs)[i]  (r1cs_to_qap.tcc:227-230)
-__global__ void input_rows_kernel(const Fr *w, Fr *outA, uint32_t nc, uint32_t count) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) st_fr(outA + nc + i, ld_fr(w + i));
+    if (i < rows) { if (sub == 0) st_fr(A.out[blockIdx.y] + i, acc); }
+    else if (i < m && sub == 0) st_fr(A.out[blockIdx.y] + i, (blockIdx.y == 0 && i - rows <= num_inputs) ? ldg_fr(w + (i - rows)) : Fr::zero());
 }
 // r1cs_constraint_system::is_satisfied (r1cs.tcc:133-164) on the evaluation vectors: flag |= (A_i * B_i != C_i)
 __global__ void sat_check_kernel(const Fr *A, const Fr *B, const Fr *C, uint32_t nc, uint32_t *flag) {
@@ -832,17 +836,25 @@ static void qap_pipeline(DevicePk *pk, Lane *ln, cudaStream_t st) {
     const uint32_t nc = (uint32_t)pk->num_constraints, m = d.m;
     const Fr *w = (const Fr *)ln->w_mont, *dict = (const Fr *)pk->coef_dict;
     Fr *A = (Fr *)ln->bufA, *B = (Fr *)ln->bufB, *C = (Fr *)ln->bufC, *T = (Fr *)ln->tmp;
-    ZK_CUDA(cudaMemsetAsync(A + nc, 0, (size_t)(m - nc) * 32, st));
-    ZK_CUDA(cudaMemsetAsync(B + nc, 0, (size_t)(m - nc) * 32, st));
-    ZK_CUDA(cudaMemsetAsync(C + nc, 0, (size_t)(m - nc) * 32, st));
     SpmvArgs sa{{pk->a.rowptr, pk->b.rowptr, pk->c.rowptr}, {pk->a.col, pk->b.col, pk->c.col}, {pk->a.coef, pk->b.coef, pk->c.coef}, {A, B, C}};
-    ZK_LAUNCH(spmv_kernel, dim3(cdiv((size_t)nc * SPMV_G, 128), 3), 128, 0, st, sa, dict, w, nc);
+    ZK_LAUNCH(spmv_kernel, dim3(cdiv((size_t)m * SPMV_G, 128), 3), 128, 0, st, sa, dict, w, nc, m, (uint32_t)pk->num_inputs);
     ZK_CUDA(cudaMemsetAsync(ln->sat_flag, 0, 4, st));
     ZK_LAUNCH(sat_check_kernel, cdiv(nc, 256), 256, 0, st, A, B, C, nc, ln->sat_flag);
     ZK_CUDA(cudaMemcpyAsync(ln->h_sat_flag, ln->sat_flag, 4, cudaMemcpyDeviceToHost, st));
-    ZK_LAUNCH(input_rows_kernel, 1, 64, 0, st, w, A, nc, (uint32_t)pk->num_inputs + 1);
     // iFFT then cosetFFT of each of A, B, C: coefficient i is multiplied by g^i (and 1/m for the basic domain) on the way
     domain_ifft(st, d, A, T, pm_none(), pm_two(d.g_lo, d.g_hi), 3, m);
+    if (!d.step && g_qap_skip_c) {
+        // Basic domain, six transforms instead of the reference's seven (r1cs_to_qap.tcc:240-311 also takes c to the coset).  With
+        // Z = x^m - 1:  a*b = c + Z*h, deg h <= m-2, and on the coset g*S the polynomial x^m is the constant g^m, so the interpolant of the
+        // coset values of a*b is  d = a*b mod (x^m - g^m) = c + (g^m - 1) h,  i.e.  h_i = (d_i - c_i) / (g^m - 1)  coefficient by
+        // coefficient -- c never has to be evaluated on the coset.  T holds m*a | m*b | m*c (the inverse transforms leave the 1/m to the
+        // next multiplication), so the last pass of the final inverse transform computes  raw_i * g^-i/(m Z) - (m c_i) * 1/(m Z).
+        // Valid for a satisfying assignment (c interpolates a.*b on S); otherwise the default proof is returned anyway.
+        domain_fft(st, d, T, A, pm_two(d.g_lo, d.g_hi_ninv), 2, m);
+        ZK_LAUNCH(qap_product_kernel, cdiv(m, 256), 256, 0, st, A, (const Fr *)B, m);
+        ntt(st, A, T, d.tw_big_i, d.log_big, pm_none(), pm_two(d.gi_lo, d.gi_hi_zninv), 1, 0, T + 2 * (size_t)m, d.c_z_over_m);
+        return;
+    }
     if (!d.step) domain_fft(st, d, T, A, pm_two(d.g_lo, d.g_hi_ninv), 3, m);
     else domain_fft(st, d, T, A, pm_none(), 3, m);
     ZK_LAUNCH(qap_pointwise_kernel, cdiv(m, 256), 256, 0, st, A, B, C, m, d.big, d.compr, (const Fr *)d.zt, to_dev(d.z1));

@@ -29,6 +29,7 @@ struct Domain {
     void *g_hi_ninv = nullptr;                          // g^i / m        (basic: iFFT scale folded into the coset shift)
     void *gi_lo = nullptr, *gi_hi = nullptr;            // g^-i
     void *gi_hi_ninv = nullptr;                         // g^-i / m
+    void *gi_hi_zninv = nullptr, *c_z_over_m = nullptr; // basic: g^-i / (m Z(g)) and the constant 1 / (m Z(g)) (six-transform QAP map)
     void *c_big_inv = nullptr, *c_small_inv = nullptr, *c_m_inv = nullptr;   // single constants 1/big, 1/small, 1/m
     void *zt = nullptr;                                 // 1/Z on the coset, `compr` distinct values for i < big
     zkh::HFr z1, over_two;                              // 1/Z for i >= big (step); 1/2

@@ -449,14 +449,15 @@ template <class F> __device__ __forceinline__ XYZZ<F> msm_bucket(const XYZZ<F> *
 constexpr int MSM_RED_THREADS = 128;
 template <class F>
 static __global__ void __launch_bounds__(MSM_RED_THREADS) msm_reduce_kernel(const XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ offsets,
-                                                                            uint32_t threads, MsmShape sh, uint32_t seg, uint32_t blocks_per_region,
-                                                                            XYZZ<F> *__restrict__ out) {
+                                                                            uint32_t threads, MsmShape sh, uint32_t seg, uint32_t seg_weighted,
+                                                                            uint32_t blocks_per_region, XYZZ<F> *__restrict__ out) {
     extern __shared__ uint32_t red_sm[];
     XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(red_sm);
     const uint32_t w = blockIdx.y;
     const bool ones = (w == sh.regions);
     const uint32_t count = ones ? sh.ones : sh.nb;
     const uint32_t base = w * sh.nb;                              // the ones region starts at regions*nb as well
+    if (!ones) seg = seg_weighted;                                // (small weighted regions take one bucket per thread: shorter chains)
     const uint32_t lo = (blockIdx.x * MSM_RED_THREADS + threadIdx.x) * seg;
     const uint32_t L = msm_range_len(__ldg(offsets + sh.total), threads);
     XYZZ<F> S = XYZZ<F>::inf(), T = XYZZ<F>::inf();

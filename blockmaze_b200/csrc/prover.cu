@@ -350,8 +350,11 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool e
     regions = expanded ? 1u : (uint32_t)windows;
     total = regions * nb + ones;
     seg = 4; if (seg > nb) seg = nb;
-    const uint32_t widest = nb > ones ? nb : ones;
-    bpw = cdiv(cdiv(widest, seg), MSM_RED_THREADS);
+    // The 8-bit windows of the witness queries leave 128 weighted buckets: one per thread there (j * B_j by double-and-add, <= 13 point
+    // operations) instead of running sums over 4 plus a 7-bit multiple -- the reduction is a chain of dependent additions, 19 us each in G2.
+    seg_weighted = nb <= 256 ? 1 : seg;
+    const uint32_t need_w = cdiv(cdiv(nb, seg_weighted), MSM_RED_THREADS), need_o = cdiv(cdiv(ones ? ones : 1, seg), MSM_RED_THREADS);
+    bpw = need_w > need_o ? need_w : need_o;
     ZK_CUDA(cudaMalloc(&counts, (size_t)(total + 1) * 4));
     ZK_CUDA(cudaMalloc(&offsets, (size_t)(total + 1) * 4));
     ZK_CUDA(cudaMalloc(&cursors, (size_t)(total + 1) * 4));
@@ -447,7 +450,7 @@ static void msm_points(cudaStream_t st, MsmPlan &p, const MsmShape &sh, const Af
     ZK_LAUNCH(msm_fold_small_kernel<F>, cdiv(p.total, 128), 128, 0, st, partial, off, p.total, T, heavy);
     ZK_LAUNCH(msm_fold_heavy_kernel<F>, 64, MSM_HEAVY_THREADS, MSM_HEAVY_THREADS * sizeof(XYZZ<F>), st, partial, off, p.total, T, (const uint32_t *)heavy);
     const dim3 rgrid(p.bpw, sh.regions + 1);
-    ZK_LAUNCH(msm_reduce_kernel<F>, rgrid, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(XYZZ<F>), st, (const XYZZ<F> *)partial, off, T, sh, p.seg, p.bpw, out);
+    ZK_LAUNCH(msm_reduce_kernel<F>, rgrid, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(XYZZ<F>), st, (const XYZZ<F> *)partial, off, T, sh, p.seg, p.seg_weighted, p.bpw, out);
     ZK_CUDA(cudaMemcpyAsync(h_out, out, (size_t)(sh.regions + 1) * p.bpw * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
 }
 
@@ -947,6 +950,23 @@ int prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64
     return 0;
 }
 
+// Waiting for the GPU.  cudaEventSynchronize / cudaStreamSynchronize hand the thread to the driver, whose wake-up costs 0.1-0.3 ms on
+// some hosts -- a tenth of a proof.  The collecting thread polls the event instead (ZKB200_SPIN=0 goes back to the blocking calls).
+static const bool g_spin = [] { const char *e = getenv("ZKB200_SPIN"); return !(e && atoi(e) == 0); }();
+static void wait_event(cudaEvent_t ev) {
+    if (!g_spin) { ZK_CUDA(cudaEventSynchronize(ev)); return; }
+    for (;;) {
+        const cudaError_t e = cudaEventQuery(ev);
+        if (e == cudaSuccess) return;
+        if (e != cudaErrorNotReady) ZK_CUDA(e);
+#if defined(__x86_64__)
+        for (int i = 0; i < 32; i++) __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+}
+
 int prove_collect(DevicePk *pk, Lane *ln, ProofPoints &out) {
     if (!ln->pending) return -1;
     device_init(pk->device);
@@ -954,15 +974,18 @@ int prove_collect(DevicePk *pk, Lane *ln, ProofPoints &out) {
     // The witness queries finish well before the H query (which waits for the QAP map): everything of the proof combination
     // (r1cs_gg_ppzksnark.tcc:487-495) that does not involve H -- above all the two 254-bit scalar multiplications s*A and r*B1, 0.2 ms of
     // host time -- is done while the GPU is still busy with it.
-    ZK_CUDA(cudaEventSynchronize(ln->ev_a)); ZK_CUDA(cudaEventSynchronize(ln->ev_b)); ZK_CUDA(cudaEventSynchronize(ln->ev_b2));
-    ZK_CUDA(cudaEventSynchronize(ln->ev_l));
+    // The G1 queries first: the G2 half of B (3x the field work, the longest bucket reduction) is the last side chain to finish -- for the
+    // smaller circuits barely before the H query -- and nothing below needs it until out.B.
+    wait_event(ln->ev_a); wait_event(ln->ev_b); wait_event(ln->ev_l);
     const HG1 eAr = msm_finish_g1(ln->mA), eB1s = msm_finish_g1(ln->mB), eLrs = msm_finish_g1(ln->mL);
-    const HG2 eB2s = msm_finish_g2(ln->mB);
     const HG1 gA = HG1::from_affine(pk->alpha_g1).add(eAr);
     const HG1 g1B = HG1::from_affine(pk->beta_g1).add(eB1s);
-    const HG2 g2B = HG2::from_affine(pk->beta_g2).add(eB2s);
     const HG1 c_part = eLrs.add(gA.mul(s)).add(g1B.mul(r));
-    out.A = gA.to_affine(); out.B = g2B.to_affine();
+    out.A = gA.to_affine();
+    wait_event(ln->ev_b2);
+    const HG2 eB2s = msm_finish_g2(ln->mB);
+    const HG2 g2B = HG2::from_affine(pk->beta_g2).add(eB2s);
+    out.B = g2B.to_affine();
     if (out.want_parts) {
         // the plain MSM values of the reference (parity hooks): strip the folded zero-knowledge terms again
         const HG1 rd = g1_mul(pk->delta_g1, r).neg(), sd = g1_mul(pk->delta_g1, s).neg();
@@ -972,7 +995,7 @@ int prove_collect(DevicePk *pk, Lane *ln, ProofPoints &out) {
         out.Bt_g = eB2s.add(HG2::from_affine(pk->delta_g2).mul(s).neg()).to_affine();
     }
 
-    ZK_CUDA(cudaStreamSynchronize(ln->s_main));
+    wait_event(ln->ev_t1);                          // recorded on s_main after everything of this proof, the side streams joined
     const double t_sync = now_s();
     ln->pending = false;
     ZK_CUDA(cudaEventElapsedTime(&out.gpu_ms, ln->ev_t0, ln->ev_t1));

@@ -46,7 +46,7 @@ struct MsmPlan {
     uint32_t n = 0;             // number of bases
     int c = 0, windows = 0;
     uint32_t nb = 0, ones = 0, total = 0;
-    uint32_t seg = 0, bpw = 0;  // reduce: buckets per thread, CTAs per window
+    uint32_t seg = 0, seg_weighted = 0, bpw = 0;  // reduce: buckets per thread (ones / weighted regions), CTAs per window
     void *counts = nullptr, *offsets = nullptr, *cursors = nullptr, *entries = nullptr;
     size_t entries_cap = 0;
     bool expanded = false;      // bases hold 2^(c*k)*P for every window k: one bucket region, no Horner

@@ -196,9 +196,6 @@ def reference_arm(args, rank, world):
     emit((line))
 
 
-FMA_PIPE_INSTR_PER_SEND_PROOF = None      # filled from profiles/r02_fma_pipe.json when present (ncu sm__inst_executed_pipe_fma.sum of one send proof)
-
-
 def load_fma_count():
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "r02_fma_pipe.json")))

@@ -758,12 +758,15 @@ __global__ void patch_wide_kernel(const WideIn *__restrict__ wide, uint32_t nwid
 // overflow bits (layout: witness_sha.hpp).  The host generator (witness.cpp) hands over a 100-byte seed per compression -- the run's first
 // variable, the 16 message words, the incoming chaining value -- and one CTA per compression re-runs the rounds (one thread, microseconds)
 // and then writes the run straight into the canonical and the Montgomery assignment.
+// SHA_PARTS CTAs share one compression: each rebuilds the trace (it is the serial part, ~15 us for one thread) and writes its slice of the run.
+constexpr uint32_t SHA_PARTS = 8;
 __global__ void __launch_bounds__(256) sha256_witness_kernel(const SeedDev *__restrict__ seeds, Fr *__restrict__ w_can, Fr *__restrict__ w_mont) {
     __shared__ zkw::ShaTrace T;
-    const SeedDev sd = seeds[blockIdx.x];
+    const SeedDev sd = seeds[blockIdx.x / SHA_PARTS];
     if (threadIdx.x == 0) zkw::sha_trace_build(sd.w, sd.h, T);
     __syncthreads();
-    for (uint32_t v = threadIdx.x; v < SHA_RUN; v += blockDim.x) {
+    const uint32_t per = (SHA_RUN + SHA_PARTS - 1) / SHA_PARTS, v0 = (blockIdx.x % SHA_PARTS) * per, v1 = min(v0 + per, SHA_RUN);
+    for (uint32_t v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
         const uint64_t x = zkw::sha_trace_value(T, v);
         Fr c = Fr::zero(); c.v[0] = (uint32_t)x; c.v[1] = (uint32_t)(x >> 32);
         st_fr(w_can + sd.base + v, c);
@@ -829,7 +832,7 @@ static void upload_compact_seeded(DevicePk *pk, Lane *ln, const uint64_t *lo, co
     ZK_CUDA(cudaMemcpyAsync(ln->w_wide, pw, nwide * sizeof(WideIn), cudaMemcpyHostToDevice, st));
     const SegDev *dsegs = (const SegDev *)((const char *)ln->d_seeds + MAX_SEEDS * sizeof(SeedDev));
     if (packed) ZK_LAUNCH(expand_segments_kernel, cdiv(packed, 256), 256, 0, st, (const uint64_t *)ln->w_lo, dsegs, nseg, packed, (Fr *)ln->w_can, (Fr *)ln->w_mont);
-    ZK_LAUNCH(sha256_witness_kernel, nseeds, 256, 0, st, (const SeedDev *)ln->d_seeds, (Fr *)ln->w_can, (Fr *)ln->w_mont);
+    ZK_LAUNCH(sha256_witness_kernel, nseeds * SHA_PARTS, 256, 0, st, (const SeedDev *)ln->d_seeds, (Fr *)ln->w_can, (Fr *)ln->w_mont);
     ZK_LAUNCH(patch_wide_kernel, 1, 64, 0, st, (const WideIn *)ln->w_wide, nwide, n + 1, (Fr *)ln->w_can, (Fr *)ln->w_mont);
 }
 

@@ -37,7 +37,16 @@ template <class F> struct XYZZ {
     ZK_HD XYZZ neg() const { XYZZ p = *this; p.Y = Y.neg(); return p; }
 
     // dbl-2008-s-1
-    ZK_EC XYZZ dbl() const {
+    ZK_EC XYZZ dbl() const { return dbl_inl(); }
+    // The doubling INSIDE add(): the operand travels by value.  Calling the member dbl() on *this from within the out-of-line add() read
+    // out-of-bounds local memory on sm_100a (compute-sanitizer, scripts/ubench/team.cu: the nested call received a stale frame address for
+    // `this`); equal summands are rare in an MSM tail but legal, so the path must not depend on that.
+#if defined(__CUDACC__)
+    static __host__ __device__ __noinline__ XYZZ dbl_value(const XYZZ p) { return p.dbl_inl(); }
+#else
+    static inline XYZZ dbl_value(const XYZZ p) { return p.dbl_inl(); }
+#endif
+    ZK_HD XYZZ dbl_inl() const {
         if (is_inf()) return *this;
         F U = Y.dbl(), V = U.sqr(), W = U * V, S = X * V;
         F XX = X.sqr(), M = XX.dbl() + XX;
@@ -103,7 +112,7 @@ template <class F> struct XYZZ {
         F U1 = X * o.ZZ, U2 = o.X * ZZ, S1 = Y * o.ZZZ, S2 = o.Y * ZZZ;
         F Pp = U2 - U1, R = S2 - S1;
         if (Pp.is_zero()) {
-            if (R.is_zero()) *this = dbl(); else *this = inf();
+            if (R.is_zero()) { const XYZZ t = *this; *this = dbl_value(t); } else *this = inf();
             return;
         }
         F PP = Pp.sqr(), PPP = Pp * PP, Q = U1 * PP;

@@ -15,7 +15,7 @@
 #include "prover.cuh"
 #include "pk_format.hpp"
 #include "ntt.cuh"
-#include "msm.cuh"
+#include "msm_team.cuh"
 #include "witness_sha.hpp"
 
 namespace zkp {
@@ -372,7 +372,7 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool e
     // A proof that has the GPU to itself cuts the entry list into `waves_alone` waves of shorter ranges: dynamic CTA placement then evens
     // out SM-level variance and the accumulate kernel is 5-10 % faster, at the price of more pieces to fold.  With other proofs in flight
     // the extra fold work costs more than the tail it removes (those proofs fill the tail anyway), so one wave is used.  G1 only.
-    waves_alone = 3; if (const char *e = getenv("ZKB200_ACC_WAVES")) { waves_alone = atoi(e); if (waves_alone < 1) waves_alone = 1; if (waves_alone > 4) waves_alone = 4; }
+    waves_alone = 2; if (const char *e = getenv("ZKB200_ACC_WAVES")) { waves_alone = atoi(e); if (waves_alone < 1) waves_alone = 1; if (waves_alone > 4) waves_alone = 4; }
     acc_threads_g1 = (uint32_t)(sms * (occ1 > 0 ? occ1 : 1) * 128);
     acc_threads_g2 = (uint32_t)(sms * (occ2 > 0 ? occ2 : 1) * 128);
     ZK_CUDA(cudaEventCreate(&ev_acc0)); ZK_CUDA(cudaEventCreate(&ev_acc1));
@@ -385,7 +385,16 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool e
         for (int r = 0; r < affine_rounds; r++) { items = items / 2 + 1; ZK_CUDA(cudaMalloc(&aff_pts[r], items * sizeof(G1Affine))); }
         ZK_CUDA(cudaMalloc(&aff_scratch, (entries_cap / 2 + 1) * 32));
     }
-    const size_t nout = (size_t)(regions + 1) * bpw;
+    team = 7; if (const char *e = getenv("ZKB200_TEAM")) team = atoi(e) & 7;          // bit 0: fold, bit 1: heavy fold, bit 2: reduction
+    if (const char *e = getenv("ZKB200_TEAM_ALWAYS")) team_always = atoi(e) != 0;
+    if (const char *e = getenv("ZKB200_TEAM_DBG")) team_dbg = atoi(e);
+    seg_team = nb <= 256 ? 1 : 4;
+    { const uint32_t cw = cdiv(cdiv(nb, seg_team), TEAM_CHAINS), co = cdiv(cdiv(ones ? ones : 1, seg), TEAM_CHAINS); bpw_team = cw > co ? cw : co; }
+    ZK_CUDA(cudaMalloc(&team_counters, (size_t)(regions + 1) * 8));               // G1 half, G2 half: the two run side by side for the B query
+    ZK_CUDA(cudaMemset(team_counters, 0, (size_t)(regions + 1) * 8));
+    const size_t nout = (size_t)(regions + 1) * (bpw > bpw_team ? bpw : bpw_team);
+    if (g1) ZK_CUDA(cudaMalloc(&final_g1, (size_t)(regions + 1) * sizeof(G1XYZZ)));
+    if (g2) ZK_CUDA(cudaMalloc(&final_g2, (size_t)(regions + 1) * sizeof(G2XYZZ)));
     if (g1) {
         ZK_CUDA(cudaMalloc(&buckets_g1, ((size_t)acc_threads_g1 * waves_alone + total + 1) * sizeof(G1XYZZ)));
         ZK_CUDA(cudaMalloc(&out_g1, nout * sizeof(G1XYZZ)));
@@ -400,7 +409,7 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool e
 float MsmPlan::last_acc_ms() const { float ms = 0; if (ev_acc0) cudaEventElapsedTime(&ms, ev_acc0, ev_acc1); return ms; }
 void MsmPlan::release() {
     void *ps[] = {counts, offsets, cursors, entries, buckets_g1, buckets_g2, out_g1, out_g2, heavy, heavy_g2, offsets_shifted, aff_pts[0], aff_pts[1], aff_pts[2],
-                  aff_pts[3], aff_scratch};
+                  aff_pts[3], aff_scratch, team_counters, final_g1, final_g2};
     if (ev_sorted) cudaEventDestroy(ev_sorted);
     for (void *p : ps) if (p) cudaFree(p);
     if (ev_acc0) cudaEventDestroy(ev_acc0);
@@ -447,8 +456,25 @@ static void msm_points(cudaStream_t st, MsmPlan &p, const MsmShape &sh, const Af
     ZK_CUDA(cudaMemsetAsync(heavy, 0, 4, st));
     ZK_LAUNCH(msm_accumulate_kernel<F>, T / 128, 128, 0, st, bases, off, entries, p.total, T, partial);
     if (timed) ZK_CUDA(cudaEventRecord(p.ev_acc1, st));
-    ZK_LAUNCH(msm_fold_small_kernel<F>, cdiv(p.total, 128), 128, 0, st, partial, off, p.total, T, heavy);
-    ZK_LAUNCH(msm_fold_heavy_kernel<F>, 64, MSM_HEAVY_THREADS, MSM_HEAVY_THREADS * sizeof(XYZZ<F>), st, partial, off, p.total, T, (const uint32_t *)heavy);
+    // Tails.  With the GPU to itself (one proof: latency is what counts) a proof runs them on team point operations (msm_team.cuh: 32 chains per
+    // CTA, the four warps share every point addition, 2.0-2.5x shorter chains; the reduction also returns ONE point per region).  With other
+    // proofs in flight the one-thread-per-chain kernels are used: the tails then hide under the other proofs' kernels anyway, and the team
+    // kernels' 4x threads and barriers cost 5-13 % of pipelined throughput (profiles/r02_notes.md).  The piece fold of a big bucket set (the H
+    // query: 32768 buckets, 150-230 k pieces) is bound by throughput, not by latency, and stays on the one-thread kernel as well.
+    const size_t tsm = team_smem_bytes<F>();
+    const int team = p.team_now;
+    if ((team & 1) && p.total <= MSM_TEAM_FOLD_MAX_BUCKETS) ZK_LAUNCH(msm_fold_small_team_kernel<F>, cdiv(p.total, TEAM_CHAINS), 128, tsm, st, partial, off, p.total, T, heavy);
+    else ZK_LAUNCH(msm_fold_small_kernel<F>, cdiv(p.total, 128), 128, 0, st, partial, off, p.total, T, heavy);
+    if (team & 2) ZK_LAUNCH(msm_fold_heavy_team_kernel<F>, 64, 128, tsm, st, partial, off, p.total, T, (const uint32_t *)heavy);
+    else ZK_LAUNCH(msm_fold_heavy_kernel<F>, 64, MSM_HEAVY_THREADS, MSM_HEAVY_THREADS * sizeof(XYZZ<F>), st, partial, off, p.total, T, (const uint32_t *)heavy);
+    if (team & 4) {
+        XYZZ<F> *fin = (XYZZ<F> *)(sizeof(F) == 32 ? p.final_g1 : p.final_g2);
+        ZK_LAUNCH(msm_reduce_team_kernel<F>, dim3(p.bpw_team, sh.regions + 1), 128, tsm, st, (const XYZZ<F> *)partial, off, T, sh, p.seg, p.seg_team, out, fin,
+                  (uint32_t *)p.team_counters + (sizeof(F) == 32 ? 0 : sh.regions + 1), p.team_dbg);
+        if (p.team_dbg & 1) ZK_CUDA(cudaMemcpyAsync(h_out, out, (size_t)(sh.regions + 1) * p.bpw_team * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+        else ZK_CUDA(cudaMemcpyAsync(h_out, fin, (size_t)(sh.regions + 1) * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+        return;
+    }
     const dim3 rgrid(p.bpw, sh.regions + 1);
     ZK_LAUNCH(msm_reduce_kernel<F>, rgrid, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(XYZZ<F>), st, (const XYZZ<F> *)partial, off, T, sh, p.seg, p.seg_weighted, p.bpw, out);
     ZK_CUDA(cudaMemcpyAsync(h_out, out, (size_t)(sh.regions + 1) * p.bpw * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
@@ -463,6 +489,7 @@ void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, con
     // A proof that has the GPU to itself skips the affine rounds: with nothing else resident they are bound by gather latency, not by the
     // multiply pipe, and the plain XYZZ accumulation finishes sooner; with other proofs in flight their 40 % fewer multiplications win.
     p.rounds_now = (p.affine_rounds && (!p.alone || p.affine_always)) ? p.affine_rounds : 0;
+    p.team_now = (p.latency || p.team_always) ? p.team : 0;
     if (p.rounds_now) ZK_CUDA(cudaMemsetAsync(p.entries, 0xff, p.entries_cap * 4, st));          // pads of the bucket runs = null entries
     ZK_LAUNCH(msm_scan_kernel, 1, 1024, 0, st, (const uint32_t *)p.counts, (uint32_t *)p.offsets, p.total, p.rounds_now,
               (uint32_t *)(p.rounds_now ? p.offsets_shifted : nullptr));
@@ -475,16 +502,17 @@ void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, con
 
 template <class P> static P msm_finish(const MsmPlan &p, const void *h_out) {
     const P *part = (const P *)h_out;
+    const uint32_t bpw = (p.team_now & 4) ? ((p.team_dbg & 1) ? p.bpw_team : 1u) : p.bpw;                                   // team tails: the regions were summed on the device
     P acc = P::inf();
     if (p.expanded) {
-        for (uint32_t b = 0; b < 2 * p.bpw; b++) acc = acc.add(part[b]);       // the single bucket region, then the ones region
+        for (uint32_t b = 0; b < 2 * bpw; b++) acc = acc.add(part[b]);         // the single bucket region, then the ones region
         return acc;
     }
     for (int w = p.windows - 1; w >= 0; w--) {                                  // windowed layout: Horner over the per-window sums
         for (int i = 0; i < p.c; i++) acc = acc.dbl();
-        for (uint32_t b = 0; b < p.bpw; b++) acc = acc.add(part[(size_t)w * p.bpw + b]);
+        for (uint32_t b = 0; b < bpw; b++) acc = acc.add(part[(size_t)w * bpw + b]);
     }
-    for (uint32_t b = 0; b < p.bpw; b++) acc = acc.add(part[(size_t)p.windows * p.bpw + b]);
+    for (uint32_t b = 0; b < bpw; b++) acc = acc.add(part[(size_t)p.windows * bpw + b]);
     return acc;
 }
 HG1 msm_finish_g1(const MsmPlan &p) { return msm_finish<HG1>(p, p.h_out_g1); }
@@ -936,14 +964,17 @@ int prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64
     };
     // H: QAP witness map, then the dense MSM over coefficients_for_H[0 .. m-1).  This is the critical path, so the QAP map is enqueued
     // first (the host needs ~0.2 ms to enqueue the side queries).  Measurement mode: H waits for the side queries.
+    // no other proof of this key in flight (a benign race: only the schedule of the MSMs depends on it)
+    bool alone = true;
+    for (int i = 0; i < pk->nlanes; i++) if (pk->lanes[i] != ln && pk->lanes[i]->pending) alone = false;
+    ln->mA.latency = ln->mB.latency = ln->mL.latency = ln->mH.latency = alone;
     ZK_CUDA(cudaEventRecord(ln->ev_q0, st));
     qap_pipeline(pk, ln, st);
     ZK_CUDA(cudaEventRecord(ln->ev_q1, st));
     side_queries();                           // enqueued while the GPU is busy with the QAP map: they run beside it and are mostly done when H starts
     if (g_isolate_h) wait_side();
     ZK_CUDA(cudaEventRecord(ln->ev_h0, st));
-    ln->mH.alone = true;                       // no other proof of this key in flight (a benign race: only the schedule depends on it)
-    for (int i = 0; i < pk->nlanes; i++) if (pk->lanes[i] != ln && pk->lanes[i]->pending) ln->mH.alone = false;
+    ln->mH.alone = alone;
     msm_run(st, ln->mH, ScalarRef{ln->tmp, nullptr, 0, 1}, pk->H_skip, pk->H, nullptr);
     ZK_CUDA(cudaEventRecord(ln->ev_h1, st));
     wait_side();

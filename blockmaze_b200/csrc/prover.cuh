@@ -59,6 +59,14 @@ struct MsmPlan {
     void *out_g1 = nullptr, *out_g2 = nullptr;           // device partial sums  [(windows+1) * bpw]
     void *h_out_g1 = nullptr, *h_out_g2 = nullptr;       // pinned host copies
     cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr;    // around the G1 accumulate kernel (roofline measurement)
+    // tails on team point operations (msm_team.cuh; ZKB200_TEAM=0 selects the one-thread-per-chain kernels of msm.cuh)
+    int team = 7, team_now = 0;                          // bit 0: fold of the pieces, bit 1: fold of oversized buckets, bit 2: reduction; what the run in flight uses
+    bool latency = true;                                 // this run has the GPU to itself (set per proof by prove_submit; stand-alone MSMs: yes)
+    bool team_always = false;                            // ZKB200_TEAM_ALWAYS=1: also with other proofs in flight (measurement)
+    int team_dbg = 0;                                    // ZKB200_TEAM_DBG: 1 host sums the CTA outputs, 2 one-thread scalar multiple, 4 one-thread point operations
+    uint32_t seg_team = 0, bpw_team = 0;                 // buckets per chain in the weighted regions, CTAs (of 32 chains) per region
+    void *team_counters = nullptr;                       // 2 x [regions + 1] (G1, G2) arrival counters of the device-side final sum, zero between launches
+    void *final_g1 = nullptr, *final_g2 = nullptr;       // [regions + 1] one point per bucket region: what goes back to the host
     // batched-affine halving rounds in front of the XYZZ accumulation (msm.cuh); G1 only, 0 = off
     int affine_rounds = 0, rounds_now = 0;               // configured / used by the run in flight (a proof alone on the GPU skips them)
     bool affine_always = false;

@@ -231,7 +231,49 @@ template <class P> struct Fp {
     // msm_accumulate_kernel stalled mostly on no_instruction, icc hit rate 74 %).
     static __device__ __noinline__ Fp mul_call(const Fp a, const Fp b) { return mul_impl(a, b); }
 #endif
-    ZK_HD static Fp mul_impl(const Fp &a, const Fp &b) {
+    ZK_HD static Fp mul_impl(const Fp &a, const Fp &b) { return mul_core<true>(a, b); }
+    // ---- lazy arithmetic for the NTT butterflies (ntt.cuh): values live in [0, 4p), 4p < 2^256 for both BN254 moduli -----------------------
+    // a < 4p (any 256-bit value whose top limb stays below 2^32 - 8), b < p  ->  a*b*R^-1 + (0 or p), below 2p, NOT reduced
+    ZK_HD static Fp mul_lazy(const Fp &a, const Fp &b) { return mul_core<false>(a, b); }
+    ZK_HD static constexpr uint32_t mod2(int i) { return i == 0 ? P::mod(0) << 1 : (P::mod(i) << 1) | (P::mod(i - 1) >> 31); }      // limb i of 2p
+    // a < 4p  ->  a or a - 2p, below 2p
+    ZK_HD static Fp condsub_2p(const Fp &a) {
+        Carry c; Fp t; uint32_t brw;
+        c.sub_cc(t.v[0], a.v[0], mod2(0));
+#pragma unroll
+        for (int i = 1; i < 8; i++) c.subc_cc(t.v[i], a.v[i], mod2(i));
+        c.subc(brw, 0, 0);
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = brw ? a.v[i] : t.v[i];
+        return r;
+    }
+    // a, b < 2p  ->  a + b, below 4p
+    ZK_HD static Fp add_lazy(const Fp &a, const Fp &b) {
+        Fp r; Carry c;
+        c.add_cc(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < 7; i++) c.addc_cc(r.v[i], a.v[i], b.v[i]);
+        c.addc(r.v[7], a.v[7], b.v[7]);
+        return r;
+    }
+    // a, b < 2p  ->  a - b + 2p, in (0, 4p)
+    ZK_HD static Fp sub_lazy(const Fp &a, const Fp &b) {
+        Fp r; Carry c;
+        c.add_cc(r.v[0], a.v[0], mod2(0));
+#pragma unroll
+        for (int i = 1; i < 7; i++) c.addc_cc(r.v[i], a.v[i], mod2(i));
+        c.addc(r.v[7], a.v[7], mod2(7));
+        Carry d;
+        d.sub_cc(r.v[0], r.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < 7; i++) d.subc_cc(r.v[i], r.v[i], b.v[i]);
+        d.subc(r.v[7], r.v[7], b.v[7]);
+        return r;
+    }
+    // a < 4p  ->  a mod p, fully reduced
+    ZK_HD static Fp reduce_4p(const Fp &a) { Fp r = condsub_2p(a); r.reduce_once(); return r; }
+    template <bool REDUCE> ZK_HD static Fp mul_core(const Fp &a, const Fp &b) {
         uint32_t acc[2][18];
 #pragma unroll
         for (int k = 0; k < 18; k++) { acc[0][k] = 0; acc[1][k] = 0; }
@@ -290,7 +332,7 @@ template <class P> struct Fp {
 #pragma unroll
         for (int k = 1; k < 7; k++) c.addc_cc(r.v[k], acc[0][8 + k], acc[1][8 + k]);
         c.addc(r.v[7], acc[0][15], 0);
-        r.reduce_once();
+        if (REDUCE) r.reduce_once();
         return r;
     }
     // (a*b + c*d) * R^-1 mod p with ONE Montgomery reduction: every row adds a*b_i, c*d_i and m_i*p to the same two accumulators, 3*64 + 8

@@ -11,6 +11,7 @@
 // by g^i on the way in (coset shift); the last pass can multiply by a per-index power table on the way out (g^-i / n).
 // Twiddles omega^j, j < n/2, come from a table built once per domain.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "ff.cuh"
 
@@ -47,19 +48,7 @@ __device__ __forceinline__ void st_fr(Fr *p, const Fr &r) {
     q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
 
-#ifndef ZK_NTT_INLINE_MUL
-#define ZK_NTT_INLINE_MUL 1      // butterfly multiplication inlined (one per loop body; measured 2-3 % faster than the call)
-#endif
-__device__ __forceinline__ Fr ntt_mul(const Fr &a, const Fr &b) {
-#if ZK_NTT_INLINE_MUL
-    return Fr::mul_impl(a, b);
-#else
-    return a * b;
-#endif
-}
-#ifndef ZK_NTT_MINBLOCKS
-#define ZK_NTT_MINBLOCKS 2       // CTAs of NTT_MAX_THREADS per SM the register allocation must allow (2 -> 128 registers, 3 -> 80, 4 -> 64)
-#endif
+constexpr int NTT_DENSE_LOG = 18;           // transforms of at least 2^18 points run with six warps per SM sub-partition (see ntt_pass_kernel)
 // Twiddles are stored PER STAGE, compactly: stage L (butterflies of span 2^L, L = 1..logn) owns the 2^(L-1) powers w_L^j of the primitive
 // 2^L-th root at offset 2^(L-1) - 1, so a stage walks its own contiguous run instead of striding through one table of n/2 powers (where
 // every stage but the last used 1/2, 1/4, ... of each line it fetched: round 1 measured 1.46 GB of DRAM reads for the 0.5 GB of the last
@@ -79,12 +68,40 @@ constexpr int NTT_TILE_LOG = 11;          // at most 2048 elements * 32 B = 64 K
 // One pass = stages s0+1 .. s0+k of the decimation-in-time schedule over `n = 2^logn` elements.
 //   set  = the 2^k elements that differ only in index bits [s0, s0+k)
 //   tile = G = 2^logG sets with consecutive low bits, so global accesses are G*32-byte contiguous runs
-template <bool FIRST>
-static __global__ void __launch_bounds__(NTT_MAX_THREADS, ZK_NTT_MINBLOCKS)
+//
+// What bounds the kernel (ncu, round 2): with 128 registers four warps share an SM sub-partition, each a chain of dependent instructions,
+// so the sub-partition issues ~0.35 instructions per clock whatever they are -- the multiply pipe is only as busy as the share of multiply
+// instructions in the stream.  Hence every instruction that is not part of a multiplication counts:
+//   * the tile lives in shared memory as two 16-byte halves per element ([half][slot]): 2 loads/stores per element instead of 8;
+//   * butterflies are LAZY: values stay in [0, 4r) (4r < 2^256), the Montgomery product skips its final subtraction (a < 4r, twiddle < r
+//     gives a result below 2r), u + t is a plain 256-bit addition and u - t + 2r a plain subtraction, and only the u leg is brought below
+//     2r first.  One conditional subtraction per butterfly instead of three; intermediate passes store unreduced values, the last pass
+//     reduces.  Results are the same field elements, bit for bit after the final reduction.
+__device__ __forceinline__ Fr ntt_ld_tile(const uint4 *sm4, int N, int slot) {
+    const uint4 a = sm4[slot], b = sm4[N + slot];
+    Fr r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void ntt_st_tile(uint4 *sm4, int N, int slot, const Fr &r) {
+    sm4[slot] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    sm4[N + slot] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+// (u, v) -> (u + w v, u - w v) on values below 4r; `unit`: the twiddle is 1
+__device__ __forceinline__ void ntt_bfly(Fr &u, Fr &v, const Fr &w, bool unit) {
+    const Fr t = unit ? Fr::condsub_2p(v) : Fr::mul_lazy(v, w);
+    const Fr a = Fr::condsub_2p(u);
+    u = Fr::add_lazy(a, t);
+    v = Fr::sub_lazy(a, t);
+}
+// MINB = CTAs of NTT_MAX_THREADS per SM the register allocation must allow: 2 -> up to 128 registers (the kernel needs 92-98: four warps per
+// sub-partition), 3 -> 80 registers (six warps; 32 bytes spilled in the first-pass variant).  Measured: 3 is faster from 2^18 up (2^24:
+// 3.97 -> 3.59 ms; deposit's QAP map 1.19 -> 1.12 ms), 2 for the smaller transforms of the step domains; 4 (64 registers) loses everywhere.
+template <bool FIRST, int MINB>
+static __global__ void __launch_bounds__(NTT_MAX_THREADS, MINB)
 ntt_pass_kernel(const Fr *__restrict__ src, Fr *__restrict__ dst, const Fr *__restrict__ tw,
                 int logn, int s0, int k, int logG, PowMul pre, PowMul post, int last, size_t batch_stride,
                 const Fr *__restrict__ sub = nullptr, const Fr *__restrict__ sub_scale = nullptr) {
-    extern __shared__ uint32_t sm[];
+    extern __shared__ uint4 sm4[];
     src += blockIdx.y * batch_stride; dst += blockIdx.y * batch_stride;      // independent transforms of one launch (A, B, C of the QAP map)
     const int N = 1 << (k + logG);
     const uint32_t set0 = blockIdx.x << logG;
@@ -96,27 +113,33 @@ ntt_pass_kernel(const Fr *__restrict__ src, Fr *__restrict__ dst, const Fr *__re
     const uint32_t set_stride = FIRST ? gridDim.x : 1u;
     const uint32_t set_base = FIRST ? blockIdx.x : set0;
     const int nthreads = blockDim.x;
-    for (int e = threadIdx.x; e < N; e += nthreads) {
-        const int g = e & ((1 << logG) - 1), t = e >> logG;
-        const uint32_t set = set_base + g * set_stride;
-        const uint32_t addr = ((set >> s0) << (s0 + k)) | ((uint32_t)t << s0) | (set & lowmask);
-        Fr x;
-        if (FIRST) {
-            const uint32_t from = __brev(addr) >> (32 - logn);
-            x = ld_fr(src + from);
-            if (pre.on()) x = x * pre.at(from);
-        } else {
-            x = ld_fr(src + addr);
-        }
-        const int slot = (g << k) | t;
+    // A CTA has N/4 threads (at least 32, at most 256): four elements per thread and trip, all four loads issued before the first use so
+    // that they share one global-memory latency.
+    for (int e0 = threadIdx.x; e0 < N; e0 += 4 * nthreads) {       // (one trip at the circuit sizes; two for the 2048-element tiles)
+        Fr x[4]; uint32_t from[4];
 #pragma unroll
-        for (int w = 0; w < 8; w++) sm[w * N + slot] = x.v[w];
+        for (int it = 0; it < 4; it++) {
+            const int e = e0 + it * nthreads;
+            const int g = e & ((1 << logG) - 1), t = e >> logG;
+            const uint32_t set = set_base + g * set_stride;
+            const uint32_t addr = ((set >> s0) << (s0 + k)) | ((uint32_t)t << s0) | (set & lowmask);
+            from[it] = FIRST ? __brev(addr) >> (32 - logn) : addr;
+            if (e < N) x[it] = ld_fr(src + from[it]);
+        }
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int e = e0 + it * nthreads;
+            if (e < N) {
+                if (FIRST && pre.on()) x[it] = Fr::mul_lazy(x[it], pre.at(from[it]));
+                const int g = e & ((1 << logG) - 1), t = e >> logG;
+                ntt_st_tile(sm4, N, (g << k) | t, x[it]);
+            }
+        }
     }
 
     // Butterfly stages.  Two stages at a time (radix-4 in registers): a thread takes the four elements that differ in index bits q-1 and
     // q, multiplies by three twiddles (four multiplications, as two radix-2 stages would) and writes them back -- half the shared-memory
-    // traffic and half the barriers of a stage-by-stage schedule, and two independent multiplications in flight.  An odd k starts
-    // with one radix-2 stage.
+    // traffic and half the barriers of a stage-by-stage schedule.  An odd k starts with one radix-2 stage.
     int q = 1;
     if (k & 1) {
         __syncthreads();
@@ -125,13 +148,11 @@ ntt_pass_kernel(const Fr *__restrict__ src, Fr *__restrict__ dst, const Fr *__re
             const int g = u >> (k - 1), tt = u & ((1 << (k - 1)) - 1);
             const int i0 = (g << k) | (tt << 1), i1 = i0 + 1;
             const uint32_t j = (set0 + g) & lowmask;                  // tlow = 0 at the first stage
-            Fr a, b;
-#pragma unroll
-            for (int w = 0; w < 8; w++) { a.v[w] = sm[w * N + i0]; b.v[w] = sm[w * N + i1]; }
-            if (j != 0) b = ntt_mul(b, ldg_fr(ntt_tw(tw, s0 + 1, j)));
-            Fr s = a + b, d = a - b;
-#pragma unroll
-            for (int w = 0; w < 8; w++) { sm[w * N + i0] = s.v[w]; sm[w * N + i1] = d.v[w]; }
+            Fr a = ntt_ld_tile(sm4, N, i0), b = ntt_ld_tile(sm4, N, i1);
+            Fr w = Fr::zero();
+            if (j != 0) w = ldg_fr(ntt_tw(tw, s0 + 1, j));
+            ntt_bfly(a, b, w, j == 0);
+            ntt_st_tile(sm4, N, i0, a); ntt_st_tile(sm4, N, i1, b);
         }
         q = 2;
     }
@@ -145,40 +166,38 @@ ntt_pass_kernel(const Fr *__restrict__ src, Fr *__restrict__ dst, const Fr *__re
             const int i0 = (g << k) | ((tt >> (q - 1)) << (q + 1)) | tlow;
             const uint32_t low = (set0 + g) & lowmask;
             const uint32_t j = ((uint32_t)tlow << s0) | low, j2 = ((uint32_t)(tlow + hq) << s0) | low;
-            Fr x0, x1, x2, x3;
-#pragma unroll
-            for (int w = 0; w < 8; w++) {
-                x0.v[w] = sm[w * N + i0]; x1.v[w] = sm[w * N + i0 + hq]; x2.v[w] = sm[w * N + i0 + 2 * hq]; x3.v[w] = sm[w * N + i0 + 3 * hq];
-            }
-            if (j != 0) {                                               // stage q: (x0, x1) and (x2, x3), same twiddle
-                const Fr w1 = ldg_fr(ntt_tw(tw, s0 + q, j));
-                x1 = ntt_mul(x1, w1); x3 = ntt_mul(x3, w1);
-            }
-            const Fr a0 = x0 + x1, a1 = x0 - x1;
-            Fr a2 = x2 + x3, a3 = x2 - x3;
-            if (j != 0) a2 = ntt_mul(a2, ldg_fr(ntt_tw(tw, s0 + q + 1, j)));      // stage q+1: (a0, a2) and (a1, a3)
-            a3 = ntt_mul(a3, ldg_fr(ntt_tw(tw, s0 + q + 1, j2)));
-            x0 = a0 + a2; x2 = a0 - a2; x1 = a1 + a3; x3 = a1 - a3;
-#pragma unroll
-            for (int w = 0; w < 8; w++) {
-                sm[w * N + i0] = x0.v[w]; sm[w * N + i0 + hq] = x1.v[w]; sm[w * N + i0 + 2 * hq] = x2.v[w]; sm[w * N + i0 + 3 * hq] = x3.v[w];
-            }
+            Fr x0 = ntt_ld_tile(sm4, N, i0), x1 = ntt_ld_tile(sm4, N, i0 + hq), x2 = ntt_ld_tile(sm4, N, i0 + 2 * hq), x3 = ntt_ld_tile(sm4, N, i0 + 3 * hq);
+            const bool unit = j == 0;
+            Fr w = Fr::zero();
+            if (!unit) w = ldg_fr(ntt_tw(tw, s0 + q, j));               // stage q: (x0, x1) and (x2, x3), same twiddle
+            ntt_bfly(x0, x1, w, unit);
+            ntt_bfly(x2, x3, w, unit);
+            if (!unit) w = ldg_fr(ntt_tw(tw, s0 + q + 1, j));           // stage q+1: (x0, x2) and (x1, x3)
+            ntt_bfly(x0, x2, w, unit);
+            ntt_bfly(x1, x3, ldg_fr(ntt_tw(tw, s0 + q + 1, j2)), false);
+            ntt_st_tile(sm4, N, i0, x0); ntt_st_tile(sm4, N, i0 + hq, x1); ntt_st_tile(sm4, N, i0 + 2 * hq, x2); ntt_st_tile(sm4, N, i0 + 3 * hq, x3);
         }
     }
     __syncthreads();
 
-    for (int e = threadIdx.x; e < N; e += nthreads) {
-        int t, g;
-        if (FIRST) { t = e & ((1 << k) - 1); g = e >> k; } else { g = e & ((1 << logG) - 1); t = e >> logG; }
-        const uint32_t set = set_base + g * set_stride;
-        const uint32_t addr = ((set >> s0) << (s0 + k)) | ((uint32_t)t << s0) | (set & lowmask);
-        const int slot = (g << k) | t;
-        Fr x;
+    for (int e0 = threadIdx.x; e0 < N; e0 += 4 * nthreads) {
 #pragma unroll
-        for (int w = 0; w < 8; w++) x.v[w] = sm[w * N + slot];
-        if (last && post.on()) x = x * post.at(addr);
-        if (last && sub) x = x - ldg_fr(sub + addr) * ldg_fr(sub_scale);      // out = x * post - sub * scale (the QAP map's h = (d - c) / Z, see prover.cu)
-        st_fr(dst + addr, x);
+        for (int it = 0; it < 4; it++) {
+            const int e = e0 + it * nthreads;
+            if (e < N) {
+                int t, g;
+                if (FIRST) { t = e & ((1 << k) - 1); g = e >> k; } else { g = e & ((1 << logG) - 1); t = e >> logG; }
+                const uint32_t set = set_base + g * set_stride;
+                const uint32_t addr = ((set >> s0) << (s0 + k)) | ((uint32_t)t << s0) | (set & lowmask);
+                Fr x = ntt_ld_tile(sm4, N, (g << k) | t);
+                if (last) {                                             // the transform's result: fully reduced
+                    if (post.on()) { x = Fr::mul_lazy(x, post.at(addr)); x.reduce_once(); }
+                    else x = Fr::reduce_4p(x);
+                    if (sub) x = x - ldg_fr(sub + addr) * ldg_fr(sub_scale);      // out = x * post - sub * scale (the QAP map's h = (d - c) / Z, see prover.cu)
+                }
+                st_fr(dst + addr, x);
+            }
+        }
     }
 }
 
@@ -215,15 +234,19 @@ static inline void ntt_launch(cudaStream_t st, const Fr *src, Fr *dst, const Fr 
         const dim3 blocks(1u << (logn - ps[p].k - ps[p].logG), (unsigned)batch);
         const int last = (p == np - 1);
         int threads = N / 4; if (threads < 32) threads = 32; if (threads > NTT_MAX_THREADS) threads = NTT_MAX_THREADS;
-        if (p == 0)
-            ntt_pass_kernel<true><<<blocks, threads, smem, st>>>(src, dst, tw, logn, ps[p].s0, ps[p].k, ps[p].logG, pre, post, last, batch_stride, sub, sub_scale);
-        else
-            ntt_pass_kernel<false><<<blocks, threads, smem, st>>>(dst, dst, tw, logn, ps[p].s0, ps[p].k, ps[p].logG, pre, post, last, batch_stride, sub, sub_scale);
+        const bool dense = logn >= NTT_DENSE_LOG;
+        const Fr *in = p == 0 ? src : dst;
+        if (p == 0 && dense) ntt_pass_kernel<true, 3><<<blocks, threads, smem, st>>>(in, dst, tw, logn, ps[p].s0, ps[p].k, ps[p].logG, pre, post, last, batch_stride, sub, sub_scale);
+        else if (p == 0) ntt_pass_kernel<true, 2><<<blocks, threads, smem, st>>>(in, dst, tw, logn, ps[p].s0, ps[p].k, ps[p].logG, pre, post, last, batch_stride, sub, sub_scale);
+        else if (dense) ntt_pass_kernel<false, 3><<<blocks, threads, smem, st>>>(in, dst, tw, logn, ps[p].s0, ps[p].k, ps[p].logG, pre, post, last, batch_stride, sub, sub_scale);
+        else ntt_pass_kernel<false, 2><<<blocks, threads, smem, st>>>(in, dst, tw, logn, ps[p].s0, ps[p].k, ps[p].logG, pre, post, last, batch_stride, sub, sub_scale);
     }
 }
 static inline void ntt_init_attrs() {
-    cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt_pass_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt_pass_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt_pass_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt_pass_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -948,6 +948,8 @@ int prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64
     ZK_CUDA(cudaEventRecord(ln->ev_w, st));
     // A, B, L queries on side streams: scalars are the canonical padded assignment [1 | w]  (r1cs_gg_ppzksnark.tcc:437-484); the trailing
     // delta base of each query picks up r, s, -rs, so the MSM results already are  eA + r*delta,  eB + s*delta,  eL - rs*delta.
+    // (Starting them after the QAP map instead -- beside the H query -- was measured for a proof alone on the GPU: the QAP map drops from
+    // 0.65 to 0.51 ms and the H query grows by as much; even a single proof keeps the multiply pipe busy, profiles/r02_notes.md.)
     auto side_queries = [&]() {
         ZK_CUDA(cudaStreamWaitEvent(ln->s_a, ln->ev_w, 0));
         ZK_CUDA(cudaStreamWaitEvent(ln->s_b, ln->ev_w, 0));

@@ -1,7 +1,7 @@
 #!/bin/bash
 # final evidence run (1 GPU): parity suite, default bench line, ncu launch list (+FMA-pipe counts) of one send proof,
 # ncu --set full of the H-query accumulate kernel, the NTT passes of the QAP map and of a 2^24 transform
-OUT=gpurun_out/r02z; mkdir -p $OUT
+OUT=gpurun_out/r02y; mkdir -p $OUT
 ( time timeout 900 python -m pytest tests -m gpu -x -q --timeout 300 --durations=5 ) > $OUT/pytest.log 2>&1
 echo "pytest rc=$?" >> $OUT/pytest.log; tail -3 $OUT/pytest.log
 ( time timeout 900 python bench.py --steps 200 --warmup 3 ) > $OUT/bench.json 2> $OUT/bench.err
@@ -12,4 +12,5 @@ tail -1 $OUT/prove_once.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:msm_accumulate -s 6 -c 2 -o $OUT/acc_full python scripts/gpu_prove_once.py send 2 > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ntt_pass -s 10 -c 6 -o $OUT/ntt_qap_full python scripts/gpu_prove_once.py send 2 > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ntt_pass -s 3 -c 3 -o $OUT/ntt24_full python scripts/gpu_ntt_once.py 24 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:msm_reduce_team -s 3 -c 1 -o $OUT/reduce_team_h_full python scripts/gpu_prove_once.py send 1 > /dev/null 2>&1
 ls -la $OUT

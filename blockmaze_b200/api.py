@@ -258,12 +258,22 @@ def _tx(circuit, args):
 def prove_batch(jobs, threads=0):
     """jobs: list of (circuit, gen<Circuit>proof argument list).  Proves them on every active device (zkb200_prove_batch).
     Returns (proof strings, number of default proofs)."""
+    return prove_batch_run(prove_batch_prepare(jobs), threads)
+
+
+def prove_batch_prepare(jobs):
+    """The zkb200_tx array of a job list (ctypes marshalling of the argument strings: Python's cost, not the library's)."""
     arr = (Tx * max(1, len(jobs)))(*[_tx(c, a) for c, a in jobs])
-    out = C.create_string_buffer(513 * max(1, len(jobs)))
-    bad = lib.zkb200_prove_batch(len(jobs), arr, out, threads)
+    return arr, len(jobs)
+
+
+def prove_batch_run(prepared, threads=0):
+    arr, n = prepared
+    out = C.create_string_buffer(513 * max(1, n))
+    bad = lib.zkb200_prove_batch(n, arr, out, threads)
     if bad < 0:
         raise ZkError("zkb200_prove_batch: bad arguments")
-    return [out.raw[513 * i:513 * i + 512].decode() for i in range(len(jobs))], bad
+    return [out.raw[513 * i:513 * i + 512].decode() for i in range(n)], bad
 
 
 def helper(name, *args):

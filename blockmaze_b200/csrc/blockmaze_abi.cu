@@ -40,6 +40,7 @@ static std::vector<uint32_t> g_words;
 static size_t g_word_pos = 0;
 static thread_local double g_last_ms[4] = {0, 0, 0, 0};      // witness generation, prove call, of which GPU, host finish (last gen*proof of this thread)
 static thread_local int g_last_device = -1, g_last_lane = -1;
+static std::atomic<long> g_device_proofs[64];                                      // gen*proof calls finished per device (zkb200_device_proofs)
 static thread_local void *g_last_pk = nullptr;
 // SHA-256 gadget runs expanded on the GPU (default) or by the host generator (ZKB200_GPU_WITNESS=0)
 static bool gpu_witness() { static const bool on = [] { const char *e = getenv("ZKB200_GPU_WITNESS"); return !(e && atoi(e) == 0); }(); return on; }
@@ -178,11 +179,13 @@ template <class Fn> static char *prove_timed(int circuit, Fn make) {
     g_last_ms[1] = now_ms() - t1; g_last_ms[2] = tm[0]; g_last_ms[3] = tm[3];
     zkb200_lane_release(pk, lane);
     sched->done(slot);
+    if (g_last_device >= 0 && g_last_device < 64) g_device_proofs[g_last_device].fetch_add(1, std::memory_order_relaxed);
     if (rc < 0) { fprintf(stderr, "zkb200: prover rejected the %s witness (%d)\n", CIRCUIT_NAMES[circuit], rc); abort(); }   // generator bug, never a wrong proof
     if (rc == 1) printf("can not generate %s proof\n", CIRCUIT_NAMES[circuit]);      // mintcgo.cpp:209
     return p;
 }
 int zkb200_last_device(void) { return g_last_device; }
+long zkb200_device_proofs(int device) { return device >= 0 && device < 64 ? g_device_proofs[device].load(std::memory_order_relaxed) : -1; }
 // parity hook: the assignment on the GPU behind this thread's last gen*proof (valid until another proof takes that lane)
 long zkb200_last_assignment(uint8_t *out, size_t cap_bytes) {
     if (!g_last_pk || g_last_lane < 0) return -1;

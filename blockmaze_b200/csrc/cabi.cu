@@ -336,6 +336,7 @@ int zkb200_qap_witness_map(void *h, const uint8_t *assignment, uint8_t *out_H, i
     return qap_witness_map(pk, assignment, out_H, satisfied);
 }
 int zkb200_last_launches(void) { return launches_last_prove(); }
+void zkb200_last_transfer_bytes(unsigned long long out[2]) { transfer_bytes_last_prove(out); }
 void zkb200_set_isolate_h(int on) { set_isolate_h(on != 0); }
 
 // ---- evaluation domains ---------------------------------------------------------------------------------------------------
@@ -433,7 +434,7 @@ float zkb200_bench_ntt(int logn, int batch, int iters) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const PowMul none{nullptr, nullptr, 0};
     for (int b = 0; b < batch; b++) ntt_launch(0, src + b * n, dst + b * n, (const Fr *)d->tw_big_f, logn, none, none);   // warm-up
-    ZK_CUDA(cudaDeviceSynchronize());
+    zkp::device_sync();
     cudaEventRecord(e0, 0);
     for (int it = 0; it < iters; it++)
         for (int b = 0; b < batch; b++) ntt_launch(0, src + b * n, dst + b * n, (const Fr *)d->tw_big_f, logn, none, none);
@@ -469,7 +470,7 @@ static void *synth_bases_device(int group, size_t first, size_t n) {
         if (n) gen_bases_kernel<Fq2><<<(unsigned)((n + 127) / 128), 128>>>((const G2Affine *)table, (G2Affine *)bases, n, first);
     }
     ZK_CUDA(cudaGetLastError());
-    ZK_CUDA(cudaDeviceSynchronize());
+    zkp::device_sync();
     cudaFree(table);
     return bases;
 }
@@ -502,15 +503,15 @@ float zkb200_bench_msm_slice(int group, size_t first, size_t n, int window_bits,
     uint32_t *sc; ZK_CUDA(cudaMalloc(&sc, (n + 1) * 32));
     if (n) fill_scalars_kernel<<<(unsigned)((n + 255) / 256), 256>>>(sc, n, first);
     void *bases = synth_bases_device(group, first, n);
-    ZK_CUDA(cudaDeviceSynchronize());
+    zkp::device_sync();
     const bool expanded = window_bits < 0;          // negative window_bits: fixed-base (expanded) layout with |window_bits| bits
     int aff = 0;                                     // affine halving rounds in front of the accumulation: off unless asked for, as in the prover
     if (const char *e = getenv("ZKB200_AFFINE_ROUNDS")) aff = atoi(e);
     MsmPlan plan; plan.init((uint32_t)n, c, 0, group == 1, group == 2, expanded, expanded ? aff : 0);
-    if (expanded) { void *e = msm_expand_bases(bases, (uint32_t)n, c, group == 2); ZK_CUDA(cudaDeviceSynchronize()); cudaFree(bases); bases = e; }
+    if (expanded) { void *e = msm_expand_bases(bases, (uint32_t)n, c, group == 2); zkp::device_sync(); cudaFree(bases); bases = e; }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     msm_run(0, plan, ScalarRef{sc, nullptr, 0, 0}, nullptr, group == 1 ? bases : nullptr, group == 2 ? bases : nullptr);
-    ZK_CUDA(cudaDeviceSynchronize());
+    zkp::device_sync();
     cudaEventRecord(e0, 0);
     for (int it = 0; it < iters; it++)
         msm_run(0, plan, ScalarRef{sc, nullptr, 0, 0}, nullptr, group == 1 ? bases : nullptr, group == 2 ? bases : nullptr);
@@ -564,7 +565,7 @@ void zkb200_flush_l2(void) {
 }
 void zkb200_device_sync(void) {
     if (ensure_device()) return;
-    for (int d : devices_in_use()) { ZK_CUDA(cudaSetDevice(d)); ZK_CUDA(cudaDeviceSynchronize()); }
+    for (int d : devices_in_use()) { ZK_CUDA(cudaSetDevice(d)); zkp::device_sync(); }
     cudaSetDevice(g_device);
 }
 // Device-clock stopwatch around a region that runs on many streams (and, in a single process driving several GPUs, on many devices): both
@@ -593,7 +594,7 @@ float zkb200_bench_imad_peak(int mode) {
     uint32_t *out; ZK_CUDA(cudaMalloc(&out, (size_t)blocks * threads * 4));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     imad_peak_kernel<<<blocks, threads>>>(out, 2, mode);
-    ZK_CUDA(cudaDeviceSynchronize());
+    zkp::device_sync();
     cudaEventRecord(e0, 0);
     imad_peak_kernel<<<blocks, threads>>>(out, iters, mode);
     cudaEventRecord(e1, 0);

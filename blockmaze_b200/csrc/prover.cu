@@ -5,12 +5,14 @@
 // proofs are in flight; a proof is one H2D copy of the (compact) assignment, ~42 kernel launches on five streams, and a D2H copy of
 // a hundred partial sums.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <mutex>
+#include <shared_mutex>
 #include <thread>
 #include "prover.cuh"
 #include "pk_format.hpp"
@@ -24,8 +26,12 @@ using zkh::HFr; using zkh::HFq; using zkh::HFq2; using zkh::HG1; using zkh::HG2;
 
 static thread_local int g_launches = 0;     // kernels launched by this thread since the last prove_submit() began
 static int g_last_launches = 0;
+static thread_local unsigned long long g_h2d_bytes = 0;      // host-to-device bytes of the proof this thread is submitting
+static thread_local unsigned long long g_last_bytes[2] = {0, 0};   // host-to-device / device-to-host bytes of the last proof this thread collected
 static bool g_isolate_h = false;            // measurement mode, see set_isolate_h()
 static const int g_spmv_bits = [] { const char *e = getenv("ZKB200_SPMV_BITS"); return e ? atoi(e) : 1; }();                        // 0: multiply even by 0 and 1
+static std::atomic<int> g_device_pending[64];          // proofs submitted and not yet collected, per device, over all resident keys
+static const bool g_use_graph = [] { const char *e = getenv("ZKB200_GRAPH"); return !(e && atoi(e) == 0); }();          // 0: enqueue every proof kernel by kernel
 static const int g_sort_v2 = [] { const char *e = getenv("ZKB200_SORT_V2"); return e ? atoi(e) : 1; }();
 static const int g_full_pow = [] { const char *e = getenv("ZKB200_FULL_POW"); return e ? atoi(e) : 1; }();                           // 0: two-level coset tables in the QAP map
 static const bool g_qap_skip_c = [] { const char *e = getenv("ZKB200_QAP_SEVEN"); return !(e && atoi(e) != 0); }();   // ZKB200_QAP_SEVEN=1: the reference's seven transforms
@@ -39,11 +45,46 @@ void cuda_check(cudaError_t e, const char *what) {
     }
 }
 int launches_last_prove() { return g_last_launches; }
+void transfer_bytes_last_prove(unsigned long long out[2]) { out[0] = g_last_bytes[0]; out[1] = g_last_bytes[1]; }
 void set_isolate_h(bool on) { g_isolate_h = on; }
+// A proof's kernels, copies and stream joins are captured ONCE per lane into a CUDA graph and replayed with one call (prove_submit).  Events
+// the HOST looks at afterwards (completion polls, CUDA-event timings) must then be external record nodes; events that only order streams
+// inside the proof stay ordinary captured dependencies.
+static thread_local bool g_capturing = false;
+static void record_for_host(cudaEvent_t ev, cudaStream_t st) {
+    if (g_capturing) ZK_CUDA(cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal));
+    else ZK_CUDA(cudaEventRecord(ev, st));
+}
+// Completion signals the host polls in plain memory: the last thing on a stream bumps a device counter and stores it to a word of pinned
+// host memory.  No driver call per poll (cudaEventQuery from two dozen threads is lock traffic inside the driver), and it works the same
+// whether the stream's work was enqueued directly or replayed from a graph (the value is not a kernel argument).
+static __global__ void signal_kernel(volatile uint32_t *host_flag, uint32_t *counter) {
+    const uint32_t v = *counter + 1;
+    *counter = v;
+    *host_flag = v;
+    __threadfence_system();
+}
+static float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {          // statistics only: never fatal
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { (void)cudaGetLastError(); ms = 0; }
+    return ms;
+}
 
 static inline Fr to_dev(const HFr &x) { Fr r; memcpy(r.v, x.v, 32); return r; }
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// cudaDeviceSynchronize is illegal while ANY stream of the device is being captured (whatever the capture mode), and keys are loaded lazily
+// by caller threads while other threads already prove: a capture holds this lock shared, whoever synchronises the device -- or loads / frees
+// a key, with its allocations and default-stream kernels -- holds it exclusively.  Captures take a millisecond, once per lane.
+static std::shared_mutex g_capture_mu[64];
+static thread_local int t_exclusive = 0;
+struct DeviceExclusive {
+    int d = 0; bool own;
+    DeviceExclusive() { cudaGetDevice(&d); own = (t_exclusive++ == 0); if (own) g_capture_mu[d & 63].lock(); }
+    ~DeviceExclusive() { if (own) g_capture_mu[d & 63].unlock(); --t_exclusive; }
+};
+void device_sync() { DeviceExclusive x; ZK_CUDA(cudaDeviceSynchronize()); }
 
 static bool g_attrs_done[64];
 static std::mutex g_attrs_mu;
@@ -83,7 +124,7 @@ static void *dev_tw_levels(HFr w, int logn) {
     Fr *levels; ZK_CUDA(cudaMalloc(&levels, (size_t)n * 32));
     ntt_tw_levels_kernel<<<cdiv(n, 256), 256>>>((const Fr *)flat, logn, levels);
     ZK_CUDA(cudaGetLastError());
-    ZK_CUDA(cudaDeviceSynchronize());
+    device_sync();
     ZK_CUDA(cudaFree(flat));
     return levels;
 }
@@ -155,7 +196,7 @@ Domain *Domain::build(uint64_t min_size) {
         const HFr go = g * om;
         d->z1 = ((go.pow64(d->big) - one) * (go.pow64(d->small) - om.pow64(d->small))).inverse();
     }
-    ZK_CUDA(cudaDeviceSynchronize());
+    device_sync();
     return d;
 }
 void Domain::release() {
@@ -351,7 +392,7 @@ static void decompress_vec(const std::vector<C> &v, A **out, uint8_t **skip, boo
         else decompress_g2_kernel<<<cdiv(n, 128), 128>>>((const zkpk::CompressedG2 *)d_in, n, k, (Affine<Fq2> *)*out, d_bad);
         ZK_CUDA(cudaGetLastError());
     }
-    ZK_CUDA(cudaDeviceSynchronize());
+    device_sync();
     ZK_CUDA(cudaFree(d_in));
     (void)g2;
 }
@@ -422,7 +463,7 @@ void MsmPlan::init(uint32_t n_, int c_, uint32_t ones_, bool g1, bool g2, bool e
         ZK_CUDA(cudaMallocHost(&h_out_g2, nout * sizeof(G2XYZZ)));
     }
 }
-float MsmPlan::last_acc_ms() const { float ms = 0; if (ev_acc0) cudaEventElapsedTime(&ms, ev_acc0, ev_acc1); return ms; }
+float MsmPlan::last_acc_ms() const { float ms = 0; if (ev_acc0 && cudaEventElapsedTime(&ms, ev_acc0, ev_acc1) != cudaSuccess) { (void)cudaGetLastError(); ms = 0; } return ms; }
 void MsmPlan::release() {
     void *ps[] = {counts, offsets, cursors, entries, buckets_g1, buckets_g2, out_g1, out_g2, heavy, heavy_g2, offsets_shifted, aff_pts[0], aff_pts[1], aff_pts[2],
                   aff_pts[3], aff_scratch, team_counters, final_g1, final_g2};
@@ -453,7 +494,7 @@ template <class F>
 static void msm_points(cudaStream_t st, MsmPlan &p, const MsmShape &sh, const Affine<F> *bases, XYZZ<F> *partial, XYZZ<F> *out, void *h_out, bool timed) {
     const uint32_t *off = (const uint32_t *)p.offsets;
     const uint32_t *entries = (const uint32_t *)p.entries;
-    if (timed) ZK_CUDA(cudaEventRecord(p.ev_acc0, st));
+    if (timed) record_for_host(p.ev_acc0, st);
     if constexpr (sizeof(F) == 32) {
         if (p.rounds_now) {
             // halving rounds: list r holds the pairwise sums of list r-1 (list -1 = the sorted entries pointing into the base table)
@@ -471,7 +512,7 @@ static void msm_points(cudaStream_t st, MsmPlan &p, const MsmShape &sh, const Af
     uint32_t *heavy = (uint32_t *)(sizeof(F) == 32 ? p.heavy : p.heavy_g2);
     if (!p.sort_v2_now) ZK_CUDA(cudaMemsetAsync(heavy, 0, 4, st));          // (sort v2: cleared by the scan kernel)
     ZK_LAUNCH(msm_accumulate_kernel<F>, T / 128, 128, 0, st, bases, off, entries, p.total, T, partial);
-    if (timed) ZK_CUDA(cudaEventRecord(p.ev_acc1, st));
+    if (timed) record_for_host(p.ev_acc1, st);
     // Tails.  With the GPU to itself (one proof: latency is what counts) a proof runs them on team point operations (msm_team.cuh: 32 chains per
     // CTA, the four warps share every point addition, 2.0-2.5x shorter chains; the reduction also returns ONE point per region).  With other
     // proofs in flight the one-thread-per-chain kernels are used: the tails then hide under the other proofs' kernels anyway, and the team
@@ -496,26 +537,31 @@ static void msm_points(cudaStream_t st, MsmPlan &p, const MsmShape &sh, const Af
     ZK_CUDA(cudaMemcpyAsync(h_out, out, (size_t)(sh.regions + 1) * p.bpw * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
 }
 
+// what the next run of the plan does, from the flags prove_submit set (alone, latency); also called when a captured proof is replayed, so
+// that msm_finish reads the partial sums the way the replayed kernels wrote them
+static void msm_set_mode(MsmPlan &p) {
+    // A proof that has the GPU to itself skips the affine rounds: with nothing else resident they are bound by gather latency, not by the
+    // multiply pipe, and the plain XYZZ accumulation finishes sooner; with other proofs in flight their 40 % fewer multiplications win.
+    p.rounds_now = (p.affine_rounds && (!p.alone || p.affine_always)) ? p.affine_rounds : 0;
+    p.team_now = (p.latency || p.team_always) ? p.team : 0;
+    p.sort_v2_now = g_sort_v2 && (p.c == 16 || p.c == 8);
+}
 void msm_run(cudaStream_t st, MsmPlan &p, ScalarRef sc, const uint8_t *skip, const void *bases_g1, const void *bases_g2, cudaStream_t st_g2) {
     const MsmShape sh = msm_shape(p.n, p.c, p.ones, p.expanded ? 1 : 0);
     ScalarSrc src{(const uint32_t *)sc.scalars, sc.map, sc.offset, sc.montgomery};
     // sort v2 (default; ZKB200_SORT_V2=0 selects the first version): the scan seeds absolute cursors, clears the counts for the next run and
     // the queues of oversized buckets, and the scatter keeps all atomics of a scalar in flight -- no memsets, shorter scatter
-    const bool v2 = g_sort_v2 && (p.c == 16 || p.c == 8);
+    msm_set_mode(p);
+    const bool v2 = p.sort_v2_now;
     if (!v2) {
         ZK_CUDA(cudaMemsetAsync(p.counts, 0, (size_t)(p.total + 1) * 4, st));
         ZK_CUDA(cudaMemsetAsync(p.cursors, 0, (size_t)(p.total + 1) * 4, st));
     }
     if (p.n) ZK_LAUNCH(msm_count_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (uint32_t *)p.counts);
-    // A proof that has the GPU to itself skips the affine rounds: with nothing else resident they are bound by gather latency, not by the
-    // multiply pipe, and the plain XYZZ accumulation finishes sooner; with other proofs in flight their 40 % fewer multiplications win.
-    p.rounds_now = (p.affine_rounds && (!p.alone || p.affine_always)) ? p.affine_rounds : 0;
-    p.team_now = (p.latency || p.team_always) ? p.team : 0;
     if (p.rounds_now) ZK_CUDA(cudaMemsetAsync(p.entries, 0xff, p.entries_cap * 4, st));          // pads of the bucket runs = null entries
     ZK_LAUNCH(msm_scan_kernel, 1, 1024, 0, st, (uint32_t *)p.counts, (uint32_t *)p.offsets, p.total, p.rounds_now,
               (uint32_t *)(p.rounds_now ? p.offsets_shifted : nullptr), (uint32_t *)(v2 ? p.cursors : nullptr), (uint32_t *)(v2 ? p.heavy : nullptr),
               (uint32_t *)(v2 ? p.heavy_g2 : nullptr));
-    p.sort_v2_now = v2;
     if (p.n && v2 && p.c == 16) ZK_LAUNCH(msm_scatter_abs_kernel<16>, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (uint32_t *)p.cursors, (uint32_t *)p.entries);
     else if (p.n && v2) ZK_LAUNCH(msm_scatter_abs_kernel<8>, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (uint32_t *)p.cursors, (uint32_t *)p.entries);
     else if (p.n) ZK_LAUNCH(msm_scatter_kernel, cdiv(p.n, 256), 256, 0, st, src, skip, sh, (const uint32_t *)p.offsets, (uint32_t *)p.cursors, (uint32_t *)p.entries);
@@ -608,6 +654,10 @@ static Lane *lane_create(const DevicePk *pk, int index) {
     ZK_CUDA(cudaStreamCreateWithPriority(&ln->s_b2, cudaStreamNonBlocking, prio_lo));
     ZK_CUDA(cudaStreamCreateWithPriority(&ln->s_sat, cudaStreamNonBlocking, prio_lo));
     ZK_CUDA(cudaEventCreateWithFlags(&ln->ev_w, cudaEventDisableTiming));
+    ZK_CUDA(cudaMalloc(&ln->sig_dev, Lane::NSIG * 4)); ZK_CUDA(cudaMemset(ln->sig_dev, 0, Lane::NSIG * 4));
+    ZK_CUDA(cudaMallocHost((void **)&ln->sig_host, Lane::NSIG * 4)); memset((void *)ln->sig_host, 0, Lane::NSIG * 4);
+    cudaEvent_t *jev[] = {&ln->ev_ja, &ln->ev_jb, &ln->ev_jl, &ln->ev_jb2};
+    for (auto *e : jev) ZK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     ZK_CUDA(cudaEventCreateWithFlags(&ln->ev_spmv, cudaEventDisableTiming));
     ZK_CUDA(cudaEventCreateWithFlags(&ln->ev_sat, cudaEventDisableTiming));
     cudaEvent_t *tev[] = {&ln->ev_t0, &ln->ev_t1, &ln->ev_q0, &ln->ev_q1, &ln->ev_h0, &ln->ev_h1, &ln->ev_a, &ln->ev_b, &ln->ev_l, &ln->ev_b2};
@@ -624,7 +674,10 @@ static void lane_destroy(Lane *ln) {
     ln->mA.release(); ln->mB.release(); ln->mH.release(); ln->mL.release();
     cudaStream_t ss[] = {ln->s_main, ln->s_a, ln->s_b, ln->s_l, ln->s_b2, ln->s_sat};
     for (auto st : ss) if (st) cudaStreamDestroy(st);
-    cudaEvent_t es[] = {ln->ev_w, ln->ev_a, ln->ev_b, ln->ev_l, ln->ev_b2, ln->ev_t0, ln->ev_t1, ln->ev_q0, ln->ev_q1, ln->ev_h0, ln->ev_h1, ln->ev_spmv, ln->ev_sat};
+    cudaEvent_t es[] = {ln->ev_w, ln->ev_a, ln->ev_b, ln->ev_l, ln->ev_b2, ln->ev_t0, ln->ev_t1, ln->ev_q0, ln->ev_q1, ln->ev_h0, ln->ev_h1, ln->ev_spmv, ln->ev_sat, ln->ev_ja, ln->ev_jb, ln->ev_jl, ln->ev_jb2};
+    for (auto &g : ln->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (ln->sig_dev) cudaFree(ln->sig_dev);
+    if (ln->sig_host) cudaFreeHost((void *)ln->sig_host);
     for (auto e : es) if (e) cudaEventDestroy(e);
     delete ln;
 }
@@ -686,6 +739,7 @@ DevicePk *pk_load(const char *path, int device, std::string &err) {
 DevicePk *pk_from_parsed(const zkpk::ParsedPk &P, int device, std::string &err, double parse_seconds) {
     const double t0 = now_s() - parse_seconds;
     device_init(device);
+    DeviceExclusive excl;
     DevicePk *pk = new DevicePk();
     pk->device = device; pk->parse_seconds = parse_seconds;
     pk->num_inputs = P.num_inputs; pk->num_vars = P.num_inputs + P.num_aux; pk->num_constraints = P.num_constraints;
@@ -743,7 +797,7 @@ DevicePk *pk_from_parsed(const zkpk::ParsedPk &P, int device, std::string &err, 
       e = msm_expand_bases(pk->B2, pk->nB, MSM_C_SIDE, true); cudaFree(pk->B2); pk->B2 = e;
       e = msm_expand_bases(pk->H, pk->nH, MSM_C, false); cudaFree(pk->H); pk->H = e;
       e = msm_expand_bases(pk->L, pk->nL, MSM_C_SIDE, false); cudaFree(pk->L); pk->L = e;
-      ZK_CUDA(cudaDeviceSynchronize()); }
+      device_sync(); }
     pk->expand_seconds = now_s() - t3;
 
     upload_csr(P.a, pk->a); upload_csr(P.b, pk->b); upload_csr(P.c, pk->c);
@@ -756,7 +810,7 @@ DevicePk *pk_from_parsed(const zkpk::ParsedPk &P, int device, std::string &err, 
     if (nl > MAX_LANES) nl = MAX_LANES;
     pk->sync = new LaneSync();
     for (int i = 0; i < nl; i++) { pk->lanes[i] = lane_create(pk, i); pk->nlanes = i + 1; }
-    ZK_CUDA(cudaDeviceSynchronize());
+    device_sync();
     pk->load_seconds = now_s() - t0;
     return pk;
 }
@@ -766,6 +820,7 @@ uint64_t *compact_staging(Lane *ln) { return (uint64_t *)ln->h_w_pinned; }
 void pk_free(DevicePk *pk) {
     if (!pk) return;
     cudaSetDevice(pk->device);
+    DeviceExclusive excl;
     cudaDeviceSynchronize();
     void *ps[] = {pk->A, pk->B1, pk->B2, pk->H, pk->L, pk->A_skip, pk->B_skip, pk->H_skip, pk->L_skip, pk->B_idx, pk->L_idx, pk->a.rowptr, pk->a.col, pk->a.coef,
                   pk->b.rowptr, pk->b.col, pk->b.coef, pk->c.rowptr, pk->c.col, pk->c.coef, pk->coef_dict};
@@ -785,10 +840,12 @@ static void upload_assignment(DevicePk *pk, Lane *ln, const uint8_t *assignment,
     if (assignment) {
         if ((const char *)assignment != pin) memcpy(pin, assignment, n * 32);
         ZK_CUDA(cudaMemcpyAsync((char *)ln->w_can + 32, pin, n * 32 + (zk_scalars ? 96 : 0), cudaMemcpyHostToDevice, st));
+        g_h2d_bytes += n * 32 + (zk_scalars ? 96 : 0);
         ZK_CUDA(cudaMemcpyAsync(ln->w_mont, ln->w_can, (n + 1) * 32, cudaMemcpyDeviceToDevice, st));
         ZK_LAUNCH(to_mont_kernel, cdiv(n + 1, 256), 256, 0, st, (Fr *)ln->w_mont, (uint32_t)(n + 1));
     } else if (zk_scalars) {                            // resident assignment: only r, s, -rs change
         ZK_CUDA(cudaMemcpyAsync((char *)ln->w_can + 32 + n * 32, pin + n * 32, 96, cudaMemcpyHostToDevice, st));
+        g_h2d_bytes += 96;
     }
 }
 
@@ -840,6 +897,7 @@ static void upload_compact(DevicePk *pk, Lane *ln, const uint64_t *lo, const Wid
     nwide += 3;
     ZK_CUDA(cudaMemcpyAsync(ln->w_lo, pin, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     ZK_CUDA(cudaMemcpyAsync(ln->w_wide, pw, nwide * sizeof(WideIn), cudaMemcpyHostToDevice, st));
+    g_h2d_bytes += (size_t)(n + 1) * 8 + nwide * sizeof(WideIn);
     ZK_LAUNCH(expand_assignment_kernel, cdiv(n + 1, 256), 256, 0, st, (const uint64_t *)ln->w_lo, n + 1, (Fr *)ln->w_can, (Fr *)ln->w_mont);
     ZK_LAUNCH(patch_wide_kernel, 1, 64, 0, st, (const WideIn *)ln->w_wide, nwide, n + 1, (Fr *)ln->w_can, (Fr *)ln->w_mont);
 }
@@ -886,6 +944,7 @@ static void upload_compact_seeded(DevicePk *pk, Lane *ln, const uint64_t *lo, co
     ZK_CUDA(cudaMemcpyAsync(ln->w_lo, pin, (size_t)packed * 8, cudaMemcpyHostToDevice, st));
     ZK_CUDA(cudaMemcpyAsync(ln->d_seeds, hs, MAX_SEEDS * sizeof(SeedDev) + (size_t)nseg * sizeof(SegDev), cudaMemcpyHostToDevice, st));
     ZK_CUDA(cudaMemcpyAsync(ln->w_wide, pw, nwide * sizeof(WideIn), cudaMemcpyHostToDevice, st));
+    g_h2d_bytes += (size_t)packed * 8 + MAX_SEEDS * sizeof(SeedDev) + (size_t)nseg * sizeof(SegDev) + nwide * sizeof(WideIn);
     const SegDev *dsegs = (const SegDev *)((const char *)ln->d_seeds + MAX_SEEDS * sizeof(SeedDev));
     if (packed) ZK_LAUNCH(expand_segments_kernel, cdiv(packed, 256), 256, 0, st, (const uint64_t *)ln->w_lo, dsegs, nseg, packed, (Fr *)ln->w_can, (Fr *)ln->w_mont);
     ZK_LAUNCH(sha256_witness_kernel, nseeds * SHA_PARTS, 256, 0, st, (const SeedDev *)ln->d_seeds, (Fr *)ln->w_can, (Fr *)ln->w_mont);
@@ -969,7 +1028,7 @@ int prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64
         }
     } else if (nseeds) return -5;
     device_init(pk->device);
-    g_launches = 0;
+    g_launches = 0; g_h2d_bytes = 0;
     cudaStream_t st = ln->s_main;
     memcpy(ln->r, r, 32); memcpy(ln->s, s, 32);
     uint64_t zks[12];
@@ -979,6 +1038,33 @@ int prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64
     if (lo && nseeds) upload_compact_seeded(pk, ln, lo, wide, nwide, (const SeedDev *)seeds, nseeds, zks, st);
     else if (lo) upload_compact(pk, ln, lo, wide, nwide, zks, st);
     else upload_assignment(pk, ln, assignment, zks, st);
+    const int upload_launches = g_launches;
+    ln->h2d_bytes = g_h2d_bytes;
+    // no other proof in flight on this device (a benign race: only the schedule of the MSMs depends on it).  Device-wide: a mixed batch keeps
+    // proofs of OTHER keys in flight on the same GPU, and the latency schedule -- team tails, two waves -- costs throughput there just the same.
+    bool alone = true;
+    for (int i = 0; i < pk->nlanes; i++) if (pk->lanes[i] != ln && pk->lanes[i]->pending) alone = false;
+    if (pk->device >= 0 && pk->device < 64 && g_device_pending[pk->device].fetch_add(1, std::memory_order_relaxed) > 0) alone = false;
+    ln->mA.latency = ln->mB.latency = ln->mL.latency = ln->mH.latency = alone;
+    ln->mH.alone = alone;
+    // Everything behind the upload is the same sequence of launches for every proof on this lane (given `alone`): it is captured into a
+    // CUDA graph the first time and replayed with ONE driver call afterwards.  The ~90 driver calls a proof otherwise takes are nothing for
+    // one GPU, but the driver serialises them per process: one process feeding 8 GPUs topped out at 3 080 proofs/s where 8 processes reached
+    // 4 800 (profiles/r02_notes.md).  ZKB200_GRAPH=0 enqueues kernel by kernel as before; the roofline's isolate mode always does.
+    const bool use_graph = g_use_graph && !g_isolate_h;
+    Lane::LaneGraph &lg = ln->graph[alone ? 1 : 0];
+    auto signal = [&](int k, cudaStream_t on) { ZK_LAUNCH(signal_kernel, 1, 1, 0, on, ln->sig_host + k, ln->sig_dev + k); };
+    if (use_graph && lg.exec) {
+        msm_set_mode(ln->mA); msm_set_mode(ln->mB); msm_set_mode(ln->mL); msm_set_mode(ln->mH);
+        ZK_CUDA(cudaGraphLaunch(lg.exec, st));
+        ZK_CUDA(cudaEventRecord(ln->ev_t1, st));
+        ln->launches = upload_launches + lg.launches;
+        ln->sig_epoch++;
+        ln->pending = true;
+        return 0;
+    }
+    std::shared_lock<std::shared_mutex> capture_lock(g_capture_mu[pk->device & 63], std::defer_lock);
+    if (use_graph) { capture_lock.lock(); ZK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed)); g_capturing = true; }
     ZK_CUDA(cudaEventRecord(ln->ev_w, st));
     // A, B, L queries on side streams: scalars are the canonical padded assignment [1 | w]  (r1cs_gg_ppzksnark.tcc:437-484); the trailing
     // delta base of each query picks up r, s, -rs, so the MSM results already are  eA + r*delta,  eB + s*delta,  eL - rs*delta.
@@ -991,30 +1077,40 @@ int prove_submit(DevicePk *pk, Lane *ln, const uint8_t *assignment, const uint64
         msm_run(ln->s_b, ln->mB, ScalarRef{ln->w_can, pk->B_idx, 0, 0}, pk->B_skip, pk->B1, pk->B2, ln->s_b2);
         msm_run(ln->s_a, ln->mA, ScalarRef{ln->w_can, nullptr, 0, 0}, pk->A_skip, pk->A, nullptr);
         msm_run(ln->s_l, ln->mL, ScalarRef{ln->w_can, pk->L_idx, 0, 0}, pk->L_skip, pk->L, nullptr);
-        ZK_CUDA(cudaEventRecord(ln->ev_a, ln->s_a)); ZK_CUDA(cudaEventRecord(ln->ev_b, ln->s_b)); ZK_CUDA(cudaEventRecord(ln->ev_l, ln->s_l));
-        ZK_CUDA(cudaEventRecord(ln->ev_b2, ln->s_b2));
+        // signals: what prove_collect polls; ev_a .. ev_b2: when the queries finished (statistics); ev_ja .. ev_jb2: the joins into s_main
+        signal(Lane::SIG_A, ln->s_a); signal(Lane::SIG_B, ln->s_b); signal(Lane::SIG_L, ln->s_l); signal(Lane::SIG_B2, ln->s_b2);
+        record_for_host(ln->ev_a, ln->s_a); record_for_host(ln->ev_b, ln->s_b); record_for_host(ln->ev_l, ln->s_l); record_for_host(ln->ev_b2, ln->s_b2);
+        ZK_CUDA(cudaEventRecord(ln->ev_ja, ln->s_a)); ZK_CUDA(cudaEventRecord(ln->ev_jb, ln->s_b)); ZK_CUDA(cudaEventRecord(ln->ev_jl, ln->s_l));
+        ZK_CUDA(cudaEventRecord(ln->ev_jb2, ln->s_b2));
     };
     auto wait_side = [&]() {
-        ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_a, 0)); ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_b, 0)); ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_l, 0));
-        ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_b2, 0));
+        ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_ja, 0)); ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_jb, 0)); ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_jl, 0));
+        ZK_CUDA(cudaStreamWaitEvent(st, ln->ev_jb2, 0));
     };
     // H: QAP witness map, then the dense MSM over coefficients_for_H[0 .. m-1).  This is the critical path, so the QAP map is enqueued
     // first (the host needs ~0.2 ms to enqueue the side queries).  Measurement mode: H waits for the side queries.
-    // no other proof of this key in flight (a benign race: only the schedule of the MSMs depends on it)
-    bool alone = true;
-    for (int i = 0; i < pk->nlanes; i++) if (pk->lanes[i] != ln && pk->lanes[i]->pending) alone = false;
-    ln->mA.latency = ln->mB.latency = ln->mL.latency = ln->mH.latency = alone;
-    ZK_CUDA(cudaEventRecord(ln->ev_q0, st));
+    record_for_host(ln->ev_q0, st);
     qap_pipeline(pk, ln, st);
-    ZK_CUDA(cudaEventRecord(ln->ev_q1, st));
+    record_for_host(ln->ev_q1, st);
     side_queries();                           // enqueued while the GPU is busy with the QAP map: they run beside it and are mostly done when H starts
     if (g_isolate_h) wait_side();
-    ZK_CUDA(cudaEventRecord(ln->ev_h0, st));
-    ln->mH.alone = alone;
+    record_for_host(ln->ev_h0, st);
     msm_run(st, ln->mH, ScalarRef{ln->tmp, nullptr, 0, 1}, pk->H_skip, pk->H, nullptr);
-    ZK_CUDA(cudaEventRecord(ln->ev_h1, st));
+    record_for_host(ln->ev_h1, st);
     wait_side();
-    ZK_CUDA(cudaEventRecord(ln->ev_t1, st));
+    signal(Lane::SIG_DONE, st);
+    if (use_graph) {
+        g_capturing = false;
+        cudaGraph_t graph = nullptr;
+        ZK_CUDA(cudaStreamEndCapture(st, &graph));
+        capture_lock.unlock();
+        ZK_CUDA(cudaGraphInstantiate(&lg.exec, graph, 0));
+        ZK_CUDA(cudaGraphDestroy(graph));
+        lg.launches = g_launches - upload_launches;
+        ZK_CUDA(cudaGraphLaunch(lg.exec, st));
+    }
+    ZK_CUDA(cudaEventRecord(ln->ev_t1, st));            // plain record behind the proof: the end of its GPU time
+    ln->sig_epoch++;
     ln->launches = g_launches;
     ln->pending = true;
     return 0;
@@ -1037,6 +1133,19 @@ static void wait_event(cudaEvent_t ev) {
     }
 }
 
+static void wait_signal(const Lane *ln, int k) {
+    const volatile uint32_t *flag = ln->sig_host + k;
+    const uint32_t want = ln->sig_epoch;
+    if (!g_spin) { while ((int32_t)(*flag - want) < 0) std::this_thread::sleep_for(std::chrono::microseconds(20)); return; }
+    while ((int32_t)(*flag - want) < 0) {
+#if defined(__x86_64__)
+        for (int i = 0; i < 32; i++) __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+}
+
 int prove_collect(DevicePk *pk, Lane *ln, ProofPoints &out) {
     if (!ln->pending) return -1;
     device_init(pk->device);
@@ -1046,13 +1155,13 @@ int prove_collect(DevicePk *pk, Lane *ln, ProofPoints &out) {
     // host time -- is done while the GPU is still busy with it.
     // The G1 queries first: the G2 half of B (3x the field work, the longest bucket reduction) is the last side chain to finish -- for the
     // smaller circuits barely before the H query -- and nothing below needs it until out.B.
-    wait_event(ln->ev_a); wait_event(ln->ev_b); wait_event(ln->ev_l);
+    wait_signal(ln, Lane::SIG_A); wait_signal(ln, Lane::SIG_B); wait_signal(ln, Lane::SIG_L);
     const HG1 eAr = msm_finish_g1(ln->mA), eB1s = msm_finish_g1(ln->mB), eLrs = msm_finish_g1(ln->mL);
     const HG1 gA = HG1::from_affine(pk->alpha_g1).add(eAr);
     const HG1 g1B = HG1::from_affine(pk->beta_g1).add(eB1s);
     const HG1 c_part = eLrs.add(gA.mul(s)).add(g1B.mul(r));
     out.A = gA.to_affine();
-    wait_event(ln->ev_b2);
+    wait_signal(ln, Lane::SIG_B2);
     const HG2 eB2s = msm_finish_g2(ln->mB);
     const HG2 g2B = HG2::from_affine(pk->beta_g2).add(eB2s);
     out.B = g2B.to_affine();
@@ -1065,19 +1174,27 @@ int prove_collect(DevicePk *pk, Lane *ln, ProofPoints &out) {
         out.Bt_g = eB2s.add(HG2::from_affine(pk->delta_g2).mul(s).neg()).to_affine();
     }
 
-    wait_event(ln->ev_t1);                          // recorded on s_main after everything of this proof, the side streams joined
+    wait_signal(ln, Lane::SIG_DONE);                // the last thing on s_main, after the side streams joined
+    wait_event(ln->ev_t1);                          // (recorded right behind it: the timings below need it complete)
     const double t_sync = now_s();
     ln->pending = false;
+    if (pk->device >= 0 && pk->device < 64) g_device_pending[pk->device].fetch_sub(1, std::memory_order_relaxed);
     ZK_CUDA(cudaEventElapsedTime(&out.gpu_ms, ln->ev_t0, ln->ev_t1));
-    ZK_CUDA(cudaEventElapsedTime(&out.qap_ms, ln->ev_q0, ln->ev_q1));
-    ZK_CUDA(cudaEventElapsedTime(&out.msm_h_ms, ln->ev_h0, ln->ev_h1));
+    out.qap_ms = elapsed_ms(ln->ev_q0, ln->ev_q1);
+    out.msm_h_ms = elapsed_ms(ln->ev_h0, ln->ev_h1);
     out.acc_h_ms = ln->mH.last_acc_ms();
-    ZK_CUDA(cudaEventElapsedTime(&out.a_done_ms, ln->ev_t0, ln->ev_a));
-    { float b1 = 0, b2 = 0; ZK_CUDA(cudaEventElapsedTime(&b1, ln->ev_t0, ln->ev_b)); ZK_CUDA(cudaEventElapsedTime(&b2, ln->ev_t0, ln->ev_b2)); out.b_done_ms = b1 > b2 ? b1 : b2; }
-    ZK_CUDA(cudaEventElapsedTime(&out.l_done_ms, ln->ev_t0, ln->ev_l));
+    out.a_done_ms = elapsed_ms(ln->ev_t0, ln->ev_a);
+    { const float b1 = elapsed_ms(ln->ev_t0, ln->ev_b), b2 = elapsed_ms(ln->ev_t0, ln->ev_b2); out.b_done_ms = b1 > b2 ? b1 : b2; }
+    out.l_done_ms = elapsed_ms(ln->ev_t0, ln->ev_l);
     out.satisfied = (*ln->h_sat_flag == 0);
     out.launches = ln->launches;
     g_last_launches = ln->launches;
+    // what crossed PCIe for this proof: the uploads of prove_submit; back: the partial sums of the four queries and the is_satisfied flag
+    auto d2h = [](const MsmPlan &p) {
+        const unsigned long long per = (p.team_now & 4) ? ((p.team_dbg & 1) ? p.bpw_team : 1u) : p.bpw;
+        return (unsigned long long)(p.regions + 1) * per * ((p.out_g1 ? sizeof(G1XYZZ) : 0) + (p.out_g2 ? sizeof(G2XYZZ) : 0));
+    };
+    g_last_bytes[0] = ln->h2d_bytes; g_last_bytes[1] = 4 + d2h(ln->mA) + d2h(ln->mB) + d2h(ln->mL) + d2h(ln->mH);
     const HG1 eH = msm_finish_g1(ln->mH);
     if (out.want_parts) out.Ht = eH.to_affine();
     out.C = eH.add(c_part).to_affine();

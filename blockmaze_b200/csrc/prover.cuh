@@ -105,11 +105,17 @@ struct Lane {
     uint32_t *sat_flag = nullptr; uint32_t *h_sat_flag = nullptr;
     MsmPlan mA, mB, mH, mL;
     cudaStream_t s_main = nullptr, s_a = nullptr, s_b = nullptr, s_l = nullptr, s_b2 = nullptr;
+    cudaEvent_t ev_ja = nullptr, ev_jb = nullptr, ev_jl = nullptr, ev_jb2 = nullptr;     // joins of the side streams into s_main (ev_a .. ev_b2 are what the host polls)
+    enum { SIG_A = 0, SIG_B, SIG_L, SIG_B2, SIG_DONE, NSIG };
+    uint32_t *sig_dev = nullptr; volatile uint32_t *sig_host = nullptr; uint32_t sig_epoch = 0;   // completion signals: device counters, pinned host words, proofs submitted
+    struct LaneGraph { cudaGraphExec_t exec = nullptr; int launches = 0; };
+    LaneGraph graph[2];                                  // everything of a proof behind the upload, captured once: [0] other proofs in flight, [1] alone
     cudaStream_t s_sat = nullptr; cudaEvent_t ev_spmv = nullptr, ev_sat = nullptr;      // is_satisfied runs beside the first inverse transforms
     cudaEvent_t ev_w = nullptr, ev_a = nullptr, ev_b = nullptr, ev_l = nullptr, ev_b2 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_q0 = nullptr, ev_q1 = nullptr,
                 ev_h0 = nullptr, ev_h1 = nullptr;
     uint64_t r[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0};   // zero-knowledge scalars of the proof in flight
     int launches = 0;                                    // kernels launched for the proof in flight
+    unsigned long long h2d_bytes = 0;                    // bytes its upload copied to the device
     bool pending = false;                                // submitted, not yet collected
 };
 constexpr int MAX_LANES = 8;
@@ -178,11 +184,13 @@ uint64_t *compact_staging(Lane *ln);                    // pinned, (num_vars + 1
 int qap_witness_map(DevicePk *pk, const uint8_t *assignment, uint8_t *out_H, int *satisfied);
 
 void device_init(int device);
+void device_sync();                                 // cudaDeviceSynchronize of the current device, never while one of its streams is being captured
 std::vector<int> devices_in_use();                  // every device device_init() has been called for
 std::string proof_hex(const ProofPoints &p);           // mintcgo.cpp:112-187 layout
 // measurement mode: the H-query MSM of the next proofs starts only after the A, B, L queries are done, so that the CUDA-event time of
 // its kernels is that of the kernels alone (roofline); costs latency, never used otherwise
 void set_isolate_h(bool on);
 int launches_last_prove();                             // number of kernels launched by the last collected proof
+void transfer_bytes_last_prove(unsigned long long out[2]);   // host-to-device, device-to-host bytes of the last proof this thread collected
 
 } // namespace zkp

@@ -70,7 +70,8 @@ enum { ZKB200_MINT = 0, ZKB200_SEND = 1, ZKB200_DEPOSIT = 2, ZKB200_REDEEM = 3 }
  *   zkb200_init           device of the layer-(2) calls that take no key handle (kernel entry points, benches).  0, or -1 if no GPU.
  *   zkb200_set_devices    active devices of layer (1); n = 0 selects every visible device.  Returns how many, or -1.  Resident keys are dropped.
  *   zkb200_active_devices copies the active device list, returns its length
- *   zkb200_last_device    device that proved this thread's last gen*proof */
+ *   zkb200_last_device    device that proved this thread's last gen*proof
+ *   zkb200_device_proofs  gen*proof calls this process has finished on `device` so far (what the scheduler dealt to it), or -1 */
 int zkb200_init(int device);
 int zkb200_ensure_device(void);
 int zkb200_device_count(void);
@@ -78,6 +79,7 @@ int zkb200_current_device(void);
 int zkb200_set_devices(const int *devices, int n);
 int zkb200_active_devices(int *out, int cap);
 int zkb200_last_device(void);
+long zkb200_device_proofs(int device);
 /* parity hook: copies the assignment (num_variables x 32 B canonical) that sits on the GPU behind this thread's last gen*proof call -- with
  * the SHA-256 gadget runs expanded on the device (default; ZKB200_GPU_WITNESS=0 has the host generator write them).  Returns the number of
  * variables or -1.  Only meaningful while no other caller has reused that lane. */
@@ -180,6 +182,9 @@ int zkb200_qap_witness_map(void *pk, const uint8_t *assignment, uint8_t *out_H, 
 void zkb200_last_breakdown_ms(double out[4]);
 /* kernels launched for the last collected proof */
 int zkb200_last_launches(void);
+/* bytes the last proof this thread made (gen*proof, zkb200_prove*) moved over PCIe: out[0] host to device (the assignment upload -- 60 KB for a
+ * send proof with the SHA-256 runs expanded on the GPU), out[1] device to host (partial sums of the four queries, the is_satisfied flag) */
+void zkb200_last_transfer_bytes(unsigned long long out[2]);
 /* measurement mode (bench.py roofline): when on, a proof's H-query MSM starts only after its A, B, L queries are done, so the CUDA-event
  * time of the H kernels (timings_ms[2], [4]) is that of the kernels running alone.  Costs latency; off by default. */
 void zkb200_set_isolate_h(int on);

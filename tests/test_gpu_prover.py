@@ -219,6 +219,29 @@ def test_cgo_concurrent_callers(zk):
         assert zk.verify_proof(c, p, zk.verify_args(c, args))
 
 
+def test_proof_accounting_counters(zk):
+    """What the bench quotes from the library: zkb200_last_transfer_bytes (a send proof with the SHA-256 runs expanded on the GPU uploads tens
+    of KB, not the 7.3 MB of its full assignment, and a few KB of partial sums come back), zkb200_device_proofs (one more proof on exactly one
+    device), zkb200_last_launches (the proof replayed from the lane's CUDA graph reports its kernels too)."""
+    import ctypes as C
+    from blockmaze_b200 import api
+    zk.set_key_dir(key_dir())
+    api.lib.zkb200_device_proofs.restype = C.c_long
+    nd = api.lib.zkb200_device_count()
+    count = lambda: sum(int(api.lib.zkb200_device_proofs(d)) for d in range(nd))
+    zk.gen_proof("send", F.synthetic("send", 70))                 # first proof on the lane: captures the graph
+    before = count()
+    args = F.synthetic("send", 71)
+    p = zk.gen_proof("send", args)                                # replayed
+    assert zk.verify_proof("send", p, zk.verify_args("send", args))
+    assert count() == before + 1
+    xfer = (C.c_ulonglong * 2)()
+    api.lib.zkb200_last_transfer_bytes(xfer)
+    assert 8 << 10 <= int(xfer[0]) <= 400 << 10, int(xfer[0])
+    assert 256 <= int(xfer[1]) <= 400 << 10, int(xfer[1])
+    assert 30 <= api.lib.zkb200_last_launches() <= 80
+
+
 @pytest.mark.parametrize("circuit", CIRCUITS)
 def test_reference_verifier_accepts_gpu_proof(zk, ref, circuit):
     """north_star: a GPU proof 'must pass the reference verifier'.  The UNMODIFIED reference verifier (verify_<c>_proof ->

@@ -1133,16 +1133,23 @@ static void wait_event(cudaEvent_t ev) {
     }
 }
 
+// A faulted GPU never sets the flag: every few milliseconds of waiting the event recorded behind the proof is queried, which reports the
+// sticky error of a crashed kernel -- and the library aborts loudly instead of hanging.
 static void wait_signal(const Lane *ln, int k) {
     const volatile uint32_t *flag = ln->sig_host + k;
     const uint32_t want = ln->sig_epoch;
-    if (!g_spin) { while ((int32_t)(*flag - want) < 0) std::this_thread::sleep_for(std::chrono::microseconds(20)); return; }
-    while ((int32_t)(*flag - want) < 0) {
+    auto alive = [&]() { const cudaError_t e = cudaEventQuery(ln->ev_t1); if (e != cudaSuccess && e != cudaErrorNotReady) ZK_CUDA(e); };
+    if (!g_spin) {
+        for (uint32_t n = 1; (int32_t)(*flag - want) < 0; n++) { std::this_thread::sleep_for(std::chrono::microseconds(20)); if ((n & 255u) == 0) alive(); }
+        return;
+    }
+    for (uint32_t n = 1; (int32_t)(*flag - want) < 0; n++) {
 #if defined(__x86_64__)
         for (int i = 0; i < 32; i++) __builtin_ia32_pause();
 #else
         std::this_thread::yield();
 #endif
+        if ((n & 8191u) == 0) alive();
     }
 }
 
